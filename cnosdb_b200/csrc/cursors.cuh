@@ -1,0 +1,389 @@
+// cursors.cuh — per-lane streaming decoders for TSM column pages (sm_100a).
+//
+// Design: one lane owns one page and walks it value by value, so decode -> filter -> bucket
+// reduce happens in registers and no decoded value is ever written to HBM. The formats are those of
+// the reference codecs (all paths relative to the reference tree):
+//   page framing     tskv/src/tsm/page.rs:31-94
+//   simple8b         tskv/src/tsm/codec/simple8b.rs:80-208
+//   timestamp delta  tskv/src/tsm/codec/timestamp.rs:177-299   (deltas NOT zig-zagged, 10^k scaler)
+//   integer delta    tskv/src/tsm/codec/integer.rs:142-248     (zig-zag deltas)
+//   gorilla          tskv/src/tsm/codec/float.rs:418-606
+//   raw ("Null")     tskv/src/tsm/codec/timestamp.rs:301-323, float.rs:387-413
+// Arithmetic wraps like the reference's release build (Cargo.toml:190-197).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/tskv_gpu.h"
+#include "kinds.h"
+
+namespace tskv {
+
+__device__ __forceinline__ uint64_t bswap64(uint64_t v) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+__device__ __forceinline__ int64_t zigzag_dec(uint64_t v) {
+  return (int64_t)((v >> 1) ^ (0 - (v & 1)));
+}
+
+// Streams an arbitrarily aligned byte range as big-endian u64 words using only aligned 8-byte
+// global loads (one load per word; the previous aligned word is kept and funnel-shifted).
+// May read up to 15 bytes past `end`: the arena carries 64 bytes of slack.
+struct BeStream {
+  const uint64_t *ap;  // next aligned word
+  uint64_t cur;        // last aligned word, little-endian
+  uint32_t sh;         // misalignment in bits
+  __device__ __forceinline__ void init(const uint8_t *p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    sh = (uint32_t)(a & 7) * 8;
+    ap = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    cur = __ldg(ap++);
+  }
+  __device__ __forceinline__ uint64_t next() {
+    uint64_t nxt = __ldg(ap++);
+    uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
+    cur = nxt;
+    return bswap64(raw);
+  }
+};
+
+__device__ __forceinline__ uint64_t load_be64(const uint8_t *p) {
+  BeStream s;
+  s.init(p);
+  return s.next();
+}
+__device__ __forceinline__ uint32_t load_be32_aligned(const uint8_t *p) {
+  return __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(p)), 0, 0x0123);
+}
+
+// Parsed page header (page.rs:78-94).
+struct PageView {
+  const uint8_t *bitset;  // 16-byte aligned (page offset is)
+  const uint8_t *data;
+  uint32_t data_len;
+  uint32_t n_rows;
+  __device__ __forceinline__ void open(const uint8_t *arena, const tskv_page_desc &d) {
+    const uint8_t *pg = arena + d.offset;
+    uint4 h = __ldg(reinterpret_cast<const uint4 *>(pg));
+    uint32_t bitset_len = __byte_perm(h.x, 0, 0x0123);
+    // rows: u64 BE at [4..12); the host validated it equals desc.num_values (< 2^32)
+    n_rows = d.num_values;
+    bitset = pg + 16;
+    data = pg + 16 + bitset_len;
+    data_len = d.size - 16 - bitset_len;
+  }
+};
+
+// Validity bitmap, Arrow LSB-first (page.rs:78-84).
+struct BitCursor {
+  const uint32_t *wp;
+  uint32_t word;
+  __device__ __forceinline__ void init(const uint8_t *bitset) {
+    wp = reinterpret_cast<const uint32_t *>(bitset);
+    word = 0;
+  }
+  // `row` must advance by one per call starting at 0.
+  __device__ __forceinline__ bool next(uint32_t row) {
+    if ((row & 31) == 0) word = __ldg(wp++);
+    bool b = word & 1;
+    word >>= 1;
+    return b;
+  }
+};
+
+__constant__ uint8_t c_s8b_count[16] = {240, 120, 60, 30, 20, 15, 12, 10, 8, 7, 6, 5, 4, 3, 2, 1};
+__constant__ uint8_t c_s8b_bits[16] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 20, 30, 60};
+
+// LEB128 (integer-encoding 4.0.2 decode_var); returns false when the slice ends first.
+__device__ inline bool decode_varint(const uint8_t *p, uint32_t len, uint64_t *out) {
+  uint64_t r = 0;
+  uint32_t shift = 0;
+  for (uint32_t i = 0; i < len; i++) {
+    uint8_t b = __ldg(p + i);
+    if (shift < 64) r |= (uint64_t)(b & 0x7f) << shift;
+    shift += 7;
+    if ((b & 0x80) == 0) {
+      *out = r;
+      return true;
+    }
+    if (shift > 63) return false;
+  }
+  return false;
+}
+
+__device__ __forceinline__ uint64_t pow10_u64(uint32_t k) {
+  uint64_t s = 1;
+  for (uint32_t i = 0; i < k; i++) s *= 10;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Delta-family cursor: RLE / simple8b / raw prefix sum / raw BE, zig-zag or scaled.
+// KIND is one of the DK_* delta kinds, or -1 for a runtime switch on `kind` (generic path).
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+struct DeltaCursor {
+  BeStream bs;
+  uint64_t v;           // running value (raw bits)
+  uint64_t delta;       // RLE delta (already scaled / zig-zag decoded)
+  uint64_t scaler;      // S8B_SC
+  uint64_t w;           // current simple8b word, consumed from the low bits
+  uint32_t words_left;  // 8-byte words not yet loaded
+  uint32_t in_word;     // values left in `w`
+  uint32_t bits;        // width of one value in `w` (0 => run of ones)
+  uint8_t kind;         // runtime kind (== KIND when KIND >= 0)
+  bool first;           // next value is the first of the page
+
+  __device__ __forceinline__ int k() const { return KIND >= 0 ? KIND : kind; }
+
+  // Returns TSKV_OK or a decode error. `pv.data` starts at the Encoding id byte; the host already
+  // classified the page, so lengths needed by the fixed header are guaranteed.
+  __device__ inline tskv_status open(const PageView &pv, uint8_t kind_) {
+    kind = KIND >= 0 ? (uint8_t)KIND : kind_;
+    first = true;
+    v = 0;
+    delta = 0;
+    scaler = 1;
+    w = 0;
+    in_word = 0;
+    bits = 0;
+    words_left = 0;
+    const uint8_t *d = pv.data;
+    switch (k()) {
+      case DK_RLE_SC: {  // timestamp.rs:226-259: data = id | kind/scaler | first(8) | varint delta | varint n
+        uint64_t dl;
+        if (!decode_varint(d + 10, pv.data_len - 10, &dl)) return TSKV_ERR_SHORT_BLOCK;
+        v = load_be64(d + 2);
+        delta = dl * pow10_u64(__ldg(d + 1) & 0xf);
+        break;
+      }
+      case DK_RLE_ZZ: {  // integer.rs:186-214
+        uint64_t dl;
+        if (!decode_varint(d + 10, pv.data_len - 10, &dl)) return TSKV_ERR_SHORT_BLOCK;
+        v = (uint64_t)zigzag_dec(load_be64(d + 2));
+        delta = (uint64_t)zigzag_dec(dl);
+        break;
+      }
+      case DK_S8B_SC:  // timestamp.rs:261-299
+        scaler = pow10_u64(__ldg(d + 1) & 0xf);
+        bs.init(d + 2);
+        v = bs.next();
+        words_left = (pv.data_len - 10) >> 3;
+        break;
+      case DK_S8B_ZZ:  // integer.rs:216-248
+        bs.init(d + 2);
+        v = (uint64_t)zigzag_dec(bs.next());
+        words_left = (pv.data_len - 10) >> 3;
+        break;
+      case DK_RAW_SC:  // timestamp.rs:201-224
+      case DK_RAW_ZZ:  // integer.rs:165-184
+        bs.init(d + 2);
+        words_left = (pv.data_len - 2) >> 3;
+        break;
+      case DK_RAWBE:  // timestamp.rs:301-323
+        bs.init(d + 1);
+        words_left = (pv.data_len - 1) >> 3;
+        break;
+      default:
+        break;
+    }
+    return TSKV_OK;
+  }
+
+  // Next simple8b payload value (simple8b.rs:95-208). Sets *ok=false when the words run out.
+  __device__ __forceinline__ uint64_t next_packed(bool *ok) {
+    if (in_word == 0) {
+      if (words_left == 0) {
+        *ok = false;
+        return 0;
+      }
+      words_left--;
+      w = bs.next();
+      uint32_t sel = (uint32_t)(w >> 60);
+      in_word = c_s8b_count[sel];
+      bits = c_s8b_bits[sel];
+      w &= 0x0fffffffffffffffull;
+    }
+    in_word--;
+    uint64_t mask = bits ? (~0ull >> (64 - bits)) : 0ull;
+    uint64_t u = bits ? (w & mask) : 1ull;
+    w >>= bits;  // bits <= 60
+    return u;
+  }
+
+  // Value for the next VALID row. *ok=false => more valid rows than encoded values.
+  __device__ __forceinline__ uint64_t next(bool *ok) {
+    switch (k()) {
+      case DK_RLE_SC:
+      case DK_RLE_ZZ:
+        if (!first) v += delta;
+        first = false;
+        return v;
+      case DK_S8B_SC:
+        if (!first) {
+          uint64_t u = next_packed(ok);
+          v += u * scaler;
+        }
+        first = false;
+        return v;
+      case DK_S8B_ZZ:
+        if (!first) {
+          uint64_t u = next_packed(ok);
+          v += (uint64_t)zigzag_dec(u);
+        }
+        first = false;
+        return v;
+      case DK_RAW_SC:
+        if (words_left == 0) {
+          *ok = false;
+          return 0;
+        }
+        words_left--;
+        v += bs.next();
+        return v;
+      case DK_RAW_ZZ:
+        if (words_left == 0) {
+          *ok = false;
+          return 0;
+        }
+        words_left--;
+        v += (uint64_t)zigzag_dec(bs.next());
+        return v;
+      case DK_RAWBE:
+        if (words_left == 0) {
+          *ok = false;
+          return 0;
+        }
+        words_left--;
+        return bs.next();
+      default:  // DK_ALLNULL and error kinds never reach here with a valid bit
+        *ok = false;
+        return 0;
+    }
+  }
+
+  // timestamp.rs:273-279 quirk: with simple8b timestamps a NULL row 0 swallows the first value.
+  __device__ __forceinline__ void skip_first_if_s8b_sc() {
+    if (k() == DK_S8B_SC) first = false;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Gorilla cursor (float.rs:418-606): MSB-first bit stream after id | 0x10 | first(8).
+// Terminates on the sentinel 0x7ff8_0000_0000_00ff (float.rs:16).
+// ------------------------------------------------------------------------------------------------
+struct GorillaCursor {
+  BeStream bs;
+  uint64_t val;
+  uint64_t buf;        // unread bits, MSB-aligned
+  uint32_t avail;      // valid bits in buf
+  uint32_t bits_left;  // bits not yet loaded into buf
+  uint32_t trailing, meaningful;
+  bool first, done, err;
+
+  __device__ inline tskv_status open(const PageView &pv) {
+    first = true;
+    done = false;
+    err = false;
+    buf = 0;
+    avail = 0;
+    trailing = 0;
+    meaningful = 64;
+    const uint8_t *d = pv.data;
+    bs.init(d + 2);
+    val = bs.next();
+    bits_left = (pv.data_len - 10) * 8;
+    return TSKV_OK;
+  }
+
+  // Reads n in [1,64] bits. Sets err when the stream ends ("unexpected end of block").
+  __device__ __forceinline__ uint64_t take(uint32_t n) {
+    uint64_t r;
+    if (n <= avail) {
+      r = buf >> (64 - n);
+      buf = (buf << 1) << (n - 1);
+      avail -= n;
+      return r;
+    }
+    uint32_t need = n - avail;  // 1..64
+    r = avail ? (buf >> (64 - avail)) : 0;
+    if (bits_left < need) {
+      err = true;
+      return 0;
+    }
+    uint64_t nxt = bs.next();
+    uint32_t got = bits_left < 64 ? bits_left : 64;
+    bits_left -= got;
+    r = ((r << 1) << (need - 1)) | (nxt >> (64 - need));
+    buf = (nxt << 1) << (need - 1);
+    avail = got - need;
+    return r;
+  }
+
+  // Decodes the next stream element; returns false at the sentinel / on error.
+  __device__ __forceinline__ bool advance() {
+    if (take(1) == 0) return !err;  // repeat previous value
+    if (err) return false;
+    if (take(1) != 0) {
+      if (err) return false;
+      uint32_t lm = (uint32_t)take(11);
+      if (err) return false;
+      uint32_t leading = (lm >> 6) & 0x1f;
+      meaningful = lm & 0x3f;
+      if (meaningful > 0) {
+        trailing = (uint8_t)(64 - leading - meaningful);  // u8 arithmetic like the reference
+      } else {
+        trailing = 0;
+        meaningful = 64;
+      }
+    }
+    if (err) return false;
+    uint64_t s = take(meaningful);
+    if (err) return false;
+    val ^= s << (trailing & 0x3f);
+    return val != 0x7ff80000000000ffull;
+  }
+
+  // Value for the next VALID row; *ok=false => stream ended before the bitset did.
+  __device__ __forceinline__ uint64_t next(bool *ok) {
+    if (first) {
+      first = false;
+      return val;
+    }
+    if (done || !advance()) {
+      done = true;
+      *ok = false;
+      return 0;
+    }
+    return val;
+  }
+};
+
+// Runtime-dispatched cursor over every supported kind (decode-only kernel and generic scan path).
+struct AnyCursor {
+  DeltaCursor<-1> d;
+  GorillaCursor g;
+  bool is_gorilla;
+  __device__ inline tskv_status open(const PageView &pv, uint8_t kind) {
+    is_gorilla = kind == DK_GORILLA;
+    if (is_gorilla) return g.open(pv);
+    return d.open(pv, kind);
+  }
+  __device__ __forceinline__ uint64_t next(bool *ok) { return is_gorilla ? g.next(ok) : d.next(ok); }
+  __device__ __forceinline__ bool stream_error() const { return is_gorilla && g.err; }
+};
+
+// Error status a page kind maps to before any decoding (host classification).
+__device__ __forceinline__ tskv_status kind_status(uint8_t kind) {
+  switch (kind) {
+    case DK_BAD_ENCODING: return TSKV_ERR_BAD_ENCODING;
+    case DK_UNSUPPORTED: return TSKV_ERR_UNSUPPORTED;
+    case DK_SHORT: return TSKV_ERR_SHORT_BLOCK;
+    case DK_BAD_LENGTH: return TSKV_ERR_BAD_LENGTH;
+    case DK_BAD_PAGE: return TSKV_ERR_PAGE_FORMAT;
+    default: return TSKV_OK;
+  }
+}
+
+}  // namespace tskv

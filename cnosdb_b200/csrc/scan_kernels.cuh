@@ -1,0 +1,764 @@
+// scan_kernels.cuh — sm_100a kernels of the tskv scan path:
+//   k_select_cg / k_flag_items / k_scan_blocks / k_scatter_items : series selection -> compacted,
+//       kind-sorted work list (replaces get_series_id_by_filter's consumer side,
+//       tskv/src/reader/iterator.rs:915-929 + SeriesGroupBatchReaderFactory::create :123-264)
+//   k_scan_aggregate<TK,VK> : fused decode -> closed time-range filter -> bucket id -> reduce
+//       (replaces ColumnGroupReader::read + decode_pages + DataFilter + the DataFusion
+//        projection/AggregateExec above the scan; SURVEY.md §3.1 hot loops A, B and C)
+//   k_export_pairs / k_mask_values / k_finalize : partial state -> dense Arrow-style result
+//   k_decode_pages : decode-only (Page::to_arrow_array, tsm/reader.rs:658-731)
+#pragma once
+#include "cursors.cuh"
+
+namespace tskv {
+
+constexpr uint32_t FULL = 0xffffffffu;
+constexpr int MAX_RANGES = 8;
+constexpr int N_TK = 3;  // time-cursor specialisations: RLE, S8B scaled, generic
+constexpr int N_VK = 3;  // value-cursor specialisations: S8B zig-zag, gorilla, generic
+constexpr int N_BINS = N_TK * N_VK;
+
+enum { TK_RLE = 0, TK_S8B = 1, TK_GEN = 2 };
+enum { VK_S8B = 0, VK_GOR = 1, VK_GEN = 2 };
+
+__host__ __device__ inline int time_class(uint8_t dk) {
+  return dk == DK_RLE_SC ? TK_RLE : dk == DK_S8B_SC ? TK_S8B : TK_GEN;
+}
+__host__ __device__ inline int value_class(uint8_t dk) {
+  return dk == DK_S8B_ZZ ? VK_S8B : dk == DK_GORILLA ? VK_GOR : VK_GEN;
+}
+
+// Per query column: where its partial state lives (offsets in 8-byte units into `state`).
+struct ColState {
+  uint64_t count_off;  // u64 count[n_cells]                       (always)
+  uint64_t sum_off;    // i64 wrapping / f64 sum[n_cells]           (SUM | MEAN)
+  uint64_t min_off;    // ordered i64 key[n_cells]                  (MIN)
+  uint64_t max_off;    // ordered i64 key[n_cells]                  (MAX)
+  uint64_t first_off;  // {i64 key, u64 val}[n_cells], 16B aligned  (FIRST)
+  uint64_t last_off;   // {i64 key, u64 val}[n_cells], 16B aligned  (LAST)
+  uint16_t column_id;
+  uint8_t phys_type;
+  uint8_t agg_mask;
+  uint32_t pad;
+};
+
+struct ScanParams {
+  const uint8_t *arena;
+  const tskv_page_desc *descs;   // device copy; .reserved = DK_* kind
+  const uint32_t *time_page_of;  // field page -> its column group's time page
+  // compacted work list (kind-sorted)
+  const uint32_t *work_page;
+  const uint32_t *work_slot;
+  const uint8_t *work_qcol;
+  const uint32_t *bin_cstart;  // [N_BINS + 1] starts of the kind bins in the work list
+  const ColState *cols;
+  uint64_t *state;
+  uint32_t *task_counter;       // [N_BINS] dynamic chunk schedulers
+  int32_t *status;              // first error (0 = ok)
+  unsigned long long *err_page; // page of the first error
+  unsigned long long *stats;    // [0] points decoded, [1] rows in range
+  tskv_time_range ranges[MAX_RANGES];
+  uint32_t n_ranges;
+  int64_t width;         // <= 0: single bucket
+  int64_t origin_mod;    // origin % width
+  int64_t first_bucket_start;
+  uint32_t n_buckets;
+  uint32_t group_by_series;
+  uint64_t n_cells;
+  // first/last tie-break key. slot_bits == 0 (one slot per cell): key = timestamp itself.
+  // Otherwise key = rel << slot_bits | slot with rel = t - (bucket_start - width) in (0, 2*width)
+  // for bucketed scans and rel = t - rel_base for unbucketed ones; the host checked the bit budget.
+  uint32_t slot_bits;
+  uint32_t slot_max;     // (1 << slot_bits) - 1
+  int64_t rel_base;
+};
+
+// ------------------------------------------------------------------------------------------------
+// selection / compaction
+// ------------------------------------------------------------------------------------------------
+// One thread per column group: series id -> slot (binary search in the sorted selection list).
+__global__ void k_select_cg(const tskv_page_desc *descs, const uint32_t *cg_time_page, uint32_t n_cg,
+                            const uint32_t *series_ids, uint32_t n_series,
+                            const uint32_t *cg_series_rank, int32_t *cg_slot) {
+  uint32_t cg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= n_cg) return;
+  int32_t slot;
+  if (series_ids == nullptr) {
+    slot = (int32_t)cg_series_rank[cg];
+  } else {
+    uint32_t id = descs[cg_time_page[cg]].series_id;
+    uint32_t lo = 0, hi = n_series;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(series_ids + mid) < id) lo = mid + 1; else hi = mid;
+    }
+    slot = (lo < n_series && __ldg(series_ids + lo) == id) ? (int32_t)lo : -1;
+  }
+  cg_slot[cg] = slot;
+}
+
+__device__ __forceinline__ int find_qcol(const ColState *cols, uint32_t n_cols, uint16_t column_id) {
+  for (uint32_t c = 0; c < n_cols; c++)
+    if (cols[c].column_id == column_id) return (int)c;
+  return -1;
+}
+
+// One thread per item (field page, in kind-sorted order): selected? -> flag, per-block counts and
+// the byte/page counters of the reference's reader metrics (column_group/mod.rs:141-193).
+__global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_page,
+                             const uint32_t *item_cg, const uint32_t *cg_time_page, uint32_t n_items,
+                             const int32_t *cg_slot, const ColState *cols, uint32_t n_cols,
+                             uint8_t *item_flag, uint32_t *block_count, unsigned long long *counters,
+                             int32_t *status) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool sel = false;
+  unsigned long long bytes = 0, pages = 0;
+  if (i < n_items) {
+    uint32_t p = item_page[i];
+    tskv_page_desc d = descs[p];
+    uint32_t cg = item_cg[i];
+    int qc = find_qcol(cols, n_cols, d.column_id);
+    if (qc >= 0 && cg_slot[cg] >= 0) {
+      if (cols[qc].phys_type != d.phys_type) {
+        atomicCAS(status, 0, TSKV_ERR_INVALID_ARG);
+      } else {
+        sel = true;
+        bytes = d.size;
+        pages = 1;
+        // the time page of a column group is read once: charge it to the group's first selected
+        // field page (field pages of a group are contiguous after the time page)
+        uint32_t tp = cg_time_page[cg];
+        bool first_sel = true;
+        for (uint32_t q = tp + 1; q < p; q++)
+          if (find_qcol(cols, n_cols, descs[q].column_id) >= 0) { first_sel = false; break; }
+        if (first_sel) { bytes += descs[tp].size; pages += 1; }
+      }
+    }
+    item_flag[i] = sel ? (uint8_t)(qc + 1) : 0;
+  }
+  // block reduce
+  __shared__ uint32_t s_cnt;
+  __shared__ unsigned long long s_bytes, s_pages;
+  if (threadIdx.x == 0) { s_cnt = 0; s_bytes = 0; s_pages = 0; }
+  __syncthreads();
+  uint32_t m = __ballot_sync(FULL, sel);
+  for (int o = 16; o; o >>= 1) {
+    bytes += __shfl_down_sync(FULL, bytes, o);
+    pages += __shfl_down_sync(FULL, pages, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_cnt, __popc(m));
+    atomicAdd(&s_bytes, bytes);
+    atomicAdd(&s_pages, pages);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    block_count[blockIdx.x] = s_cnt;
+    if (s_pages) { atomicAdd(&counters[0], s_pages); atomicAdd(&counters[1], s_bytes); }
+  }
+}
+
+// Single-block exclusive scan of the per-block counts (n_blocks is small: n_items / 1024).
+__global__ void k_scan_blocks(uint32_t *block_count, uint32_t n_blocks, uint32_t *total) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < n_blocks ? block_count[i] : 0;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(FULL, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+      uint32_t xs = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, xs, o);
+        if (threadIdx.x >= o) xs += y;
+      }
+      s_warp[threadIdx.x] = xs - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    uint32_t excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
+    if (i < n_blocks) block_count[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+
+// Ordered scatter: keeps the kind-sorted order, so the compacted list is still binned by kind;
+// bin_cstart[k] = compacted position of the first item of bin k.
+__global__ void k_scatter_items(const uint32_t *item_page, const uint32_t *item_cg, uint32_t n_items,
+                                const uint8_t *item_flag, const uint32_t *block_offset,
+                                const int32_t *cg_slot, const uint32_t *bin_start, uint32_t *work_page,
+                                uint32_t *work_slot, uint8_t *work_qcol, uint32_t *bin_cstart,
+                                const uint32_t *total) {
+  __shared__ uint32_t s_warp[32];
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t f = i < n_items ? item_flag[i] : 0;
+  uint32_t m = __ballot_sync(FULL, f != 0);
+  uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_warp[wid] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+    uint32_t xs = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(FULL, xs, o);
+      if (threadIdx.x >= o) xs += y;
+    }
+    s_warp[threadIdx.x] = xs - w;
+  }
+  __syncthreads();
+  uint32_t pos = block_offset[blockIdx.x] + s_warp[wid] + __popc(m & ((1u << lane) - 1));
+  if (i < n_items) {
+    if (f) {
+      work_page[pos] = item_page[i];
+      work_slot[pos] = (uint32_t)cg_slot[item_cg[i]];
+      work_qcol[pos] = (uint8_t)(f - 1);
+    }
+    for (int k = 0; k < N_BINS; k++)
+      if (bin_start[k] == i) bin_cstart[k] = pos;
+  }
+  if (i == 0) {
+    for (int k = 0; k <= N_BINS; k++)
+      if (bin_start[k] >= n_items) bin_cstart[k] = *total;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused scan
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cas128(unsigned long long *addr, unsigned long long cmp_lo,
+                                       unsigned long long cmp_hi, unsigned long long new_lo,
+                                       unsigned long long new_hi, unsigned long long *old_lo,
+                                       unsigned long long *old_hi) {
+  unsigned long long olo, ohi;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(olo), "=l"(ohi)
+      : "l"(cmp_lo), "l"(cmp_hi), "l"(new_lo), "l"(new_hi), "l"(addr)
+      : "memory");
+  *old_lo = olo;
+  *old_hi = ohi;
+  return olo == cmp_lo && ohi == cmp_hi;
+}
+
+// pair = {i64 key, u64 val}; keep the pair with the smaller (IS_MIN) / larger key.
+template <bool IS_MIN>
+__device__ __forceinline__ void atomic_select_pair(uint64_t *pair, int64_t key, uint64_t val) {
+  unsigned long long *p = reinterpret_cast<unsigned long long *>(pair);
+  unsigned long long cur_k = IS_MIN ? 0x7fffffffffffffffull : 0x8000000000000000ull;  // identity
+  unsigned long long cur_v = 0;
+  for (;;) {
+    bool better = IS_MIN ? key < (int64_t)cur_k : key > (int64_t)cur_k;
+    if (!better) return;
+    unsigned long long ok, ov;
+    if (cas128(p, cur_k, cur_v, (unsigned long long)key, val, &ok, &ov)) return;
+    cur_k = ok;
+    cur_v = ov;
+  }
+}
+
+// Ordered i64 key of a value of physical type pt (signed compare == typed compare; f64: IEEE
+// totalOrder).
+__device__ __forceinline__ int64_t okey(uint64_t v, uint8_t pt) {
+  uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull
+                  : pt == TSKV_PT_F64 ? (uint64_t)(((int64_t)v >> 63) & 0x7fffffffffffffffll)
+                                      : 0ull;
+  return (int64_t)(v ^ flip);
+}
+__host__ __device__ inline uint64_t okey_inv(int64_t k, uint8_t pt) {
+  uint64_t v = (uint64_t)k;
+  if (pt == TSKV_PT_U64) return v ^ 0x8000000000000000ull;
+  if (pt == TSKV_PT_F64) return v ^ (uint64_t)((k >> 63) & 0x7fffffffffffffffll);
+  return v;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  return ((uint64_t)__shfl_sync(FULL, (uint32_t)(v >> 32), src) << 32) |
+         __shfl_sync(FULL, (uint32_t)v, src);
+}
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  return ((uint64_t)__shfl_xor_sync(FULL, (uint32_t)(v >> 32), m) << 32) |
+         __shfl_xor_sync(FULL, (uint32_t)v, m);
+}
+
+// Partial aggregate of one (page, bucket) run, held in registers by one lane.
+struct RunAcc {
+  uint32_t count;
+  uint64_t sum;      // i64 wrapping sum bits, or f64 sum bits
+  int64_t kmin, kmax;
+  int64_t first_ts, last_ts;
+  uint64_t first_val, last_val;
+  bool first_ok, last_ok;  // the run's min/max-time row had a non-null value (first.rs:91-94)
+};
+
+struct ScanCtx {
+  const ScanParams *P;
+};
+
+// Warp-converged flush of run partials into the global state. `active` lanes carry a finished
+// run for cell `gcell` (= qcol * n_cells + cell). When every flushing lane targets the same cell
+// (the common lock-step case of GROUP BY bucket) the partials are combined with a butterfly first
+// and one lane issues the atomics.
+__device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uint32_t qcol,
+                                           uint64_t cell, int64_t bucket, uint8_t pt, uint8_t mask,
+                                           RunAcc &a, uint32_t slot) {
+  uint32_t m = __ballot_sync(FULL, active);
+  if (m == 0) return;
+  const uint64_t gcell = (uint64_t)qcol * P.n_cells + cell;
+  int leader = __ffs(m) - 1;
+  uint64_t lcell = shfl_u64(gcell, leader);
+  bool same = __all_sync(FULL, !active || gcell == lcell);
+  // first/last keys (only meaningful on active lanes)
+  int64_t kf = a.first_ts, kl = a.last_ts;
+  if (P.slot_bits) {
+    // rel > 0 by construction (see ScanParams); the host checked rel_bits + slot_bits <= 62
+    uint64_t base = P.width > 0 ? (uint64_t)P.first_bucket_start + (uint64_t)(bucket - 1) * (uint64_t)P.width
+                                : (uint64_t)P.rel_base;
+    kf = (int64_t)((((uint64_t)a.first_ts - base) << P.slot_bits) | slot);
+    kl = (int64_t)((((uint64_t)a.last_ts - base) << P.slot_bits) | (P.slot_max - slot));
+  }
+  const bool is_f64 = (uint8_t)__shfl_sync(FULL, (uint32_t)pt, leader) == TSKV_PT_F64;
+  const bool own_f64 = pt == TSKV_PT_F64;
+  if (same && __popc(m) > 1) {
+    uint32_t cnt = active ? a.count : 0;
+    uint64_t sum = active ? a.sum : 0;  // 0 bits == +0.0
+    int64_t kmin = (active && a.count) ? a.kmin : INT64_MAX;
+    int64_t kmax = (active && a.count) ? a.kmax : INT64_MIN;
+    int64_t fk = (active && a.first_ok) ? kf : INT64_MAX;
+    int64_t lk = (active && a.last_ok) ? kl : -1;
+    uint32_t tot = __reduce_add_sync(FULL, cnt);
+    for (int o = 16; o; o >>= 1) {
+      uint64_t s2 = shfl_xor_u64(sum, o);
+      if (is_f64) sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)s2));
+      else sum += s2;
+      int64_t mn = (int64_t)shfl_xor_u64((uint64_t)kmin, o);
+      int64_t mx = (int64_t)shfl_xor_u64((uint64_t)kmax, o);
+      kmin = mn < kmin ? mn : kmin;
+      kmax = mx > kmax ? mx : kmax;
+      int64_t f2 = (int64_t)shfl_xor_u64((uint64_t)fk, o);
+      int64_t l2 = (int64_t)shfl_xor_u64((uint64_t)lk, o);
+      fk = f2 < fk ? f2 : fk;
+      lk = l2 > lk ? l2 : lk;
+    }
+    // owners of the winning first / last keys supply the values
+    uint32_t mf = __ballot_sync(FULL, active && a.first_ok && kf == fk);
+    uint32_t ml = __ballot_sync(FULL, active && a.last_ok && kl == lk);
+    uint64_t fv = shfl_u64(a.first_val, mf ? __ffs(mf) - 1 : 0);
+    uint64_t lv = shfl_u64(a.last_val, ml ? __ffs(ml) - 1 : 0);
+    if ((int)(threadIdx.x & 31) == leader) {
+      const ColState &cs = P.cols[qcol];
+      uint64_t *st = P.state;
+      if (tot) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.count_off + cell), (unsigned long long)tot);
+        if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
+          if (is_f64) atomicAdd(reinterpret_cast<double *>(st + cs.sum_off + cell), __longlong_as_double((long long)sum));
+          else atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.sum_off + cell), (unsigned long long)sum);
+        }
+        if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)kmin);
+        if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)kmax);
+      }
+      if ((mask & TSKV_AGG_FIRST) && mf) atomic_select_pair<true>(st + cs.first_off + 2 * cell, fk, fv);
+      if ((mask & TSKV_AGG_LAST) && ml) atomic_select_pair<false>(st + cs.last_off + 2 * cell, lk, lv);
+    }
+  } else if (active) {
+    const ColState &cs = P.cols[qcol];
+    uint64_t *st = P.state;
+    if (a.count) {
+      atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.count_off + cell), (unsigned long long)a.count);
+      if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
+        if (own_f64) atomicAdd(reinterpret_cast<double *>(st + cs.sum_off + cell), __longlong_as_double((long long)a.sum));
+        else atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.sum_off + cell), (unsigned long long)a.sum);
+      }
+      if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)a.kmin);
+      if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)a.kmax);
+    }
+    if ((mask & TSKV_AGG_FIRST) && a.first_ok) atomic_select_pair<true>(st + cs.first_off + 2 * cell, kf, a.first_val);
+    if ((mask & TSKV_AGG_LAST) && a.last_ok) atomic_select_pair<false>(st + cs.last_off + 2 * cell, kl, a.last_val);
+  }
+}
+
+__device__ __forceinline__ void report_error(const ScanParams &P, tskv_status st, uint32_t page) {
+  if (atomicCAS(P.status, 0, (int)st) == 0) *P.err_page = page;
+}
+
+// Bucket bookkeeping of one lane: [lo, hi) bounds of the bucket the last row fell into.
+struct BucketState {
+  int64_t lo, hi;   // timestamps in [lo, hi) map to bucket `idx`
+  uint32_t idx;
+  bool valid;
+  bool floor_regime;  // dividend >= 0: the bucket is [start, start + w)
+};
+
+// `sliding_window(t, w, w, origin, 0)` (time_window.rs:184-198): start = t - ((t - o + w) % w) with
+// truncating %, so for a negative dividend the window is (start - w, start] (kept as-is).
+__device__ __forceinline__ bool locate_bucket(const ScanParams &P, int64_t t, BucketState &b) {
+  if (P.width <= 0) {
+    b.lo = INT64_MIN; b.hi = INT64_MAX; b.idx = 0; b.valid = true; b.floor_regime = false;
+    return true;  // hi is exclusive: t == INT64_MAX handled by the caller's "same bucket" test
+  }
+  const int64_t w = P.width;
+  if (b.valid && b.floor_regime && t >= b.hi && (uint64_t)t - (uint64_t)b.hi < (uint64_t)w &&
+      b.idx + 1 < P.n_buckets) {
+    b.lo = b.hi; b.hi = b.hi + w; b.idx += 1;  // next bucket of the floor-aligned regime
+    return true;
+  }
+  int64_t dividend = (int64_t)((uint64_t)t - (uint64_t)P.origin_mod + (uint64_t)w);
+  int64_t rem = dividend % w;
+  int64_t start = (int64_t)((uint64_t)t - (uint64_t)rem);
+  int64_t diff = (int64_t)((uint64_t)start - (uint64_t)P.first_bucket_start);
+  if (diff < 0 || diff % w != 0 || diff / w >= (int64_t)P.n_buckets) return false;
+  b.idx = (uint32_t)(diff / w);
+  if (dividend >= 0) { b.lo = start; b.hi = start + w; }
+  else { b.lo = start - w + 1; b.hi = start + 1; }
+  b.floor_regime = dividend >= 0;
+  b.valid = true;
+  return true;
+}
+
+// One chunk of <= 32 work items, one lane per field page. The whole warp stays converged; lanes
+// without a page (or past their last row) idle through the loop.
+template <int TK, int VK>
+__device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t item_end) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t item = item_begin + lane;
+  const bool have_item = item < item_end;
+
+  uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
+  uint8_t pt = TSKV_PT_I64, mask = 0;
+  PageView tpv, vpv;
+  BitCursor tbits, vbits;
+  using TCur = DeltaCursor<TK == TK_RLE ? DK_RLE_SC : TK == TK_S8B ? DK_S8B_SC : -1>;
+  TCur tcur;
+  using VCurS8B = DeltaCursor<DK_S8B_ZZ>;
+  VCurS8B vcur_s;
+  GorillaCursor vcur_g;
+  AnyCursor vcur_a;
+  bool vk_any_allnull = false;
+
+  if (have_item) {
+    page = P.work_page[item];
+    slot = P.work_slot[item];
+    qcol = P.work_qcol[item];
+    const tskv_page_desc vd = P.descs[page];
+    const uint32_t tpage = P.time_page_of[page];
+    const tskv_page_desc td = P.descs[tpage];
+    pt = P.cols[qcol].phys_type;
+    mask = P.cols[qcol].agg_mask;
+    tskv_status st = kind_status(td.reserved);
+    if (st == TSKV_OK) st = kind_status(vd.reserved);
+    if (st != TSKV_OK) {
+      report_error(P, st, st == kind_status(td.reserved) ? tpage : page);
+    } else {
+      tpv.open(P.arena, td);
+      vpv.open(P.arena, vd);
+      n_rows = vd.num_values;
+      tbits.init(tpv.bitset);
+      vbits.init(vpv.bitset);
+      st = tcur.open(tpv, td.reserved);
+      if (st == TSKV_OK) {
+        if (VK == VK_S8B) st = vcur_s.open(vpv, DK_S8B_ZZ);
+        else if (VK == VK_GOR) st = vcur_g.open(vpv);
+        else { st = vcur_a.open(vpv, vd.reserved); vk_any_allnull = vd.reserved == DK_ALLNULL; }
+      }
+      if (st != TSKV_OK) { report_error(P, st, page); n_rows = 0; }
+      if (td.reserved == DK_ALLNULL) n_rows = 0;  // no time values: every row fails is_not_null(time)
+    }
+  }
+
+  RunAcc acc;
+  acc.count = 0; acc.sum = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+  acc.first_ts = acc.last_ts = 0; acc.first_val = acc.last_val = 0; acc.first_ok = acc.last_ok = false;
+  BucketState bk; bk.valid = false; bk.floor_regime = false; bk.lo = 0; bk.hi = 0; bk.idx = 0;
+  bool have_run = false;
+  uint32_t run_idx = 0;
+  uint32_t row = 0;
+  uint32_t n_points = 0, n_inrange = 0;
+  const bool is_f64 = pt == TSKV_PT_F64;
+  const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
+
+  for (;;) {
+    const bool has = row < n_rows;
+    if (!__any_sync(FULL, has || have_run)) break;
+    bool flush = false, inr = false, vv = false, newrun = false;
+    int64_t t = 0;
+    uint64_t v = 0;
+    if (has) {
+      const bool tv = tbits.next(row);
+      vv = vbits.next(row) && !vk_any_allnull;
+      bool ok = true;
+      if (tv) t = (int64_t)tcur.next(&ok);
+      else if (row == 0) tcur.skip_first_if_s8b_sc();
+      if (!ok) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = 0; }
+      if (vv && ok) {
+        if (VK == VK_S8B) v = vcur_s.next(&ok);
+        else if (VK == VK_GOR) v = vcur_g.next(&ok);
+        else { v = vcur_a.next(&ok); }
+        if (!ok) {
+          bool serr = VK == VK_GOR ? vcur_g.err : (VK == VK_GEN ? vcur_a.stream_error() : false);
+          report_error(P, serr ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
+          n_rows = 0;
+        } else {
+          n_points++;
+        }
+      }
+      row++;
+      if (ok && tv) {
+        inr = P.n_ranges == 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < P.n_ranges && !inr; k++) inr = t >= P.ranges[k].min_ts && t <= P.ranges[k].max_ts;
+      }
+      if (inr) {
+        n_inrange++;
+        bool same_bucket = bk.valid && t >= bk.lo && (t < bk.hi || P.width <= 0);
+        if (!same_bucket) {
+          if (!locate_bucket(P, t, bk)) {
+            report_error(P, TSKV_ERR_BUCKET_RANGE, page);
+            inr = false;
+            bk.valid = false;
+          }
+        }
+        if (inr && (!have_run || bk.idx != run_idx)) { newrun = true; flush = have_run; }
+      }
+    } else {
+      flush = have_run;
+    }
+    warp_flush(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+    if (flush) have_run = false;
+    if (has && inr) {
+      if (newrun) {
+        have_run = true;
+        run_idx = bk.idx;
+        acc.count = 0; acc.sum = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+        acc.first_ts = acc.last_ts = t;
+        acc.first_val = acc.last_val = v;
+        acc.first_ok = acc.last_ok = vv;
+      } else {
+        if (t < acc.first_ts) { acc.first_ts = t; acc.first_val = v; acc.first_ok = vv; }
+        if (t > acc.last_ts) { acc.last_ts = t; acc.last_val = v; acc.last_ok = vv; }
+      }
+      if (vv) {
+        acc.count++;
+        if (is_f64) acc.sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)acc.sum) + __longlong_as_double((long long)v));
+        else acc.sum += v;
+        int64_t k = okey(v, pt);
+        acc.kmin = k < acc.kmin ? k : acc.kmin;
+        acc.kmax = k > acc.kmax ? k : acc.kmax;
+      }
+    }
+  }
+  // The reference decodes a gorilla page to its sentinel (float.rs:480-591): a stream that ends
+  // without one is an error even when enough values were produced.
+  if (VK != VK_S8B && have_item && n_rows != 0) {
+    GorillaCursor *g = VK == VK_GOR ? &vcur_g : (vcur_a.is_gorilla ? &vcur_a.g : nullptr);
+    if (g && !g->first) {
+      while (!g->done) { if (!g->advance()) g->done = true; }
+      if (g->err) report_error(P, TSKV_ERR_SHORT_BLOCK, page);
+    }
+  }
+  // statistics
+  n_points = __reduce_add_sync(FULL, n_points);
+  n_inrange = __reduce_add_sync(FULL, n_inrange);
+  if (lane == 0) {
+    if (n_points) atomicAdd(&P.stats[0], (unsigned long long)n_points);
+    if (n_inrange) atomicAdd(&P.stats[1], (unsigned long long)n_inrange);
+  }
+}
+
+// Persistent grid, one kernel instantiation per decode-kind bin (separate register budgets); each
+// warp repeatedly grabs one 32-item chunk of the bin's compacted range.
+template <int TK, int VK>
+__global__ void __launch_bounds__(256, 2) k_scan_aggregate(const __grid_constant__ ScanParams P) {
+  constexpr int bin = TK * N_VK + VK;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
+  const uint32_t n_chunks = (end0 - begin0 + 31) >> 5;
+  for (;;) {
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(P.task_counter + bin, 1u);
+    c = __shfl_sync(FULL, c, 0);
+    if (c >= n_chunks) break;
+    uint32_t begin = begin0 + (c << 5);
+    scan_chunk<TK, VK>(P, begin, min(begin + 32, end0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// state init / export / finalize
+// ------------------------------------------------------------------------------------------------
+struct StateLayout {
+  uint64_t sum_i64_off, sum_i64_len;  // counts + integer sums
+  uint64_t sum_f64_off, sum_f64_len;
+  uint64_t min_off, min_len;          // MIN keys then exported FIRST keys
+  uint64_t max_off, max_len;          // MAX keys then exported LAST keys
+  uint64_t selval_off, selval_len;    // exported FIRST values then LAST values
+  uint64_t first_pairs_off, first_cells;  // {key,val} pairs used by the scan kernel
+  uint64_t last_pairs_off, last_cells;
+  uint64_t first_keys_off, last_keys_off; // inside the min / max sections
+  uint64_t snap_off;                      // snapshot of local first+last keys (multi-GPU masking)
+  uint64_t total;
+};
+
+__global__ void k_init_state(uint64_t *state, StateLayout L) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < L.total; k += stride) {
+    uint64_t v = 0;
+    if (k >= L.min_off && k < L.min_off + L.min_len) v = 0x7fffffffffffffffull;
+    else if (k >= L.max_off && k < L.max_off + L.max_len) v = 0x8000000000000000ull;
+    else if (k >= L.first_pairs_off && k < L.first_pairs_off + 2 * L.first_cells) v = ((k - L.first_pairs_off) & 1) ? 0 : 0x7fffffffffffffffull;
+    else if (k >= L.last_pairs_off && k < L.last_pairs_off + 2 * L.last_cells) v = ((k - L.last_pairs_off) & 1) ? 0 : 0x8000000000000000ull;
+    state[k] = v;
+  }
+}
+
+// De-interleave the {key,val} pairs into the contiguous key / value sections.
+__global__ void k_export_pairs(uint64_t *state, StateLayout L) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < L.first_cells; k += stride) {
+    state[L.first_keys_off + k] = state[L.first_pairs_off + 2 * k];
+    state[L.selval_off + k] = state[L.first_pairs_off + 2 * k + 1];
+  }
+  for (uint64_t k = i; k < L.last_cells; k += stride) {
+    state[L.last_keys_off + k] = state[L.last_pairs_off + 2 * k];
+    state[L.selval_off + L.first_cells + k] = state[L.last_pairs_off + 2 * k + 1];
+  }
+}
+
+__global__ void k_snapshot_keys(uint64_t *state, StateLayout L) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < L.first_cells; k += stride) state[L.snap_off + k] = state[L.first_keys_off + k];
+  for (uint64_t k = i; k < L.last_cells; k += stride) state[L.snap_off + L.first_cells + k] = state[L.last_keys_off + k];
+}
+
+// After the key all-reduce: ranks whose local key lost contribute 0 to the value SUM all-reduce.
+__global__ void k_mask_values(uint64_t *state, StateLayout L) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < L.first_cells; k += stride) {
+    uint64_t key = state[L.first_keys_off + k];
+    if (state[L.snap_off + k] != key || key == 0x7fffffffffffffffull) state[L.selval_off + k] = 0;
+  }
+  for (uint64_t k = i; k < L.last_cells; k += stride) {
+    uint64_t key = state[L.last_keys_off + k];
+    if (state[L.snap_off + L.first_cells + k] != key || key == 0x8000000000000000ull) state[L.selval_off + L.first_cells + k] = 0;
+  }
+}
+
+// Per output column: which state arrays feed it.
+struct OutCol {
+  uint64_t count_off;  // counts of the source column
+  uint64_t src_off;    // sum / min key / max key / exported first-or-last key
+  uint64_t val_off;    // FIRST/LAST: exported values
+  uint8_t agg;         // single TSKV_AGG_* bit
+  uint8_t phys_type;
+  uint8_t pad[6];
+};
+
+// Dense result: 8-byte value + Arrow LSB-first validity per cell (one warp packs 32 bits).
+__global__ void k_finalize(const uint64_t *state, const OutCol *outs, uint32_t n_out, uint64_t n_cells,
+                           uint64_t bitmap_stride, uint64_t *values, uint8_t *validity) {
+  const OutCol oc = outs[blockIdx.y];
+  uint64_t cell = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  uint64_t v = 0;
+  if (cell < n_cells) {
+    uint64_t cnt = state[oc.count_off + cell];
+    switch (oc.agg) {
+      case TSKV_AGG_COUNT: v = cnt; valid = true; break;
+      case TSKV_AGG_SUM: valid = cnt > 0; if (valid) v = state[oc.src_off + cell]; break;
+      case TSKV_AGG_MIN:
+      case TSKV_AGG_MAX: valid = cnt > 0; if (valid) v = okey_inv((int64_t)state[oc.src_off + cell], oc.phys_type); break;
+      case TSKV_AGG_MEAN:
+        valid = cnt > 0;
+        if (valid) {
+          uint64_t s = state[oc.src_off + cell];
+          double d = oc.phys_type == TSKV_PT_F64 ? __longlong_as_double((long long)s)
+                     : oc.phys_type == TSKV_PT_I64 ? (double)(long long)s : (double)s;
+          v = (uint64_t)__double_as_longlong(d / (double)cnt);
+        }
+        break;
+      case TSKV_AGG_FIRST: valid = state[oc.src_off + cell] != 0x7fffffffffffffffull; if (valid) v = state[oc.val_off + cell]; break;
+      case TSKV_AGG_LAST: valid = state[oc.src_off + cell] != 0x8000000000000000ull; if (valid) v = state[oc.val_off + cell]; break;
+      default: break;
+    }
+    values[(uint64_t)blockIdx.y * n_cells + cell] = v;
+  }
+  uint32_t bits = __ballot_sync(FULL, valid);
+  if ((threadIdx.x & 31) == 0 && (cell >> 3) < bitmap_stride)
+    *reinterpret_cast<uint32_t *>(validity + (uint64_t)blockIdx.y * bitmap_stride + (cell >> 3)) = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode only: one lane per page, values + validity bitmap to HBM
+// ------------------------------------------------------------------------------------------------
+__global__ void k_decode_pages(const uint8_t *arena, const tskv_page_desc *descs, uint64_t first_page,
+                               uint32_t n_pages, const uint64_t *row_off, const uint64_t *bm_off,
+                               uint64_t *out_values, uint8_t *out_validity, int32_t *status,
+                               unsigned long long *err_page, unsigned long long *stats) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pages) return;
+  const uint32_t page = (uint32_t)first_page + i;
+  const tskv_page_desc d = descs[page];
+  tskv_status st = kind_status(d.reserved);
+  uint64_t *ov = out_values + row_off[i];
+  uint32_t *ob = reinterpret_cast<uint32_t *>(out_validity + bm_off[i]);
+  const uint32_t n_rows = d.num_values;
+  unsigned long long points = 0;
+  if (st == TSKV_OK) {
+    PageView pv;
+    pv.open(arena, d);
+    BitCursor bits;
+    bits.init(pv.bitset);
+    AnyCursor cur;
+    st = cur.open(pv, d.reserved);
+    const bool allnull = d.reserved == DK_ALLNULL;
+    uint32_t wbits = 0;
+    for (uint32_t r = 0; r < n_rows && st == TSKV_OK; r++) {
+      bool valid = bits.next(r) && !allnull;
+      uint64_t v = 0;
+      if (valid) {
+        bool ok = true;
+        v = cur.next(&ok);
+        if (!ok) { st = cur.stream_error() ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH; break; }
+        points++;
+      } else if (r == 0 && !cur.is_gorilla) {
+        cur.d.skip_first_if_s8b_sc();
+      }
+      ov[r] = v;
+      wbits |= (valid ? 1u : 0u) << (r & 31);
+      if ((r & 31) == 31) { ob[r >> 5] = wbits; wbits = 0; }
+    }
+    if (st == TSKV_OK) {
+      if (n_rows & 31) ob[n_rows >> 5] = wbits;
+      // zero the tail of the 8-byte-padded bitmap
+      uint32_t words = ((n_rows + 63) / 64) * 2;
+      for (uint32_t w = (n_rows + 31) / 32; w < words; w++) ob[w] = 0;
+      if (cur.is_gorilla && !cur.g.first) {
+        while (!cur.g.done) { if (!cur.g.advance()) cur.g.done = true; }
+        if (cur.g.err) st = TSKV_ERR_SHORT_BLOCK;
+      }
+    }
+  }
+  if (st != TSKV_OK) {
+    if (atomicCAS(status, 0, (int)st) == 0) *err_page = page;
+  }
+  if (points) atomicAdd(&stats[0], points);
+}
+
+}  // namespace tskv

@@ -1,0 +1,926 @@
+// tskv_gpu.cu — C-ABI entry points of include/tskv_gpu.h: context, page upload, decode-only and the
+// fused scan/aggregate launches. Host logic only; the device code is in scan_kernels.cuh.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "host_util.h"
+#include "scan_kernels.cuh"
+
+using namespace tskv;
+
+#define CU_TRY(ctx, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+      return e__ == cudaErrorMemoryAllocation ? TSKV_ERR_OOM : TSKV_ERR_CUDA;          \
+    }                                                                                  \
+  } while (0)
+
+struct tskv_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  std::mutex mu;
+  std::string err;
+  int64_t err_page = -1;
+  tskv_counters counters{};
+  void set_error(const std::string &m, int64_t page = -1) {
+    err = m;
+    err_page = page;
+  }
+};
+
+struct tskv_pages {
+  tskv_ctx *ctx = nullptr;
+  uint8_t *d_arena = nullptr;
+  uint64_t arena_len = 0;
+  tskv_page_desc *d_descs = nullptr;
+  std::vector<tskv_page_desc> h_descs;  // with .reserved = DK kind
+  uint64_t n_descs = 0;
+  uint32_t *d_time_page_of = nullptr;
+  uint32_t n_cg = 0;
+  uint32_t *d_cg_time_page = nullptr;
+  uint32_t *d_cg_series_rank = nullptr;
+  uint32_t n_items = 0;
+  uint32_t *d_item_page = nullptr;
+  uint32_t *d_item_cg = nullptr;
+  uint32_t h_bin_start[N_BINS + 1]{};
+  uint32_t *d_bin_start = nullptr;
+  std::vector<uint32_t> series;  // sorted distinct ids
+};
+
+struct tskv_scan {
+  const tskv_pages *pages = nullptr;
+  tskv_output_layout layout{};
+  StateLayout sl{};
+  ScanParams params{};
+  uint32_t n_cols = 0, n_out = 0;
+  bool has_sel = false;  // any FIRST/LAST
+  // device buffers
+  uint32_t *d_series = nullptr;
+  int32_t *d_cg_slot = nullptr;
+  uint8_t *d_item_flag = nullptr;
+  uint32_t *d_block_count = nullptr;
+  uint32_t n_blocks = 0;
+  uint32_t *d_work_page = nullptr, *d_work_slot = nullptr;
+  uint8_t *d_work_qcol = nullptr;
+  uint32_t *d_bin_cstart = nullptr;  // [N_BINS+1] then [1] total
+  ColState *d_cols = nullptr;
+  OutCol *d_outs = nullptr;
+  uint64_t *d_state = nullptr;
+  uint32_t *d_task_counter = nullptr;
+  int32_t *d_status = nullptr;
+  unsigned long long *d_err_page = nullptr;
+  unsigned long long *d_stats = nullptr;     // [0] points [1] rows in range
+  unsigned long long *d_counters = nullptr;  // [0] pages [1] bytes
+  uint64_t *d_values = nullptr;
+  uint8_t *d_validity = nullptr;
+  int grid[N_BINS] = {0};
+};
+
+namespace {
+
+const char *status_text(tskv_status st) {
+  switch (st) {
+    case TSKV_OK: return "ok";
+    case TSKV_ERR_INVALID_ARG: return "invalid argument";
+    case TSKV_ERR_BAD_ENCODING: return "invalid block encoding";
+    case TSKV_ERR_SHORT_BLOCK: return "not enough data to decode / unexpected end of block";
+    case TSKV_ERR_CRC_MISMATCH: return "page crc32 mismatch";
+    case TSKV_ERR_BITSET_MISMATCH: return "Mismatch between bit set and decoded values";
+    case TSKV_ERR_UNSUPPORTED: return "unsupported encoding or query shape";
+    case TSKV_ERR_BUCKET_RANGE: return "row outside the requested bucket range";
+    case TSKV_ERR_CUDA: return "CUDA error";
+    case TSKV_ERR_OOM: return "out of device memory";
+    case TSKV_ERR_BAD_LENGTH: return "invalid uncompressed block length";
+    case TSKV_ERR_PAGE_FORMAT: return "page shorter than its header/bitset";
+    default: return "error";
+  }
+}
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+unsigned bits_for(uint64_t max_value) {  // bits needed to represent values in [0, max_value]
+  unsigned b = 0;
+  while (max_value) {
+    b++;
+    max_value >>= 1;
+  }
+  return b;
+}
+
+unsigned popc8(unsigned x) { return (unsigned)__builtin_popcount(x & TSKV_AGG_ALL); }
+
+typedef void (*scan_kernel_t)(const ScanParams);
+scan_kernel_t scan_kernel_for_bin(int bin) {
+  switch (bin) {
+    case TK_RLE * N_VK + VK_S8B: return k_scan_aggregate<TK_RLE, VK_S8B>;
+    case TK_RLE * N_VK + VK_GOR: return k_scan_aggregate<TK_RLE, VK_GOR>;
+    case TK_RLE * N_VK + VK_GEN: return k_scan_aggregate<TK_RLE, VK_GEN>;
+    case TK_S8B * N_VK + VK_S8B: return k_scan_aggregate<TK_S8B, VK_S8B>;
+    case TK_S8B * N_VK + VK_GOR: return k_scan_aggregate<TK_S8B, VK_GOR>;
+    case TK_S8B * N_VK + VK_GEN: return k_scan_aggregate<TK_S8B, VK_GEN>;
+    case TK_GEN * N_VK + VK_S8B: return k_scan_aggregate<TK_GEN, VK_S8B>;
+    case TK_GEN * N_VK + VK_GOR: return k_scan_aggregate<TK_GEN, VK_GOR>;
+    default: return k_scan_aggregate<TK_GEN, VK_GEN>;
+  }
+}
+
+tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_output_layout *out) {
+  if (!pages || !q || !out || q->n_buckets == 0 || q->n_columns == 0 || !q->columns) return TSKV_ERR_INVALID_ARG;
+  if (q->width <= 0 && q->n_buckets != 1) return TSKV_ERR_INVALID_ARG;
+  uint64_t n_out = 0;
+  for (uint32_t c = 0; c < q->n_columns; c++) n_out += popc8(q->columns[c].agg_mask);
+  uint64_t n_groups = 1;
+  if (q->group_by_series) n_groups = q->series_ids ? q->n_series : pages->series.size();
+  out->n_out = n_out;
+  out->n_groups = n_groups;
+  out->n_cells = n_groups * q->n_buckets;
+  out->bitmap_stride = (out->n_cells + 63) / 64 * 8;
+  out->values_bytes = n_out * out->n_cells * 8;
+  out->validity_bytes = n_out * out->bitmap_stride;
+  return TSKV_OK;
+}
+
+void free_scan(tskv_scan *s) {
+  if (!s) return;
+  cudaFree(s->d_series);
+  cudaFree(s->d_cg_slot);
+  cudaFree(s->d_item_flag);
+  cudaFree(s->d_block_count);
+  cudaFree(s->d_work_page);
+  cudaFree(s->d_work_slot);
+  cudaFree(s->d_work_qcol);
+  cudaFree(s->d_bin_cstart);
+  cudaFree(s->d_cols);
+  cudaFree(s->d_outs);
+  cudaFree(s->d_state);
+  cudaFree(s->d_task_counter);
+  cudaFree(s->d_values);
+  cudaFree(s->d_validity);
+  delete s;
+}
+
+// Reads back the device status word; maps it to a message.
+tskv_status fetch_status(tskv_ctx *ctx, int32_t *d_status, unsigned long long *d_err_page) {
+  int32_t st = 0;
+  unsigned long long pg = 0;
+  if (cudaMemcpyAsync(&st, d_status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(&pg, d_err_page, sizeof(pg), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    ctx->set_error(std::string("status readback: ") + cudaGetErrorString(cudaGetLastError()));
+    return TSKV_ERR_CUDA;
+  }
+  if (st != TSKV_OK) ctx->set_error(std::string(status_text(st)) + " (page " + std::to_string(pg) + ")", (int64_t)pg);
+  return st;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tskvgpu_version(void) { return "tskv-b200 0.1.0 sm_100a"; }
+
+tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
+  if (!out_ctx) return TSKV_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device_id < 0 || device_id >= n) return TSKV_ERR_CUDA;
+  tskv_ctx *ctx = new tskv_ctx();
+  ctx->device = device_id;
+  if (cudaSetDevice(device_id) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return TSKV_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+  *out_ctx = ctx;
+  return TSKV_OK;
+}
+
+void tskvgpu_ctx_destroy(tskv_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  delete ctx;
+}
+
+const char *tskvgpu_last_error(const tskv_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t tskvgpu_last_error_page(const tskv_ctx *ctx) { return ctx ? ctx->err_page : -1; }
+tskv_status tskvgpu_get_counters(const tskv_ctx *ctx, tskv_counters *out) {
+  if (!ctx || !out) return TSKV_ERR_INVALID_ARG;
+  *out = ctx->counters;
+  return TSKV_OK;
+}
+uint64_t tskvgpu_ctx_stream(const tskv_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+// ------------------------------------------------------------------------------------------------
+tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t arena_len,
+                                 const tskv_page_desc *descs, uint64_t n_descs, uint32_t flags,
+                                 tskv_pages **out_pages) {
+  if (!ctx || !out_pages || (!arena && arena_len) || (!descs && n_descs)) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  *out_pages = nullptr;
+  ctx->set_error("");
+  if (n_descs >= (1ull << 32)) {
+    ctx->set_error("too many pages for one arena (2^32)");
+    return TSKV_ERR_INVALID_ARG;
+  }
+  cudaSetDevice(ctx->device);
+  tskv_pages *pg = new tskv_pages();
+  pg->ctx = ctx;
+  pg->arena_len = arena_len;
+  pg->n_descs = n_descs;
+  pg->h_descs.assign(descs, descs + n_descs);
+
+  // ---- framing validation + decode-kind classification (+ CRC), parallel over pages ----------
+  std::atomic<int> bad_status{0};
+  std::atomic<int64_t> bad_page{-1};
+  auto fail = [&](int st, int64_t p) {
+    int exp = 0;
+    if (bad_status.compare_exchange_strong(exp, st)) bad_page = p;
+  };
+  unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  unsigned nthreads = n_descs > 4096 ? hw : 1;
+  auto work = [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi && bad_status.load(std::memory_order_relaxed) == 0; i++) {
+      tskv_page_desc &d = pg->h_descs[i];
+      if (d.offset & 15 || d.offset + d.size > arena_len || d.phys_type > TSKV_PT_F64 || d.reserved != 0) {
+        fail(TSKV_ERR_INVALID_ARG, (int64_t)i);
+        return;
+      }
+      PageHeader h;
+      if (!parse_page(arena + d.offset, d.size, &h)) {
+        d.reserved = DK_BAD_PAGE;
+        continue;
+      }
+      if (h.n_rows != d.num_values) {
+        d.reserved = DK_BAD_PAGE;
+        continue;
+      }
+      if ((flags & TSKV_UPLOAD_VERIFY_CRC) && crc32_ieee(h.data, h.data_len) != h.crc) {
+        fail(TSKV_ERR_CRC_MISMATCH, (int64_t)i);
+        return;
+      }
+      d.reserved = classify_page(h, d.phys_type);
+    }
+  };
+  if (nthreads == 1) {
+    work(0, n_descs);
+  } else {
+    std::vector<std::thread> th;
+    uint64_t per = (n_descs + nthreads - 1) / nthreads;
+    for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, std::min(n_descs, t * per), std::min(n_descs, (t + 1) * per));
+    for (auto &t : th) t.join();
+  }
+  if (bad_status.load()) {
+    tskv_status st = bad_status.load();
+    ctx->set_error(st == TSKV_ERR_CRC_MISMATCH ? "TsmPageFileHashCheckFailed: page crc32 mismatch"
+                                               : "malformed page descriptor (alignment, bounds, type or reserved != 0)",
+                   bad_page.load());
+    delete pg;
+    return st;
+  }
+
+  // ---- column groups, items (field pages) sorted by decode-kind bin ---------------------------
+  std::vector<uint32_t> time_page_of(n_descs, 0), cg_time_page, item_page, item_cg;
+  {
+    uint64_t i = 0;
+    while (i < n_descs) {
+      if (pg->h_descs[i].phys_type != TSKV_PT_TIME) {
+        ctx->set_error("descriptor table: column group does not start with a time page", (int64_t)i);
+        delete pg;
+        return TSKV_ERR_INVALID_ARG;
+      }
+      uint32_t cg = (uint32_t)cg_time_page.size();
+      cg_time_page.push_back((uint32_t)i);
+      time_page_of[i] = (uint32_t)i;
+      uint64_t j = i + 1;
+      while (j < n_descs && pg->h_descs[j].phys_type != TSKV_PT_TIME) {
+        if (pg->h_descs[j].series_id != pg->h_descs[i].series_id || pg->h_descs[j].num_values != pg->h_descs[i].num_values) {
+          ctx->set_error("descriptor table: field page disagrees with its time page", (int64_t)j);
+          delete pg;
+          return TSKV_ERR_INVALID_ARG;
+        }
+        time_page_of[j] = (uint32_t)i;
+        item_page.push_back((uint32_t)j);
+        item_cg.push_back(cg);
+        j++;
+      }
+      i = j;
+    }
+  }
+  pg->n_cg = (uint32_t)cg_time_page.size();
+  pg->n_items = (uint32_t)item_page.size();
+  // series ranks
+  pg->series.reserve(pg->n_cg);
+  for (uint32_t cg = 0; cg < pg->n_cg; cg++) pg->series.push_back(pg->h_descs[cg_time_page[cg]].series_id);
+  std::sort(pg->series.begin(), pg->series.end());
+  pg->series.erase(std::unique(pg->series.begin(), pg->series.end()), pg->series.end());
+  std::vector<uint32_t> cg_rank(pg->n_cg);
+  for (uint32_t cg = 0; cg < pg->n_cg; cg++)
+    cg_rank[cg] = (uint32_t)(std::lower_bound(pg->series.begin(), pg->series.end(), pg->h_descs[cg_time_page[cg]].series_id) - pg->series.begin());
+  // sort items by (bin, column id, arena order): warps are homogeneous in codec and, for GROUP BY
+  // bucket, lanes of a warp flush the same (column, bucket) cell in lock step.
+  {
+    std::vector<uint32_t> order(pg->n_items);
+    std::vector<uint64_t> key(pg->n_items);
+    for (uint32_t k = 0; k < pg->n_items; k++) {
+      const tskv_page_desc &vd = pg->h_descs[item_page[k]];
+      const tskv_page_desc &td = pg->h_descs[time_page_of[item_page[k]]];
+      uint64_t bin = (uint64_t)time_class(td.reserved) * N_VK + value_class(vd.reserved);
+      key[k] = (bin << 48) | ((uint64_t)vd.column_id << 32) | k;
+      order[k] = k;
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<uint32_t> ip(pg->n_items), ic(pg->n_items);
+    uint32_t counts[N_BINS] = {0};
+    for (uint32_t k = 0; k < pg->n_items; k++) {
+      uint32_t src = (uint32_t)(key[k] & 0xffffffffu);
+      ip[k] = item_page[src];
+      ic[k] = item_cg[src];
+      counts[key[k] >> 48]++;
+    }
+    item_page.swap(ip);
+    item_cg.swap(ic);
+    pg->h_bin_start[0] = 0;
+    for (int b = 0; b < N_BINS; b++) pg->h_bin_start[b + 1] = pg->h_bin_start[b] + counts[b];
+  }
+
+  // ---- device copies ----------------------------------------------------------------------------
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  auto up = [&](auto **dptr, const auto *src, size_t n) -> cudaError_t {
+    cudaError_t e = dev_alloc(dptr, n);
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(*dptr, src, n * sizeof(**dptr), cudaMemcpyHostToDevice, ctx->stream);
+    return e;
+  };
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&pg->d_arena), arena_len + 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(pg->d_arena + arena_len, 0, 64, ctx->stream);
+  if (e == cudaSuccess && arena_len) e = cudaMemcpyAsync(pg->d_arena, arena, arena_len, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = up(&pg->d_descs, pg->h_descs.data(), n_descs);
+  if (e == cudaSuccess) e = up(&pg->d_time_page_of, time_page_of.data(), n_descs);
+  if (e == cudaSuccess) e = up(&pg->d_cg_time_page, cg_time_page.data(), pg->n_cg);
+  if (e == cudaSuccess) e = up(&pg->d_cg_series_rank, cg_rank.data(), pg->n_cg);
+  if (e == cudaSuccess) e = up(&pg->d_item_page, item_page.data(), pg->n_items);
+  if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
+  if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("upload: ") + cudaGetErrorString(e));
+    tskvgpu_pages_destroy(nullptr, pg);
+    return e == cudaErrorMemoryAllocation ? TSKV_ERR_OOM : TSKV_ERR_CUDA;
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->counters.elapsed_h2d_ms = ms;
+  *out_pages = pg;
+  return TSKV_OK;
+}
+
+void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
+  (void)ctx;
+  if (!pg) return;
+  if (pg->ctx) cudaSetDevice(pg->ctx->device);
+  cudaFree(pg->d_arena);
+  cudaFree(pg->d_descs);
+  cudaFree(pg->d_time_page_of);
+  cudaFree(pg->d_cg_time_page);
+  cudaFree(pg->d_cg_series_rank);
+  cudaFree(pg->d_item_page);
+  cudaFree(pg->d_item_cg);
+  cudaFree(pg->d_bin_start);
+  delete pg;
+}
+
+uint64_t tskvgpu_pages_series_count(const tskv_pages *pages) { return pages ? pages->series.size() : 0; }
+
+// ------------------------------------------------------------------------------------------------
+tskv_status tskvgpu_decode_pages(tskv_ctx *ctx, const tskv_pages *pages, uint64_t first_page,
+                                 uint64_t n_pages, uint64_t *out_values, uint8_t *out_validity) {
+  if (!ctx || !pages || first_page + n_pages > pages->n_descs || (n_pages && (!out_values || !out_validity)))
+    return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_error("");
+  if (n_pages == 0) return TSKV_OK;
+  cudaSetDevice(ctx->device);
+  std::vector<uint64_t> row_off(n_pages), bm_off(n_pages);
+  uint64_t rows = 0, bm = 0;
+  for (uint64_t i = 0; i < n_pages; i++) {
+    row_off[i] = rows;
+    bm_off[i] = bm;
+    rows += pages->h_descs[first_page + i].num_values;
+    bm += ((uint64_t)pages->h_descs[first_page + i].num_values + 63) / 64 * 8;
+  }
+  uint64_t *d_row_off = nullptr, *d_bm_off = nullptr, *d_vals = nullptr;
+  uint8_t *d_valid = nullptr;
+  int32_t *d_status = nullptr;
+  unsigned long long *d_aux = nullptr;  // [0] err_page, [1] points
+  tskv_status ret = TSKV_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_row_off);
+    cudaFree(d_bm_off);
+    cudaFree(d_vals);
+    cudaFree(d_valid);
+    cudaFree(d_status);
+    cudaFree(d_aux);
+  };
+  cudaError_t e = dev_alloc(&d_row_off, n_pages);
+  if (e == cudaSuccess) e = dev_alloc(&d_bm_off, n_pages);
+  if (e == cudaSuccess) e = dev_alloc(&d_vals, rows);
+  if (e == cudaSuccess) e = dev_alloc(&d_valid, bm);
+  if (e == cudaSuccess) e = dev_alloc(&d_status, 1);
+  if (e == cudaSuccess) e = dev_alloc(&d_aux, 2);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_row_off, row_off.data(), n_pages * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_bm_off, bm_off.data(), n_pages * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_aux, 0, 16, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_vals, 0, std::max<uint64_t>(rows, 1) * 8, ctx->stream);
+  if (e == cudaSuccess) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    uint32_t threads = 128;
+    uint32_t blocks = (uint32_t)((n_pages + threads - 1) / threads);
+    k_decode_pages<<<blocks, threads, 0, ctx->stream>>>(pages->d_arena, pages->d_descs, first_page, (uint32_t)n_pages,
+                                                        d_row_off, d_bm_off, d_vals, d_valid, d_status, d_aux, d_aux + 1);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_values, d_vals, rows * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_validity, d_valid, bm, cudaMemcpyDeviceToHost, ctx->stream);
+  unsigned long long points = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&points, d_aux + 1, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) {
+    ret = fetch_status(ctx, d_status, d_aux);
+  } else {
+    ctx->set_error(std::string("decode: ") + cudaGetErrorString(e));
+    ret = e == cudaErrorMemoryAllocation ? TSKV_ERR_OOM : TSKV_ERR_CUDA;
+  }
+  if (ret == TSKV_OK) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->counters.elapsed_scan_ms = ms;
+    ctx->counters.points_decoded = points;
+    ctx->counters.kernel_launches = 1;
+    ctx->counters.page_read_count = n_pages;
+  }
+  cleanup();
+  return ret;
+}
+
+// ------------------------------------------------------------------------------------------------
+tskv_status tskvgpu_query_output_layout(const tskv_pages *pages, const tskv_query *q,
+                                        tskv_output_layout *out) {
+  return compute_layout(pages, q, out);
+}
+
+tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const tskv_query *q,
+                                 tskv_scan **out_scan) {
+  if (!ctx || !pages || !q || !out_scan) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_error("");
+  *out_scan = nullptr;
+  tskv_output_layout L;
+  tskv_status st = compute_layout(pages, q, &L);
+  if (st != TSKV_OK) {
+    ctx->set_error("invalid query (buckets / columns)");
+    return st;
+  }
+  if (q->n_columns > 255 || q->n_time_ranges > MAX_RANGES || (q->n_time_ranges && !q->time_ranges) ||
+      (q->series_ids == nullptr && q->n_series != 0 && false)) {
+    ctx->set_error("invalid query: at most 255 columns and 8 time ranges");
+    return TSKV_ERR_INVALID_ARG;
+  }
+  for (uint32_t c = 0; c < q->n_columns; c++) {
+    const tskv_agg_column &qc = q->columns[c];
+    if (qc.phys_type < TSKV_PT_I64 || qc.phys_type > TSKV_PT_F64 || (qc.agg_mask & ~TSKV_AGG_ALL) || qc.agg_mask == 0) {
+      ctx->set_error("invalid query column (type or aggregate mask)");
+      return TSKV_ERR_INVALID_ARG;
+    }
+    for (uint32_t c2 = 0; c2 < c; c2++)
+      if (q->columns[c2].column_id == qc.column_id) {
+        ctx->set_error("duplicate query column id");
+        return TSKV_ERR_INVALID_ARG;
+      }
+  }
+  if (q->series_ids)
+    for (uint32_t i = 1; i < q->n_series; i++)
+      if (q->series_ids[i] <= q->series_ids[i - 1]) {
+        ctx->set_error("series_ids must be sorted ascending and unique");
+        return TSKV_ERR_INVALID_ARG;
+      }
+  cudaSetDevice(ctx->device);
+  tskv_scan *s = new tskv_scan();
+  s->pages = pages;
+  s->layout = L;
+  s->n_cols = q->n_columns;
+  s->n_out = (uint32_t)L.n_out;
+  const uint64_t n_cells = L.n_cells;
+
+  // ---- first/last key budget ---------------------------------------------------------------------
+  bool any_sel = false;
+  for (uint32_t c = 0; c < q->n_columns; c++) any_sel |= (q->columns[c].agg_mask & (TSKV_AGG_FIRST | TSKV_AGG_LAST)) != 0;
+  s->has_sel = any_sel;
+  uint64_t n_slots = q->series_ids ? q->n_series : pages->series.size();
+  uint32_t slot_bits = (q->group_by_series || n_slots <= 1) ? 0 : bits_for(n_slots - 1);
+  int64_t rel_base = 0;
+  if (any_sel && slot_bits > 0) {
+    unsigned rel_bits = 64;
+    if (q->width > 0) {
+      if (q->width < (int64_t)1 << 61) rel_bits = bits_for(2 * (uint64_t)q->width);
+    } else if (q->n_time_ranges > 0) {
+      int64_t lo = q->time_ranges[0].min_ts, hi = q->time_ranges[0].max_ts;
+      for (uint32_t k = 1; k < q->n_time_ranges; k++) {
+        lo = std::min(lo, q->time_ranges[k].min_ts);
+        hi = std::max(hi, q->time_ranges[k].max_ts);
+      }
+      if (hi >= lo) {
+        uint64_t span = (uint64_t)hi - (uint64_t)lo;
+        rel_bits = bits_for(span);
+        rel_base = lo;
+      }
+    }
+    if (rel_bits + slot_bits > 62) {
+      ctx->set_error("first/last across series: (bucket width or time span) x series count does not fit the 62-bit tie-break key");
+      delete s;
+      return TSKV_ERR_UNSUPPORTED;
+    }
+  }
+
+  // ---- state layout ------------------------------------------------------------------------------
+  std::vector<ColState> cols(q->n_columns);
+  StateLayout &sl = s->sl;
+  uint64_t off = 0;
+  sl.sum_i64_off = off;
+  for (uint32_t c = 0; c < q->n_columns; c++) {
+    const tskv_agg_column &qc = q->columns[c];
+    cols[c] = ColState{};
+    cols[c].column_id = qc.column_id;
+    cols[c].phys_type = qc.phys_type;
+    cols[c].agg_mask = qc.agg_mask;
+    cols[c].count_off = off;
+    off += n_cells;
+    if ((qc.agg_mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) && qc.phys_type != TSKV_PT_F64) {
+      cols[c].sum_off = off;
+      off += n_cells;
+    }
+  }
+  sl.sum_i64_len = off - sl.sum_i64_off;
+  sl.sum_f64_off = off;
+  for (uint32_t c = 0; c < q->n_columns; c++)
+    if ((q->columns[c].agg_mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) && q->columns[c].phys_type == TSKV_PT_F64) {
+      cols[c].sum_off = off;
+      off += n_cells;
+    }
+  sl.sum_f64_len = off - sl.sum_f64_off;
+  uint64_t n_first = 0, n_last = 0;
+  for (uint32_t c = 0; c < q->n_columns; c++) {
+    if (q->columns[c].agg_mask & TSKV_AGG_FIRST) n_first += n_cells;
+    if (q->columns[c].agg_mask & TSKV_AGG_LAST) n_last += n_cells;
+  }
+  sl.first_cells = n_first;
+  sl.last_cells = n_last;
+  sl.min_off = off;
+  for (uint32_t c = 0; c < q->n_columns; c++)
+    if (q->columns[c].agg_mask & TSKV_AGG_MIN) {
+      cols[c].min_off = off;
+      off += n_cells;
+    }
+  sl.first_keys_off = off;
+  off += n_first;
+  sl.min_len = off - sl.min_off;
+  sl.max_off = off;
+  for (uint32_t c = 0; c < q->n_columns; c++)
+    if (q->columns[c].agg_mask & TSKV_AGG_MAX) {
+      cols[c].max_off = off;
+      off += n_cells;
+    }
+  sl.last_keys_off = off;
+  off += n_last;
+  sl.max_len = off - sl.max_off;
+  sl.selval_off = off;
+  off += n_first + n_last;
+  sl.selval_len = n_first + n_last;
+  off = (off + 1) & ~1ull;  // 16-byte alignment of the pair arrays
+  sl.first_pairs_off = off;
+  {
+    uint64_t o = off;
+    for (uint32_t c = 0; c < q->n_columns; c++)
+      if (q->columns[c].agg_mask & TSKV_AGG_FIRST) {
+        cols[c].first_off = o;
+        o += 2 * n_cells;
+      }
+    off = o;
+  }
+  sl.last_pairs_off = off;
+  {
+    uint64_t o = off;
+    for (uint32_t c = 0; c < q->n_columns; c++)
+      if (q->columns[c].agg_mask & TSKV_AGG_LAST) {
+        cols[c].last_off = o;
+        o += 2 * n_cells;
+      }
+    off = o;
+  }
+  sl.snap_off = off;
+  off += n_first + n_last;
+  sl.total = off;
+
+  // output column table
+  std::vector<OutCol> outs;
+  {
+    uint64_t fk = sl.first_keys_off, lk = sl.last_keys_off, fv = sl.selval_off, lv = sl.selval_off + n_first;
+    for (uint32_t c = 0; c < q->n_columns; c++) {
+      const tskv_agg_column &qc = q->columns[c];
+      for (unsigned bit = 0; bit < 7; bit++) {
+        unsigned agg = 1u << bit;
+        if (!(qc.agg_mask & agg)) continue;
+        OutCol oc{};
+        oc.count_off = cols[c].count_off;
+        oc.agg = (uint8_t)agg;
+        oc.phys_type = qc.phys_type;
+        switch (agg) {
+          case TSKV_AGG_SUM:
+          case TSKV_AGG_MEAN: oc.src_off = cols[c].sum_off; break;
+          case TSKV_AGG_MIN: oc.src_off = cols[c].min_off; break;
+          case TSKV_AGG_MAX: oc.src_off = cols[c].max_off; break;
+          case TSKV_AGG_FIRST: oc.src_off = fk; oc.val_off = fv; break;
+          case TSKV_AGG_LAST: oc.src_off = lk; oc.val_off = lv; break;
+          default: break;
+        }
+        outs.push_back(oc);
+      }
+      if (qc.agg_mask & TSKV_AGG_FIRST) { fk += n_cells; fv += n_cells; }
+      if (qc.agg_mask & TSKV_AGG_LAST) { lk += n_cells; lv += n_cells; }
+    }
+  }
+
+  // ---- device allocations --------------------------------------------------------------------------
+  const uint32_t n_items = pages->n_items;
+  s->n_blocks = (n_items + 1023) / 1024;
+  cudaError_t e = cudaSuccess;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  if (q->series_ids) {
+    e = dev_alloc(&s->d_series, q->n_series);
+    if (e == cudaSuccess && q->n_series)
+      e = cudaMemcpyAsync(s->d_series, q->series_ids, (size_t)q->n_series * 4, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess) e = dev_alloc(&s->d_cg_slot, pages->n_cg);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_item_flag, n_items);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_block_count, s->n_blocks);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_work_page, n_items);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_work_slot, n_items);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_work_qcol, n_items);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_bin_cstart, N_BINS + 2);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_cols, cols.size());
+  if (e == cudaSuccess) e = dev_alloc(&s->d_outs, outs.size());
+  if (e == cudaSuccess) e = dev_alloc(&s->d_state, sl.total);
+  // task counters [N_BINS x u32, padded to 8 x u64] | status | err_page | stats[2] | counters[2]
+  if (e == cudaSuccess) e = dev_alloc(reinterpret_cast<unsigned long long **>(&s->d_task_counter), 16);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_values, L.n_out * L.n_cells);
+  if (e == cudaSuccess) e = dev_alloc(&s->d_validity, L.validity_bytes + 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_cols, cols.data(), cols.size() * sizeof(ColState), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_outs, outs.data(), outs.size() * sizeof(OutCol), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->set_error(std::string("scan_prepare: ") + cudaGetErrorString(e));
+    free_scan(s);
+    return e == cudaErrorMemoryAllocation ? TSKV_ERR_OOM : TSKV_ERR_CUDA;
+  }
+  unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
+  s->d_status = reinterpret_cast<int32_t *>(aux + 8);
+  s->d_err_page = aux + 9;
+  s->d_stats = aux + 10;
+  s->d_counters = aux + 12;
+  cudaMemsetAsync(aux, 0, 16 * 8, ctx->stream);
+  cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream);
+
+  // ---- selection -> compacted work list -------------------------------------------------------------
+  uint64_t launches = 0;
+  if (pages->n_cg) {
+    k_select_cg<<<(pages->n_cg + 255) / 256, 256, 0, ctx->stream>>>(pages->d_descs, pages->d_cg_time_page, pages->n_cg,
+                                                                     s->d_series, q->series_ids ? q->n_series : 0,
+                                                                     pages->d_cg_series_rank, s->d_cg_slot);
+    launches++;
+  }
+  if (n_items) {
+    k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_page, pages->d_item_cg,
+                                                        pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
+                                                        q->n_columns, s->d_item_flag, s->d_block_count, s->d_counters,
+                                                        s->d_status);
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(s->d_block_count, s->n_blocks, s->d_bin_cstart + N_BINS + 1);
+    k_scatter_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_item_page, pages->d_item_cg, n_items, s->d_item_flag,
+                                                           s->d_block_count, s->d_cg_slot, pages->d_bin_start,
+                                                           s->d_work_page, s->d_work_slot, s->d_work_qcol,
+                                                           s->d_bin_cstart, s->d_bin_cstart + N_BINS + 1);
+    launches += 3;
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+
+  // ---- kernel parameters ------------------------------------------------------------------------------
+  ScanParams &P = s->params;
+  P.arena = pages->d_arena;
+  P.descs = pages->d_descs;
+  P.time_page_of = pages->d_time_page_of;
+  P.work_page = s->d_work_page;
+  P.work_slot = s->d_work_slot;
+  P.work_qcol = s->d_work_qcol;
+  P.bin_cstart = s->d_bin_cstart;
+  P.cols = s->d_cols;
+  P.state = s->d_state;
+  P.task_counter = s->d_task_counter;
+  P.status = s->d_status;
+  P.err_page = s->d_err_page;
+  P.stats = s->d_stats;
+  P.n_ranges = q->n_time_ranges;
+  for (uint32_t k = 0; k < q->n_time_ranges; k++) P.ranges[k] = q->time_ranges[k];
+  P.width = q->width;
+  P.origin_mod = q->width > 0 ? q->origin % q->width : 0;
+  P.first_bucket_start = q->first_bucket_start;
+  P.n_buckets = q->n_buckets;
+  P.group_by_series = q->group_by_series;
+  P.n_cells = n_cells;
+  P.slot_bits = slot_bits;
+  P.slot_max = slot_bits ? (uint32_t)((1ull << slot_bits) - 1) : 0;
+  P.rel_base = rel_base;
+
+  for (int b = 0; b < N_BINS; b++) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel_for_bin(b), 256, 0);
+    s->grid[b] = std::max(1, per_sm) * ctx->sm_count;
+  }
+
+  st = fetch_status(ctx, s->d_status, s->d_err_page);
+  if (st != TSKV_OK) {
+    if (st == TSKV_ERR_INVALID_ARG) ctx->set_error("page type does not match the query column type", ctx->err_page);
+    free_scan(s);
+    return st;
+  }
+  unsigned long long cnt[2] = {0, 0};
+  cudaMemcpy(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->counters.elapsed_h2d_ms = ms;
+  ctx->counters.page_read_count = cnt[0];
+  ctx->counters.page_read_bytes = cnt[1];
+  ctx->counters.kernel_launches = launches;
+  *out_scan = s;
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *s) {
+  if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
+  CU_TRY(ctx, cudaMemsetAsync(aux, 0, 12 * 8, ctx->stream));  // task counters, status, err page, stats
+  uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
+  k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
+  uint64_t launches = 1;
+  for (int b = 0; b < N_BINS; b++) {
+    // the compacted bin is a subset of the arena's bin: skip kinds the arena does not contain
+    uint32_t n_bin = s->pages->h_bin_start[b + 1] - s->pages->h_bin_start[b];
+    if (n_bin == 0) continue;
+    uint32_t chunks = (n_bin + 31) / 32;
+    uint32_t grid = std::min<uint32_t>((uint32_t)s->grid[b], (chunks + 7) / 8);
+    void *args[] = {(void *)&s->params};
+    CU_TRY(ctx, cudaLaunchKernel((const void *)scan_kernel_for_bin(b), dim3(grid), dim3(256), args, 0, ctx->stream));
+    launches++;
+  }
+  if (s->has_sel) {
+    uint32_t b = (uint32_t)std::min<uint64_t>((std::max(s->sl.first_cells, s->sl.last_cells) + 255) / 256, 4096);
+    k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl);
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  tskv_status st = fetch_status(ctx, s->d_status, s->d_err_page);
+  if (st != TSKV_OK) return st;
+  unsigned long long stats[2] = {0, 0};
+  CU_TRY(ctx, cudaMemcpy(stats, s->d_stats, 16, cudaMemcpyDeviceToHost));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->counters.elapsed_scan_ms = ms;
+  ctx->counters.points_decoded = stats[0];
+  ctx->counters.rows_in_range = stats[1];
+  ctx->counters.kernel_launches = launches + (s->has_sel ? 1 : 0);
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *s, tskv_partials_view *out) {
+  if (!ctx || !s || !out) return TSKV_ERR_INVALID_ARG;
+  const StateLayout &L = s->sl;
+  uint64_t base = (uint64_t)(uintptr_t)s->d_state;
+  out->sum_i64_ptr = base + L.sum_i64_off * 8;
+  out->sum_i64_len = L.sum_i64_len;
+  out->sum_f64_ptr = base + L.sum_f64_off * 8;
+  out->sum_f64_len = L.sum_f64_len;
+  out->min_i64_ptr = base + L.min_off * 8;
+  out->min_i64_len = L.min_len;
+  out->max_i64_ptr = base + L.max_off * 8;
+  out->max_i64_len = L.max_len;
+  out->sel_val_ptr = base + L.selval_off * 8;
+  out->sel_val_len = L.selval_len;
+  out->sel_first_len = L.first_cells;
+  out->sel_last_len = L.last_cells;
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *s) {
+  if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (s->has_sel) {
+    k_snapshot_keys<<<256, 256, 0, ctx->stream>>>(s->d_state, s->sl);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_mask_values(tskv_ctx *ctx, tskv_scan *s) {
+  if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (s->has_sel) {
+    k_mask_values<<<256, 256, 0, ctx->stream>>>(s->d_state, s->sl);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return TSKV_OK;
+}
+
+static tskv_status finalize_device(tskv_ctx *ctx, tskv_scan *s) {
+  const tskv_output_layout &L = s->layout;
+  dim3 grid((uint32_t)((L.n_cells + 255) / 256), s->n_out);
+  k_finalize<<<grid, 256, 0, ctx->stream>>>(s->d_state, s->d_outs, s->n_out, L.n_cells, L.bitmap_stride, s->d_values,
+                                            s->d_validity);
+  CU_TRY(ctx, cudaGetLastError());
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_finalize(tskv_ctx *ctx, tskv_scan *s, uint64_t *out_values, uint8_t *out_validity) {
+  if (!ctx || !s || !out_values || !out_validity) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  tskv_status st = finalize_device(ctx, s);
+  if (st != TSKV_OK) return st;
+  CU_TRY(ctx, cudaMemcpyAsync(out_values, s->d_values, s->layout.values_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(out_validity, s->d_validity, s->layout.validity_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_finalize_device(tskv_ctx *ctx, tskv_scan *s, uint64_t *out_values_dptr,
+                                         uint64_t *out_validity_dptr) {
+  if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  tskv_status st = finalize_device(ctx, s);
+  if (st != TSKV_OK) return st;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (out_values_dptr) *out_values_dptr = (uint64_t)(uintptr_t)s->d_values;
+  if (out_validity_dptr) *out_validity_dptr = (uint64_t)(uintptr_t)s->d_validity;
+  return TSKV_OK;
+}
+
+void tskvgpu_scan_destroy(tskv_ctx *ctx, tskv_scan *s) {
+  if (ctx) cudaSetDevice(ctx->device);
+  free_scan(s);
+}
+
+tskv_status tskvgpu_scan_aggregate(tskv_ctx *ctx, const tskv_pages *pages, const tskv_query *q,
+                                   uint64_t *out_values, uint8_t *out_validity) {
+  if (!out_values || !out_validity) return TSKV_ERR_INVALID_ARG;
+  tskv_scan *s = nullptr;
+  tskv_status st = tskvgpu_scan_prepare(ctx, pages, q, &s);
+  if (st != TSKV_OK) return st;
+  tskv_counters c0 = ctx->counters;
+  st = tskvgpu_scan_run(ctx, s);
+  if (st == TSKV_OK) st = tskvgpu_scan_finalize(ctx, s, out_values, out_validity);
+  ctx->counters.page_read_count = c0.page_read_count;
+  ctx->counters.page_read_bytes = c0.page_read_bytes;
+  ctx->counters.elapsed_h2d_ms = c0.elapsed_h2d_ms;
+  ctx->counters.kernel_launches += c0.kernel_launches + 1;
+  tskvgpu_scan_destroy(ctx, s);
+  return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's reader interface for the scan path, over the C ABI.
+
+Reference seam (paths relative to the reference tree):
+  QueryOption / time ranges / aggregates   tskv/src/reader/iterator.rs:713-741
+  BatchReader::process                      tskv/src/reader/mod.rs:159-164
+  TsmReader::read_adjacent_pages + CRC      tskv/src/tsm/reader.rs:236-264
+  Page::to_arrow_array                      tskv/src/tsm/page.rs:96-98
+This module only marshals arguments: all compute happens in libtskv_gpu.so (CUDA, sm_100a).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import cabi
+from .cabi import (TSKV_AGG_COUNT, TSKV_AGG_FIRST, TSKV_AGG_LAST, TSKV_AGG_MAX, TSKV_AGG_MEAN,
+                   TSKV_AGG_MIN, TSKV_AGG_SUM, TSKV_PT_F64, TSKV_PT_I64, TSKV_PT_TIME, TSKV_PT_U64)
+
+AGG_BITS = {"count": TSKV_AGG_COUNT, "sum": TSKV_AGG_SUM, "min": TSKV_AGG_MIN, "max": TSKV_AGG_MAX,
+            "mean": TSKV_AGG_MEAN, "avg": TSKV_AGG_MEAN, "first": TSKV_AGG_FIRST, "last": TSKV_AGG_LAST}
+
+
+class TskvError(RuntimeError):
+    """Mirrors TskvError::Decode / TsmPageFileHashCheckFailed: carries the status code."""
+
+    def __init__(self, status, message, page=-1):
+        super().__init__("%s (status %d = %s, page %d)" % (
+            message, status, cabi.STATUS_NAMES.get(status, "?"), page))
+        self.status = status
+        self.page = page
+
+
+class PushedAggregate:
+    """One projected value column with its aggregate set (extends PushedAggregateFunction::Count)."""
+
+    def __init__(self, column_id, phys_type, aggs):
+        self.column_id = int(column_id)
+        self.phys_type = int(phys_type)
+        if isinstance(aggs, int):
+            self.agg_mask = aggs
+        else:
+            self.agg_mask = 0
+            for a in aggs:
+                self.agg_mask |= AGG_BITS[a]
+
+    def agg_list(self):
+        return [b for b in (1, 2, 4, 8, 16, 32, 64) if self.agg_mask & b]
+
+
+class QueryOption:
+    """The pushed-down scan: series selection, closed time ranges, bucket expression, aggregates."""
+
+    def __init__(self, columns, series_ids=None, time_ranges=(), origin=0, width=0,
+                 first_bucket_start=0, n_buckets=1, group_by_series=False):
+        self.columns = list(columns)
+        self.series_ids = None if series_ids is None else np.ascontiguousarray(series_ids, dtype=np.uint32)
+        self.time_ranges = [(int(a), int(b)) for a, b in time_ranges]
+        self.origin = int(origin)
+        self.width = int(width)
+        self.first_bucket_start = int(first_bucket_start)
+        self.n_buckets = int(n_buckets)
+        self.group_by_series = bool(group_by_series)
+        self._keep = None
+
+    def to_c(self):
+        q = cabi.Query()
+        if self.series_ids is not None:
+            q.series_ids = self.series_ids.ctypes.data_as(C.POINTER(C.c_uint32))
+            q.n_series = len(self.series_ids)
+        tr = (cabi.TimeRange * max(1, len(self.time_ranges)))()
+        for i, (a, b) in enumerate(self.time_ranges):
+            tr[i].min_ts, tr[i].max_ts = a, b
+        q.time_ranges = tr
+        q.n_time_ranges = len(self.time_ranges)
+        q.origin, q.width = self.origin, self.width
+        q.first_bucket_start, q.n_buckets = self.first_bucket_start, self.n_buckets
+        q.group_by_series = 1 if self.group_by_series else 0
+        cols = (cabi.AggColumn * len(self.columns))()
+        for i, c in enumerate(self.columns):
+            cols[i].column_id, cols[i].phys_type, cols[i].agg_mask = c.column_id, c.phys_type, c.agg_mask
+        q.columns = cols
+        q.n_columns = len(self.columns)
+        self._keep = (tr, cols)  # keep the ctypes arrays alive as long as the query
+        return q
+
+    def output_names(self):
+        return [(c.column_id, cabi.AGG_NAMES[a]) for c in self.columns for a in c.agg_list()]
+
+
+class ScanResult:
+    """Dense result: values[j, cell] (u64 bit patterns) + validity[j, cell] (bool)."""
+
+    def __init__(self, query, layout, values, bitmaps):
+        self.names = query.output_names()
+        self.n_groups = int(layout.n_groups)
+        self.n_buckets = query.n_buckets
+        self.values = values.reshape(int(layout.n_out), int(layout.n_cells))
+        bits = np.unpackbits(bitmaps.reshape(int(layout.n_out), int(layout.bitmap_stride)), axis=1,
+                             bitorder="little")
+        self.validity = bits[:, : int(layout.n_cells)].astype(bool)
+        self.phys = {(c.column_id): c.phys_type for c in query.columns}
+
+    def column(self, column_id, agg):
+        """(typed values, validity) of one output column, shaped [n_groups, n_buckets]."""
+        j = self.names.index((column_id, agg))
+        raw = self.values[j]
+        pt = self.phys[column_id]
+        if agg == "count":
+            v = raw.view(np.uint64)
+        elif agg == "mean" or pt == TSKV_PT_F64:
+            v = raw.view(np.float64)
+        elif pt == TSKV_PT_I64:
+            v = raw.view(np.int64)
+        else:
+            v = raw.view(np.uint64)
+        return (v.reshape(self.n_groups, self.n_buckets),
+                self.validity[j].reshape(self.n_groups, self.n_buckets))
+
+
+class PageSet:
+    """Device-resident page arena + descriptor tables (the engine's view of cached TsmReaders)."""
+
+    def __init__(self, engine, handle, n_pages):
+        self.engine = engine
+        self.handle = handle
+        self.n_pages = n_pages
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.tskvgpu_pages_destroy(self.engine.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PreparedScan:
+    def __init__(self, engine, pages, query, handle, layout):
+        self.engine, self.pages, self.query, self.handle, self.layout = engine, pages, query, handle, layout
+
+    def run(self):
+        self.engine._check(self.engine.lib.tskvgpu_scan_run(self.engine.ctx, self.handle))
+
+    def partials(self):
+        v = cabi.PartialsView()
+        self.engine._check(self.engine.lib.tskvgpu_scan_partials(self.engine.ctx, self.handle, C.byref(v)))
+        return v
+
+    def snapshot_keys(self):
+        self.engine._check(self.engine.lib.tskvgpu_scan_snapshot_keys(self.engine.ctx, self.handle))
+
+    def mask_values(self):
+        self.engine._check(self.engine.lib.tskvgpu_scan_mask_values(self.engine.ctx, self.handle))
+
+    def finalize(self):
+        L = self.layout
+        values = np.empty(int(L.n_out * L.n_cells), dtype=np.uint64)
+        bitmaps = np.empty(int(L.validity_bytes), dtype=np.uint8)
+        self.engine._check(self.engine.lib.tskvgpu_scan_finalize(
+            self.engine.ctx, self.handle, values.ctypes.data, bitmaps.ctypes.data))
+        return ScanResult(self.query, L, values, bitmaps)
+
+    def finalize_device(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.engine._check(self.engine.lib.tskvgpu_scan_finalize_device(
+            self.engine.ctx, self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.tskvgpu_scan_destroy(self.engine.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One CUDA device + stream (tskv_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = cabi.load_gpu_library()
+        ctx = C.c_void_p()
+        st = self.lib.tskvgpu_ctx_create(int(device), C.byref(ctx))
+        if st != cabi.TSKV_OK:
+            raise TskvError(st, "tskvgpu_ctx_create(device=%d) failed: no usable CUDA device" % device)
+        self.ctx = ctx
+        self.device = int(device)
+
+    def close(self):
+        if self.ctx:
+            self.lib.tskvgpu_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != cabi.TSKV_OK:
+            msg = self.lib.tskvgpu_last_error(self.ctx).decode()
+            raise TskvError(st, msg, self.lib.tskvgpu_last_error_page(self.ctx))
+
+    def version(self):
+        return self.lib.tskvgpu_version().decode()
+
+    def stream(self):
+        return int(self.lib.tskvgpu_ctx_stream(self.ctx))
+
+    def counters(self):
+        c = cabi.Counters()
+        self._check(self.lib.tskvgpu_get_counters(self.ctx, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in cabi.Counters._fields_ if k != "reserved"}
+
+    def upload_pages(self, arena, descs, verify_crc=True):
+        """arena: uint8 array (or (ptr, len)); descs: array of PAGE_DESC_DTYPE."""
+        if isinstance(arena, tuple):
+            aptr, alen = arena
+        else:
+            arena = np.ascontiguousarray(arena, dtype=np.uint8)
+            aptr, alen = arena.ctypes.data, arena.size
+        descs = np.ascontiguousarray(descs, dtype=cabi.PAGE_DESC_DTYPE)
+        h = C.c_void_p()
+        st = self.lib.tskvgpu_upload_pages(self.ctx, aptr, alen, descs.ctypes.data, len(descs),
+                                           cabi.TSKV_UPLOAD_VERIFY_CRC if verify_crc else 0, C.byref(h))
+        self._check(st)
+        return PageSet(self, h, len(descs))
+
+    def decode_pages(self, pages, descs, first_page=0, n_pages=None):
+        """Page::to_arrow_array for a page range: returns a list of (u64 values, bool validity)."""
+        descs = np.ascontiguousarray(descs, dtype=cabi.PAGE_DESC_DTYPE)
+        n_pages = len(descs) - first_page if n_pages is None else n_pages
+        rows = descs["num_values"][first_page:first_page + n_pages].astype(np.uint64)
+        bm = (rows + 63) // 64 * 8
+        values = np.zeros(int(rows.sum()), dtype=np.uint64)
+        bitmaps = np.zeros(int(bm.sum()), dtype=np.uint8)
+        self._check(self.lib.tskvgpu_decode_pages(self.ctx, pages.handle, first_page, n_pages,
+                                                  values.ctypes.data, bitmaps.ctypes.data))
+        out, ro, bo = [], 0, 0
+        for r, b in zip(rows, bm):
+            r, b = int(r), int(b)
+            valid = np.unpackbits(bitmaps[bo:bo + b], bitorder="little")[:r].astype(bool)
+            out.append((values[ro:ro + r], valid))
+            ro += r
+            bo += b
+        return out
+
+    def output_layout(self, pages, query):
+        L = cabi.OutputLayout()
+        q = query.to_c()
+        st = self.lib.tskvgpu_query_output_layout(pages.handle, C.byref(q), C.byref(L))
+        if st != cabi.TSKV_OK:
+            raise TskvError(st, "invalid query")
+        return L
+
+    def scan_aggregate(self, pages, query):
+        """End-to-end call: query args H2D, fused scan, result D2H (BatchReader::process analogue)."""
+        L = self.output_layout(pages, query)
+        values = np.empty(int(L.n_out * L.n_cells), dtype=np.uint64)
+        bitmaps = np.empty(int(L.validity_bytes), dtype=np.uint8)
+        q = query.to_c()
+        self._check(self.lib.tskvgpu_scan_aggregate(self.ctx, pages.handle, C.byref(q),
+                                                    values.ctypes.data, bitmaps.ctypes.data))
+        return ScanResult(query, L, values, bitmaps)
+
+    def prepare(self, pages, query):
+        L = self.output_layout(pages, query)
+        q = query.to_c()
+        h = C.c_void_p()
+        self._check(self.lib.tskvgpu_scan_prepare(self.ctx, pages.handle, C.byref(q), C.byref(h)))
+        return PreparedScan(self, pages, query, h, L)

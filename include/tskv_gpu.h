@@ -1,0 +1,253 @@
+/*
+ * tskv_gpu.h — C ABI of the B200-native tskv scan/aggregate engine.
+ *
+ * This is the drop-in boundary for ONE path of cnosdb/cnosdb (all citations are relative to the
+ * reference tree): TSM page decode -> time-range + series-selection filter -> time-bucketed
+ * aggregate. The reference has no FFI; the seam it replaces is the `BatchReader` tree built by
+ * `SeriesGroupBatchReaderFactory::create` (tskv/src/reader/iterator.rs:123-264) and polled through
+ * `BatchReader::process` (tskv/src/reader/mod.rs:159-164). A Rust shim implementing that trait
+ * binds the functions below (see INTEGRATION.md for the `extern "C"` block a maintainer would add).
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; device memory is addressed as uint64_t.
+ *   - every entry point returns a tskv_status (0 = ok); nothing throws or aborts across the ABI.
+ *   - the caller owns every host buffer it passes; the library copies and never frees them.
+ *   - a context is bound to one CUDA device; calls on one context are serialised internally
+ *     (thread-safe), different contexts are independent (one per tokio blocking thread / per GPU).
+ */
+#ifndef TSKV_GPU_H_
+#define TSKV_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* Status codes. The decode codes map 1:1 onto the reference's codec error strings, which the   */
+/* Rust side surfaces as TskvError::Decode (tskv/src/error.rs:293-299).                         */
+/* ------------------------------------------------------------------------------------------- */
+typedef int32_t tskv_status;
+enum {
+  TSKV_OK = 0,
+  TSKV_ERR_INVALID_ARG = 1,     /* null pointer, malformed descriptor table, unsorted selection */
+  TSKV_ERR_BAD_ENCODING = 2,    /* "invalid block encoding" (timestamp.rs:197, integer.rs:161) */
+  TSKV_ERR_SHORT_BLOCK = 3,     /* "not enough data to decode ..." / "unexpected end of block"
+                                   (timestamp.rs:228,263; integer.rs:188,218; float.rs:462) */
+  TSKV_ERR_CRC_MISMATCH = 4,    /* TsmPageFileHashCheckFailed (tskv/src/tsm/page.rs:58-76) */
+  TSKV_ERR_BITSET_MISMATCH = 5, /* "Mismatch between bit set and decoded values" (float.rs:598);
+                                   also: fewer decoded values than valid bits in ts/i64 pages,
+                                   which the reference turns into an Arrow length error */
+  TSKV_ERR_UNSUPPORTED = 6,     /* Quantile(pco)/bool/string pages, or a first/last key that does
+                                   not fit 63 bits */
+  TSKV_ERR_BUCKET_RANGE = 7,    /* an in-range row fell outside [first_bucket_start, +n*width) */
+  TSKV_ERR_CUDA = 8,
+  TSKV_ERR_NCCL = 9,            /* reserved (collectives are driven by the host runtime) */
+  TSKV_ERR_OOM = 10,
+  TSKV_ERR_BAD_LENGTH = 11,     /* "invalid uncompressed block length" (timestamp.rs:203) */
+  TSKV_ERR_PAGE_FORMAT = 12     /* page shorter than its own header / bitset (page.rs:78-94) */
+};
+
+/* Physical column type of a page: PhysicalCType::Time / PhysicalDType::{Integer,Unsigned,Float}
+ * (dispatch in tskv/src/tsm/reader.rs:658-731). */
+enum {
+  TSKV_PT_TIME = 0,
+  TSKV_PT_I64 = 1,
+  TSKV_PT_U64 = 2,
+  TSKV_PT_F64 = 3
+};
+
+/* Encoding ids stored in data[0] of a page (common/models/src/codec.rs:37-54). */
+enum {
+  TSKV_ENC_DEFAULT = 0,
+  TSKV_ENC_NULL = 1,
+  TSKV_ENC_DELTA = 2,
+  TSKV_ENC_QUANTILE = 3,
+  TSKV_ENC_GORILLA = 6,
+  TSKV_ENC_DELTA_TS = 11
+};
+
+/* One encoded page inside the arena. Replaces `PageWriteSpec{offset,size,meta}`
+ * (tskv/src/tsm/page.rs:599-620) + the `Page.bytes` it addresses (page.rs:31-39).
+ * Pages are listed column group by column group (tskv/src/tsm/column_group.rs:9-17): a TIME page
+ * opens a column group and is followed by that group's field pages (ascending column id,
+ * mem_cache/series_data.rs:226-230). All pages of a group carry the same series_id / num_values.
+ * `offset` must be 16-byte aligned inside the arena. 24 bytes. */
+typedef struct tskv_page_desc {
+  uint64_t offset;     /* byte offset of the page (header+bitset+data) in the arena */
+  uint32_t size;       /* page size in bytes */
+  uint32_t num_values; /* PageMeta.num_values = rows incl. nulls (page.rs:347-351) */
+  uint32_t series_id;  /* SeriesId (common/models/src/lib.rs:40), local to the vnode */
+  uint16_t column_id;  /* TableColumn.id; ignored for the time page */
+  uint8_t phys_type;   /* TSKV_PT_* */
+  uint8_t reserved;    /* must be 0 (the library stores its decode-kind here on the device) */
+} tskv_page_desc;
+
+/* Closed interval, exactly `TimeRange{min_ts,max_ts}` (common/models/src/predicate/domain.rs:35-98). */
+typedef struct tskv_time_range {
+  int64_t min_ts;
+  int64_t max_ts;
+} tskv_time_range;
+
+/* Aggregate bits. count/sum/min/max/avg follow DataFusion's builtins; first/last follow
+ * query_server/query/src/extension/expr/aggregate_function/{first,last}.rs. */
+enum {
+  TSKV_AGG_COUNT = 1u << 0, /* valid (non-null) values in range; u64 */
+  TSKV_AGG_SUM = 1u << 1,   /* i64/u64: wrapping; f64: double */
+  TSKV_AGG_MIN = 1u << 2,
+  TSKV_AGG_MAX = 1u << 3,
+  TSKV_AGG_MEAN = 1u << 4,  /* f64 = sum / count */
+  TSKV_AGG_FIRST = 1u << 5, /* value at the smallest timestamp */
+  TSKV_AGG_LAST = 1u << 6,  /* value at the largest timestamp */
+  TSKV_AGG_ALL = 0x7f
+};
+
+/* One projected value column and the aggregates wanted for it. Extends
+ * `PushedAggregateFunction` (common/models/src/predicate/domain.rs:1840-1843), which today only
+ * has Count(col). */
+typedef struct tskv_agg_column {
+  uint16_t column_id;
+  uint8_t phys_type; /* TSKV_PT_I64 / U64 / F64: pages of another type under this id are an error */
+  uint8_t agg_mask;  /* TSKV_AGG_* bits */
+} tskv_agg_column;
+
+/* The pushed-down scan. Mirrors the fields of `QueryOption` the hot path consumes
+ * (tskv/src/reader/iterator.rs:713-741): split.time_ranges(), the series ids produced by
+ * `get_series_id_by_filter` (tskv/src/kvcore.rs:249-279), the aggregate list; plus the bucket
+ * expression `time_window(time, width)` / `date_bin(width, time, origin)` that today runs in
+ * DataFusion (query_server/query/src/extension/analyse/transform_time_window.rs:251-296). */
+typedef struct tskv_query {
+  const uint32_t *series_ids; /* sorted ascending, unique; NULL => every series of the arena.
+                                 The position of an id in this list is its "slot": it is the
+                                 group index when group_by_series != 0 and the tie-break order of
+                                 first/last ("earlier-seen point wins", first.rs:103-107). */
+  uint32_t n_series;
+  uint32_t n_time_ranges; /* 0 => all time */
+  const tskv_time_range *time_ranges;
+  int64_t origin;             /* start_time of the window expression */
+  int64_t width;              /* bucket width in the time column's unit; <= 0 => no bucketing */
+  int64_t first_bucket_start; /* start of output bucket 0 (must be a value the formula yields) */
+  uint32_t n_buckets;         /* >= 1 (1 when width <= 0) */
+  uint32_t group_by_series;   /* 0: GROUP BY bucket ; 1: GROUP BY series, bucket */
+  const tskv_agg_column *columns;
+  uint32_t n_columns;
+  uint32_t reserved;
+} tskv_query;
+
+/* Result layout. Outputs are dense: for output column j (query columns in order, and inside a
+ * column the set agg bits in ascending bit order) and cell c = group * n_buckets + bucket:
+ *   values  [j * n_cells + c]                     8-byte cell (i64 / u64 / f64 bit pattern)
+ *   validity[j * bitmap_stride + (c >> 3)] bit (c & 7)   Arrow LSB-first validity
+ * so a shim can wrap each output column zero-copy as an Arrow array. */
+typedef struct tskv_output_layout {
+  uint64_t n_out;         /* number of output columns */
+  uint64_t n_groups;      /* 1, or number of series slots when group_by_series */
+  uint64_t n_cells;       /* n_groups * n_buckets */
+  uint64_t bitmap_stride; /* bytes per validity bitmap, multiple of 8 */
+  uint64_t values_bytes;  /* n_out * n_cells * 8 */
+  uint64_t validity_bytes;/* n_out * bitmap_stride */
+} tskv_output_layout;
+
+/* Counters mirroring the reference's per-operator metrics (reader/column_group/mod.rs:141-193:
+ * page_read_count, page_read_bytes, elapsed_page_scan_time, elapsed_page_to_array_time). */
+typedef struct tskv_counters {
+  uint64_t page_read_count;     /* pages touched by the last scan */
+  uint64_t page_read_bytes;     /* encoded bytes of those pages (algorithmic bytes numerator) */
+  uint64_t points_decoded;      /* valid values decoded by the last scan/decode */
+  uint64_t rows_in_range;       /* rows that passed the time filter */
+  double elapsed_scan_ms;       /* device time of the last scan (CUDA events) */
+  double elapsed_h2d_ms;        /* host->device time of the last upload / query arguments */
+  uint64_t kernel_launches;     /* kernels launched by the last call */
+  uint64_t reserved[5];
+} tskv_counters;
+
+typedef struct tskv_ctx tskv_ctx;       /* one CUDA device + stream */
+typedef struct tskv_pages tskv_pages;   /* a device-resident page arena + descriptor tables */
+
+/* ---- context ------------------------------------------------------------------------------ */
+tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx);
+void tskvgpu_ctx_destroy(tskv_ctx *ctx);
+/* Last error message of this context (valid until the next call on it). */
+const char *tskvgpu_last_error(const tskv_ctx *ctx);
+/* Index of the page that caused the last decode error, or -1. */
+int64_t tskvgpu_last_error_page(const tskv_ctx *ctx);
+tskv_status tskvgpu_get_counters(const tskv_ctx *ctx, tskv_counters *out);
+/* Raw cudaStream_t of the context (as an integer) so a host runtime can order its own
+ * collectives after a scan. */
+uint64_t tskvgpu_ctx_stream(const tskv_ctx *ctx);
+
+/* ---- pages ---------------------------------------------------------------------------------
+ * Replaces TsmReader::read_adjacent_pages + Page::crc_validation (tskv/src/tsm/reader.rs:236-264,
+ * page.rs:58-76): copies `arena` to the device, validates framing, optionally verifies each
+ * page's CRC32 (flags & TSKV_UPLOAD_VERIFY_CRC) like the reference does on every read. */
+enum { TSKV_UPLOAD_VERIFY_CRC = 1u };
+tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t arena_len,
+                                 const tskv_page_desc *descs, uint64_t n_descs, uint32_t flags,
+                                 tskv_pages **out_pages);
+void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pages);
+/* Number of distinct series in the arena. */
+uint64_t tskvgpu_pages_series_count(const tskv_pages *pages);
+
+/* ---- decode only ---------------------------------------------------------------------------
+ * Replaces Page::to_arrow_array / data_buf_to_arrow_array (tskv/src/tsm/reader.rs:658-731) for
+ * pages [first_page, first_page + n_pages): row r of page p lands at out_values[row_offsets[p]+r]
+ * where row_offsets is the exclusive prefix sum of num_values over the requested pages; validity
+ * is one Arrow LSB-first bitmap per page, page p starting at byte validity_offsets[p] =
+ * sum over previous pages of ((num_values + 63) / 64) * 8. Null rows hold 0. Host buffers. */
+tskv_status tskvgpu_decode_pages(tskv_ctx *ctx, const tskv_pages *pages, uint64_t first_page,
+                                 uint64_t n_pages, uint64_t *out_values, uint8_t *out_validity);
+
+/* ---- scan + filter + bucket aggregate ------------------------------------------------------ */
+tskv_status tskvgpu_query_output_layout(const tskv_pages *pages, const tskv_query *q,
+                                        tskv_output_layout *out);
+/* Fused decode -> filter -> bucket reduce. `out_values` / `out_validity` are HOST buffers sized by
+ * tskvgpu_query_output_layout (query arguments go host->device and results device->host inside
+ * this call: this is the end-to-end path a BatchReader::process() would take). */
+tskv_status tskvgpu_scan_aggregate(tskv_ctx *ctx, const tskv_pages *pages, const tskv_query *q,
+                                   uint64_t *out_values, uint8_t *out_validity);
+
+/* Device-resident variant used for multi-GPU partial reduction and for kernel-only timing:
+ *   prepare  : uploads the query (selection list, ranges), builds the compacted work list and
+ *              allocates the partial-aggregate state on the device.
+ *   run      : zeroes the state and runs the fused kernel (no host<->device traffic).
+ *   partials : exposes the raw state as four device sections a host runtime can all-reduce
+ *              element-wise (i64 SUM / f64 SUM / i64 MIN / i64 MAX; see DESIGN.md "Multi-GPU").
+ *   finalize : turns the (possibly all-reduced) state into the dense result and copies it to
+ *              the host buffers. */
+typedef struct tskv_scan tskv_scan;
+typedef struct tskv_partials_view {
+  uint64_t sum_i64_ptr, sum_i64_len; /* counts, i64/u64 sums          : all-reduce SUM as int64 */
+  uint64_t sum_f64_ptr, sum_f64_len; /* f64 sums                      : all-reduce SUM as float64 */
+  uint64_t min_i64_ptr, min_i64_len; /* ordered keys of MIN and FIRST : all-reduce MIN as int64 */
+  uint64_t max_i64_ptr, max_i64_len; /* ordered keys of MAX and LAST  : all-reduce MAX as int64 */
+  uint64_t sel_val_ptr, sel_val_len; /* FIRST then LAST values, same order as their keys; after
+                                        the key all-reduce call tskvgpu_scan_mask_values and
+                                        all-reduce SUM this section as int64 */
+  uint64_t sel_first_len;            /* number of FIRST cells (prefix of sel_val / suffix of min) */
+  uint64_t sel_last_len;             /* number of LAST cells */
+} tskv_partials_view;
+
+tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const tskv_query *q,
+                                 tskv_scan **out_scan);
+tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *scan);
+tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *scan, tskv_partials_view *out);
+/* Snapshot the local first/last keys before they are all-reduced in place (multi-GPU only). */
+tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *scan);
+/* Zero every first/last value whose local key (snapshot) lost the key all-reduce. */
+tskv_status tskvgpu_scan_mask_values(tskv_ctx *ctx, tskv_scan *scan);
+tskv_status tskvgpu_scan_finalize(tskv_ctx *ctx, tskv_scan *scan, uint64_t *out_values,
+                                  uint8_t *out_validity);
+/* Same as finalize but leaves the dense result on the device (no D2H): device pointers out. */
+tskv_status tskvgpu_scan_finalize_device(tskv_ctx *ctx, tskv_scan *scan, uint64_t *out_values_dptr,
+                                         uint64_t *out_validity_dptr);
+void tskvgpu_scan_destroy(tskv_ctx *ctx, tskv_scan *scan);
+
+/* Library version / build info ("tskv-b200 <semver> sm_100a"). */
+const char *tskvgpu_version(void);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* TSKV_GPU_H_ */

@@ -1,0 +1,452 @@
+// oracle/scan.cc — CPU restatement of the reference scan: per series, per column group decode
+// (tsm/reader.rs:494-560) -> closed time-range filter (predicate/domain.rs:35-98, reader/filter.rs)
+// -> bucket key (transform_time_window.rs:251-296) -> aggregates (DataFusion builtins + first.rs /
+// last.rs semantics). TEST INFRASTRUCTURE ONLY (see tskv_oracle.h).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tskv_oracle.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+
+// `sliding_window` (query_server/query/src/extension/expr/window/time_window.rs:184-198); Rust `%`
+// keeps the sign of the dividend, like C; release builds wrap on overflow.
+inline void sliding_window(int64_t t, int64_t w, int64_t s, int64_t start_time, int64_t i,
+                           int64_t *ws, int64_t *we) {
+  int64_t st = start_time % w;
+  int64_t dividend = (int64_t)((uint64_t)t - (uint64_t)st + (uint64_t)s);
+  int64_t last_start = (int64_t)((uint64_t)t - (uint64_t)(dividend % s));
+  *ws = (int64_t)((uint64_t)last_start - (uint64_t)i * (uint64_t)s);
+  *we = (int64_t)((uint64_t)*ws + (uint64_t)w);
+}
+
+// Total order on f64 bit patterns (NaN handling of DataFusion min/max is unpinned in the
+// reference tree; generators never aggregate NaN).
+inline int64_t f64_okey(uint64_t b) { return (int64_t)(b ^ (((int64_t)b >> 63) & 0x7fffffffffffffffll)); }
+
+inline bool less_typed(uint8_t pt, uint64_t a, uint64_t b) {
+  if (pt == TSKV_PT_I64) return (int64_t)a < (int64_t)b;
+  if (pt == TSKV_PT_U64) return a < b;
+  return f64_okey(a) < f64_okey(b);
+}
+
+struct Cell {
+  uint64_t count = 0;
+  uint64_t sum_bits = 0;  // i64/u64 wrapping sum
+  double sum_d = 0.0;     // f64 sum (arrival order); for ints: sum of values cast to f64 (avg)
+  uint64_t minv = 0, maxv = 0;
+  bool has_first = false, has_last = false;
+  int64_t first_ts = 0, last_ts = 0;
+  uint64_t first_val = 0, last_val = 0;
+};
+
+struct ColumnGroup {
+  uint64_t first_desc;  // the TIME page
+  uint64_t n_descs;     // incl. the time page
+};
+
+struct Index {
+  std::vector<uint32_t> series;                 // sorted distinct ids
+  std::map<uint32_t, std::vector<ColumnGroup>> cgs;  // series -> column groups in arena order
+};
+
+tskv_status build_index(const tskv_page_desc *descs, uint64_t n, Index &ix) {
+  uint64_t i = 0;
+  while (i < n) {
+    if (descs[i].phys_type != TSKV_PT_TIME) {
+      g_err = "descriptor table: column group does not start with a time page";
+      return TSKV_ERR_INVALID_ARG;
+    }
+    uint64_t j = i + 1;
+    while (j < n && descs[j].phys_type != TSKV_PT_TIME) {
+      if (descs[j].series_id != descs[i].series_id || descs[j].num_values != descs[i].num_values) {
+        g_err = "descriptor table: field page disagrees with its time page";
+        return TSKV_ERR_INVALID_ARG;
+      }
+      j++;
+    }
+    ix.cgs[descs[i].series_id].push_back(ColumnGroup{i, j - i});
+    i = j;
+  }
+  for (auto &kv : ix.cgs) ix.series.push_back(kv.first);
+  return TSKV_OK;
+}
+
+inline unsigned popc(unsigned x) { return (unsigned)__builtin_popcount(x); }
+
+struct Scan {
+  const uint8_t *arena;
+  uint64_t arena_len;
+  const tskv_page_desc *descs;
+  const tskv_query *q;
+  int verify_crc;
+  const Index *ix;
+  std::vector<uint32_t> slots;  // slot -> series id
+  uint64_t n_cells;
+};
+
+// One worker: slots [s0, s1) into `cells` (n_columns * n_cells). Returns status.
+tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, bool shared_table,
+                       uint64_t *points) {
+  const tskv_query &q = *S.q;
+  std::vector<uint64_t> ts, vals;
+  std::vector<uint8_t> tvalid, vvalid;
+  for (uint64_t slot = s0; slot < s1; slot++) {
+    auto it = S.ix->cgs.find(S.slots[slot]);
+    if (it == S.ix->cgs.end()) continue;  // selected id absent from this arena
+    uint64_t group = q.group_by_series ? slot : 0;
+    (void)shared_table;
+    for (const ColumnGroup &cg : it->second) {
+      const tskv_page_desc &td = S.descs[cg.first_desc];
+      uint64_t n_rows = td.num_values;
+      ts.assign(n_rows ? n_rows : 1, 0);
+      tvalid.assign(n_rows ? n_rows : 1, 0);
+      bool time_decoded = false;
+      for (uint32_t c = 0; c < q.n_columns; c++) {
+        const tskv_agg_column &qc = q.columns[c];
+        const tskv_page_desc *fd = nullptr;
+        for (uint64_t k = 1; k < cg.n_descs; k++)
+          if (S.descs[cg.first_desc + k].column_id == qc.column_id) {
+            fd = &S.descs[cg.first_desc + k];
+            break;
+          }
+        if (!fd) continue;  // column absent from this column group (null-filled by SchemaAlignmenter)
+        if (fd->phys_type != qc.phys_type) {
+          g_err = "page type does not match the query column type";
+          return TSKV_ERR_INVALID_ARG;
+        }
+        if (!time_decoded) {
+          uint64_t nr = 0;
+          if (td.offset + td.size > S.arena_len) return TSKV_ERR_INVALID_ARG;
+          tskv_status st = orc_page_decode(TSKV_PT_TIME, S.arena + td.offset, td.size, S.verify_crc,
+                                           ts.data(), tvalid.data(), n_rows, &nr);
+          if (st != TSKV_OK) return st;
+          if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
+          time_decoded = true;
+        }
+        vals.assign(n_rows ? n_rows : 1, 0);
+        vvalid.assign(n_rows ? n_rows : 1, 0);
+        uint64_t nr = 0;
+        if (fd->offset + fd->size > S.arena_len) return TSKV_ERR_INVALID_ARG;
+        tskv_status st = orc_page_decode(fd->phys_type, S.arena + fd->offset, fd->size, S.verify_crc,
+                                         vals.data(), vvalid.data(), n_rows, &nr);
+        if (st != TSKV_OK) return st;
+        if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
+        const uint8_t pt = qc.phys_type;
+        Cell *ccells = cells + (uint64_t)c * S.n_cells + group * q.n_buckets;
+        // Run state for first/last: the rows of one (page, bucket) form one DataFusion group slice;
+        // FirstAccumulator::update_batch picks its min-time row and drops it when the VALUE is null
+        // (first.rs:139-148 + :91-94). Pages are time-sorted (mem_cache/series_data.rs:218-262), so a
+        // (page, bucket) group is one contiguous run of rows.
+        int64_t run_bucket = -1;
+        uint64_t run_first = 0, run_last = 0;
+        auto close_run = [&]() {
+          if (run_bucket < 0) return;
+          Cell &cell = ccells[run_bucket];
+          if ((qc.agg_mask & TSKV_AGG_FIRST) && vvalid[run_first]) {
+            int64_t t = (int64_t)ts[run_first];
+            if (!cell.has_first || t < cell.first_ts) {  // strictly less: ties keep the earlier-seen
+              cell.has_first = true;
+              cell.first_ts = t;
+              cell.first_val = vals[run_first];
+            }
+          }
+          if ((qc.agg_mask & TSKV_AGG_LAST) && vvalid[run_last]) {
+            int64_t t = (int64_t)ts[run_last];
+            if (!cell.has_last || t > cell.last_ts) {
+              cell.has_last = true;
+              cell.last_ts = t;
+              cell.last_val = vals[run_last];
+            }
+          }
+        };
+        for (uint64_t r = 0; r < n_rows; r++) {
+          if (vvalid[r] && points) (*points)++;
+          if (!tvalid[r]) continue;  // is_not_null(time) (transform_time_window.rs:313)
+          int64_t t = (int64_t)ts[r];
+          bool in = q.n_time_ranges == 0;
+          for (uint32_t k = 0; k < q.n_time_ranges && !in; k++)
+            in = t >= q.time_ranges[k].min_ts && t <= q.time_ranges[k].max_ts;  // TimeRange::contains
+          if (!in) continue;
+          int64_t b = 0;
+          if (q.width > 0) {
+            int64_t ws, we;
+            sliding_window(t, q.width, q.width, q.origin, 0, &ws, &we);
+            int64_t diff = (int64_t)((uint64_t)ws - (uint64_t)q.first_bucket_start);
+            if (diff < 0 || diff % q.width != 0 || diff / q.width >= (int64_t)q.n_buckets) {
+              g_err = "row outside the requested bucket range";
+              return TSKV_ERR_BUCKET_RANGE;
+            }
+            b = diff / q.width;
+          }
+          if (b != run_bucket) {
+            close_run();
+            run_bucket = b;
+            run_first = run_last = r;
+          } else {
+            if ((int64_t)ts[r] < (int64_t)ts[run_first]) run_first = r;
+            if ((int64_t)ts[r] > (int64_t)ts[run_last]) run_last = r;
+          }
+          if (!vvalid[r]) continue;
+          Cell &cell = ccells[b];
+          uint64_t v = vals[r];
+          if (cell.count == 0) {
+            cell.minv = cell.maxv = v;
+          } else {
+            if (less_typed(pt, v, cell.minv)) cell.minv = v;
+            if (less_typed(pt, cell.maxv, v)) cell.maxv = v;
+          }
+          cell.count++;
+          if (pt == TSKV_PT_F64) {
+            double d;
+            memcpy(&d, &v, 8);
+            cell.sum_d += d;
+          } else {
+            cell.sum_bits += v;
+            cell.sum_d += pt == TSKV_PT_I64 ? (double)(int64_t)v : (double)v;
+          }
+        }
+        close_run();
+      }
+    }
+  }
+  return TSKV_OK;
+}
+
+void merge_cell(Cell &a, const Cell &b, uint8_t pt) {
+  if (b.count) {
+    if (a.count == 0) {
+      a.minv = b.minv;
+      a.maxv = b.maxv;
+    } else {
+      if (less_typed(pt, b.minv, a.minv)) a.minv = b.minv;
+      if (less_typed(pt, a.maxv, b.maxv)) a.maxv = b.maxv;
+    }
+    a.count += b.count;
+    a.sum_bits += b.sum_bits;
+    a.sum_d += b.sum_d;
+  }
+  if (b.has_first && (!a.has_first || b.first_ts < a.first_ts)) {
+    a.has_first = true;
+    a.first_ts = b.first_ts;
+    a.first_val = b.first_val;
+  }
+  if (b.has_last && (!a.has_last || b.last_ts > a.last_ts)) {
+    a.has_last = true;
+    a.last_ts = b.last_ts;
+    a.last_val = b.last_val;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *orc_last_error(void) { return g_err.c_str(); }
+
+void orc_sliding_window(int64_t t, int64_t window, int64_t slide, int64_t start_time, int64_t i,
+                        int64_t *out_start, int64_t *out_end) {
+  sliding_window(t, window, slide, start_time, i, out_start, out_end);
+}
+
+// time_window.rs:97-147
+void orc_ceil_sliding_window(int64_t t, int64_t window, int64_t slide, int64_t start_time,
+                             int64_t *out_start, int64_t *out_end) {
+  int64_t overlapping = (window + slide - 1) / slide;
+  int64_t cs = 0, ce = 0;
+  bool have = false;
+  for (int64_t i = overlapping - 1; i >= 0; i--) {
+    int64_t s, e;
+    sliding_window(t, window, slide, start_time, i, &s, &e);
+    if (t >= s && t < e) {
+      *out_start = s;
+      *out_end = e;
+      return;
+    }
+    cs = s;
+    ce = e;
+    have = true;
+  }
+  if (have) {
+    while (t >= ce) {
+      cs += slide;
+      ce += slide;
+    }
+  }
+  *out_start = cs;
+  *out_end = ce;
+}
+
+// time_window.rs:151-182
+void orc_floor_sliding_window(int64_t t, int64_t window, int64_t slide, int64_t start_time,
+                              int64_t *out_start, int64_t *out_end) {
+  int64_t s, e;
+  sliding_window(t, window, slide, start_time, 0, &s, &e);
+  if (!(t >= s && t < e)) {
+    while (t < s) {
+      s -= slide;
+      e -= slide;
+    }
+  }
+  *out_start = s;
+  *out_end = e;
+}
+
+tskv_status orc_query_output_layout(const tskv_page_desc *descs, uint64_t n_descs,
+                                    const tskv_query *q, tskv_output_layout *out) {
+  if (!q || !out || q->n_buckets == 0 || q->n_columns == 0 || !q->columns) return TSKV_ERR_INVALID_ARG;
+  uint64_t n_out = 0;
+  for (uint32_t c = 0; c < q->n_columns; c++) n_out += popc(q->columns[c].agg_mask & TSKV_AGG_ALL);
+  uint64_t n_groups = 1;
+  if (q->group_by_series) {
+    if (q->series_ids) {
+      n_groups = q->n_series;
+    } else {
+      std::vector<uint32_t> ids;
+      for (uint64_t i = 0; i < n_descs; i++)
+        if (descs[i].phys_type == TSKV_PT_TIME) ids.push_back(descs[i].series_id);
+      std::sort(ids.begin(), ids.end());
+      n_groups = (uint64_t)(std::unique(ids.begin(), ids.end()) - ids.begin());
+    }
+  }
+  out->n_out = n_out;
+  out->n_groups = n_groups;
+  out->n_cells = n_groups * q->n_buckets;
+  out->bitmap_stride = (out->n_cells + 63) / 64 * 8;
+  out->values_bytes = n_out * out->n_cells * 8;
+  out->validity_bytes = n_out * out->bitmap_stride;
+  return TSKV_OK;
+}
+
+tskv_status orc_scan_aggregate(const uint8_t *arena, uint64_t arena_len,
+                               const tskv_page_desc *descs, uint64_t n_descs, const tskv_query *q,
+                               int verify_crc, int n_threads, uint64_t *out_values,
+                               uint8_t *out_validity, uint64_t *out_points) {
+  g_err.clear();
+  tskv_output_layout L;
+  tskv_status st = orc_query_output_layout(descs, n_descs, q, &L);
+  if (st != TSKV_OK) return st;
+  Index ix;
+  st = build_index(descs, n_descs, ix);
+  if (st != TSKV_OK) return st;
+  Scan S{arena, arena_len, descs, q, verify_crc, &ix, {}, L.n_cells};
+  if (q->series_ids) {
+    for (uint32_t i = 0; i < q->n_series; i++) {
+      if (i && q->series_ids[i] <= q->series_ids[i - 1]) {
+        g_err = "series_ids must be sorted ascending and unique";
+        return TSKV_ERR_INVALID_ARG;
+      }
+      S.slots.push_back(q->series_ids[i]);
+    }
+  } else {
+    S.slots = ix.series;
+  }
+  uint64_t n_slots = S.slots.size();
+  uint64_t table = (uint64_t)q->n_columns * L.n_cells;
+  std::vector<Cell> cells(table);
+  uint64_t points = 0;
+  if (n_threads <= 1 || n_slots < 2) {
+    st = scan_slots(S, 0, n_slots, cells.data(), true, &points);
+    if (st != TSKV_OK) return st;
+  } else {
+    // contiguous chunks of (n + ncpu) / ncpu series, like tskv/src/reader/iterator.rs:232-235
+    uint64_t ncpu = (uint64_t)n_threads;
+    uint64_t cs = (n_slots + ncpu) / ncpu;
+    uint64_t n_chunks = (n_slots + cs - 1) / cs;
+    std::vector<tskv_status> sts(n_chunks, TSKV_OK);
+    std::vector<uint64_t> pts(n_chunks, 0);
+    std::vector<std::string> errs(n_chunks);
+    std::vector<std::vector<Cell>> priv;
+    if (!q->group_by_series) priv.assign(n_chunks, std::vector<Cell>(table));
+    std::vector<std::thread> th;
+    for (uint64_t k = 0; k < n_chunks; k++) {
+      th.emplace_back([&, k]() {
+        Cell *dst = q->group_by_series ? cells.data() : priv[k].data();  // disjoint cells per slot
+        sts[k] = scan_slots(S, k * cs, std::min(n_slots, (k + 1) * cs), dst, false, &pts[k]);
+        errs[k] = g_err;
+      });
+    }
+    for (auto &t : th) t.join();
+    for (uint64_t k = 0; k < n_chunks; k++) {
+      if (sts[k] != TSKV_OK) {
+        g_err = errs[k];
+        return sts[k];
+      }
+      points += pts[k];
+      if (!q->group_by_series)
+        for (uint32_t c = 0; c < q->n_columns; c++)
+          for (uint64_t i = 0; i < L.n_cells; i++)
+            merge_cell(cells[(uint64_t)c * L.n_cells + i], priv[k][(uint64_t)c * L.n_cells + i],
+                       q->columns[c].phys_type);
+    }
+  }
+  if (out_points) *out_points = points;
+  // finalize into the dense layout of include/tskv_gpu.h
+  memset(out_validity, 0, L.validity_bytes);
+  uint64_t j = 0;
+  for (uint32_t c = 0; c < q->n_columns; c++) {
+    const tskv_agg_column &qc = q->columns[c];
+    for (unsigned bit = 0; bit < 7; bit++) {
+      unsigned agg = 1u << bit;
+      if (!(qc.agg_mask & agg)) continue;
+      uint64_t *ov = out_values + j * L.n_cells;
+      uint8_t *ob = out_validity + j * L.bitmap_stride;
+      for (uint64_t i = 0; i < L.n_cells; i++) {
+        const Cell &cell = cells[(uint64_t)c * L.n_cells + i];
+        uint64_t v = 0;
+        bool valid = false;
+        switch (agg) {
+          case TSKV_AGG_COUNT:
+            v = cell.count;
+            valid = true;
+            break;
+          case TSKV_AGG_SUM:
+            valid = cell.count > 0;
+            if (valid) {
+              if (qc.phys_type == TSKV_PT_F64)
+                memcpy(&v, &cell.sum_d, 8);
+              else
+                v = cell.sum_bits;
+            }
+            break;
+          case TSKV_AGG_MIN:
+            valid = cell.count > 0;
+            if (valid) v = cell.minv;
+            break;
+          case TSKV_AGG_MAX:
+            valid = cell.count > 0;
+            if (valid) v = cell.maxv;
+            break;
+          case TSKV_AGG_MEAN:
+            valid = cell.count > 0;
+            if (valid) {
+              double m = cell.sum_d / (double)cell.count;
+              memcpy(&v, &m, 8);
+            }
+            break;
+          case TSKV_AGG_FIRST:
+            valid = cell.has_first;
+            if (valid) v = cell.first_val;
+            break;
+          case TSKV_AGG_LAST:
+            valid = cell.has_last;
+            if (valid) v = cell.last_val;
+            break;
+        }
+        ov[i] = v;
+        if (valid) ob[i >> 3] |= (uint8_t)(1u << (i & 7));
+      }
+      j++;
+    }
+  }
+  return TSKV_OK;
+}
+
+}  // extern "C"
