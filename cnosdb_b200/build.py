@@ -2,7 +2,8 @@
 
   cnosdb_b200/libtskv_gpu.so      CUDA kernels + C ABI (include/tskv_gpu.h), sm_100a only
   cnosdb_b200/libtskv_hostgen.so  host-side TSM page writer + synthetic data generator
-  oracle/libtskv_oracle.so        CPU oracle (test infrastructure; built here, never loaded by the package)
+(The CPU checker under oracle/ is test infrastructure with its own Makefile; __graft_entry__.build()
+and tests/conftest.py build it, this package never does.)
 """
 import os
 import shutil
@@ -61,16 +62,8 @@ def build_hostgen(force=False):
     return target
 
 
-def build_oracle(force=False):
-    odir = os.path.join(ROOT, "oracle")
-    if force:
-        _run(["make", "-C", odir, "clean"])
-    _run(["make", "-C", odir])
-    return os.path.join(odir, "libtskv_oracle.so")
-
-
 def build_all(force=False):
-    return build_gpu(force), build_hostgen(force), build_oracle(force)
+    return build_gpu(force), build_hostgen(force)
 
 
 if __name__ == "__main__":

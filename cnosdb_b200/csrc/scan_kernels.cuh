@@ -36,6 +36,7 @@ struct ColState {
   uint64_t max_off;    // ordered i64 key[n_cells]                  (MAX)
   uint64_t first_off;  // {i64 key, u64 val}[n_cells], 16B aligned  (FIRST)
   uint64_t last_off;   // {i64 key, u64 val}[n_cells], 16B aligned  (LAST)
+  uint64_t sumhi_off;  // i64 high word of the exact 128-bit integer sum (MEAN on i64/u64 columns)
   uint16_t column_id;
   uint8_t phys_type;
   uint8_t agg_mask;
@@ -295,10 +296,25 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
          __shfl_xor_sync(FULL, (uint32_t)v, m);
 }
 
+// Integer sum: the low word is the reference's wrapping i64/u64 SUM; with MEAN the carries go to a high
+// word so that mean = exact 128-bit sum / count (DataFusion's avg accumulates in f64 and never wraps).
+__device__ __forceinline__ void add_int_sum(uint64_t *st, const ColState &cs, uint64_t cell, uint8_t mask,
+                                            uint64_t lo, int64_t hi) {
+  unsigned long long *plo = reinterpret_cast<unsigned long long *>(st + cs.sum_off + cell);
+  if (mask & TSKV_AGG_MEAN) {
+    unsigned long long old = atomicAdd(plo, (unsigned long long)lo);
+    hi += (old + lo < old) ? 1 : 0;
+    if (hi) atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.sumhi_off + cell), (unsigned long long)hi);
+  } else {
+    atomicAdd(plo, (unsigned long long)lo);
+  }
+}
+
 // Partial aggregate of one (page, bucket) run, held in registers by one lane.
 struct RunAcc {
   uint32_t count;
   uint64_t sum;      // i64 wrapping sum bits, or f64 sum bits
+  int64_t sum_hi;    // high word of the exact integer sum (only maintained for MEAN on int columns)
   int64_t kmin, kmax;
   int64_t first_ts, last_ts;
   uint64_t first_val, last_val;
@@ -336,6 +352,7 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
   if (same && __popc(m) > 1) {
     uint32_t cnt = active ? a.count : 0;
     uint64_t sum = active ? a.sum : 0;  // 0 bits == +0.0
+    int64_t shi = active ? a.sum_hi : 0;
     int64_t kmin = (active && a.count) ? a.kmin : INT64_MAX;
     int64_t kmax = (active && a.count) ? a.kmax : INT64_MIN;
     int64_t fk = (active && a.first_ok) ? kf : INT64_MAX;
@@ -343,8 +360,9 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
     uint32_t tot = __reduce_add_sync(FULL, cnt);
     for (int o = 16; o; o >>= 1) {
       uint64_t s2 = shfl_xor_u64(sum, o);
+      int64_t h2 = (int64_t)shfl_xor_u64((uint64_t)shi, o);
       if (is_f64) sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)s2));
-      else sum += s2;
+      else { sum += s2; shi += h2 + (sum < s2 ? 1 : 0); }
       int64_t mn = (int64_t)shfl_xor_u64((uint64_t)kmin, o);
       int64_t mx = (int64_t)shfl_xor_u64((uint64_t)kmax, o);
       kmin = mn < kmin ? mn : kmin;
@@ -366,7 +384,7 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
         atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.count_off + cell), (unsigned long long)tot);
         if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
           if (is_f64) atomicAdd(reinterpret_cast<double *>(st + cs.sum_off + cell), __longlong_as_double((long long)sum));
-          else atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.sum_off + cell), (unsigned long long)sum);
+          else add_int_sum(st, cs, cell, mask, sum, shi);
         }
         if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)kmin);
         if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)kmax);
@@ -381,7 +399,7 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
       atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.count_off + cell), (unsigned long long)a.count);
       if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
         if (own_f64) atomicAdd(reinterpret_cast<double *>(st + cs.sum_off + cell), __longlong_as_double((long long)a.sum));
-        else atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.sum_off + cell), (unsigned long long)a.sum);
+        else add_int_sum(st, cs, cell, mask, a.sum, a.sum_hi);
       }
       if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)a.kmin);
       if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)a.kmax);
@@ -480,7 +498,7 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
   }
 
   RunAcc acc;
-  acc.count = 0; acc.sum = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+  acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
   acc.first_ts = acc.last_ts = 0; acc.first_val = acc.last_val = 0; acc.first_ok = acc.last_ok = false;
   BucketState bk; bk.valid = false; bk.floor_regime = false; bk.lo = 0; bk.hi = 0; bk.idx = 0;
   bool have_run = false;
@@ -488,6 +506,7 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
   uint32_t row = 0;
   uint32_t n_points = 0, n_inrange = 0;
   const bool is_f64 = pt == TSKV_PT_F64;
+  const bool mean_hi = !is_f64 && (mask & TSKV_AGG_MEAN);
   const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
 
   for (;;) {
@@ -542,7 +561,7 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
       if (newrun) {
         have_run = true;
         run_idx = bk.idx;
-        acc.count = 0; acc.sum = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+        acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
         acc.first_ts = acc.last_ts = t;
         acc.first_val = acc.last_val = v;
         acc.first_ok = acc.last_ok = vv;
@@ -553,7 +572,10 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
       if (vv) {
         acc.count++;
         if (is_f64) acc.sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)acc.sum) + __longlong_as_double((long long)v));
-        else acc.sum += v;
+        else {
+          acc.sum += v;
+          if (mean_hi) acc.sum_hi += (acc.sum < v ? 1 : 0) + (pt == TSKV_PT_I64 ? ((int64_t)v >> 63) : 0);
+        }
         int64_t k = okey(v, pt);
         acc.kmin = k < acc.kmin ? k : acc.kmin;
         acc.kmax = k > acc.kmax ? k : acc.kmax;
@@ -625,10 +647,29 @@ __global__ void k_init_state(uint64_t *state, StateLayout L) {
   }
 }
 
-// De-interleave the {key,val} pairs into the contiguous key / value sections.
-__global__ void k_export_pairs(uint64_t *state, StateLayout L) {
+// MEAN on an integer column: (hi:lo) exact sum -> f64 cell of the SUM_F64 section.
+struct MeanExport {
+  uint64_t lo_off, hi_off, dst_off;
+  uint32_t is_signed, pad;
+};
+
+// De-interleave the {key,val} pairs into the contiguous key / value sections and convert the exact
+// integer sums of MEAN columns to f64.
+__global__ void k_export_pairs(uint64_t *state, StateLayout L, const MeanExport *means, uint32_t n_means,
+                               uint64_t n_cells) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint32_t m = 0; m < n_means; m++) {
+    const MeanExport me = means[m];
+    for (uint64_t k = i; k < n_cells; k += stride) {
+      uint64_t lo = state[me.lo_off + k];
+      int64_t hi = (int64_t)state[me.hi_off + k];
+      double d;
+      if (me.is_signed) d = (double)(((__int128)hi << 64) + (__int128)(unsigned __int128)lo);
+      else d = (double)(((unsigned __int128)(uint64_t)hi << 64) | (unsigned __int128)lo);
+      state[me.dst_off + k] = (uint64_t)__double_as_longlong(d);
+    }
+  }
   for (uint64_t k = i; k < L.first_cells; k += stride) {
     state[L.first_keys_off + k] = state[L.first_pairs_off + 2 * k];
     state[L.selval_off + k] = state[L.first_pairs_off + 2 * k + 1];
@@ -686,10 +727,8 @@ __global__ void k_finalize(const uint64_t *state, const OutCol *outs, uint32_t n
       case TSKV_AGG_MAX: valid = cnt > 0; if (valid) v = okey_inv((int64_t)state[oc.src_off + cell], oc.phys_type); break;
       case TSKV_AGG_MEAN:
         valid = cnt > 0;
-        if (valid) {
-          uint64_t s = state[oc.src_off + cell];
-          double d = oc.phys_type == TSKV_PT_F64 ? __longlong_as_double((long long)s)
-                     : oc.phys_type == TSKV_PT_I64 ? (double)(long long)s : (double)s;
+        if (valid) {  // src = f64 sum (f64 columns) or exported exact integer sum
+          double d = __longlong_as_double((long long)state[oc.src_off + cell]);
           v = (uint64_t)__double_as_longlong(d / (double)cnt);
         }
         break;
@@ -702,6 +741,44 @@ __global__ void k_finalize(const uint64_t *state, const OutCol *outs, uint32_t n
   uint32_t bits = __ballot_sync(FULL, valid);
   if ((threadIdx.x & 31) == 0 && (cell >> 3) < bitmap_stride)
     *reinterpret_cast<uint32_t *>(validity + (uint64_t)blockIdx.y * bitmap_stride + (cell >> 3)) = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload-time statistics: min / max timestamp of the arena (the reference keeps them per page in
+// PageMeta.statistics, written at flush time: tsm/page.rs:212-231). One lane per time page.
+__global__ void k_time_bounds(const uint8_t *arena, const tskv_page_desc *descs, const uint32_t *cg_time_page,
+                              uint32_t n_cg, long long *bounds /* [0]=min [1]=max */) {
+  uint32_t cg = blockIdx.x * blockDim.x + threadIdx.x;
+  long long lo = INT64_MAX, hi = INT64_MIN;
+  if (cg < n_cg) {
+    const tskv_page_desc d = descs[cg_time_page[cg]];
+    if (kind_status(d.reserved) == TSKV_OK && d.reserved != DK_ALLNULL) {
+      PageView pv;
+      pv.open(arena, d);
+      BitCursor bits;
+      bits.init(pv.bitset);
+      DeltaCursor<-1> cur;
+      if (cur.open(pv, d.reserved) == TSKV_OK) {
+        for (uint32_t r = 0; r < d.num_values; r++) {
+          if (!bits.next(r)) { if (r == 0) cur.skip_first_if_s8b_sc(); continue; }
+          bool ok = true;
+          long long t = (long long)cur.next(&ok);
+          if (!ok) break;
+          lo = t < lo ? t : lo;
+          hi = t > hi ? t : hi;
+        }
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    long long l2 = (long long)shfl_xor_u64((uint64_t)lo, o), h2 = (long long)shfl_xor_u64((uint64_t)hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(bounds, lo);
+    atomicMax(bounds + 1, hi);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

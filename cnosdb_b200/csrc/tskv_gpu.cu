@@ -57,6 +57,7 @@ struct tskv_pages {
   uint32_t h_bin_start[N_BINS + 1]{};
   uint32_t *d_bin_start = nullptr;
   std::vector<uint32_t> series;  // sorted distinct ids
+  int64_t ts_min = INT64_MAX, ts_max = INT64_MIN;  // arena-wide time bounds (k_time_bounds)
 };
 
 struct tskv_scan {
@@ -77,6 +78,8 @@ struct tskv_scan {
   uint32_t *d_bin_cstart = nullptr;  // [N_BINS+1] then [1] total
   ColState *d_cols = nullptr;
   OutCol *d_outs = nullptr;
+  MeanExport *d_means = nullptr;
+  uint32_t n_means = 0;
   uint64_t *d_state = nullptr;
   uint32_t *d_task_counter = nullptr;
   int32_t *d_status = nullptr;
@@ -167,6 +170,7 @@ void free_scan(tskv_scan *s) {
   cudaFree(s->d_bin_cstart);
   cudaFree(s->d_cols);
   cudaFree(s->d_outs);
+  cudaFree(s->d_means);
   cudaFree(s->d_state);
   cudaFree(s->d_task_counter);
   cudaFree(s->d_values);
@@ -385,6 +389,24 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
   cudaEventRecord(ctx->ev1, ctx->stream);
+  // arena-wide timestamp bounds (device pass over the time pages)
+  long long *d_bounds = nullptr;
+  if (e == cudaSuccess) e = dev_alloc(&d_bounds, 2);
+  if (e == cudaSuccess) {
+    long long init[2] = {INT64_MAX, INT64_MIN};
+    e = cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && pg->n_cg) {
+      k_time_bounds<<<(pg->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pg->d_arena, pg->d_descs, pg->d_cg_time_page,
+                                                                    pg->n_cg, d_bounds);
+      e = cudaGetLastError();
+    }
+    long long b[2] = {INT64_MAX, INT64_MIN};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b, d_bounds, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    pg->ts_min = b[0];
+    pg->ts_max = b[1];
+  }
+  cudaFree(d_bounds);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     ctx->set_error(std::string("upload: ") + cudaGetErrorString(e));
@@ -547,13 +569,22 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     unsigned rel_bits = 64;
     if (q->width > 0) {
       if (q->width < (int64_t)1 << 61) rel_bits = bits_for(2 * (uint64_t)q->width);
-    } else if (q->n_time_ranges > 0) {
-      int64_t lo = q->time_ranges[0].min_ts, hi = q->time_ranges[0].max_ts;
-      for (uint32_t k = 1; k < q->n_time_ranges; k++) {
-        lo = std::min(lo, q->time_ranges[k].min_ts);
-        hi = std::max(hi, q->time_ranges[k].max_ts);
+    } else {
+      // unbucketed: rel = t - (lower bound of every in-range timestamp); the arena's own time
+      // bounds (upload-time statistics) tighten unbounded / loose query ranges
+      int64_t lo = pages->ts_min, hi = pages->ts_max;
+      if (q->n_time_ranges > 0) {
+        int64_t qlo = q->time_ranges[0].min_ts, qhi = q->time_ranges[0].max_ts;
+        for (uint32_t k = 1; k < q->n_time_ranges; k++) {
+          qlo = std::min(qlo, q->time_ranges[k].min_ts);
+          qhi = std::max(qhi, q->time_ranges[k].max_ts);
+        }
+        lo = std::max(lo, qlo);
+        hi = std::min(hi, qhi);
       }
-      if (hi >= lo) {
+      if (hi < lo) {
+        rel_bits = 0;  // nothing can be in range
+      } else {
         uint64_t span = (uint64_t)hi - (uint64_t)lo;
         rel_bits = bits_for(span);
         rel_base = lo;
@@ -589,6 +620,13 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   for (uint32_t c = 0; c < q->n_columns; c++)
     if ((q->columns[c].agg_mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) && q->columns[c].phys_type == TSKV_PT_F64) {
       cols[c].sum_off = off;
+      off += n_cells;
+    }
+  std::vector<MeanExport> means;
+  std::vector<uint64_t> msum_off(q->n_columns, 0);
+  for (uint32_t c = 0; c < q->n_columns; c++)
+    if ((q->columns[c].agg_mask & TSKV_AGG_MEAN) && q->columns[c].phys_type != TSKV_PT_F64) {
+      msum_off[c] = off;  // exported exact integer sum as f64 (all-reducible)
       off += n_cells;
     }
   sl.sum_f64_len = off - sl.sum_f64_off;
@@ -643,6 +681,12 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   }
   sl.snap_off = off;
   off += n_first + n_last;
+  for (uint32_t c = 0; c < q->n_columns; c++)
+    if (msum_off[c]) {
+      cols[c].sumhi_off = off;
+      means.push_back(MeanExport{cols[c].sum_off, off, msum_off[c], q->columns[c].phys_type == TSKV_PT_I64 ? 1u : 0u, 0});
+      off += n_cells;
+    }
   sl.total = off;
 
   // output column table
@@ -659,8 +703,8 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
         oc.agg = (uint8_t)agg;
         oc.phys_type = qc.phys_type;
         switch (agg) {
-          case TSKV_AGG_SUM:
-          case TSKV_AGG_MEAN: oc.src_off = cols[c].sum_off; break;
+          case TSKV_AGG_SUM: oc.src_off = cols[c].sum_off; break;
+          case TSKV_AGG_MEAN: oc.src_off = msum_off[c] ? msum_off[c] : cols[c].sum_off; break;
           case TSKV_AGG_MIN: oc.src_off = cols[c].min_off; break;
           case TSKV_AGG_MAX: oc.src_off = cols[c].max_off; break;
           case TSKV_AGG_FIRST: oc.src_off = fk; oc.val_off = fv; break;
@@ -693,6 +737,10 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   if (e == cudaSuccess) e = dev_alloc(&s->d_bin_cstart, N_BINS + 2);
   if (e == cudaSuccess) e = dev_alloc(&s->d_cols, cols.size());
   if (e == cudaSuccess) e = dev_alloc(&s->d_outs, outs.size());
+  s->n_means = (uint32_t)means.size();
+  if (e == cudaSuccess) e = dev_alloc(&s->d_means, means.size());
+  if (e == cudaSuccess && !means.empty())
+    e = cudaMemcpyAsync(s->d_means, means.data(), means.size() * sizeof(MeanExport), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = dev_alloc(&s->d_state, sl.total);
   // task counters [N_BINS x u32, padded to 8 x u64] | status | err_page | stats[2] | counters[2]
   if (e == cudaSuccess) e = dev_alloc(reinterpret_cast<unsigned long long **>(&s->d_task_counter), 16);
@@ -806,9 +854,11 @@ tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *s) {
     CU_TRY(ctx, cudaLaunchKernel((const void *)scan_kernel_for_bin(b), dim3(grid), dim3(256), args, 0, ctx->stream));
     launches++;
   }
-  if (s->has_sel) {
-    uint32_t b = (uint32_t)std::min<uint64_t>((std::max(s->sl.first_cells, s->sl.last_cells) + 255) / 256, 4096);
-    k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl);
+  const bool need_export = s->has_sel || s->n_means;
+  if (need_export) {
+    uint64_t work = std::max(std::max(s->sl.first_cells, s->sl.last_cells), s->n_means ? s->layout.n_cells : 0);
+    uint32_t b = (uint32_t)std::min<uint64_t>((work + 255) / 256, 4096);
+    k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl, s->d_means, s->n_means, s->layout.n_cells);
   }
   cudaEventRecord(ctx->ev1, ctx->stream);
   tskv_status st = fetch_status(ctx, s->d_status, s->d_err_page);
@@ -820,7 +870,7 @@ tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *s) {
   ctx->counters.elapsed_scan_ms = ms;
   ctx->counters.points_decoded = stats[0];
   ctx->counters.rows_in_range = stats[1];
-  ctx->counters.kernel_launches = launches + (s->has_sel ? 1 : 0);
+  ctx->counters.kernel_launches = launches + (need_export ? 1 : 0);
   return TSKV_OK;
 }
 

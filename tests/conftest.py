@@ -17,8 +17,11 @@ def native_libs():
     """Build the in-tree shared libraries when they are missing (nvcc cross-compiles without a GPU)."""
     from cnosdb_b200 import build, cabi
     need = [cabi.gpu_library_path(), cabi.hostgen_library_path(), os.path.join(ROOT, "oracle", "libtskv_oracle.so")]
-    if not all(os.path.exists(p) for p in need):
+    if not all(os.path.exists(p) for p in need[:2]):
         build.build_all()
+    if not os.path.exists(need[2]):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     return need
 
 

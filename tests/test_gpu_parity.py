@@ -1,0 +1,365 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. Bit-exact for decode, counts,
+integer aggregates and f64 min/max/first/last; f64 sum/mean within 1e-6 relative."""
+import numpy as np
+import pytest
+
+from cnosdb_b200 import cabi, datagen
+from cnosdb_b200.engine import PushedAggregate, QueryOption, TskvError
+from oracle import pyoracle as orc
+from tests.helpers import ALL_AGGS, assert_results_equal, bucket_spec, make_query, random_arena
+
+pytestmark = pytest.mark.gpu
+
+
+def bits_to_f64(bits):
+    return np.array([int(b, 16) for b in bits], dtype=np.uint64).view(np.float64)
+
+
+def check_decode(engine, arena, descs):
+    pages = engine.upload_pages(arena, descs)
+    got = engine.decode_pages(pages, descs)
+    exp = orc.decode_pages(arena, descs)
+    assert len(got) == len(exp)
+    for i, ((gv, gb), (ev, eb)) in enumerate(zip(got, exp)):
+        assert (gb == eb).all(), "validity differs on page %d" % i
+        assert (gv == ev).all(), "values differ on page %d: %s" % (i, np.nonzero(gv != ev)[0][:5])
+    pages.close()
+
+
+def test_decode_golden_corpora(engine, golden):
+    """Every reference codec corpus, decoded on the GPU, bit-exact (incl. NaN payloads)."""
+    g = golden["codec_vectors"]
+    b = datagen.ArenaBuilder()
+    sid = 0
+
+    def add(pt, data, n):
+        nonlocal sid
+        b.add_page(datagen.build_page(datagen.encode_timestamps(np.arange(n)), n), sid, 0, cabi.TSKV_PT_TIME, n)
+        b.add_page(datagen.build_page(data, n), sid, 1, pt, n)
+        sid += 1
+
+    for grp in ("i64_rle", "i64_simple8b"):
+        for t in g[grp]["tests"]:
+            add(cabi.TSKV_PT_I64, datagen.encode_integers(t["input"]), len(t["input"]))
+    add(cabi.TSKV_PT_I64, datagen.encode_integers(g["i64_uncompressed"]["input"]), 4)
+    add(cabi.TSKV_PT_I64, datagen.encode_integers(np.full(509, 809201799168)), 509)
+    add(cabi.TSKV_PT_I64, datagen.encode_integers([346]), 1)
+    for grp in ("ts_rle", "ts_simple8b"):
+        for t in g[grp]["tests"]:  # timestamp codec on an i64 column (Encoding::DeltaTs, instance.rs:379)
+            add(cabi.TSKV_PT_I64, datagen.encode_timestamps(t["input"]), len(t["input"]))
+            add(cabi.TSKV_PT_TIME, datagen.encode_timestamps(t["input"]), len(t["input"]))
+    add(cabi.TSKV_PT_TIME, datagen.encode_timestamps(g["ts_uncompressed"]["input"]), 4)
+    add(cabi.TSKV_PT_TIME, datagen.encode_integers(g["ts_uncompressed"]["input"]), 4)  # Delta on a time column
+    for t in g["u64_rle"]["tests"] + g["u64_simple8b"]["tests"]:
+        add(cabi.TSKV_PT_U64, datagen.encode_integers(np.array(t["input"], dtype=np.uint64).view(np.int64)), len(t["input"]))
+    add(cabi.TSKV_PT_U64, datagen.encode_integers(np.full(1000, 1232342341234)), 1000)
+    for t in g["f64_roundtrip"]["tests"]:
+        v = bits_to_f64(t["input_bits"])
+        add(cabi.TSKV_PT_F64, datagen.encode_floats(v), len(v))
+    v = bits_to_f64(g["f64_special_values"]["input_bits"])
+    add(cabi.TSKV_PT_F64, datagen.encode_floats(v), len(v))
+    add(cabi.TSKV_PT_F64, datagen.encode_raw(v.view(np.uint64)), len(v))  # Encoding::Null
+    add(cabi.TSKV_PT_I64, datagen.encode_raw(np.arange(7, dtype=np.uint64)), 7)
+    arena, descs = b.finish()
+    check_decode(engine, arena, descs)
+
+
+def test_decode_simple8b_all_widths_and_runs(engine):
+    rng = np.random.default_rng(231)
+    b = datagen.ArenaBuilder()
+    cases = []
+    for bits in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 20, 30, 59):
+        cases.append(np.cumsum(rng.integers(0, 2**bits, 1000).astype(np.int64) // 2 * rng.choice([-1, 1], 1000)))
+    cases.append(np.cumsum(np.ones(1000, dtype=np.int64)) * -1)   # zigzag(−1) = 1: runs of ones → selectors 0/1
+    ones = np.ones(500, dtype=np.int64) * -1
+    ones[119] = 5
+    ones[240] = 9
+    cases.append(np.cumsum(ones))
+    cases.append(rng.integers(-2**62, 2**62, 300))                # raw
+    for i, v in enumerate(cases):
+        b.add_column_group(i, np.arange(len(v)), [(1, cabi.TSKV_PT_I64, v, None)])
+    arena, descs = b.finish()
+    check_decode(engine, arena, descs)
+
+
+def test_decode_c1_shape(engine):
+    """BASELINE config C1: 1 series x 10 000 i64, Delta (zigzag + simple8b) decode only, seed 1."""
+    g = datagen.generate(1, n_fields=1, n_points=10_000, value_kind=datagen.I64_WALK, seed=1)
+    check_decode(engine, g.arena, g.descs)
+    # forced RLE (constant step) and raw (|delta| >= 2^59) sub-cases
+    b = datagen.ArenaBuilder()
+    b.add_column_group(0, np.arange(10_000) * 10, [(1, cabi.TSKV_PT_I64, np.arange(10_000) * 3 - 7, None)])
+    big = (np.arange(10_000, dtype=np.int64) % 2) * (2**61) - 2**60
+    b.add_column_group(1, np.arange(10_000) * 10, [(1, cabi.TSKV_PT_I64, big, None)])
+    arena, descs = b.finish()
+    check_decode(engine, arena, descs)
+
+
+def test_decode_nulls_and_generated_mix(engine):
+    g = datagen.generate(200, n_fields=3, n_points=1000, value_kind=datagen.MIXED, seed=4, jitter_permille=300,
+                         jitter_max=999_999, null_page_permille=300, null_row_permille=50, raw_encoding_permille=100)
+    check_decode(engine, g.arena, g.descs)
+    rng = np.random.default_rng(7)
+    arena, descs, _ = random_arena(rng, n_series=30, n_points=257, null_frac=0.4,
+                                   fields=((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64), (3, cabi.TSKV_PT_U64)))
+    check_decode(engine, arena, descs)
+
+
+def test_decode_empty_and_all_null_pages(engine):
+    b = datagen.ArenaBuilder()
+    b.add_column_group(0, np.arange(40), [(1, cabi.TSKV_PT_I64, np.arange(40), np.zeros(40, dtype=bool)),
+                                          (2, cabi.TSKV_PT_F64, np.arange(40.0), np.zeros(40, dtype=bool))])
+    v = np.zeros(9, dtype=bool)
+    v[4] = True
+    b.add_column_group(1, np.arange(9), [(1, cabi.TSKV_PT_I64, np.arange(9), v), (2, cabi.TSKV_PT_F64, np.arange(9.0), v)])
+    arena, descs = b.finish()
+    check_decode(engine, arena, descs)
+
+
+SCAN_FIELDS = ((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64), (3, cabi.TSKV_PT_U64))
+
+
+@pytest.mark.parametrize("group_by_series", [False, True])
+@pytest.mark.parametrize("variant", ["plain", "nulls", "jitter", "multi_cg", "raw"])
+def test_scan_parity_small(engine, group_by_series, variant):
+    rng = np.random.default_rng(hash((variant, group_by_series)) % 2**32)
+    kw = dict(n_series=70, n_points=333, fields=SCAN_FIELDS)
+    if variant == "nulls":
+        kw["null_frac"] = 0.2
+    if variant == "jitter":
+        kw["jitter"] = 300
+    if variant == "multi_cg":
+        kw.update(multi_cg=True, null_frac=0.05)
+    if variant == "raw":
+        kw["raw_frac"] = 0.5
+    arena, descs, _ = random_arena(rng, **kw)
+    pages = engine.upload_pages(arena, descs)
+    sel = np.array(sorted(rng.choice(np.arange(80), 45, replace=False)), dtype=np.uint32)
+    t_lo, t_hi = 1_000_000 + 20_500, 1_000_000 + 300_000
+    fbs, nb = bucket_spec(t_lo, t_hi, 17_000, origin=3)
+    for series_ids in (sel, None):
+        for ranges in ([(t_lo, t_hi)], [(t_lo, t_lo + 50_000), (t_lo + 90_000, t_hi)], []):
+            if not ranges:
+                lo = 1_000_000 - 400
+                hi = int(max(int(descs["num_values"].max()) * 2 * 1000 + 1_000_000 + 400, t_hi))
+                f2, n2 = bucket_spec(lo, hi, 17_000, origin=3)
+                q = make_query(SCAN_FIELDS, series_ids=series_ids, time_ranges=[], origin=3, width=17_000,
+                               first_bucket_start=f2, n_buckets=n2, group_by_series=group_by_series)
+            else:
+                q = make_query(SCAN_FIELDS, series_ids=series_ids, time_ranges=ranges, origin=3, width=17_000,
+                               first_bucket_start=fbs, n_buckets=nb, group_by_series=group_by_series)
+            got = engine.scan_aggregate(pages, q)
+            exp, pts = orc.scan_aggregate(arena, descs, q, return_points=True)
+            assert_results_equal(got, exp, what="%s %s" % (variant, ranges))
+            assert engine.counters()["points_decoded"] == pts
+    # unbucketed: one cell per group
+    q = make_query(SCAN_FIELDS, series_ids=sel, time_ranges=[(t_lo, t_hi)], group_by_series=group_by_series)
+    assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q), what="unbucketed")
+    pages.close()
+
+
+def test_scan_c2_shape(engine):
+    """BASELINE C2 (scaled to 2 000 series for the oracle): f64 Gorilla, closed range rows 250..749, sum+count."""
+    for kind in (datagen.F64_INT, datagen.F64_NOISE):
+        g = datagen.generate(2000, n_fields=1, n_points=1000, value_kind=kind, seed=2)
+        pages = engine.upload_pages(g.arena, g.descs)
+        lo, hi = datagen.TSBS_T0 + 250 * datagen.TSBS_STEP, datagen.TSBS_T0 + 749 * datagen.TSBS_STEP
+        for gbs in (True, False):
+            q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_F64, ["sum", "count"])], time_ranges=[(lo, hi)],
+                            group_by_series=gbs)
+            got, exp = engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8)
+            assert_results_equal(got, exp, what="C2")
+            assert (got.column(1, "count")[0] == (500 if gbs else 500 * 2000)).all()
+        pages.close()
+
+
+def test_scan_c3_shape(engine):
+    """BASELINE C3 (scaled to 3 000 hosts): 10 fields, 1-min mean/max over 167 buckets."""
+    for kind, pt in ((datagen.I64_WALK, cabi.TSKV_PT_I64), (datagen.F64_INT, cabi.TSKV_PT_F64)):
+        g = datagen.generate(3000, n_fields=10, n_points=1000, value_kind=kind, seed=3)
+        pages = engine.upload_pages(g.arena, g.descs)
+        w = 60_000_000_000
+        fbs, nb = bucket_spec(datagen.TSBS_T0, datagen.TSBS_T0 + 999 * datagen.TSBS_STEP, w)
+        assert nb == 167
+        q = QueryOption([PushedAggregate(c, pt, ["mean", "max"]) for c in range(1, 11)], width=w,
+                        first_bucket_start=fbs, n_buckets=nb)
+        got, exp = engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8)
+        assert_results_equal(got, exp, what="C3")
+        assert engine.counters()["points_decoded"] == 3000 * 10 * 1000
+        pages.close()
+
+
+def test_scan_c4_shape(engine):
+    """BASELINE C4 (scaled to 20 000 series): mixed i64/f64, 20% jittered timestamps, 1% pages with 5% nulls,
+    10% tag selection (hash(id) % 10 == 0), group by 1-min bucket."""
+    g = datagen.generate(20_000, n_fields=1, n_points=1000, value_kind=datagen.MIXED, seed=4, jitter_permille=200,
+                         jitter_max=999_999, null_page_permille=10, null_row_permille=50)
+    pages = engine.upload_pages(g.arena, g.descs)
+    ids = np.arange(20_000, dtype=np.uint64)
+    sel = ids[((ids * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(32)) % np.uint64(10) == 0].astype(np.uint32)
+    w = 60_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0 - 1_000_000, datagen.TSBS_T0 + 999 * datagen.TSBS_STEP + 1_000_000, w)
+    for pt in (cabi.TSKV_PT_I64, cabi.TSKV_PT_F64):
+        sub = sel[(sel % 2) == (0 if pt == cabi.TSKV_PT_I64 else 1)]
+        q = QueryOption([PushedAggregate(1, pt, ALL_AGGS)], series_ids=sub, width=w, first_bucket_start=fbs, n_buckets=nb)
+        got, exp = engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8)
+        assert_results_equal(got, exp, what="C4")
+    pages.close()
+
+
+def test_scan_c5_shape(engine):
+    """BASELINE C5 (scaled): last point per series + 5-min window max over the last hour (360 pts, 12 buckets)."""
+    g = datagen.generate(5000, n_fields=5, n_points=360, value_kind=datagen.I64_WALK, seed=5)
+    pages = engine.upload_pages(g.arena, g.descs)
+    cols = [PushedAggregate(c, cabi.TSKV_PT_I64, ["last"]) for c in range(1, 6)]
+    q = QueryOption(cols, group_by_series=True)
+    assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8), what="C5 last")
+    w = 300_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0, datagen.TSBS_T0 + 359 * datagen.TSBS_STEP, w)
+    assert nb == 12
+    q = QueryOption([PushedAggregate(c, cabi.TSKV_PT_I64, ["max"]) for c in range(1, 6)], width=w,
+                    first_bucket_start=fbs, n_buckets=nb)
+    assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8), what="C5 max")
+    pages.close()
+
+
+def test_full_size_properties(engine):
+    """Size-independent properties at a larger size than the oracle is run on: counts sum to the number of
+    in-range rows, sum over buckets == unbucketed sum (i64, exact), per-series totals == global totals."""
+    n_series = 50_000
+    g = datagen.generate(n_series, n_fields=2, n_points=1000, value_kind=datagen.I64_WALK, seed=11)
+    pages = engine.upload_pages(g.arena, g.descs)
+    w = 60_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0, datagen.TSBS_T0 + 999 * datagen.TSBS_STEP, w)
+    cols = [PushedAggregate(c, cabi.TSKV_PT_I64, ["count", "sum", "min", "max"]) for c in (1, 2)]
+    rb = engine.scan_aggregate(pages, QueryOption(cols, width=w, first_bucket_start=fbs, n_buckets=nb))
+    assert engine.counters()["points_decoded"] == n_series * 2 * 1000
+    ru = engine.scan_aggregate(pages, QueryOption(cols))
+    rs = engine.scan_aggregate(pages, QueryOption(cols, group_by_series=True))
+    for c in (1, 2):
+        assert rb.column(c, "count")[0].sum() == n_series * 1000 == ru.column(c, "count")[0][0, 0]
+        assert rb.column(c, "sum")[0].sum() == ru.column(c, "sum")[0][0, 0] == rs.column(c, "sum")[0].sum()
+        assert rb.column(c, "min")[0].min() == ru.column(c, "min")[0][0, 0] == rs.column(c, "min")[0].min()
+        assert rb.column(c, "max")[0].max() == ru.column(c, "max")[0][0, 0] == rs.column(c, "max")[0].max()
+        assert (rs.column(c, "count")[0] == 1000).all()
+    pages.close()
+
+
+def test_first_last_semantics_match_reference_rules(engine):
+    b = datagen.ArenaBuilder()
+    ts = np.array([10, 20, 30, 40], dtype=np.int64)
+    b.add_column_group(1, ts, [(1, cabi.TSKV_PT_I64, np.array([1, 2, 3, 4]), np.array([False, True, True, True]))])
+    b.add_column_group(2, ts + 1, [(1, cabi.TSKV_PT_I64, np.array([5, 6, 7, 8]), None)])
+    for sid, (a, z) in enumerate([(11, 12), (21, 22), (31, 32)]):
+        b.add_column_group(sid + 5, np.array([100, 200]), [(2, cabi.TSKV_PT_F64, np.array([a, z], dtype=np.float64), None)])
+    arena, descs = b.finish()
+    pages = engine.upload_pages(arena, descs)
+    q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_I64, ["first", "last", "count"]),
+                     PushedAggregate(2, cabi.TSKV_PT_F64, ["first", "last"])])
+    got = engine.scan_aggregate(pages, q)
+    assert_results_equal(got, orc.scan_aggregate(arena, descs, q))
+    assert got.column(1, "first")[0][0, 0] == 5 and got.column(2, "first")[0][0, 0] == 11.0
+    assert got.column(2, "last")[0][0, 0] == 12.0
+    pages.close()
+
+
+def test_negative_timestamps_keep_the_window_quirk(engine):
+    rng = np.random.default_rng(17)
+    b = datagen.ArenaBuilder()
+    for sid in range(20):
+        ts = np.sort(rng.choice(np.arange(-4000, 3000), 150, replace=False)).astype(np.int64)
+        b.add_column_group(sid, ts, [(1, cabi.TSKV_PT_I64, rng.integers(-9, 10, 150), None)])
+    arena, descs = b.finish()
+    pages = engine.upload_pages(arena, descs)
+    w, origin = 500, 130
+    fbs, _ = orc.sliding_window(-4000, w, w, origin)
+    last, _ = orc.sliding_window(3000, w, w, origin)
+    nb = (last - fbs) // w + 1
+    q = make_query([(1, cabi.TSKV_PT_I64)], origin=origin, width=w, first_bucket_start=fbs, n_buckets=nb)
+    assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q), what="negative ts")
+    pages.close()
+
+
+def _corrupt(arena, descs, page_idx, fn):
+    a = arena.copy()
+    d = descs[page_idx]
+    off, size, n = int(d["offset"]), int(d["size"]), int(d["num_values"])
+    data_off = off + 16 + (n + 7) // 8
+    fn(a, off, data_off, size)
+    # re-seal the CRC so that the decoder (not the checksum) sees the corruption
+    crc = orc.crc32(a[data_off:off + size])
+    a[off + 12:off + 16] = np.frombuffer(int(crc).to_bytes(4, "big"), dtype=np.uint8)
+    return a
+
+
+@pytest.mark.parametrize("case,status", [
+    ("bad_sub_encoding", cabi.TSKV_ERR_BAD_ENCODING),
+    ("quantile", cabi.TSKV_ERR_UNSUPPORTED),
+    ("truncated_gorilla", cabi.TSKV_ERR_SHORT_BLOCK),
+    ("too_few_values", cabi.TSKV_ERR_BITSET_MISMATCH),
+])
+def test_decode_errors_match_oracle(engine, case, status):
+    b = datagen.ArenaBuilder()
+    n = 64
+    b.add_column_group(0, np.arange(n), [(1, cabi.TSKV_PT_I64, np.cumsum(np.arange(n) % 7), None),
+                                         (2, cabi.TSKV_PT_F64, np.arange(n) * 1.25 + 0.1, None)])
+    arena, descs = b.finish()
+    if case == "bad_sub_encoding":
+        a = _corrupt(arena, descs, 1, lambda a, off, d, size: a.__setitem__(d + 1, 0x30))
+        bad = 1
+    elif case == "quantile":
+        a = _corrupt(arena, descs, 1, lambda a, off, d, size: a.__setitem__(d, 3))
+        bad = 1
+    elif case == "truncated_gorilla":
+        # keep the framing but zero the tail of the stream: the sentinel disappears
+        a = _corrupt(arena, descs, 2, lambda a, off, d, size: a.__setitem__(slice(off + size - 40, off + size), 0))
+        bad = 2
+    else:
+        # claim more valid rows than there are encoded values: shrink data by one simple8b word
+        bb = datagen.ArenaBuilder()
+        v = np.cumsum(np.arange(n) % 7)
+        data = datagen.encode_integers(v)[:-8]
+        bb.add_page(datagen.build_page(datagen.encode_timestamps(np.arange(n)), n), 0, 0, cabi.TSKV_PT_TIME, n)
+        bb.add_page(datagen.build_page(data, n), 0, 1, cabi.TSKV_PT_I64, n)
+        a, descs = bb.finish()
+        bad = 1
+    with pytest.raises(orc.OracleError) as oe:
+        orc.decode_pages(a, descs)
+    assert oe.value.status == status
+    pages = engine.upload_pages(a, descs)
+    with pytest.raises(TskvError) as ge:
+        engine.decode_pages(pages, descs)
+    assert ge.value.status == status and ge.value.page == bad
+    pt = int(descs[bad]["phys_type"])
+    with pytest.raises(TskvError) as se:
+        engine.scan_aggregate(pages, QueryOption([PushedAggregate(int(descs[bad]["column_id"]), pt, ["count"])]))
+    assert se.value.status == status
+    pages.close()
+
+
+def test_crc_mismatch_is_detected_at_upload(engine):
+    g = datagen.generate(10, n_fields=1, n_points=100, seed=8)
+    a = g.arena.copy()
+    a[int(g.descs[3]["offset"]) + int(g.descs[3]["size"]) - 1] ^= 0x40
+    with pytest.raises(TskvError) as e:
+        engine.upload_pages(a, g.descs)
+    assert e.value.status == cabi.TSKV_ERR_CRC_MISMATCH and e.value.page == 3
+    engine.upload_pages(a, g.descs, verify_crc=False).close()
+
+
+def test_query_validation_errors(engine):
+    g = datagen.generate(10, n_fields=1, n_points=100, seed=8)
+    pages = engine.upload_pages(g.arena, g.descs)
+    with pytest.raises(TskvError) as e:   # rows outside the bucket range
+        engine.scan_aggregate(pages, make_query([(1, cabi.TSKV_PT_I64)], width=1000, first_bucket_start=datagen.TSBS_T0, n_buckets=2))
+    assert e.value.status == cabi.TSKV_ERR_BUCKET_RANGE
+    with pytest.raises(TskvError) as e:   # wrong column type
+        engine.scan_aggregate(pages, make_query([(1, cabi.TSKV_PT_F64)]))
+    assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
+    with pytest.raises(TskvError) as e:   # unsorted selection
+        engine.scan_aggregate(pages, make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.array([3, 1], dtype=np.uint32)))
+    assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
+    # a selection that matches nothing gives empty (invalid) cells and count 0
+    r = engine.scan_aggregate(pages, make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.array([77], dtype=np.uint32)))
+    assert r.column(1, "count")[0][0, 0] == 0 and not r.column(1, "sum")[1][0, 0]
+    pages.close()

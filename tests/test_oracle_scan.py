@@ -1,0 +1,195 @@
+"""Oracle scan/aggregate semantics: checked against the reference's SQL goldens (func_tb2) and against an
+independent numpy brute force. No GPU needed."""
+import numpy as np
+import pytest
+
+from cnosdb_b200 import cabi, datagen
+from cnosdb_b200.engine import PushedAggregate, QueryOption
+from oracle import pyoracle as orc
+from tests.helpers import ALL_AGGS, bucket_spec, make_query, random_arena
+
+
+def func_tb2(golden):
+    t = golden["sql_goldens"]["func_tb2"]
+    b = datagen.ArenaBuilder()
+    b.add_column_group(1, np.array(t["time"], dtype=np.int64), [
+        (1, cabi.TSKV_PT_U64, np.array(t["f0_u64"], dtype=np.uint64), None),
+        (2, cabi.TSKV_PT_F64, np.array(t["f1_f64"], dtype=np.float64), None),
+        (5, cabi.TSKV_PT_I64, np.array(t["f4_i64"], dtype=np.int64), None)])
+    return b.finish()
+
+
+def test_sql_goldens_func_tb2(golden):
+    """sqllogicaltests/cases/function/common/{sum,avg,min,max,count,first,last}.slt over setup.slt:46-56."""
+    arena, descs = func_tb2(golden)
+    q = make_query([(1, cabi.TSKV_PT_U64), (2, cabi.TSKV_PT_F64), (5, cabi.TSKV_PT_I64)])
+    res = orc.scan_aggregate(arena, descs, q)
+    exp = golden["sql_goldens"]["expected"]
+    name = {1: "f0", 2: "f1", 5: "f4"}
+    sqlname = {"mean": "avg"}
+    checked = 0
+    for col in (1, 2, 5):
+        for agg in ALL_AGGS:
+            key = "%s(%s)" % (sqlname.get(agg, agg), name[col])
+            if key not in exp:
+                continue
+            v, valid = res.column(col, agg)
+            assert valid.all()
+            assert float(v[0, 0]) == float(exp[key]), key
+            checked += 1
+    assert checked >= 19
+
+
+def test_time_window_sql_golden():
+    """function/time_window.slt:101-110: rows at 1970-01-01 and 1980-01-01, tumbling window of 10 ms:
+    each row is alone in its window; sum(f0)=111, count(f1)=1 per window."""
+    b = datagen.ArenaBuilder()
+    t1980 = 315_532_800_000_000_000
+    b.add_column_group(7, np.array([0, t1980], dtype=np.int64),
+                       [(1, cabi.TSKV_PT_I64, np.array([111, 111]), None), (2, cabi.TSKV_PT_I64, np.array([5, 6]), None)])
+    arena, descs = b.finish()
+    w = 10_000_000
+    for t in (0, t1980):
+        start, end = orc.sliding_window(t, w, w, 0)
+        assert start == t and end == t + w
+        q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_I64, ["sum"]), PushedAggregate(2, cabi.TSKV_PT_I64, ["count"])],
+                        time_ranges=[(t, t + w - 1)], width=w, first_bucket_start=start, n_buckets=1)
+        r = orc.scan_aggregate(arena, descs, q)
+        assert r.column(1, "sum")[0][0, 0] == 111 and r.column(2, "count")[0][0, 0] == 1
+
+
+def brute_force(truth, query, slots):
+    """Independent numpy/python re-computation of the dense result: dict (col, agg) -> (values, valid)."""
+    nb = query.n_buckets
+    n_groups = len(slots) if query.group_by_series else 1
+    out = {}
+    for c in query.columns:
+        acc = [[dict(count=0, vals=[], first=None, last=None) for _ in range(nb)] for _ in range(n_groups)]
+        for slot, sid in enumerate(slots):
+            g = slot if query.group_by_series else 0
+            for ts, cols in truth.get(sid, []):
+                if c.column_id not in cols:
+                    continue
+                vals, valid = cols[c.column_id]
+                keep = np.zeros(len(ts), dtype=bool) if query.time_ranges else np.ones(len(ts), dtype=bool)
+                for lo, hi in query.time_ranges:
+                    keep |= (ts >= lo) & (ts <= hi)
+                if query.width > 0:
+                    o = query.origin % query.width
+                    start = ts - ((ts - o + query.width) % query.width)  # floor regime only (t >= 0)
+                    b = (start - query.first_bucket_start) // query.width
+                else:
+                    b = np.zeros(len(ts), dtype=np.int64)
+                for bi in np.unique(b[keep]):
+                    rows = np.nonzero(keep & (b == bi))[0]
+                    cell = acc[g][int(bi)]
+                    vrows = rows[valid[rows]]
+                    cell["count"] += len(vrows)
+                    cell["vals"].extend(vals[vrows].tolist())
+                    r0, r1 = rows[np.argmin(ts[rows])], rows[np.argmax(ts[rows])]
+                    if valid[r0] and (cell["first"] is None or ts[r0] < cell["first"][0]):
+                        cell["first"] = (ts[r0], vals[r0])
+                    if valid[r1] and (cell["last"] is None or ts[r1] > cell["last"][0]):
+                        cell["last"] = (ts[r1], vals[r1])
+        out[c.column_id] = acc
+    return out
+
+
+@pytest.mark.parametrize("group_by_series", [False, True])
+@pytest.mark.parametrize("null_frac", [0.0, 0.15])
+def test_oracle_matches_brute_force(group_by_series, null_frac):
+    rng = np.random.default_rng(100 + int(group_by_series) + int(null_frac * 100))
+    fields = ((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64), (3, cabi.TSKV_PT_U64))
+    arena, descs, truth = random_arena(rng, n_series=12, n_points=120, fields=fields, null_frac=null_frac,
+                                       jitter=200, multi_cg=True)
+    sel = np.array(sorted(rng.choice(np.arange(14), 9, replace=False)), dtype=np.uint32)
+    t_lo, t_hi = 1_000_000 + 7_000, 1_000_000 + 150_000
+    width = 13_000
+    fbs, nb = bucket_spec(t_lo, t_hi, width, origin=5)
+    q = make_query(fields, series_ids=sel, time_ranges=[(t_lo, t_hi)], origin=5, width=width,
+                   first_bucket_start=fbs, n_buckets=nb, group_by_series=group_by_series)
+    res = orc.scan_aggregate(arena, descs, q)
+    bf = brute_force(truth, q, sel.tolist())
+    for c in q.columns:
+        for agg in ALL_AGGS:
+            v, valid = res.column(c.column_id, agg)
+            for g in range(v.shape[0]):
+                for b in range(nb):
+                    cell = bf[c.column_id][g][b]
+                    vals = cell["vals"]
+                    if agg == "count":
+                        assert v[g, b] == cell["count"] and valid[g, b]
+                        continue
+                    if agg in ("first", "last"):
+                        assert valid[g, b] == (cell[agg] is not None)
+                        if valid[g, b]:
+                            assert v[g, b] == cell[agg][1]
+                        continue
+                    assert valid[g, b] == (len(vals) > 0)
+                    if not vals:
+                        continue
+                    if agg == "sum":
+                        if c.phys_type == cabi.TSKV_PT_F64:
+                            assert abs(v[g, b] - sum(vals)) <= 1e-9 * max(1, abs(sum(vals)))
+                        else:
+                            assert int(v[g, b]) == sum(int(x) for x in vals) % 2**64 or int(v[g, b]) == sum(int(x) for x in vals)
+                    elif agg == "min":
+                        assert v[g, b] == min(vals)
+                    elif agg == "max":
+                        assert v[g, b] == max(vals)
+                    elif agg == "mean":
+                        assert abs(v[g, b] - sum(float(x) for x in vals) / len(vals)) <= 1e-9 * max(1, abs(v[g, b]))
+    # multi-threaded driver (series chunks like iterator.rs:232-235) agrees
+    res_mt = orc.scan_aggregate(arena, descs, q, n_threads=4)
+    from tests.helpers import assert_results_equal
+    assert_results_equal(res_mt, res, what="mt")
+
+
+def test_first_skips_null_valued_head_row():
+    """first.rs:139-148 + :91-94: the min-time row of a (page, bucket) group decides; when its VALUE is null
+    that group contributes nothing to first() - it does not fall through to the next row."""
+    b = datagen.ArenaBuilder()
+    ts = np.array([10, 20, 30, 40], dtype=np.int64)
+    b.add_column_group(1, ts, [(1, cabi.TSKV_PT_I64, np.array([1, 2, 3, 4]), np.array([False, True, True, True]))])
+    b.add_column_group(2, ts + 1, [(1, cabi.TSKV_PT_I64, np.array([5, 6, 7, 8]), None)])
+    arena, descs = b.finish()
+    r = orc.scan_aggregate(arena, descs, make_query([(1, cabi.TSKV_PT_I64)], aggs=("first", "last", "count")))
+    assert r.column(1, "first")[0][0, 0] == 5      # series 1's head row is null => series 2 wins although later
+    assert r.column(1, "last")[0][0, 0] == 8
+    assert r.column(1, "count")[0][0, 0] == 7
+
+
+def test_first_last_ties_keep_earlier_series():
+    """first.rs:103-107: replace only when strictly less/greater => the earlier-seen (lower slot) point wins."""
+    b = datagen.ArenaBuilder()
+    ts = np.array([100, 200], dtype=np.int64)
+    for sid, (a, z) in enumerate([(11, 12), (21, 22), (31, 32)]):
+        b.add_column_group(sid + 5, ts, [(1, cabi.TSKV_PT_I64, np.array([a, z]), None)])
+    arena, descs = b.finish()
+    r = orc.scan_aggregate(arena, descs, make_query([(1, cabi.TSKV_PT_I64)], aggs=("first", "last")))
+    assert r.column(1, "first")[0][0, 0] == 11 and r.column(1, "last")[0][0, 0] == 12
+    r = orc.scan_aggregate(arena, descs, make_query([(1, cabi.TSKV_PT_I64)], aggs=("first", "last"),
+                                                    series_ids=np.array([6, 7], dtype=np.uint32)))
+    assert r.column(1, "first")[0][0, 0] == 21 and r.column(1, "last")[0][0, 0] == 22
+
+
+def test_negative_time_window_quirk_is_kept():
+    """Rust % keeps the dividend's sign: for t < origin%w - w the window start is not a floor
+    (time_window.rs:184-198). (0,5,2,0) -> (-4,1) in the reference KAT is the same arithmetic."""
+    assert orc.sliding_window(-7, 5, 5, 0) == (-5, 0)      # dividend -2 -> rem -2 -> start = -7+2
+    assert orc.sliding_window(-5, 5, 5, 0) == (-5, 0)      # dividend 0
+    assert orc.sliding_window(-3, 5, 5, 0) == (-5, 0)      # floor regime
+    assert orc.sliding_window(-12, 5, 5, 0) == (-10, -5)   # ceil-like: -12 lands in (-15,-10]
+
+
+def test_bucket_range_error_and_bad_args():
+    rng = np.random.default_rng(3)
+    arena, descs, _ = random_arena(rng, n_series=3, n_points=50, fields=((1, cabi.TSKV_PT_I64),))
+    q = make_query([(1, cabi.TSKV_PT_I64)], width=1000, first_bucket_start=1_000_000, n_buckets=3)
+    with pytest.raises(orc.OracleError) as e:
+        orc.scan_aggregate(arena, descs, q)
+    assert e.value.status == cabi.TSKV_ERR_BUCKET_RANGE
+    q = make_query([(1, cabi.TSKV_PT_F64)])
+    with pytest.raises(orc.OracleError) as e:
+        orc.scan_aggregate(arena, descs, q)
+    assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
