@@ -34,6 +34,7 @@ TSKV_AGG_COUNT, TSKV_AGG_SUM, TSKV_AGG_MIN, TSKV_AGG_MAX = 1, 2, 4, 8
 TSKV_AGG_MEAN, TSKV_AGG_FIRST, TSKV_AGG_LAST, TSKV_AGG_ALL = 16, 32, 64, 0x7F
 AGG_NAMES = {1: "count", 2: "sum", 4: "min", 8: "max", 16: "mean", 32: "first", 64: "last"}
 TSKV_UPLOAD_VERIFY_CRC = 1
+TSKV_UPLOAD_HOST_RESIDENT = 2
 
 # numpy view of tskv_page_desc (24 bytes)
 PAGE_DESC_DTYPE = np.dtype(
@@ -75,7 +76,9 @@ class Counters(C.Structure):
     _fields_ = [("page_read_count", C.c_uint64), ("page_read_bytes", C.c_uint64),
                 ("points_decoded", C.c_uint64), ("rows_in_range", C.c_uint64),
                 ("elapsed_scan_ms", C.c_double), ("elapsed_h2d_ms", C.c_double),
-                ("kernel_launches", C.c_uint64), ("reserved", C.c_uint64 * 5)]
+                ("kernel_launches", C.c_uint64), ("elapsed_fused_ms", C.c_double),
+                ("dominant_kernel_ms", C.c_double), ("dominant_kernel_bytes", C.c_uint64),
+                ("dominant_kernel_bin", C.c_uint64), ("h2d_bytes", C.c_uint64)]
 
 
 class PartialsView(C.Structure):
@@ -92,7 +95,8 @@ GPU_SYMBOLS = [
     "tskvgpu_ctx_create", "tskvgpu_ctx_destroy", "tskvgpu_last_error", "tskvgpu_last_error_page",
     "tskvgpu_get_counters", "tskvgpu_ctx_stream", "tskvgpu_upload_pages", "tskvgpu_pages_destroy",
     "tskvgpu_pages_series_count", "tskvgpu_decode_pages", "tskvgpu_query_output_layout",
-    "tskvgpu_scan_aggregate", "tskvgpu_scan_prepare", "tskvgpu_scan_run", "tskvgpu_scan_partials",
+    "tskvgpu_scan_aggregate", "tskvgpu_scan_prepare", "tskvgpu_scan_run", "tskvgpu_scan_enqueue",
+    "tskvgpu_scan_sync", "tskvgpu_scan_partials",
     "tskvgpu_scan_snapshot_keys", "tskvgpu_scan_mask_values", "tskvgpu_scan_finalize",
     "tskvgpu_scan_finalize_device", "tskvgpu_scan_destroy", "tskvgpu_version",
 ]
@@ -143,6 +147,8 @@ def load_gpu_library():
     lib.tskvgpu_scan_aggregate.argtypes = [vp, vp, C.POINTER(Query), vp, vp]
     lib.tskvgpu_scan_prepare.argtypes = [vp, vp, C.POINTER(Query), C.POINTER(vp)]
     lib.tskvgpu_scan_run.argtypes = [vp, vp]
+    lib.tskvgpu_scan_enqueue.argtypes = [vp, vp]
+    lib.tskvgpu_scan_sync.argtypes = [vp, vp]
     lib.tskvgpu_scan_partials.argtypes = [vp, vp, C.POINTER(PartialsView)]
     lib.tskvgpu_scan_snapshot_keys.argtypes = [vp, vp]
     lib.tskvgpu_scan_mask_values.argtypes = [vp, vp]

@@ -27,14 +27,18 @@ __device__ __forceinline__ int64_t zigzag_dec(uint64_t v) {
   return (int64_t)((v >> 1) ^ (0 - (v & 1)));
 }
 
-// Streams an arbitrarily aligned byte range as big-endian u64 words using only aligned 8-byte
-// global loads (one load per word; the previous aligned word is kept and funnel-shifted).
-// May read up to 15 bytes past `end`: the arena carries 64 bytes of slack.
+// Streams an arbitrarily aligned byte range as big-endian u64 words. Two implementations with the
+// same interface:
+//   BeStream      aligned 8-byte global loads (one per word; previous word kept and funnel-shifted).
+//   RingStream    the same words, prefetched RING_WORDS ahead into a per-lane shared-memory ring with
+//                 cp.async (LDGSTS): a lane-serial decoder otherwise exposes a full HBM/L2 round trip on
+//                 every word it consumes.
+// Both may read up to RING_WORDS*8+8 bytes past the end of the page: the arena carries 128 bytes of slack.
 struct BeStream {
   const uint64_t *ap;  // next aligned word
   uint64_t cur;        // last aligned word, little-endian
   uint32_t sh;         // misalignment in bits
-  __device__ __forceinline__ void init(const uint8_t *p) {
+  __device__ __forceinline__ void init(const uint8_t *p, uint32_t /*smem_slot*/ = 0) {
     uintptr_t a = reinterpret_cast<uintptr_t>(p);
     sh = (uint32_t)(a & 7) * 8;
     ap = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
@@ -42,6 +46,52 @@ struct BeStream {
   }
   __device__ __forceinline__ uint64_t next() {
     uint64_t nxt = __ldg(ap++);
+    uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
+    cur = nxt;
+    return bswap64(raw);
+  }
+};
+
+constexpr int RING_WORDS = 8;  // 64 bytes of lookahead per stream per lane
+
+// Ring layout: word k of lane l lives at slot_base + k * 256 + l * 8 (shared space): whatever ring
+// position each lane is at, lane l always hits banks 2l, 2l+1 => conflict-free 64-bit LDS.
+struct RingStream {
+  const uint64_t *gp;  // next aligned global word to prefetch
+  uint32_t sbase;      // shared-space address of this lane's word 0
+  uint32_t rd;         // ring position of the next word to consume
+  uint64_t cur;
+  uint32_t sh;
+  __device__ __forceinline__ void prefetch(uint32_t slot) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;\n"
+                 :: "r"(sbase + slot * 256u), "l"(gp) : "memory");
+    gp++;
+  }
+  __device__ __forceinline__ uint64_t pop() {
+    // every consumed word was followed by exactly one newer commit group, so at most RING_WORDS - 1
+    // groups may still be in flight when the oldest one is needed
+    asm volatile("cp.async.wait_group %0;\n" :: "n"(RING_WORDS - 2) : "memory");
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(sbase + rd * 256u) : "memory");
+    // refill the slot consumed by the PREVIOUS pop (its read retired long ago)
+    prefetch((rd + RING_WORDS - 1) & (RING_WORDS - 1));
+    rd = (rd + 1) & (RING_WORDS - 1);
+    return v;
+  }
+  // `slot_base`: shared-space address reserved for this stream of this lane (see scan_chunk)
+  __device__ __forceinline__ void init(const uint8_t *p, uint32_t slot_base) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    sh = (uint32_t)(a & 7) * 8;
+    gp = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    sbase = slot_base;
+    rd = 0;
+    // fill slots 0 .. RING_WORDS-2; slot RING_WORDS-1 is refilled by the first pop
+#pragma unroll
+    for (int k = 0; k < RING_WORDS - 1; k++) prefetch(k);
+    cur = pop();
+  }
+  __device__ __forceinline__ uint64_t next() {
+    uint64_t nxt = pop();
     uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
     cur = nxt;
     return bswap64(raw);
@@ -78,14 +128,18 @@ struct PageView {
 // Validity bitmap, Arrow LSB-first (page.rs:78-84).
 struct BitCursor {
   const uint32_t *wp;
-  uint32_t word;
+  uint32_t word, ahead;  // `ahead` = the next 32 rows, loaded one word early to hide the latency
   __device__ __forceinline__ void init(const uint8_t *bitset) {
     wp = reinterpret_cast<const uint32_t *>(bitset);
     word = 0;
+    ahead = __ldg(wp++);
   }
-  // `row` must advance by one per call starting at 0.
+  // `row` must advance by one per call starting at 0. Reads at most 8 bytes past the bitmap.
   __device__ __forceinline__ bool next(uint32_t row) {
-    if ((row & 31) == 0) word = __ldg(wp++);
+    if ((row & 31) == 0) {
+      word = ahead;
+      ahead = __ldg(wp++);
+    }
     bool b = word & 1;
     word >>= 1;
     return b;
@@ -122,9 +176,9 @@ __device__ __forceinline__ uint64_t pow10_u64(uint32_t k) {
 // Delta-family cursor: RLE / simple8b / raw prefix sum / raw BE, zig-zag or scaled.
 // KIND is one of the DK_* delta kinds, or -1 for a runtime switch on `kind` (generic path).
 // ------------------------------------------------------------------------------------------------
-template <int KIND>
+template <int KIND, typename STREAM = BeStream>
 struct DeltaCursor {
-  BeStream bs;
+  STREAM bs;
   uint64_t v;           // running value (raw bits)
   uint64_t delta;       // RLE delta (already scaled / zig-zag decoded)
   uint64_t scaler;      // S8B_SC
@@ -139,7 +193,7 @@ struct DeltaCursor {
 
   // Returns TSKV_OK or a decode error. `pv.data` starts at the Encoding id byte; the host already
   // classified the page, so lengths needed by the fixed header are guaranteed.
-  __device__ inline tskv_status open(const PageView &pv, uint8_t kind_) {
+  __device__ inline tskv_status open(const PageView &pv, uint8_t kind_, uint32_t smem_slot = 0) {
     kind = KIND >= 0 ? (uint8_t)KIND : kind_;
     first = true;
     v = 0;
@@ -167,22 +221,22 @@ struct DeltaCursor {
       }
       case DK_S8B_SC:  // timestamp.rs:261-299
         scaler = pow10_u64(__ldg(d + 1) & 0xf);
-        bs.init(d + 2);
+        bs.init(d + 2, smem_slot);
         v = bs.next();
         words_left = (pv.data_len - 10) >> 3;
         break;
       case DK_S8B_ZZ:  // integer.rs:216-248
-        bs.init(d + 2);
+        bs.init(d + 2, smem_slot);
         v = (uint64_t)zigzag_dec(bs.next());
         words_left = (pv.data_len - 10) >> 3;
         break;
       case DK_RAW_SC:  // timestamp.rs:201-224
       case DK_RAW_ZZ:  // integer.rs:165-184
-        bs.init(d + 2);
+        bs.init(d + 2, smem_slot);
         words_left = (pv.data_len - 2) >> 3;
         break;
       case DK_RAWBE:  // timestamp.rs:301-323
-        bs.init(d + 1);
+        bs.init(d + 1, smem_slot);
         words_left = (pv.data_len - 1) >> 3;
         break;
       default:
@@ -273,75 +327,75 @@ struct DeltaCursor {
 // Gorilla cursor (float.rs:418-606): MSB-first bit stream after id | 0x10 | first(8).
 // Terminates on the sentinel 0x7ff8_0000_0000_00ff (float.rs:16).
 // ------------------------------------------------------------------------------------------------
+template <typename STREAM = BeStream>
 struct GorillaCursor {
-  BeStream bs;
+  STREAM bs;
   uint64_t val;
-  uint64_t buf;        // unread bits, MSB-aligned
-  uint32_t avail;      // valid bits in buf
-  uint32_t bits_left;  // bits not yet loaded into buf
+  uint64_t hi, lo;     // 128-bit window of the MSB-first bit stream; `pos` bits of hi are consumed
+  uint32_t pos;        // 0..63
+  uint32_t bits_used;  // bits consumed so far
+  uint32_t bits_total; // (data_len - 10) * 8
   uint32_t trailing, meaningful;
   bool first, done, err;
 
-  __device__ inline tskv_status open(const PageView &pv) {
+  __device__ inline tskv_status open(const PageView &pv, uint32_t smem_slot = 0) {
     first = true;
     done = false;
     err = false;
-    buf = 0;
-    avail = 0;
     trailing = 0;
     meaningful = 64;
     const uint8_t *d = pv.data;
-    bs.init(d + 2);
+    bs.init(d + 2, smem_slot);
     val = bs.next();
-    bits_left = (pv.data_len - 10) * 8;
+    hi = bs.next();
+    lo = bs.next();
+    pos = 0;
+    bits_used = 0;
+    bits_total = (pv.data_len - 10) * 8;
     return TSKV_OK;
   }
 
-  // Reads n in [1,64] bits. Sets err when the stream ends ("unexpected end of block").
-  __device__ __forceinline__ uint64_t take(uint32_t n) {
-    uint64_t r;
-    if (n <= avail) {
-      r = buf >> (64 - n);
-      buf = (buf << 1) << (n - 1);
-      avail -= n;
-      return r;
+  // Next 64 bits of the stream, MSB-aligned, without consuming them.
+  __device__ __forceinline__ uint64_t peek() const { return (hi << pos) | ((lo >> 1) >> (63 - pos)); }
+  // Consumes n in [1,64] bits.
+  __device__ __forceinline__ void skip(uint32_t n) {
+    pos += n;
+    bits_used += n;
+    if (pos >= 64) {
+      pos -= 64;
+      hi = lo;
+      lo = bs.next();
     }
-    uint32_t need = n - avail;  // 1..64
-    r = avail ? (buf >> (64 - avail)) : 0;
-    if (bits_left < need) {
-      err = true;
-      return 0;
-    }
-    uint64_t nxt = bs.next();
-    uint32_t got = bits_left < 64 ? bits_left : 64;
-    bits_left -= got;
-    r = ((r << 1) << (need - 1)) | (nxt >> (64 - need));
-    buf = (nxt << 1) << (need - 1);
-    avail = got - need;
-    return r;
   }
 
-  // Decodes the next stream element; returns false at the sentinel / on error.
+  // Decodes the next stream element; returns false at the sentinel / on error
+  // ("unexpected end of block": the stream ended before the sentinel).
   __device__ __forceinline__ bool advance() {
-    if (take(1) == 0) return !err;  // repeat previous value
-    if (err) return false;
-    if (take(1) != 0) {
-      if (err) return false;
-      uint32_t lm = (uint32_t)take(11);
-      if (err) return false;
-      uint32_t leading = (lm >> 6) & 0x1f;
-      meaningful = lm & 0x3f;
-      if (meaningful > 0) {
-        trailing = (uint8_t)(64 - leading - meaningful);  // u8 arithmetic like the reference
+    uint32_t x = (uint32_t)(peek() >> 51);  // 13 bits: c0 c1 lead[5] sig[6]
+    if (!(x & 0x1000)) {
+      skip(1);  // repeat previous value
+    } else {
+      if (!(x & 0x0800)) {
+        skip(2);  // reuse the previous (leading, trailing) window
       } else {
-        trailing = 0;
-        meaningful = 64;
+        skip(13);
+        uint32_t leading = (x >> 6) & 0x1f;
+        meaningful = x & 0x3f;
+        if (meaningful > 0) {
+          trailing = (uint8_t)(64 - leading - meaningful);  // u8 arithmetic like the reference
+        } else {
+          trailing = 0;
+          meaningful = 64;
+        }
       }
+      uint64_t s = peek() >> (64 - meaningful);
+      skip(meaningful);
+      val ^= s << (trailing & 0x3f);
     }
-    if (err) return false;
-    uint64_t s = take(meaningful);
-    if (err) return false;
-    val ^= s << (trailing & 0x3f);
+    if (bits_used > bits_total) {
+      err = true;
+      return false;
+    }
     return val != 0x7ff80000000000ffull;
   }
 
@@ -361,14 +415,15 @@ struct GorillaCursor {
 };
 
 // Runtime-dispatched cursor over every supported kind (decode-only kernel and generic scan path).
+template <typename STREAM = BeStream>
 struct AnyCursor {
-  DeltaCursor<-1> d;
-  GorillaCursor g;
+  DeltaCursor<-1, STREAM> d;
+  GorillaCursor<STREAM> g;
   bool is_gorilla;
-  __device__ inline tskv_status open(const PageView &pv, uint8_t kind) {
+  __device__ inline tskv_status open(const PageView &pv, uint8_t kind, uint32_t smem_slot = 0) {
     is_gorilla = kind == DK_GORILLA;
-    if (is_gorilla) return g.open(pv);
-    return d.open(pv, kind);
+    if (is_gorilla) return g.open(pv, smem_slot);
+    return d.open(pv, kind, smem_slot);
   }
   __device__ __forceinline__ uint64_t next(bool *ok) { return is_gorilla ? g.next(ok) : d.next(ok); }
   __device__ __forceinline__ bool stream_error() const { return is_gorilla && g.err; }

@@ -54,7 +54,7 @@ struct ScanParams {
   const uint32_t *bin_cstart;  // [N_BINS + 1] starts of the kind bins in the work list
   const ColState *cols;
   uint64_t *state;
-  uint32_t *task_counter;       // [N_BINS] dynamic chunk schedulers
+  uint32_t *task_counter;       // dynamic chunk scheduler
   int32_t *status;              // first error (0 = ok)
   unsigned long long *err_page; // page of the first error
   unsigned long long *stats;    // [0] points decoded, [1] rows in range
@@ -104,58 +104,83 @@ __device__ __forceinline__ int find_qcol(const ColState *cols, uint32_t n_cols, 
   return -1;
 }
 
-// One thread per item (field page, in kind-sorted order): selected? -> flag, per-block counts and
-// the byte/page counters of the reference's reader metrics (column_group/mod.rs:141-193).
+// One thread per item (field page, in kind-sorted order): selected? -> flag (query column + 1, bit 7 =
+// "this item also brings its column group's time page"), per-block counts and the byte/page counters
+// of the reference's reader metrics (column_group/mod.rs:141-193), split per decode-kind bin.
+// counters: [0] pages, [1] bytes, [2 + bin] bytes read by bin's fused kernel.
 __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_page,
                              const uint32_t *item_cg, const uint32_t *cg_time_page, uint32_t n_items,
                              const int32_t *cg_slot, const ColState *cols, uint32_t n_cols,
-                             uint8_t *item_flag, uint32_t *block_count, unsigned long long *counters,
-                             int32_t *status) {
+                             const uint32_t *bin_start, uint8_t *item_flag, uint32_t *block_count,
+                             unsigned long long *counters, int32_t *status) {
+  __shared__ uint32_t s_cnt;
+  __shared__ unsigned long long s_pages, s_bytes[N_BINS];
+  if (threadIdx.x == 0) { s_cnt = 0; s_pages = 0; }
+  if (threadIdx.x < N_BINS) s_bytes[threadIdx.x] = 0;
+  __syncthreads();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool sel = false;
-  unsigned long long bytes = 0, pages = 0;
   if (i < n_items) {
     uint32_t p = item_page[i];
     tskv_page_desc d = descs[p];
     uint32_t cg = item_cg[i];
     int qc = find_qcol(cols, n_cols, d.column_id);
+    bool first_sel = false;
     if (qc >= 0 && cg_slot[cg] >= 0) {
       if (cols[qc].phys_type != d.phys_type) {
         atomicCAS(status, 0, TSKV_ERR_INVALID_ARG);
       } else {
         sel = true;
-        bytes = d.size;
-        pages = 1;
+        unsigned long long bytes = d.size, pages = 1;
         // the time page of a column group is read once: charge it to the group's first selected
         // field page (field pages of a group are contiguous after the time page)
         uint32_t tp = cg_time_page[cg];
-        bool first_sel = true;
+        first_sel = true;
         for (uint32_t q = tp + 1; q < p; q++)
           if (find_qcol(cols, n_cols, descs[q].column_id) >= 0) { first_sel = false; break; }
         if (first_sel) { bytes += descs[tp].size; pages += 1; }
+        int bin = 0;
+        for (int k = 1; k < N_BINS; k++) bin += (i >= bin_start[k]) ? 1 : 0;
+        atomicAdd(&s_bytes[bin], bytes);
+        atomicAdd(&s_pages, pages);
       }
     }
-    item_flag[i] = sel ? (uint8_t)(qc + 1) : 0;
+    item_flag[i] = sel ? (uint8_t)((qc + 1) | (first_sel ? 0x80 : 0)) : 0;
   }
-  // block reduce
-  __shared__ uint32_t s_cnt;
-  __shared__ unsigned long long s_bytes, s_pages;
-  if (threadIdx.x == 0) { s_cnt = 0; s_bytes = 0; s_pages = 0; }
-  __syncthreads();
   uint32_t m = __ballot_sync(FULL, sel);
-  for (int o = 16; o; o >>= 1) {
-    bytes += __shfl_down_sync(FULL, bytes, o);
-    pages += __shfl_down_sync(FULL, pages, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&s_cnt, __popc(m));
-    atomicAdd(&s_bytes, bytes);
-    atomicAdd(&s_pages, pages);
-  }
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
   __syncthreads();
   if (threadIdx.x == 0) {
     block_count[blockIdx.x] = s_cnt;
-    if (s_pages) { atomicAdd(&counters[0], s_pages); atomicAdd(&counters[1], s_bytes); }
+    if (s_pages) atomicAdd(&counters[0], s_pages);
+  }
+  if (threadIdx.x < N_BINS && s_bytes[threadIdx.x]) {
+    atomicAdd(&counters[1], s_bytes[threadIdx.x]);
+    atomicAdd(&counters[2 + threadIdx.x], s_bytes[threadIdx.x]);
+  }
+}
+
+// Host-resident arenas: pull the selected pages over PCIe into the device arena (same offsets).
+// One warp per work item, 16-byte coalesced loads from the mapped host range. Replaces the per-series
+// file reads of TsmReader::read_adjacent_pages (tsm/reader.rs:236-264).
+__global__ void k_gather_pages(const uint8_t *host_arena, uint8_t *dev_arena, const tskv_page_desc *descs,
+                               const uint32_t *time_page_of, const uint32_t *work_page,
+                               const uint8_t *work_qcol, const uint32_t *total) {
+  const uint32_t n = *total;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+    const uint32_t page = work_page[w];
+    const bool with_time = work_qcol[w] & 0x80;
+    for (int pass = 0; pass < (with_time ? 2 : 1); pass++) {
+      const tskv_page_desc d = descs[pass == 0 ? page : time_page_of[page]];
+      const uint4 *src = reinterpret_cast<const uint4 *>(host_arena + d.offset);
+      uint4 *dst = reinterpret_cast<uint4 *>(dev_arena + d.offset);
+      const uint32_t n16 = d.size >> 4;
+      for (uint32_t k = lane; k < n16; k += 32) dst[k] = src[k];
+      const uint32_t tail = d.size & 15;
+      if (lane < tail) dev_arena[d.offset + (n16 << 4) + lane] = host_arena[d.offset + (n16 << 4) + lane];
+    }
   }
 }
 
@@ -223,7 +248,7 @@ __global__ void k_scatter_items(const uint32_t *item_page, const uint32_t *item_
     if (f) {
       work_page[pos] = item_page[i];
       work_slot[pos] = (uint32_t)cg_slot[item_cg[i]];
-      work_qcol[pos] = (uint8_t)(f - 1);
+      work_qcol[pos] = (uint8_t)(((f & 0x7f) - 1) | (f & 0x80));
     }
     for (int k = 0; k < N_BINS; k++)
       if (bin_start[k] == i) bin_cstart[k] = pos;
@@ -329,6 +354,7 @@ struct ScanCtx {
 // run for cell `gcell` (= qcol * n_cells + cell). When every flushing lane targets the same cell
 // (the common lock-step case of GROUP BY bucket) the partials are combined with a butterfly first
 // and one lane issues the atomics.
+template <bool SEL>
 __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uint32_t qcol,
                                            uint64_t cell, int64_t bucket, uint8_t pt, uint8_t mask,
                                            RunAcc &a, uint32_t slot) {
@@ -340,7 +366,7 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
   bool same = __all_sync(FULL, !active || gcell == lcell);
   // first/last keys (only meaningful on active lanes)
   int64_t kf = a.first_ts, kl = a.last_ts;
-  if (P.slot_bits) {
+  if (SEL && P.slot_bits) {
     // rel > 0 by construction (see ScanParams); the host checked rel_bits + slot_bits <= 62
     uint64_t base = P.width > 0 ? (uint64_t)P.first_bucket_start + (uint64_t)(bucket - 1) * (uint64_t)P.width
                                 : (uint64_t)P.rel_base;
@@ -355,8 +381,8 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
     int64_t shi = active ? a.sum_hi : 0;
     int64_t kmin = (active && a.count) ? a.kmin : INT64_MAX;
     int64_t kmax = (active && a.count) ? a.kmax : INT64_MIN;
-    int64_t fk = (active && a.first_ok) ? kf : INT64_MAX;
-    int64_t lk = (active && a.last_ok) ? kl : -1;
+    int64_t fk = (SEL && active && a.first_ok) ? kf : INT64_MAX;
+    int64_t lk = (SEL && active && a.last_ok) ? kl : INT64_MIN;
     uint32_t tot = __reduce_add_sync(FULL, cnt);
     for (int o = 16; o; o >>= 1) {
       uint64_t s2 = shfl_xor_u64(sum, o);
@@ -367,16 +393,22 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
       int64_t mx = (int64_t)shfl_xor_u64((uint64_t)kmax, o);
       kmin = mn < kmin ? mn : kmin;
       kmax = mx > kmax ? mx : kmax;
-      int64_t f2 = (int64_t)shfl_xor_u64((uint64_t)fk, o);
-      int64_t l2 = (int64_t)shfl_xor_u64((uint64_t)lk, o);
-      fk = f2 < fk ? f2 : fk;
-      lk = l2 > lk ? l2 : lk;
+      if (SEL) {
+        int64_t f2 = (int64_t)shfl_xor_u64((uint64_t)fk, o);
+        int64_t l2 = (int64_t)shfl_xor_u64((uint64_t)lk, o);
+        fk = f2 < fk ? f2 : fk;
+        lk = l2 > lk ? l2 : lk;
+      }
     }
     // owners of the winning first / last keys supply the values
-    uint32_t mf = __ballot_sync(FULL, active && a.first_ok && kf == fk);
-    uint32_t ml = __ballot_sync(FULL, active && a.last_ok && kl == lk);
-    uint64_t fv = shfl_u64(a.first_val, mf ? __ffs(mf) - 1 : 0);
-    uint64_t lv = shfl_u64(a.last_val, ml ? __ffs(ml) - 1 : 0);
+    uint32_t mf = 0, ml = 0;
+    uint64_t fv = 0, lv = 0;
+    if (SEL) {
+      mf = __ballot_sync(FULL, active && a.first_ok && kf == fk);
+      ml = __ballot_sync(FULL, active && a.last_ok && kl == lk);
+      fv = shfl_u64(a.first_val, mf ? __ffs(mf) - 1 : 0);
+      lv = shfl_u64(a.last_val, ml ? __ffs(ml) - 1 : 0);
+    }
     if ((int)(threadIdx.x & 31) == leader) {
       const ColState &cs = P.cols[qcol];
       uint64_t *st = P.state;
@@ -389,8 +421,8 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
         if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)kmin);
         if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)kmax);
       }
-      if ((mask & TSKV_AGG_FIRST) && mf) atomic_select_pair<true>(st + cs.first_off + 2 * cell, fk, fv);
-      if ((mask & TSKV_AGG_LAST) && ml) atomic_select_pair<false>(st + cs.last_off + 2 * cell, lk, lv);
+      if (SEL && (mask & TSKV_AGG_FIRST) && mf) atomic_select_pair<true>(st + cs.first_off + 2 * cell, fk, fv);
+      if (SEL && (mask & TSKV_AGG_LAST) && ml) atomic_select_pair<false>(st + cs.last_off + 2 * cell, lk, lv);
     }
   } else if (active) {
     const ColState &cs = P.cols[qcol];
@@ -404,8 +436,8 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
       if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)a.kmin);
       if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)a.kmax);
     }
-    if ((mask & TSKV_AGG_FIRST) && a.first_ok) atomic_select_pair<true>(st + cs.first_off + 2 * cell, kf, a.first_val);
-    if ((mask & TSKV_AGG_LAST) && a.last_ok) atomic_select_pair<false>(st + cs.last_off + 2 * cell, kl, a.last_val);
+    if (SEL && (mask & TSKV_AGG_FIRST) && a.first_ok) atomic_select_pair<true>(st + cs.first_off + 2 * cell, kf, a.first_val);
+    if (SEL && (mask & TSKV_AGG_LAST) && a.last_ok) atomic_select_pair<false>(st + cs.last_off + 2 * cell, kl, a.last_val);
   }
 }
 
@@ -413,9 +445,9 @@ __device__ __forceinline__ void report_error(const ScanParams &P, tskv_status st
   if (atomicCAS(P.status, 0, (int)st) == 0) *P.err_page = page;
 }
 
-// Bucket bookkeeping of one lane: [lo, hi) bounds of the bucket the last row fell into.
+// Bucket bookkeeping of one lane: timestamps in [lo, hi] (inclusive) map to bucket `idx`.
 struct BucketState {
-  int64_t lo, hi;   // timestamps in [lo, hi) map to bucket `idx`
+  int64_t lo, hi;
   uint32_t idx;
   bool valid;
   bool floor_regime;  // dividend >= 0: the bucket is [start, start + w)
@@ -426,12 +458,12 @@ struct BucketState {
 __device__ __forceinline__ bool locate_bucket(const ScanParams &P, int64_t t, BucketState &b) {
   if (P.width <= 0) {
     b.lo = INT64_MIN; b.hi = INT64_MAX; b.idx = 0; b.valid = true; b.floor_regime = false;
-    return true;  // hi is exclusive: t == INT64_MAX handled by the caller's "same bucket" test
+    return true;
   }
   const int64_t w = P.width;
-  if (b.valid && b.floor_regime && t >= b.hi && (uint64_t)t - (uint64_t)b.hi < (uint64_t)w &&
+  if (b.valid && b.floor_regime && t > b.hi && (uint64_t)t - (uint64_t)b.hi <= (uint64_t)w &&
       b.idx + 1 < P.n_buckets) {
-    b.lo = b.hi; b.hi = b.hi + w; b.idx += 1;  // next bucket of the floor-aligned regime
+    b.lo = b.hi + 1; b.hi = b.hi + w; b.idx += 1;  // next bucket of the floor-aligned regime
     return true;
   }
   int64_t dividend = (int64_t)((uint64_t)t - (uint64_t)P.origin_mod + (uint64_t)w);
@@ -440,37 +472,58 @@ __device__ __forceinline__ bool locate_bucket(const ScanParams &P, int64_t t, Bu
   int64_t diff = (int64_t)((uint64_t)start - (uint64_t)P.first_bucket_start);
   if (diff < 0 || diff % w != 0 || diff / w >= (int64_t)P.n_buckets) return false;
   b.idx = (uint32_t)(diff / w);
-  if (dividend >= 0) { b.lo = start; b.hi = start + w; }
-  else { b.lo = start - w + 1; b.hi = start + 1; }
+  if (dividend >= 0) { b.lo = start; b.hi = start + (w - 1); }
+  else { b.lo = start - w + 1; b.hi = start; }
   b.floor_regime = dividend >= 0;
   b.valid = true;
   return true;
 }
 
+// Closed time ranges (TimeRange::contains, predicate/domain.rs:95-98): is t selected, and over which
+// inclusive interval [lo, hi] around t does that answer stay the same?
+__device__ __forceinline__ bool range_span(const ScanParams &P, int64_t t, int64_t &lo, int64_t &hi) {
+  lo = INT64_MIN;
+  hi = INT64_MAX;
+  if (P.n_ranges == 0) return true;
+  bool in = false;
+#pragma unroll 1
+  for (uint32_t k = 0; k < P.n_ranges; k++) {
+    const int64_t a = P.ranges[k].min_ts, b = P.ranges[k].max_ts;
+    if (t >= a && t <= b) {
+      if (!in) { lo = a; hi = b; in = true; }
+    } else if (!in) {
+      if (a > t && a - 1 < hi) hi = a - 1;
+      if (b < t && a <= b && b + 1 > lo) lo = b + 1;
+    }
+  }
+  return in;
+}
+
 // One chunk of <= 32 work items, one lane per field page. The whole warp stays converged; lanes
-// without a page (or past their last row) idle through the loop.
-template <int TK, int VK>
-__device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t item_end) {
+// without a page (or past their last row) idle through the loop. `ring_base` = shared-space address of
+// this warp's 2 x RING_WORDS x 256 B prefetch rings (time stream, value stream).
+// SEL: the query wants FIRST/LAST somewhere (tracks the (ts, value) of each run's end rows).
+template <int TK, int VK, bool SEL>
+__device__ __noinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
+                                             uint32_t ring_base) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
+  const uint32_t tslot = ring_base + lane * 8, vslot = ring_base + RING_WORDS * 256 + lane * 8;
 
   uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
   uint8_t pt = TSKV_PT_I64, mask = 0;
   PageView tpv, vpv;
   BitCursor tbits, vbits;
-  using TCur = DeltaCursor<TK == TK_RLE ? DK_RLE_SC : TK == TK_S8B ? DK_S8B_SC : -1>;
-  TCur tcur;
-  using VCurS8B = DeltaCursor<DK_S8B_ZZ>;
-  VCurS8B vcur_s;
-  GorillaCursor vcur_g;
-  AnyCursor vcur_a;
-  bool vk_any_allnull = false;
+  DeltaCursor<TK == TK_RLE ? DK_RLE_SC : TK == TK_S8B ? DK_S8B_SC : -1, RingStream> tcur;
+  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, RingStream> vcur_d;
+  GorillaCursor<RingStream> vcur_g;
+  bool allnull = false;
 
   if (have_item) {
     page = P.work_page[item];
     slot = P.work_slot[item];
-    qcol = P.work_qcol[item];
+    qcol = P.work_qcol[item] & 0x7f;
     const tskv_page_desc vd = P.descs[page];
     const uint32_t tpage = P.time_page_of[page];
     const tskv_page_desc td = P.descs[tpage];
@@ -486,11 +539,10 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
       n_rows = vd.num_values;
       tbits.init(tpv.bitset);
       vbits.init(vpv.bitset);
-      st = tcur.open(tpv, td.reserved);
+      st = tcur.open(tpv, td.reserved, tslot);
       if (st == TSKV_OK) {
-        if (VK == VK_S8B) st = vcur_s.open(vpv, DK_S8B_ZZ);
-        else if (VK == VK_GOR) st = vcur_g.open(vpv);
-        else { st = vcur_a.open(vpv, vd.reserved); vk_any_allnull = vd.reserved == DK_ALLNULL; }
+        if (VK == VK_GOR) st = vcur_g.open(vpv, vslot);
+        else { st = vcur_d.open(vpv, vd.reserved, vslot); allnull = vd.reserved == DK_ALLNULL; }
       }
       if (st != TSKV_OK) { report_error(P, st, page); n_rows = 0; }
       if (td.reserved == DK_ALLNULL) n_rows = 0;  // no time values: every row fails is_not_null(time)
@@ -517,18 +569,15 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
     uint64_t v = 0;
     if (has) {
       const bool tv = tbits.next(row);
-      vv = vbits.next(row) && !vk_any_allnull;
+      vv = vbits.next(row) && !allnull;
       bool ok = true;
       if (tv) t = (int64_t)tcur.next(&ok);
       else if (row == 0) tcur.skip_first_if_s8b_sc();
       if (!ok) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = 0; }
       if (vv && ok) {
-        if (VK == VK_S8B) v = vcur_s.next(&ok);
-        else if (VK == VK_GOR) v = vcur_g.next(&ok);
-        else { v = vcur_a.next(&ok); }
+        v = VK == VK_GOR ? vcur_g.next(&ok) : vcur_d.next(&ok);
         if (!ok) {
-          bool serr = VK == VK_GOR ? vcur_g.err : (VK == VK_GEN ? vcur_a.stream_error() : false);
-          report_error(P, serr ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
+          report_error(P, (VK == VK_GOR && vcur_g.err) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
           n_rows = 0;
         } else {
           n_points++;
@@ -542,7 +591,7 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
       }
       if (inr) {
         n_inrange++;
-        bool same_bucket = bk.valid && t >= bk.lo && (t < bk.hi || P.width <= 0);
+        bool same_bucket = bk.valid && t >= bk.lo && t <= bk.hi;
         if (!same_bucket) {
           if (!locate_bucket(P, t, bk)) {
             report_error(P, TSKV_ERR_BUCKET_RANGE, page);
@@ -555,17 +604,19 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
     } else {
       flush = have_run;
     }
-    warp_flush(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+    warp_flush<SEL>(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
     if (flush) have_run = false;
     if (has && inr) {
       if (newrun) {
         have_run = true;
         run_idx = bk.idx;
         acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
-        acc.first_ts = acc.last_ts = t;
-        acc.first_val = acc.last_val = v;
-        acc.first_ok = acc.last_ok = vv;
-      } else {
+        if (SEL) {
+          acc.first_ts = acc.last_ts = t;
+          acc.first_val = acc.last_val = v;
+          acc.first_ok = acc.last_ok = vv;
+        }
+      } else if (SEL) {
         if (t < acc.first_ts) { acc.first_ts = t; acc.first_val = v; acc.first_ok = vv; }
         if (t > acc.last_ts) { acc.last_ts = t; acc.last_val = v; acc.last_ok = vv; }
       }
@@ -584,13 +635,12 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
   }
   // The reference decodes a gorilla page to its sentinel (float.rs:480-591): a stream that ends
   // without one is an error even when enough values were produced.
-  if (VK != VK_S8B && have_item && n_rows != 0) {
-    GorillaCursor *g = VK == VK_GOR ? &vcur_g : (vcur_a.is_gorilla ? &vcur_a.g : nullptr);
-    if (g && !g->first) {
-      while (!g->done) { if (!g->advance()) g->done = true; }
-      if (g->err) report_error(P, TSKV_ERR_SHORT_BLOCK, page);
-    }
+  if (VK == VK_GOR && have_item && n_rows != 0 && !vcur_g.first) {
+    while (!vcur_g.done) { if (!vcur_g.advance()) vcur_g.done = true; }
+    if (vcur_g.err) report_error(P, TSKV_ERR_SHORT_BLOCK, page);
   }
+  // drain the prefetch rings before the next chunk reuses them
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   // statistics
   n_points = __reduce_add_sync(FULL, n_points);
   n_inrange = __reduce_add_sync(FULL, n_inrange);
@@ -600,21 +650,212 @@ __device__ void scan_chunk(const ScanParams &P, uint32_t item_begin, uint32_t it
   }
 }
 
-// Persistent grid, one kernel instantiation per decode-kind bin (separate register budgets); each
-// warp repeatedly grabs one 32-item chunk of the bin's compacted range.
-template <int TK, int VK>
-__global__ void __launch_bounds__(256, 2) k_scan_aggregate(const __grid_constant__ ScanParams P) {
-  constexpr int bin = TK * N_VK + VK;
+// Segment-wise variant for time pages without nulls (every reference-written page: flush rejects a
+// time column with nulls, mem_cache/series_data.rs:303-340) - the fast path. Per lane:
+//   1. a lean look-ahead loop over the TIMESTAMPS finds the next segment = maximal run of rows whose
+//      (selected by the time ranges, bucket) is the same;
+//   2. the warp flushes finished runs (converged, once per segment instead of once per row);
+//   3. a tight loop decodes the segment's VALUES and accumulates them in registers.
+// Rows of a page are time-sorted (tsm/chunk.rs:100-110), so the first / last row of a run carry its
+// min / max timestamp (what first()/last() pick with sort_to_indices, first.rs:139-148).
+template <int TK, int VK, bool SEL>
+__device__ __noinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
+                                            uint32_t ring_base) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
-  const uint32_t n_chunks = (end0 - begin0 + 31) >> 5;
+  const uint32_t item = item_begin + lane;
+  const bool have_item = item < item_end;
+  const uint32_t tslot = ring_base + lane * 8, vslot = ring_base + RING_WORDS * 256 + lane * 8;
+
+  uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
+  uint8_t pt = TSKV_PT_I64, mask = 0;
+  PageView tpv, vpv;
+  BitCursor vbits;
+  DeltaCursor<TK == TK_RLE ? DK_RLE_SC : DK_S8B_SC, RingStream> tcur;
+  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, RingStream> vcur_d;
+  GorillaCursor<RingStream> vcur_g;
+  bool allnull = false;
+  int64_t pend_t = 0;  // timestamp of row `row`
+
+  if (have_item) {
+    page = P.work_page[item];
+    slot = P.work_slot[item];
+    qcol = P.work_qcol[item] & 0x7f;
+    const tskv_page_desc vd = P.descs[page];
+    const uint32_t tpage = P.time_page_of[page];
+    const tskv_page_desc td = P.descs[tpage];
+    pt = P.cols[qcol].phys_type;
+    mask = P.cols[qcol].agg_mask;
+    tskv_status st = kind_status(vd.reserved);  // the time page is RLE / simple8b here: always decodable
+    if (st != TSKV_OK) {
+      report_error(P, st, page);
+    } else {
+      tpv.open(P.arena, td);
+      vpv.open(P.arena, vd);
+      n_rows = vd.num_values;
+      vbits.init(vpv.bitset);
+      st = tcur.open(tpv, td.reserved, tslot);
+      if (st == TSKV_OK) {
+        if (VK == VK_GOR) st = vcur_g.open(vpv, vslot);
+        else { st = vcur_d.open(vpv, vd.reserved, vslot); allnull = vd.reserved == DK_ALLNULL; }
+      }
+      if (st == TSKV_OK && n_rows) {
+        bool ok = true;
+        pend_t = (int64_t)tcur.next(&ok);
+        if (!ok) st = TSKV_ERR_BITSET_MISMATCH;
+      }
+      if (st != TSKV_OK) { report_error(P, st, st == TSKV_ERR_BITSET_MISMATCH ? tpage : page); n_rows = 0; }
+    }
+  }
+
+  RunAcc acc;
+  acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+  acc.first_ts = acc.last_ts = 0; acc.first_val = acc.last_val = 0; acc.first_ok = acc.last_ok = false;
+  BucketState bk; bk.valid = false; bk.floor_regime = false; bk.lo = 0; bk.hi = 0; bk.idx = 0;
+  bool have_run = false;
+  uint32_t run_idx = 0;
+  uint32_t row = 0;
+  uint32_t n_points = 0, n_inrange = 0;
+  const bool is_f64 = pt == TSKV_PT_F64;
+  const bool mean_hi = !is_f64 && (mask & TSKV_AGG_MEAN);
+  const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
+
+  for (;;) {
+    const bool has = row < n_rows;
+    if (!__any_sync(FULL, has || have_run)) break;
+    // ---- 1. next segment: rows [row, row + n) share (selected, bucket) --------------------------
+    uint32_t n = 0;
+    bool seg_in = false;
+    int64_t seg_first_t = pend_t, seg_last_t = pend_t;
+    if (has) {
+      int64_t lim_lo, lim_hi;
+      seg_in = range_span(P, pend_t, lim_lo, lim_hi);
+      if (seg_in) {
+        if (!(bk.valid && pend_t >= bk.lo && pend_t <= bk.hi) && !locate_bucket(P, pend_t, bk)) {
+          report_error(P, TSKV_ERR_BUCKET_RANGE, page);
+          seg_in = false;
+          bk.valid = false;
+          lim_lo = lim_hi = pend_t;
+        } else {
+          lim_lo = lim_lo > bk.lo ? lim_lo : bk.lo;
+          lim_hi = lim_hi < bk.hi ? lim_hi : bk.hi;
+        }
+      }
+      const uint32_t left = n_rows - row;
+      bool ok = true;
+      do {
+        n++;
+        seg_last_t = pend_t;
+        if (n < left) pend_t = (int64_t)tcur.next(&ok);
+      } while (n < left && ok && pend_t >= lim_lo && pend_t <= lim_hi);
+      if (!ok) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row + n; }
+      if (seg_in) n_inrange += n;
+    }
+    // ---- 2. flush the finished run (warp-converged) ----------------------------------------------
+    const bool newrun = has && seg_in && (!have_run || bk.idx != run_idx);
+    const bool flush = have_run && (newrun || !has);
+    warp_flush<SEL>(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+    if (flush) have_run = false;
+    if (newrun) {
+      have_run = true;
+      run_idx = bk.idx;
+      acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+    }
+    // ---- 3. values of the segment ----------------------------------------------------------------
+    if (has) {
+      bool ok = true;
+      for (uint32_t k = 0; k < n && ok; k++) {
+        const bool vv = vbits.next(row + k) && !allnull;
+        uint64_t v = 0;
+        if (vv) {
+          v = VK == VK_GOR ? vcur_g.next(&ok) : vcur_d.next(&ok);
+          n_points += ok ? 1 : 0;
+        }
+        if (seg_in && ok) {
+          if (SEL) {
+            if (k == 0 && newrun) { acc.first_ts = seg_first_t; acc.first_val = v; acc.first_ok = vv; }
+            if (k == n - 1) { acc.last_ts = seg_last_t; acc.last_val = v; acc.last_ok = vv; }
+          }
+          if (vv) {
+            acc.count++;
+            if (is_f64) acc.sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)acc.sum) + __longlong_as_double((long long)v));
+            else {
+              acc.sum += v;
+              if (mean_hi) acc.sum_hi += (acc.sum < v ? 1 : 0) + (pt == TSKV_PT_I64 ? ((int64_t)v >> 63) : 0);
+            }
+            const int64_t key = okey(v, pt);
+            acc.kmin = key < acc.kmin ? key : acc.kmin;
+            acc.kmax = key > acc.kmax ? key : acc.kmax;
+          }
+        }
+      }
+      if (!ok) {
+        report_error(P, (VK == VK_GOR && vcur_g.err) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
+        n_rows = 0;
+      }
+      row += n;
+    }
+  }
+  if (VK == VK_GOR && have_item && n_rows != 0 && !vcur_g.first) {  // decode to the sentinel (float.rs:480-591)
+    while (!vcur_g.done) { if (!vcur_g.advance()) vcur_g.done = true; }
+    if (vcur_g.err) report_error(P, TSKV_ERR_SHORT_BLOCK, page);
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");  // drain the rings before the next chunk reuses them
+  n_points = __reduce_add_sync(FULL, n_points);
+  n_inrange = __reduce_add_sync(FULL, n_inrange);
+  if (lane == 0) {
+    if (n_points) atomicAdd(&P.stats[0], (unsigned long long)n_points);
+    if (n_inrange) atomicAdd(&P.stats[1], (unsigned long long)n_inrange);
+  }
+}
+
+// Order in which the decode-kind bins are drained: longest tasks first (gorilla, generic, simple8b).
+__constant__ uint8_t c_bin_order[N_BINS] = {TK_S8B * N_VK + VK_GOR, TK_GEN * N_VK + VK_GOR, TK_RLE * N_VK + VK_GOR,
+                                            TK_S8B * N_VK + VK_GEN, TK_GEN * N_VK + VK_GEN, TK_RLE * N_VK + VK_GEN,
+                                            TK_S8B * N_VK + VK_S8B, TK_GEN * N_VK + VK_S8B, TK_RLE * N_VK + VK_S8B};
+
+// The fused decode -> filter -> bucket-reduce kernel. Persistent grid; each warp repeatedly grabs one
+// 32-item chunk (homogeneous in time codec x value codec) from a global counter and runs the matching
+// specialisation. SEL = the query asks for FIRST/LAST.
+template <bool SEL>
+__global__ void __launch_bounds__(256, 2) k_scan_aggregate(const __grid_constant__ ScanParams P) {
+  __shared__ __align__(16) uint64_t s_ring[8][2][RING_WORDS][32];  // 32 KB: per warp, per stream
+  __shared__ uint32_t s_cstart[N_BINS + 1], s_chunk_base[N_BINS + 1];
+  if (threadIdx.x == 0) {
+    for (int k = 0; k <= N_BINS; k++) s_cstart[k] = P.bin_cstart[k];
+    uint32_t base = 0;
+    for (int j = 0; j < N_BINS; j++) {
+      s_chunk_base[j] = base;
+      int b = c_bin_order[j];
+      base += (s_cstart[b + 1] - s_cstart[b] + 31) >> 5;
+    }
+    s_chunk_base[N_BINS] = base;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0][0]);
+  const uint32_t n_chunks = s_chunk_base[N_BINS];
   for (;;) {
     uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(P.task_counter + bin, 1u);
+    if (lane == 0) c = atomicAdd(P.task_counter, 1u);
     c = __shfl_sync(FULL, c, 0);
     if (c >= n_chunks) break;
-    uint32_t begin = begin0 + (c << 5);
-    scan_chunk<TK, VK>(P, begin, min(begin + 32, end0));
+    int j = 0;
+#pragma unroll
+    for (int k = 1; k < N_BINS; k++) j += (c >= s_chunk_base[k]) ? 1 : 0;
+    const int bin = c_bin_order[j];
+    const uint32_t begin = s_cstart[bin] + ((c - s_chunk_base[j]) << 5);
+    const uint32_t end = min(begin + 32, s_cstart[bin + 1]);
+    switch (bin) {
+      case TK_RLE * N_VK + VK_S8B: scan_chunk_seg<TK_RLE, VK_S8B, SEL>(P, begin, end, ring_base); break;
+      case TK_RLE * N_VK + VK_GOR: scan_chunk_seg<TK_RLE, VK_GOR, SEL>(P, begin, end, ring_base); break;
+      case TK_RLE * N_VK + VK_GEN: scan_chunk_seg<TK_RLE, VK_GEN, SEL>(P, begin, end, ring_base); break;
+      case TK_S8B * N_VK + VK_S8B: scan_chunk_seg<TK_S8B, VK_S8B, SEL>(P, begin, end, ring_base); break;
+      case TK_S8B * N_VK + VK_GOR: scan_chunk_seg<TK_S8B, VK_GOR, SEL>(P, begin, end, ring_base); break;
+      case TK_S8B * N_VK + VK_GEN: scan_chunk_seg<TK_S8B, VK_GEN, SEL>(P, begin, end, ring_base); break;
+      case TK_GEN * N_VK + VK_S8B: scan_chunk_rows<TK_GEN, VK_S8B, SEL>(P, begin, end, ring_base); break;
+      case TK_GEN * N_VK + VK_GOR: scan_chunk_rows<TK_GEN, VK_GOR, SEL>(P, begin, end, ring_base); break;
+      default: scan_chunk_rows<TK_GEN, VK_GEN, SEL>(P, begin, end, ring_base); break;
+    }
   }
 }
 
@@ -802,7 +1043,7 @@ __global__ void k_decode_pages(const uint8_t *arena, const tskv_page_desc *descs
     pv.open(arena, d);
     BitCursor bits;
     bits.init(pv.bitset);
-    AnyCursor cur;
+    AnyCursor<> cur;
     st = cur.open(pv, d.reserved);
     const bool allnull = d.reserved == DK_ALLNULL;
     uint32_t wbits = 0;

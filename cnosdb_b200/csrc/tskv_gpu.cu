@@ -29,6 +29,7 @@ struct tskv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // boundaries of the per-bin fused kernels
   int sm_count = 148;
   std::mutex mu;
   std::string err;
@@ -42,7 +43,9 @@ struct tskv_ctx {
 
 struct tskv_pages {
   tskv_ctx *ctx = nullptr;
-  uint8_t *d_arena = nullptr;
+  uint8_t *d_arena = nullptr;       // device copy (or, host-resident mode: gather target)
+  const uint8_t *h_mapped = nullptr; // host-resident mode: device-visible alias of the caller's arena
+  void *h_registered = nullptr;      // range this library page-locked (unregistered on destroy)
   uint64_t arena_len = 0;
   tskv_page_desc *d_descs = nullptr;
   std::vector<tskv_page_desc> h_descs;  // with .reserved = DK kind
@@ -88,7 +91,10 @@ struct tskv_scan {
   unsigned long long *d_counters = nullptr;  // [0] pages [1] bytes
   uint64_t *d_values = nullptr;
   uint8_t *d_validity = nullptr;
-  int grid[N_BINS] = {0};
+  int grid = 0;
+  tskv_ctx *ctx = nullptr;
+  uint32_t n_series_sel = 0;
+  bool enqueued = false;
 };
 
 namespace {
@@ -127,21 +133,6 @@ unsigned bits_for(uint64_t max_value) {  // bits needed to represent values in [
 
 unsigned popc8(unsigned x) { return (unsigned)__builtin_popcount(x & TSKV_AGG_ALL); }
 
-typedef void (*scan_kernel_t)(const ScanParams);
-scan_kernel_t scan_kernel_for_bin(int bin) {
-  switch (bin) {
-    case TK_RLE * N_VK + VK_S8B: return k_scan_aggregate<TK_RLE, VK_S8B>;
-    case TK_RLE * N_VK + VK_GOR: return k_scan_aggregate<TK_RLE, VK_GOR>;
-    case TK_RLE * N_VK + VK_GEN: return k_scan_aggregate<TK_RLE, VK_GEN>;
-    case TK_S8B * N_VK + VK_S8B: return k_scan_aggregate<TK_S8B, VK_S8B>;
-    case TK_S8B * N_VK + VK_GOR: return k_scan_aggregate<TK_S8B, VK_GOR>;
-    case TK_S8B * N_VK + VK_GEN: return k_scan_aggregate<TK_S8B, VK_GEN>;
-    case TK_GEN * N_VK + VK_S8B: return k_scan_aggregate<TK_GEN, VK_S8B>;
-    case TK_GEN * N_VK + VK_GOR: return k_scan_aggregate<TK_GEN, VK_GOR>;
-    default: return k_scan_aggregate<TK_GEN, VK_GEN>;
-  }
-}
-
 tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_output_layout *out) {
   if (!pages || !q || !out || q->n_buckets == 0 || q->n_columns == 0 || !q->columns) return TSKV_ERR_INVALID_ARG;
   if (q->width <= 0 && q->n_buckets != 1) return TSKV_ERR_INVALID_ARG;
@@ -158,24 +149,22 @@ tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_ou
   return TSKV_OK;
 }
 
+// Per-scan buffers are stream-ordered (cudaMallocAsync on the context stream): no device-wide
+// synchronisation on the query path, memory is recycled by the pool.
 void free_scan(tskv_scan *s) {
   if (!s) return;
-  cudaFree(s->d_series);
-  cudaFree(s->d_cg_slot);
-  cudaFree(s->d_item_flag);
-  cudaFree(s->d_block_count);
-  cudaFree(s->d_work_page);
-  cudaFree(s->d_work_slot);
-  cudaFree(s->d_work_qcol);
-  cudaFree(s->d_bin_cstart);
-  cudaFree(s->d_cols);
-  cudaFree(s->d_outs);
-  cudaFree(s->d_means);
-  cudaFree(s->d_state);
-  cudaFree(s->d_task_counter);
-  cudaFree(s->d_values);
-  cudaFree(s->d_validity);
+  cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
+  void *bufs[] = {s->d_series, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
+                  s->d_work_qcol, s->d_bin_cstart, s->d_cols, s->d_outs, s->d_means, s->d_state,
+                  s->d_task_counter, s->d_values, s->d_validity};
+  for (void *b : bufs)
+    if (b) cudaFreeAsync(b, st);
   delete s;
+}
+
+template <typename T>
+cudaError_t stream_alloc(tskv_ctx *ctx, T **p, size_t n) {
+  return cudaMallocAsync(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T), ctx->stream);
 }
 
 // Reads back the device status word; maps it to a message.
@@ -212,6 +201,13 @@ tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
     return TSKV_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+  for (int b = 0; b <= N_BINS; b++) cudaEventCreate(&ctx->ev_bin[b]);
+  // per-scan buffers come from the stream-ordered pool; keep freed memory cached in the pool
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
   *out_ctx = ctx;
   return TSKV_OK;
 }
@@ -225,6 +221,8 @@ void tskvgpu_ctx_destroy(tskv_ctx *ctx) {
   }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int b = 0; b <= N_BINS; b++)
+    if (ctx->ev_bin[b]) cudaEventDestroy(ctx->ev_bin[b]);
   delete ctx;
 }
 
@@ -257,6 +255,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   pg->h_descs.assign(descs, descs + n_descs);
 
   // ---- framing validation + decode-kind classification (+ CRC), parallel over pages ----------
+  std::vector<uint8_t> time_has_nulls(n_descs, 0);
   std::atomic<int> bad_status{0};
   std::atomic<int64_t> bad_page{-1};
   auto fail = [&](int st, int64_t p) {
@@ -286,6 +285,12 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
         return;
       }
       d.reserved = classify_page(h, d.phys_type);
+      if (d.phys_type == TSKV_PT_TIME) {  // the fast time cursors assume a time column without nulls
+        bool all_valid = true;
+        for (uint64_t r = 0; r + 8 <= h.n_rows && all_valid; r += 8) all_valid = h.bitset[r >> 3] == 0xff;
+        for (uint64_t r = h.n_rows & ~7ull; r < h.n_rows && all_valid; r++) all_valid = (h.bitset[r >> 3] >> (r & 7)) & 1;
+        time_has_nulls[i] = all_valid ? 0 : 1;
+      }
     }
   };
   if (nthreads == 1) {
@@ -351,7 +356,8 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
     for (uint32_t k = 0; k < pg->n_items; k++) {
       const tskv_page_desc &vd = pg->h_descs[item_page[k]];
       const tskv_page_desc &td = pg->h_descs[time_page_of[item_page[k]]];
-      uint64_t bin = (uint64_t)time_class(td.reserved) * N_VK + value_class(vd.reserved);
+      int tclass = time_has_nulls[time_page_of[item_page[k]]] ? TK_GEN : time_class(td.reserved);
+      uint64_t bin = (uint64_t)tclass * N_VK + value_class(vd.reserved);
       key[k] = (bin << 48) | ((uint64_t)vd.column_id << 32) | k;
       order[k] = k;
     }
@@ -380,7 +386,18 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   };
   cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&pg->d_arena), arena_len + 64);
   if (e == cudaSuccess) e = cudaMemsetAsync(pg->d_arena + arena_len, 0, 64, ctx->stream);
-  if (e == cudaSuccess && arena_len) e = cudaMemcpyAsync(pg->d_arena, arena, arena_len, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && arena_len && (flags & TSKV_UPLOAD_HOST_RESIDENT)) {
+    // pages stay in (page-locked) host memory like the reference's page cache; each scan pulls the
+    // selected pages over PCIe itself (k_gather_pages)
+    e = cudaHostRegister(const_cast<uint8_t *>(arena), arena_len, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e == cudaSuccess) pg->h_registered = const_cast<uint8_t *>(arena);
+    else if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); e = cudaSuccess; }
+    void *dp = nullptr;
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dp, const_cast<uint8_t *>(arena), 0);
+    pg->h_mapped = static_cast<const uint8_t *>(dp);
+  } else if (e == cudaSuccess && arena_len) {
+    e = cudaMemcpyAsync(pg->d_arena, arena, arena_len, cudaMemcpyHostToDevice, ctx->stream);
+  }
   if (e == cudaSuccess) e = up(&pg->d_descs, pg->h_descs.data(), n_descs);
   if (e == cudaSuccess) e = up(&pg->d_time_page_of, time_page_of.data(), n_descs);
   if (e == cudaSuccess) e = up(&pg->d_cg_time_page, cg_time_page.data(), pg->n_cg);
@@ -396,8 +413,8 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
     long long init[2] = {INT64_MAX, INT64_MIN};
     e = cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && pg->n_cg) {
-      k_time_bounds<<<(pg->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pg->d_arena, pg->d_descs, pg->d_cg_time_page,
-                                                                    pg->n_cg, d_bounds);
+      k_time_bounds<<<(pg->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pg->h_mapped ? pg->h_mapped : pg->d_arena, pg->d_descs,
+                                                                    pg->d_cg_time_page, pg->n_cg, d_bounds);
       e = cudaGetLastError();
     }
     long long b[2] = {INT64_MAX, INT64_MIN};
@@ -424,6 +441,8 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   (void)ctx;
   if (!pg) return;
   if (pg->ctx) cudaSetDevice(pg->ctx->device);
+  if (pg->ctx && pg->ctx->stream) cudaStreamSynchronize(pg->ctx->stream);
+  if (pg->h_registered) cudaHostUnregister(pg->h_registered);
   cudaFree(pg->d_arena);
   cudaFree(pg->d_descs);
   cudaFree(pg->d_time_page_of);
@@ -527,9 +546,9 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     ctx->set_error("invalid query (buckets / columns)");
     return st;
   }
-  if (q->n_columns > 255 || q->n_time_ranges > MAX_RANGES || (q->n_time_ranges && !q->time_ranges) ||
+  if (q->n_columns > 126 || q->n_time_ranges > MAX_RANGES || (q->n_time_ranges && !q->time_ranges) ||
       (q->series_ids == nullptr && q->n_series != 0 && false)) {
-    ctx->set_error("invalid query: at most 255 columns and 8 time ranges");
+    ctx->set_error("invalid query: at most 126 columns and 8 time ranges");
     return TSKV_ERR_INVALID_ARG;
   }
   for (uint32_t c = 0; c < q->n_columns; c++) {
@@ -718,36 +737,42 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     }
   }
 
-  // ---- device allocations --------------------------------------------------------------------------
+  // ---- device allocations (stream-ordered) + query arguments H2D --------------------------------------
   const uint32_t n_items = pages->n_items;
+  s->ctx = ctx;
+  s->n_series_sel = q->series_ids ? q->n_series : 0;
   s->n_blocks = (n_items + 1023) / 1024;
   cudaError_t e = cudaSuccess;
   cudaEventRecord(ctx->ev0, ctx->stream);
+  uint64_t h2d = 0;
   if (q->series_ids) {
-    e = dev_alloc(&s->d_series, q->n_series);
+    e = stream_alloc(ctx, &s->d_series, q->n_series);
     if (e == cudaSuccess && q->n_series)
       e = cudaMemcpyAsync(s->d_series, q->series_ids, (size_t)q->n_series * 4, cudaMemcpyHostToDevice, ctx->stream);
+    h2d += (uint64_t)q->n_series * 4;
   }
-  if (e == cudaSuccess) e = dev_alloc(&s->d_cg_slot, pages->n_cg);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_item_flag, n_items);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_block_count, s->n_blocks);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_work_page, n_items);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_work_slot, n_items);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_work_qcol, n_items);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_bin_cstart, N_BINS + 2);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_cols, cols.size());
-  if (e == cudaSuccess) e = dev_alloc(&s->d_outs, outs.size());
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_cg_slot, pages->n_cg);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_item_flag, n_items);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_block_count, s->n_blocks);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_work_page, n_items);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_work_slot, n_items);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_work_qcol, n_items);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_bin_cstart, N_BINS + 2);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_cols, cols.size());
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_outs, outs.size());
   s->n_means = (uint32_t)means.size();
-  if (e == cudaSuccess) e = dev_alloc(&s->d_means, means.size());
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_means, means.size());
   if (e == cudaSuccess && !means.empty())
     e = cudaMemcpyAsync(s->d_means, means.data(), means.size() * sizeof(MeanExport), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_state, sl.total);
-  // task counters [N_BINS x u32, padded to 8 x u64] | status | err_page | stats[2] | counters[2]
-  if (e == cudaSuccess) e = dev_alloc(reinterpret_cast<unsigned long long **>(&s->d_task_counter), 16);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_values, L.n_out * L.n_cells);
-  if (e == cudaSuccess) e = dev_alloc(&s->d_validity, L.validity_bytes + 8);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_state, sl.total);
+  // aux block (8-byte units): [0..7] task counters (N_BINS x u32) | 8 status | 9 err_page | 10,11 stats
+  //                           | 12 pages 13 bytes 14..22 per-bin bytes
+  if (e == cudaSuccess) e = stream_alloc(ctx, reinterpret_cast<unsigned long long **>(&s->d_task_counter), 24);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_values, L.n_out * L.n_cells);
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_validity, L.validity_bytes + 8);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_cols, cols.data(), cols.size() * sizeof(ColState), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_outs, outs.data(), outs.size() * sizeof(OutCol), cudaMemcpyHostToDevice, ctx->stream);
+  h2d += cols.size() * sizeof(ColState) + outs.size() * sizeof(OutCol) + means.size() * sizeof(MeanExport) + sizeof(ScanParams);
   if (e != cudaSuccess) {
     ctx->set_error(std::string("scan_prepare: ") + cudaGetErrorString(e));
     free_scan(s);
@@ -758,29 +783,6 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   s->d_err_page = aux + 9;
   s->d_stats = aux + 10;
   s->d_counters = aux + 12;
-  cudaMemsetAsync(aux, 0, 16 * 8, ctx->stream);
-  cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream);
-
-  // ---- selection -> compacted work list -------------------------------------------------------------
-  uint64_t launches = 0;
-  if (pages->n_cg) {
-    k_select_cg<<<(pages->n_cg + 255) / 256, 256, 0, ctx->stream>>>(pages->d_descs, pages->d_cg_time_page, pages->n_cg,
-                                                                     s->d_series, q->series_ids ? q->n_series : 0,
-                                                                     pages->d_cg_series_rank, s->d_cg_slot);
-    launches++;
-  }
-  if (n_items) {
-    k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_page, pages->d_item_cg,
-                                                        pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
-                                                        q->n_columns, s->d_item_flag, s->d_block_count, s->d_counters,
-                                                        s->d_status);
-    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(s->d_block_count, s->n_blocks, s->d_bin_cstart + N_BINS + 1);
-    k_scatter_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_item_page, pages->d_item_cg, n_items, s->d_item_flag,
-                                                           s->d_block_count, s->d_cg_slot, pages->d_bin_start,
-                                                           s->d_work_page, s->d_work_slot, s->d_work_qcol,
-                                                           s->d_bin_cstart, s->d_bin_cstart + N_BINS + 1);
-    launches += 3;
-  }
   cudaEventRecord(ctx->ev1, ctx->stream);
 
   // ---- kernel parameters ------------------------------------------------------------------------------
@@ -810,68 +812,123 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   P.slot_max = slot_bits ? (uint32_t)((1ull << slot_bits) - 1) : 0;
   P.rel_base = rel_base;
 
-  for (int b = 0; b < N_BINS; b++) {
+  {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel_for_bin(b), 256, 0);
-    s->grid[b] = std::max(1, per_sm) * ctx->sm_count;
+    if (s->has_sel) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_aggregate<true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_aggregate<false>, 256, 0);
+    s->grid = std::max(1, per_sm) * ctx->sm_count;
   }
-
-  st = fetch_status(ctx, s->d_status, s->d_err_page);
-  if (st != TSKV_OK) {
-    if (st == TSKV_ERR_INVALID_ARG) ctx->set_error("page type does not match the query column type", ctx->err_page);
-    free_scan(s);
-    return st;
-  }
-  unsigned long long cnt[2] = {0, 0};
-  cudaMemcpy(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-  ctx->counters.elapsed_h2d_ms = ms;
-  ctx->counters.page_read_count = cnt[0];
-  ctx->counters.page_read_bytes = cnt[1];
-  ctx->counters.kernel_launches = launches;
+  ctx->counters.h2d_bytes = h2d;
   *out_scan = s;
   return TSKV_OK;
+}
+
+// Enqueues one full pass on the context stream, no host synchronisation:
+//   selection -> compacted work list -> (host-resident arenas: PCIe gather of the selected pages)
+//   -> state init -> one fused decode/filter/reduce kernel per decode-kind bin -> export.
+static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
+  const tskv_pages *pages = s->pages;
+  const uint32_t n_items = pages->n_items;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
+  CU_TRY(ctx, cudaMemsetAsync(aux, 0, 24 * 8, ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream));
+  uint64_t launches = 0;
+  if (pages->n_cg) {
+    k_select_cg<<<(pages->n_cg + 255) / 256, 256, 0, ctx->stream>>>(pages->d_descs, pages->d_cg_time_page, pages->n_cg,
+                                                                     s->d_series, s->n_series_sel,
+                                                                     pages->d_cg_series_rank, s->d_cg_slot);
+    launches++;
+  }
+  if (n_items) {
+    k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_page, pages->d_item_cg,
+                                                        pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
+                                                        s->n_cols, pages->d_bin_start, s->d_item_flag,
+                                                        s->d_block_count, s->d_counters, s->d_status);
+    k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(s->d_block_count, s->n_blocks, s->d_bin_cstart + N_BINS + 1);
+    k_scatter_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_item_page, pages->d_item_cg, n_items, s->d_item_flag,
+                                                           s->d_block_count, s->d_cg_slot, pages->d_bin_start,
+                                                           s->d_work_page, s->d_work_slot, s->d_work_qcol,
+                                                           s->d_bin_cstart, s->d_bin_cstart + N_BINS + 1);
+    launches += 3;
+    if (pages->h_mapped) {
+      k_gather_pages<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(pages->h_mapped, pages->d_arena, pages->d_descs,
+                                                                 pages->d_time_page_of, s->d_work_page, s->d_work_qcol,
+                                                                 s->d_bin_cstart + N_BINS + 1);
+      launches++;
+    }
+  }
+  uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
+  k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
+  launches++;
+  cudaEventRecord(ctx->ev_bin[0], ctx->stream);
+  if (n_items) {
+    // an upper bound of the work (the compacted list is a subset of the items) sizes the grid
+    uint32_t grid = std::min<uint32_t>((uint32_t)s->grid, std::max(1u, (n_items / 32 + 7) / 8));
+    if (s->has_sel) k_scan_aggregate<true><<<grid, 256, 0, ctx->stream>>>(s->params);
+    else k_scan_aggregate<false><<<grid, 256, 0, ctx->stream>>>(s->params);
+    launches++;
+  }
+  cudaEventRecord(ctx->ev_bin[N_BINS], ctx->stream);
+  if (s->has_sel || s->n_means) {
+    uint64_t work = std::max(std::max(s->sl.first_cells, s->sl.last_cells), s->n_means ? s->layout.n_cells : 0);
+    uint32_t b = (uint32_t)std::min<uint64_t>((work + 255) / 256, 4096);
+    k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl, s->d_means, s->n_means, s->layout.n_cells);
+    launches++;
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  CU_TRY(ctx, cudaGetLastError());
+  ctx->counters.kernel_launches = launches;
+  s->enqueued = true;
+  return TSKV_OK;
+}
+
+// Waits for the stream, surfaces device-side decode errors and refreshes the counters.
+static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
+  tskv_status st = fetch_status(ctx, s->d_status, s->d_err_page);
+  if (st != TSKV_OK) {
+    if (st == TSKV_ERR_INVALID_ARG) ctx->set_error("page type does not match the query column type", ctx->err_page);
+    return st;
+  }
+  unsigned long long aux[14] = {0};  // stats[2], pages, bytes, per-bin bytes[9] (+1 spare)
+  CU_TRY(ctx, cudaMemcpy(aux, s->d_stats, 13 * 8, cudaMemcpyDeviceToHost));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->counters.elapsed_scan_ms = ms;
+  ctx->counters.points_decoded = aux[0];
+  ctx->counters.rows_in_range = aux[1];
+  ctx->counters.page_read_count = aux[2];
+  ctx->counters.page_read_bytes = aux[3];
+  float fused = 0;
+  cudaEventElapsedTime(&fused, ctx->ev_bin[0], ctx->ev_bin[N_BINS]);
+  ctx->counters.elapsed_fused_ms = fused;
+  ctx->counters.dominant_kernel_ms = fused;          // one fused kernel per scan
+  ctx->counters.dominant_kernel_bytes = aux[3];
+  ctx->counters.dominant_kernel_bin = 0;
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_enqueue(tskv_ctx *ctx, tskv_scan *s) {
+  if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return enqueue_scan(ctx, s);
+}
+
+tskv_status tskvgpu_scan_sync(tskv_ctx *ctx, tskv_scan *s) {
+  if (!ctx || !s || !s->enqueued) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  return sync_scan(ctx, s);
 }
 
 tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *s) {
   if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
   cudaSetDevice(ctx->device);
-  cudaEventRecord(ctx->ev0, ctx->stream);
-  unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
-  CU_TRY(ctx, cudaMemsetAsync(aux, 0, 12 * 8, ctx->stream));  // task counters, status, err page, stats
-  uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
-  k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
-  uint64_t launches = 1;
-  for (int b = 0; b < N_BINS; b++) {
-    // the compacted bin is a subset of the arena's bin: skip kinds the arena does not contain
-    uint32_t n_bin = s->pages->h_bin_start[b + 1] - s->pages->h_bin_start[b];
-    if (n_bin == 0) continue;
-    uint32_t chunks = (n_bin + 31) / 32;
-    uint32_t grid = std::min<uint32_t>((uint32_t)s->grid[b], (chunks + 7) / 8);
-    void *args[] = {(void *)&s->params};
-    CU_TRY(ctx, cudaLaunchKernel((const void *)scan_kernel_for_bin(b), dim3(grid), dim3(256), args, 0, ctx->stream));
-    launches++;
-  }
-  const bool need_export = s->has_sel || s->n_means;
-  if (need_export) {
-    uint64_t work = std::max(std::max(s->sl.first_cells, s->sl.last_cells), s->n_means ? s->layout.n_cells : 0);
-    uint32_t b = (uint32_t)std::min<uint64_t>((work + 255) / 256, 4096);
-    k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl, s->d_means, s->n_means, s->layout.n_cells);
-  }
-  cudaEventRecord(ctx->ev1, ctx->stream);
-  tskv_status st = fetch_status(ctx, s->d_status, s->d_err_page);
+  tskv_status st = enqueue_scan(ctx, s);
   if (st != TSKV_OK) return st;
-  unsigned long long stats[2] = {0, 0};
-  CU_TRY(ctx, cudaMemcpy(stats, s->d_stats, 16, cudaMemcpyDeviceToHost));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-  ctx->counters.elapsed_scan_ms = ms;
-  ctx->counters.points_decoded = stats[0];
-  ctx->counters.rows_in_range = stats[1];
-  ctx->counters.kernel_launches = launches + (need_export ? 1 : 0);
-  return TSKV_OK;
+  return sync_scan(ctx, s);
 }
 
 tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *s, tskv_partials_view *out) {
@@ -900,7 +957,6 @@ tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *s) {
   if (s->has_sel) {
     k_snapshot_keys<<<256, 256, 0, ctx->stream>>>(s->d_state, s->sl);
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return TSKV_OK;
 }
@@ -912,7 +968,6 @@ tskv_status tskvgpu_scan_mask_values(tskv_ctx *ctx, tskv_scan *s) {
   if (s->has_sel) {
     k_mask_values<<<256, 256, 0, ctx->stream>>>(s->d_state, s->sl);
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return TSKV_OK;
 }
@@ -945,7 +1000,6 @@ tskv_status tskvgpu_scan_finalize_device(tskv_ctx *ctx, tskv_scan *s, uint64_t *
   cudaSetDevice(ctx->device);
   tskv_status st = finalize_device(ctx, s);
   if (st != TSKV_OK) return st;
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (out_values_dptr) *out_values_dptr = (uint64_t)(uintptr_t)s->d_values;
   if (out_validity_dptr) *out_validity_dptr = (uint64_t)(uintptr_t)s->d_validity;
   return TSKV_OK;
@@ -962,13 +1016,9 @@ tskv_status tskvgpu_scan_aggregate(tskv_ctx *ctx, const tskv_pages *pages, const
   tskv_scan *s = nullptr;
   tskv_status st = tskvgpu_scan_prepare(ctx, pages, q, &s);
   if (st != TSKV_OK) return st;
-  tskv_counters c0 = ctx->counters;
   st = tskvgpu_scan_run(ctx, s);
   if (st == TSKV_OK) st = tskvgpu_scan_finalize(ctx, s, out_values, out_validity);
-  ctx->counters.page_read_count = c0.page_read_count;
-  ctx->counters.page_read_bytes = c0.page_read_bytes;
-  ctx->counters.elapsed_h2d_ms = c0.elapsed_h2d_ms;
-  ctx->counters.kernel_launches += c0.kernel_launches + 1;
+  ctx->counters.kernel_launches += 1;
   tskvgpu_scan_destroy(ctx, s);
   return st;
 }

@@ -143,6 +143,13 @@ class PreparedScan:
     def run(self):
         self.engine._check(self.engine.lib.tskvgpu_scan_run(self.engine.ctx, self.handle))
 
+    def enqueue(self):
+        """Launches one full pass on the engine stream without synchronising the host."""
+        self.engine._check(self.engine.lib.tskvgpu_scan_enqueue(self.engine.ctx, self.handle))
+
+    def sync(self):
+        self.engine._check(self.engine.lib.tskvgpu_scan_sync(self.engine.ctx, self.handle))
+
     def partials(self):
         v = cabi.PartialsView()
         self.engine._check(self.engine.lib.tskvgpu_scan_partials(self.engine.ctx, self.handle, C.byref(v)))
@@ -219,8 +226,10 @@ class Engine:
         self._check(self.lib.tskvgpu_get_counters(self.ctx, C.byref(c)))
         return {k: getattr(c, k) for k, _ in cabi.Counters._fields_ if k != "reserved"}
 
-    def upload_pages(self, arena, descs, verify_crc=True):
-        """arena: uint8 array (or (ptr, len)); descs: array of PAGE_DESC_DTYPE."""
+    def upload_pages(self, arena, descs, verify_crc=True, host_resident=False):
+        """arena: uint8 array (or (ptr, len)); descs: array of PAGE_DESC_DTYPE.
+        host_resident=True keeps the page bytes in (page-locked) host memory: every scan then pulls the
+        selected pages over PCIe itself; the caller must keep `arena` alive until PageSet.close()."""
         if isinstance(arena, tuple):
             aptr, alen = arena
         else:
@@ -228,10 +237,12 @@ class Engine:
             aptr, alen = arena.ctypes.data, arena.size
         descs = np.ascontiguousarray(descs, dtype=cabi.PAGE_DESC_DTYPE)
         h = C.c_void_p()
-        st = self.lib.tskvgpu_upload_pages(self.ctx, aptr, alen, descs.ctypes.data, len(descs),
-                                           cabi.TSKV_UPLOAD_VERIFY_CRC if verify_crc else 0, C.byref(h))
+        flags = (cabi.TSKV_UPLOAD_VERIFY_CRC if verify_crc else 0) | (cabi.TSKV_UPLOAD_HOST_RESIDENT if host_resident else 0)
+        st = self.lib.tskvgpu_upload_pages(self.ctx, aptr, alen, descs.ctypes.data, len(descs), flags, C.byref(h))
         self._check(st)
-        return PageSet(self, h, len(descs))
+        ps = PageSet(self, h, len(descs))
+        ps._keep = arena if host_resident else None
+        return ps
 
     def decode_pages(self, pages, descs, first_page=0, n_pages=None):
         """Page::to_arrow_array for a page range: returns a list of (u64 values, bool validity)."""

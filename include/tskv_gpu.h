@@ -132,7 +132,7 @@ typedef struct tskv_query {
   uint32_t n_buckets;         /* >= 1 (1 when width <= 0) */
   uint32_t group_by_series;   /* 0: GROUP BY bucket ; 1: GROUP BY series, bucket */
   const tskv_agg_column *columns;
-  uint32_t n_columns;
+  uint32_t n_columns;         /* 1..126 */
   uint32_t reserved;
 } tskv_query;
 
@@ -160,7 +160,11 @@ typedef struct tskv_counters {
   double elapsed_scan_ms;       /* device time of the last scan (CUDA events) */
   double elapsed_h2d_ms;        /* host->device time of the last upload / query arguments */
   uint64_t kernel_launches;     /* kernels launched by the last call */
-  uint64_t reserved[5];
+  double elapsed_fused_ms;      /* device time of the fused decode/filter/reduce kernels alone */
+  double dominant_kernel_ms;    /* slowest fused kernel (one per decode-kind bin) of the last scan */
+  uint64_t dominant_kernel_bytes; /* encoded page bytes that kernel read (its algorithmic bytes) */
+  uint64_t dominant_kernel_bin; /* time-codec class * 3 + value-codec class */
+  uint64_t h2d_bytes;           /* query arguments copied host->device by the last prepare */
 } tskv_counters;
 
 typedef struct tskv_ctx tskv_ctx;       /* one CUDA device + stream */
@@ -182,7 +186,15 @@ uint64_t tskvgpu_ctx_stream(const tskv_ctx *ctx);
  * Replaces TsmReader::read_adjacent_pages + Page::crc_validation (tskv/src/tsm/reader.rs:236-264,
  * page.rs:58-76): copies `arena` to the device, validates framing, optionally verifies each
  * page's CRC32 (flags & TSKV_UPLOAD_VERIFY_CRC) like the reference does on every read. */
-enum { TSKV_UPLOAD_VERIFY_CRC = 1u };
+enum {
+  TSKV_UPLOAD_VERIFY_CRC = 1u,
+  /* Keep the page bytes in the caller's host memory (page-locked by the library; the caller must keep
+   * `arena` alive and unchanged until tskvgpu_pages_destroy) and let every scan pull only the
+   * selected pages over PCIe — the analogue of the reference reading pages of the selected series
+   * from the page cache on each query. Descriptor tables still live on the device (TsmReader
+   * metadata is cached in the reference too: tsfamily/version.rs:158-172). */
+  TSKV_UPLOAD_HOST_RESIDENT = 2u
+};
 tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t arena_len,
                                  const tskv_page_desc *descs, uint64_t n_descs, uint32_t flags,
                                  tskv_pages **out_pages);
@@ -232,6 +244,10 @@ typedef struct tskv_partials_view {
 tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const tskv_query *q,
                                  tskv_scan **out_scan);
 tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *scan);
+/* scan_run == scan_enqueue (launches only, no host synchronisation; safe to call repeatedly) followed
+ * by scan_sync (waits, reports device-side decode errors, refreshes the counters). */
+tskv_status tskvgpu_scan_enqueue(tskv_ctx *ctx, tskv_scan *scan);
+tskv_status tskvgpu_scan_sync(tskv_ctx *ctx, tskv_scan *scan);
 tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *scan, tskv_partials_view *out);
 /* Snapshot the local first/last keys before they are all-reduced in place (multi-GPU only). */
 tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *scan);

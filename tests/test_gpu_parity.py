@@ -199,11 +199,17 @@ def test_scan_c4_shape(engine):
     sel = ids[((ids * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(32)) % np.uint64(10) == 0].astype(np.uint32)
     w = 60_000_000_000
     fbs, nb = bucket_spec(datagen.TSBS_T0 - 1_000_000, datagen.TSBS_T0 + 999 * datagen.TSBS_STEP + 1_000_000, w)
-    for pt in (cabi.TSKV_PT_I64, cabi.TSKV_PT_F64):
-        sub = sel[(sel % 2) == (0 if pt == cabi.TSKV_PT_I64 else 1)]
-        q = QueryOption([PushedAggregate(1, pt, ALL_AGGS)], series_ids=sub, width=w, first_bucket_start=fbs, n_buckets=nb)
-        got, exp = engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8)
-        assert_results_equal(got, exp, what="C4")
+    # even ids carry the i64 column 1, odd ids the f64 column 2 (a column absent from a group is skipped)
+    q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_I64, ALL_AGGS), PushedAggregate(2, cabi.TSKV_PT_F64, ALL_AGGS)],
+                    series_ids=sel, width=w, first_bucket_start=fbs, n_buckets=nb)
+    got, exp = engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=8)
+    assert_results_equal(got, exp, what="C4")
+    assert engine.counters()["points_decoded"] > 0.99 * len(sel) * 1000
+    # the same scan with the pages left in host memory (PCIe gather of the selected pages per query)
+    hp = engine.upload_pages(g.arena, g.descs, host_resident=True)
+    assert_results_equal(engine.scan_aggregate(hp, q), exp, what="C4 host-resident")
+    assert engine.counters()["page_read_bytes"] < 0.2 * g.arena.size
+    hp.close()
     pages.close()
 
 
