@@ -175,6 +175,10 @@ __device__ __forceinline__ uint64_t pow10_u64(uint32_t k) {
 // ------------------------------------------------------------------------------------------------
 // Delta-family cursor: RLE / simple8b / raw prefix sum / raw BE, zig-zag or scaled.
 // KIND is one of the DK_* delta kinds, or -1 for a runtime switch on `kind` (generic path).
+// next() has no "first value" special case: open() arranges the state so that the first call
+// yields the page's first value (RLE: v = first - delta; simple8b: one fake zero delta queued).
+// Running out of encoded values sets the sticky `exhausted` flag (and yields garbage): callers check
+// it once per segment / page instead of once per value.
 // ------------------------------------------------------------------------------------------------
 template <int KIND, typename STREAM = BeStream>
 struct DeltaCursor {
@@ -183,11 +187,13 @@ struct DeltaCursor {
   uint64_t delta;       // RLE delta (already scaled / zig-zag decoded)
   uint64_t scaler;      // S8B_SC
   uint64_t w;           // current simple8b word, consumed from the low bits
+  uint64_t mask;        // low `bits` bits
   uint32_t words_left;  // 8-byte words not yet loaded
   uint32_t in_word;     // values left in `w`
-  uint32_t bits;        // width of one value in `w` (0 => run of ones)
+  uint32_t bits;        // width of one value in `w`
+  uint32_t ones;        // 1 for the run-of-ones selectors (payload ignored), else 0
   uint8_t kind;         // runtime kind (== KIND when KIND >= 0)
-  bool first;           // next value is the first of the page
+  bool exhausted;
 
   __device__ __forceinline__ int k() const { return KIND >= 0 ? KIND : kind; }
 
@@ -195,28 +201,30 @@ struct DeltaCursor {
   // classified the page, so lengths needed by the fixed header are guaranteed.
   __device__ inline tskv_status open(const PageView &pv, uint8_t kind_, uint32_t smem_slot = 0) {
     kind = KIND >= 0 ? (uint8_t)KIND : kind_;
-    first = true;
+    exhausted = false;
     v = 0;
     delta = 0;
     scaler = 1;
     w = 0;
+    mask = 0;
     in_word = 0;
     bits = 0;
+    ones = 0;
     words_left = 0;
     const uint8_t *d = pv.data;
     switch (k()) {
       case DK_RLE_SC: {  // timestamp.rs:226-259: data = id | kind/scaler | first(8) | varint delta | varint n
         uint64_t dl;
         if (!decode_varint(d + 10, pv.data_len - 10, &dl)) return TSKV_ERR_SHORT_BLOCK;
-        v = load_be64(d + 2);
         delta = dl * pow10_u64(__ldg(d + 1) & 0xf);
+        v = load_be64(d + 2) - delta;
         break;
       }
       case DK_RLE_ZZ: {  // integer.rs:186-214
         uint64_t dl;
         if (!decode_varint(d + 10, pv.data_len - 10, &dl)) return TSKV_ERR_SHORT_BLOCK;
-        v = (uint64_t)zigzag_dec(load_be64(d + 2));
         delta = (uint64_t)zigzag_dec(dl);
+        v = (uint64_t)zigzag_dec(load_be64(d + 2)) - delta;
         break;
       }
       case DK_S8B_SC:  // timestamp.rs:261-299
@@ -224,11 +232,13 @@ struct DeltaCursor {
         bs.init(d + 2, smem_slot);
         v = bs.next();
         words_left = (pv.data_len - 10) >> 3;
+        in_word = 1;  // fake zero delta in front of the packed ones
         break;
       case DK_S8B_ZZ:  // integer.rs:216-248
         bs.init(d + 2, smem_slot);
         v = (uint64_t)zigzag_dec(bs.next());
         words_left = (pv.data_len - 10) >> 3;
+        in_word = 1;
         break;
       case DK_RAW_SC:  // timestamp.rs:201-224
       case DK_RAW_ZZ:  // integer.rs:165-184
@@ -245,87 +255,62 @@ struct DeltaCursor {
     return TSKV_OK;
   }
 
-  // Next simple8b payload value (simple8b.rs:95-208). Sets *ok=false when the words run out.
-  __device__ __forceinline__ uint64_t next_packed(bool *ok) {
-    if (in_word == 0) {
-      if (words_left == 0) {
-        *ok = false;
-        return 0;
-      }
-      words_left--;
-      w = bs.next();
-      uint32_t sel = (uint32_t)(w >> 60);
-      in_word = c_s8b_count[sel];
-      bits = c_s8b_bits[sel];
-      w &= 0x0fffffffffffffffull;
+  __device__ __forceinline__ void refill() {
+    if (words_left == 0) {
+      exhausted = true;
+      in_word = 0x7fffffff;  // keep yielding zeros without refilling again
+      w = 0; mask = 0; bits = 0; ones = 0;
+      return;
     }
+    words_left--;
+    w = bs.next();
+    const uint32_t sel = (uint32_t)(w >> 60);
+    in_word = c_s8b_count[sel];
+    bits = c_s8b_bits[sel];
+    ones = sel < 2 ? 1u : 0u;
+    mask = bits ? (~0ull >> (64 - bits)) : 0ull;
+  }
+  // Next simple8b payload value (simple8b.rs:95-208).
+  __device__ __forceinline__ uint64_t next_packed() {
+    if (in_word == 0) refill();
     in_word--;
-    uint64_t mask = bits ? (~0ull >> (64 - bits)) : 0ull;
-    uint64_t u = bits ? (w & mask) : 1ull;
+    const uint64_t u = (w & mask) | ones;
     w >>= bits;  // bits <= 60
     return u;
   }
+  __device__ __forceinline__ uint64_t next_word() {
+    if (words_left == 0) {
+      exhausted = true;
+      return 0;
+    }
+    words_left--;
+    return bs.next();
+  }
 
-  // Value for the next VALID row. *ok=false => more valid rows than encoded values.
-  __device__ __forceinline__ uint64_t next(bool *ok) {
+  // Value for the next VALID row.
+  __device__ __forceinline__ uint64_t next() {
     switch (k()) {
       case DK_RLE_SC:
-      case DK_RLE_ZZ:
-        if (!first) v += delta;
-        first = false;
-        return v;
-      case DK_S8B_SC:
-        if (!first) {
-          uint64_t u = next_packed(ok);
-          v += u * scaler;
-        }
-        first = false;
-        return v;
-      case DK_S8B_ZZ:
-        if (!first) {
-          uint64_t u = next_packed(ok);
-          v += (uint64_t)zigzag_dec(u);
-        }
-        first = false;
-        return v;
-      case DK_RAW_SC:
-        if (words_left == 0) {
-          *ok = false;
-          return 0;
-        }
-        words_left--;
-        v += bs.next();
-        return v;
-      case DK_RAW_ZZ:
-        if (words_left == 0) {
-          *ok = false;
-          return 0;
-        }
-        words_left--;
-        v += (uint64_t)zigzag_dec(bs.next());
-        return v;
-      case DK_RAWBE:
-        if (words_left == 0) {
-          *ok = false;
-          return 0;
-        }
-        words_left--;
-        return bs.next();
-      default:  // DK_ALLNULL and error kinds never reach here with a valid bit
-        *ok = false;
-        return 0;
+      case DK_RLE_ZZ: v += delta; return v;
+      case DK_S8B_SC: v += next_packed() * scaler; return v;
+      case DK_S8B_ZZ: v += (uint64_t)zigzag_dec(next_packed()); return v;
+      case DK_RAW_SC: v += next_word(); return v;
+      case DK_RAW_ZZ: v += (uint64_t)zigzag_dec(next_word()); return v;
+      case DK_RAWBE: return next_word();
+      default: exhausted = true; return 0;  // DK_ALLNULL never reaches here with a valid bit
     }
   }
 
   // timestamp.rs:273-279 quirk: with simple8b timestamps a NULL row 0 swallows the first value.
   __device__ __forceinline__ void skip_first_if_s8b_sc() {
-    if (k() == DK_S8B_SC) first = false;
+    if (k() == DK_S8B_SC) in_word = 0;
   }
 };
 
 // ------------------------------------------------------------------------------------------------
 // Gorilla cursor (float.rs:418-606): MSB-first bit stream after id | 0x10 | first(8).
-// Terminates on the sentinel 0x7ff8_0000_0000_00ff (float.rs:16).
+// Terminates on the sentinel 0x7ff8_0000_0000_00ff (float.rs:16). Like DeltaCursor, the first next()
+// needs no special case: a fake "repeat" control bit is queued in front of the stream.
 // ------------------------------------------------------------------------------------------------
 template <typename STREAM = BeStream>
 struct GorillaCursor {
@@ -333,13 +318,12 @@ struct GorillaCursor {
   uint64_t val;
   uint64_t hi, lo;     // 128-bit window of the MSB-first bit stream; `pos` bits of hi are consumed
   uint32_t pos;        // 0..63
-  uint32_t bits_used;  // bits consumed so far
-  uint32_t bits_total; // (data_len - 10) * 8
+  uint32_t bits_used;  // bits consumed so far (incl. the fake one)
+  uint32_t bits_total; // (data_len - 10) * 8 + 1
   uint32_t trailing, meaningful;
-  bool first, done, err;
+  bool done, err;      // done: sentinel reached or error; err: stream ended before the sentinel
 
   __device__ inline tskv_status open(const PageView &pv, uint32_t smem_slot = 0) {
-    first = true;
     done = false;
     err = false;
     trailing = 0;
@@ -347,13 +331,14 @@ struct GorillaCursor {
     const uint8_t *d = pv.data;
     bs.init(d + 2, smem_slot);
     val = bs.next();
-    hi = bs.next();
+    hi = 0;  // its last bit is the fake control bit 0 = "repeat the previous value"
     lo = bs.next();
-    pos = 0;
+    pos = 63;
     bits_used = 0;
-    bits_total = (pv.data_len - 10) * 8;
+    bits_total = (pv.data_len - 10) * 8 + 1;
     return TSKV_OK;
   }
+  __device__ __forceinline__ bool consumed_any() const { return bits_used != 0; }
 
   // Next 64 bits of the stream, MSB-aligned, without consuming them.
   __device__ __forceinline__ uint64_t peek() const { return (hi << pos) | ((lo >> 1) >> (63 - pos)); }
@@ -371,7 +356,7 @@ struct GorillaCursor {
   // Decodes the next stream element; returns false at the sentinel / on error
   // ("unexpected end of block": the stream ended before the sentinel).
   __device__ __forceinline__ bool advance() {
-    uint32_t x = (uint32_t)(peek() >> 51);  // 13 bits: c0 c1 lead[5] sig[6]
+    const uint32_t x = (uint32_t)(peek() >> 51);  // 13 bits: c0 c1 lead[5] sig[6]
     if (!(x & 0x1000)) {
       skip(1);  // repeat previous value
     } else {
@@ -379,7 +364,7 @@ struct GorillaCursor {
         skip(2);  // reuse the previous (leading, trailing) window
       } else {
         skip(13);
-        uint32_t leading = (x >> 6) & 0x1f;
+        const uint32_t leading = (x >> 6) & 0x1f;
         meaningful = x & 0x3f;
         if (meaningful > 0) {
           trailing = (uint8_t)(64 - leading - meaningful);  // u8 arithmetic like the reference
@@ -388,7 +373,7 @@ struct GorillaCursor {
           meaningful = 64;
         }
       }
-      uint64_t s = peek() >> (64 - meaningful);
+      const uint64_t s = peek() >> (64 - meaningful);
       skip(meaningful);
       val ^= s << (trailing & 0x3f);
     }
@@ -399,22 +384,22 @@ struct GorillaCursor {
     return val != 0x7ff80000000000ffull;
   }
 
-  // Value for the next VALID row; *ok=false => stream ended before the bitset did.
-  __device__ __forceinline__ uint64_t next(bool *ok) {
-    if (first) {
-      first = false;
-      return val;
-    }
-    if (done || !advance()) {
-      done = true;
-      *ok = false;
-      return 0;
-    }
+  // Value for the next VALID row; sets `done` when the stream ended before the bitset did.
+  __device__ __forceinline__ uint64_t next() {
+    if (done || !advance()) done = true;
     return val;
+  }
+  // The reference decodes to the sentinel (float.rs:480-591): a stream without one is an error even
+  // when enough values were produced. Returns false on "unexpected end of block".
+  __device__ __forceinline__ bool drain() {
+    while (!done) {
+      if (!advance()) done = true;
+    }
+    return !err;
   }
 };
 
-// Runtime-dispatched cursor over every supported kind (decode-only kernel and generic scan path).
+// Runtime-dispatched cursor over every supported kind (decode-only kernel).
 template <typename STREAM = BeStream>
 struct AnyCursor {
   DeltaCursor<-1, STREAM> d;
@@ -425,7 +410,9 @@ struct AnyCursor {
     if (is_gorilla) return g.open(pv, smem_slot);
     return d.open(pv, kind, smem_slot);
   }
-  __device__ __forceinline__ uint64_t next(bool *ok) { return is_gorilla ? g.next(ok) : d.next(ok); }
+  __device__ __forceinline__ uint64_t next() { return is_gorilla ? g.next() : d.next(); }
+  // more valid rows than encoded values (BITSET_MISMATCH) / truncated stream (SHORT_BLOCK)
+  __device__ __forceinline__ bool failed() const { return is_gorilla ? g.done : d.exhausted; }
   __device__ __forceinline__ bool stream_error() const { return is_gorilla && g.err; }
 };
 

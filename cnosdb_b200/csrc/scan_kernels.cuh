@@ -54,7 +54,7 @@ struct ScanParams {
   const uint32_t *bin_cstart;  // [N_BINS + 1] starts of the kind bins in the work list
   const ColState *cols;
   uint64_t *state;
-  uint32_t *task_counter;       // dynamic chunk scheduler
+  uint32_t *task_counter;       // [N_BINS] dynamic chunk schedulers
   int32_t *status;              // first error (0 = ok)
   unsigned long long *err_page; // page of the first error
   unsigned long long *stats;    // [0] points decoded, [1] rows in range
@@ -335,6 +335,33 @@ __device__ __forceinline__ void add_int_sum(uint64_t *st, const ColState &cs, ui
   }
 }
 
+// Warp reductions on REDUX (one instruction per 32-bit word instead of a 5-step shuffle butterfly).
+// max / min of signed 64-bit values: reduce the high words, then the low words of the lanes that tie.
+__device__ __forceinline__ int64_t warp_max_i64(int64_t v) {
+  const int32_t hi = (int32_t)(v >> 32);
+  const int32_t mh = __reduce_max_sync(FULL, hi);
+  const uint32_t lo = hi == mh ? (uint32_t)v : 0u;
+  const uint32_t ml = __reduce_max_sync(FULL, lo);
+  return (int64_t)(((uint64_t)(uint32_t)mh << 32) | ml);
+}
+__device__ __forceinline__ int64_t warp_min_i64(int64_t v) {
+  const int32_t hi = (int32_t)(v >> 32);
+  const int32_t mh = __reduce_min_sync(FULL, hi);
+  const uint32_t lo = hi == mh ? (uint32_t)v : 0xffffffffu;
+  const uint32_t ml = __reduce_min_sync(FULL, lo);
+  return (int64_t)(((uint64_t)(uint32_t)mh << 32) | ml);
+}
+// Wrapping sum of 32 u64 values plus the carries out of bit 63 (three 22-bit limbs; 32 * 2^22 < 2^32).
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v, uint32_t *carry) {
+  const uint32_t s0 = __reduce_add_sync(FULL, (uint32_t)v & 0x3fffffu);
+  const uint32_t s1 = __reduce_add_sync(FULL, (uint32_t)(v >> 22) & 0x3fffffu);
+  const uint32_t s2 = __reduce_add_sync(FULL, (uint32_t)(v >> 44));  // 20 bits
+  const uint64_t low = (uint64_t)s0 + ((uint64_t)s1 << 22);           // < 2^50
+  const uint64_t top = (uint64_t)s2 + (low >> 44);                     // units of 2^44, < 2^26
+  *carry = (uint32_t)(top >> 20);
+  return (low & 0xfffffffffffull) | (top << 44);
+}
+
 // Partial aggregate of one (page, bucket) run, held in registers by one lane.
 struct RunAcc {
   uint32_t count;
@@ -376,29 +403,27 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
   const bool is_f64 = (uint8_t)__shfl_sync(FULL, (uint32_t)pt, leader) == TSKV_PT_F64;
   const bool own_f64 = pt == TSKV_PT_F64;
   if (same && __popc(m) > 1) {
-    uint32_t cnt = active ? a.count : 0;
+    const uint32_t cnt = active ? a.count : 0;
     uint64_t sum = active ? a.sum : 0;  // 0 bits == +0.0
     int64_t shi = active ? a.sum_hi : 0;
-    int64_t kmin = (active && a.count) ? a.kmin : INT64_MAX;
-    int64_t kmax = (active && a.count) ? a.kmax : INT64_MIN;
-    int64_t fk = (SEL && active && a.first_ok) ? kf : INT64_MAX;
-    int64_t lk = (SEL && active && a.last_ok) ? kl : INT64_MIN;
-    uint32_t tot = __reduce_add_sync(FULL, cnt);
-    for (int o = 16; o; o >>= 1) {
-      uint64_t s2 = shfl_xor_u64(sum, o);
-      int64_t h2 = (int64_t)shfl_xor_u64((uint64_t)shi, o);
-      if (is_f64) sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)s2));
-      else { sum += s2; shi += h2 + (sum < s2 ? 1 : 0); }
-      int64_t mn = (int64_t)shfl_xor_u64((uint64_t)kmin, o);
-      int64_t mx = (int64_t)shfl_xor_u64((uint64_t)kmax, o);
-      kmin = mn < kmin ? mn : kmin;
-      kmax = mx > kmax ? mx : kmax;
-      if (SEL) {
-        int64_t f2 = (int64_t)shfl_xor_u64((uint64_t)fk, o);
-        int64_t l2 = (int64_t)shfl_xor_u64((uint64_t)lk, o);
-        fk = f2 < fk ? f2 : fk;
-        lk = l2 > lk ? l2 : lk;
+    const uint32_t tot = __reduce_add_sync(FULL, cnt);
+    int64_t kmin = INT64_MAX, kmax = INT64_MIN, fk = INT64_MAX, lk = INT64_MIN;
+    if (tot) {  // warp-uniform
+      if (is_f64) {
+        double d = __longlong_as_double((long long)sum);
+        for (int o = 16; o; o >>= 1) d += __longlong_as_double((long long)shfl_xor_u64((uint64_t)__double_as_longlong(d), o));
+        sum = (uint64_t)__double_as_longlong(d);
+      } else {
+        uint32_t carry;
+        sum = warp_sum_u64(sum, &carry);
+        shi = (int64_t)(int32_t)__reduce_add_sync(FULL, (uint32_t)shi) + carry;  // |per-lane hi| < 2^26
       }
+      kmin = warp_min_i64((active && a.count) ? a.kmin : INT64_MAX);
+      kmax = warp_max_i64((active && a.count) ? a.kmax : INT64_MIN);
+    }
+    if (SEL) {
+      fk = warp_min_i64((active && a.first_ok) ? kf : INT64_MAX);
+      lk = warp_max_i64((active && a.last_ok) ? kl : INT64_MIN);
     }
     // owners of the winning first / last keys supply the values
     uint32_t mf = 0, ml = 0;
@@ -504,7 +529,7 @@ __device__ __forceinline__ bool range_span(const ScanParams &P, int64_t t, int64
 // this warp's 2 x RING_WORDS x 256 B prefetch rings (time stream, value stream).
 // SEL: the query wants FIRST/LAST somewhere (tracks the (ts, value) of each run's end rows).
 template <int TK, int VK, bool SEL>
-__device__ __noinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
+__device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
                                              uint32_t ring_base) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
@@ -571,11 +596,12 @@ __device__ __noinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_
       const bool tv = tbits.next(row);
       vv = vbits.next(row) && !allnull;
       bool ok = true;
-      if (tv) t = (int64_t)tcur.next(&ok);
+      if (tv) { t = (int64_t)tcur.next(); ok = !tcur.exhausted; }
       else if (row == 0) tcur.skip_first_if_s8b_sc();
       if (!ok) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = 0; }
       if (vv && ok) {
-        v = VK == VK_GOR ? vcur_g.next(&ok) : vcur_d.next(&ok);
+        v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+        ok = VK == VK_GOR ? !vcur_g.done : !vcur_d.exhausted;
         if (!ok) {
           report_error(P, (VK == VK_GOR && vcur_g.err) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
           n_rows = 0;
@@ -635,10 +661,8 @@ __device__ __noinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_
   }
   // The reference decodes a gorilla page to its sentinel (float.rs:480-591): a stream that ends
   // without one is an error even when enough values were produced.
-  if (VK == VK_GOR && have_item && n_rows != 0 && !vcur_g.first) {
-    while (!vcur_g.done) { if (!vcur_g.advance()) vcur_g.done = true; }
-    if (vcur_g.err) report_error(P, TSKV_ERR_SHORT_BLOCK, page);
-  }
+  if (VK == VK_GOR && have_item && n_rows != 0 && vcur_g.consumed_any() && !vcur_g.drain())
+    report_error(P, TSKV_ERR_SHORT_BLOCK, page);
   // drain the prefetch rings before the next chunk reuses them
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   // statistics
@@ -655,24 +679,48 @@ __device__ __noinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_
 //   1. a lean look-ahead loop over the TIMESTAMPS finds the next segment = maximal run of rows whose
 //      (selected by the time ranges, bucket) is the same;
 //   2. the warp flushes finished runs (converged, once per segment instead of once per row);
-//   3. a tight loop decodes the segment's VALUES and accumulates them in registers.
+//   3. a tight loop decodes the segment's VALUES and accumulates them in registers, one validity-bitmap
+//      word (<= 32 rows) at a time with an all-valid fast path.
 // Rows of a page are time-sorted (tsm/chunk.rs:100-110), so the first / last row of a run carry its
 // min / max timestamp (what first()/last() pick with sort_to_indices, first.rs:139-148).
+template <int VK>
+struct ValueAcc {  // count / sum / min / max of one run; VK fixes the arithmetic at compile time
+  uint32_t count;
+  uint64_t sum;
+  int64_t sum_hi;
+  int64_t kmin, kmax;
+  __device__ __forceinline__ void reset() { count = 0; sum = 0; sum_hi = 0; kmin = INT64_MAX; kmax = INT64_MIN; }
+  // pt / flip / mean_hi are per-lane constants (flip = okey's xor mask for integer columns)
+  __device__ __forceinline__ void add(uint64_t v, uint8_t pt, uint64_t flip, bool mean_hi) {
+    int64_t key;
+    if (VK == VK_GOR || (VK == VK_GEN && pt == TSKV_PT_F64)) {
+      sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)v));
+      key = (int64_t)(v ^ (uint64_t)(((int64_t)v >> 63) & 0x7fffffffffffffffll));
+    } else {
+      sum += v;
+      if (mean_hi) sum_hi += (sum < v ? 1 : 0) + (pt == TSKV_PT_I64 ? ((int64_t)v >> 63) : 0);
+      key = (int64_t)(v ^ flip);
+    }
+    kmin = key < kmin ? key : kmin;
+    kmax = key > kmax ? key : kmax;
+  }
+};
+
 template <int TK, int VK, bool SEL>
-__device__ __noinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
-                                            uint32_t ring_base) {
+__device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
+                                               uint32_t ring_base) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
   const uint32_t tslot = ring_base + lane * 8, vslot = ring_base + RING_WORDS * 256 + lane * 8;
 
   uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
-  uint8_t pt = TSKV_PT_I64, mask = 0;
+  uint8_t pt = VK == VK_GOR ? TSKV_PT_F64 : TSKV_PT_I64, mask = 0;
   PageView tpv, vpv;
-  BitCursor vbits;
   DeltaCursor<TK == TK_RLE ? DK_RLE_SC : DK_S8B_SC, RingStream> tcur;
   DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, RingStream> vcur_d;
   GorillaCursor<RingStream> vcur_g;
+  const uint32_t *vbm = nullptr;  // value validity bitmap, 32 rows per word
   bool allnull = false;
   int64_t pend_t = 0;  // timestamp of row `row`
 
@@ -683,7 +731,7 @@ __device__ __noinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_b
     const tskv_page_desc vd = P.descs[page];
     const uint32_t tpage = P.time_page_of[page];
     const tskv_page_desc td = P.descs[tpage];
-    pt = P.cols[qcol].phys_type;
+    if (VK != VK_GOR) pt = P.cols[qcol].phys_type;
     mask = P.cols[qcol].agg_mask;
     tskv_status st = kind_status(vd.reserved);  // the time page is RLE / simple8b here: always decodable
     if (st != TSKV_OK) {
@@ -692,31 +740,32 @@ __device__ __noinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_b
       tpv.open(P.arena, td);
       vpv.open(P.arena, vd);
       n_rows = vd.num_values;
-      vbits.init(vpv.bitset);
+      vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
       st = tcur.open(tpv, td.reserved, tslot);
       if (st == TSKV_OK) {
         if (VK == VK_GOR) st = vcur_g.open(vpv, vslot);
         else { st = vcur_d.open(vpv, vd.reserved, vslot); allnull = vd.reserved == DK_ALLNULL; }
       }
       if (st == TSKV_OK && n_rows) {
-        bool ok = true;
-        pend_t = (int64_t)tcur.next(&ok);
-        if (!ok) st = TSKV_ERR_BITSET_MISMATCH;
+        pend_t = (int64_t)tcur.next();
+        if (tcur.exhausted) st = TSKV_ERR_BITSET_MISMATCH;
       }
       if (st != TSKV_OK) { report_error(P, st, st == TSKV_ERR_BITSET_MISMATCH ? tpage : page); n_rows = 0; }
     }
   }
 
-  RunAcc acc;
-  acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+  ValueAcc<VK> va;
+  va.reset();
+  RunAcc acc;  // flush image (+ first/last state when SEL)
   acc.first_ts = acc.last_ts = 0; acc.first_val = acc.last_val = 0; acc.first_ok = acc.last_ok = false;
   BucketState bk; bk.valid = false; bk.floor_regime = false; bk.lo = 0; bk.hi = 0; bk.idx = 0;
   bool have_run = false;
   uint32_t run_idx = 0;
   uint32_t row = 0;
   uint32_t n_points = 0, n_inrange = 0;
-  const bool is_f64 = pt == TSKV_PT_F64;
-  const bool mean_hi = !is_f64 && (mask & TSKV_AGG_MEAN);
+  uint32_t vword = 0, vahead = vbm ? __ldg(vbm) : 0;  // bitmap word of `row`, and the next one (prefetched)
+  const bool mean_hi = VK != VK_GOR && pt != TSKV_PT_F64 && (mask & TSKV_AGG_MEAN);
+  const uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull : 0ull;
   const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
 
   for (;;) {
@@ -741,64 +790,84 @@ __device__ __noinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_b
         }
       }
       const uint32_t left = n_rows - row;
-      bool ok = true;
-      do {
+      int64_t t = pend_t;
+      do {  // look ahead: t = timestamp of row + n
         n++;
-        seg_last_t = pend_t;
-        if (n < left) pend_t = (int64_t)tcur.next(&ok);
-      } while (n < left && ok && pend_t >= lim_lo && pend_t <= lim_hi);
-      if (!ok) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row + n; }
+        seg_last_t = t;
+        t = (int64_t)tcur.next();
+      } while (n < left && t >= lim_lo && t <= lim_hi);
+      pend_t = t;  // (past the last row: the next() above ran one value too far - harmless, see below)
+      if (tcur.exhausted && n < left) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row + n; }
       if (seg_in) n_inrange += n;
     }
     // ---- 2. flush the finished run (warp-converged) ----------------------------------------------
     const bool newrun = has && seg_in && (!have_run || bk.idx != run_idx);
     const bool flush = have_run && (newrun || !has);
-    warp_flush<SEL>(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+    if (__any_sync(FULL, flush)) {
+      acc.count = va.count; acc.sum = va.sum; acc.sum_hi = va.sum_hi; acc.kmin = va.kmin; acc.kmax = va.kmax;
+      warp_flush<SEL>(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+    }
     if (flush) have_run = false;
     if (newrun) {
       have_run = true;
       run_idx = bk.idx;
-      acc.count = 0; acc.sum = 0; acc.sum_hi = 0; acc.kmin = INT64_MAX; acc.kmax = INT64_MIN;
+      va.reset();
     }
-    // ---- 3. values of the segment ----------------------------------------------------------------
+    // ---- 3. values of the segment, one bitmap word at a time --------------------------------------
     if (has) {
-      bool ok = true;
-      for (uint32_t k = 0; k < n && ok; k++) {
-        const bool vv = vbits.next(row + k) && !allnull;
+      uint32_t r = row;
+      const uint32_t rend = row + n;
+      while (r < rend) {
+        if ((r & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
+          vword = vahead;
+          vahead = __ldg(vbm + (r >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
+        }
+        const uint32_t off = r & 31;
+        const uint32_t span = min(32u - off, rend - r);
+        const uint32_t want = span == 32 ? 0xffffffffu : ((1u << span) - 1);
+        uint32_t m = allnull ? 0u : ((vword >> off) & want);
+        n_points += __popc(m);
         uint64_t v = 0;
-        if (vv) {
-          v = VK == VK_GOR ? vcur_g.next(&ok) : vcur_d.next(&ok);
-          n_points += ok ? 1 : 0;
-        }
-        if (seg_in && ok) {
-          if (SEL) {
-            if (k == 0 && newrun) { acc.first_ts = seg_first_t; acc.first_val = v; acc.first_ok = vv; }
-            if (k == n - 1) { acc.last_ts = seg_last_t; acc.last_val = v; acc.last_ok = vv; }
-          }
-          if (vv) {
-            acc.count++;
-            if (is_f64) acc.sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)acc.sum) + __longlong_as_double((long long)v));
-            else {
-              acc.sum += v;
-              if (mean_hi) acc.sum_hi += (acc.sum < v ? 1 : 0) + (pt == TSKV_PT_I64 ? ((int64_t)v >> 63) : 0);
+        if (!SEL && seg_in) {
+          va.count += __popc(m);
+          if (m == want) {
+#pragma unroll 1
+            for (uint32_t j = 0; j < span; j++) {
+              v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+              va.add(v, pt, flip, mean_hi);
             }
-            const int64_t key = okey(v, pt);
-            acc.kmin = key < acc.kmin ? key : acc.kmin;
-            acc.kmax = key > acc.kmax ? key : acc.kmax;
+          } else {
+            for (; m; m &= m - 1) {
+              v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+              va.add(v, pt, flip, mean_hi);
+            }
+          }
+        } else if (!SEL) {  // rows outside the time ranges: decode (the streams are sequential), drop
+          for (uint32_t c = __popc(m); c; c--) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+        } else {            // FIRST / LAST wanted: per-row, the run's end rows keep (ts, value, valid)
+          for (uint32_t j = 0; j < span; j++) {
+            const bool vv = (m >> j) & 1;
+            if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+            if (seg_in) {
+              if (r + j == row && newrun) { acc.first_ts = seg_first_t; acc.first_val = vv ? v : 0; acc.first_ok = vv; }
+              if (r + j == rend - 1) { acc.last_ts = seg_last_t; acc.last_val = vv ? v : 0; acc.last_ok = vv; }
+              if (vv) { va.count++; va.add(v, pt, flip, mean_hi); }
+            }
           }
         }
+        r += span;
       }
-      if (!ok) {
+      const bool bad = VK == VK_GOR ? vcur_g.done : vcur_d.exhausted;
+      if (bad) {
         report_error(P, (VK == VK_GOR && vcur_g.err) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
         n_rows = 0;
+        have_run = false;
       }
-      row += n;
+      row = rend;
     }
   }
-  if (VK == VK_GOR && have_item && n_rows != 0 && !vcur_g.first) {  // decode to the sentinel (float.rs:480-591)
-    while (!vcur_g.done) { if (!vcur_g.advance()) vcur_g.done = true; }
-    if (vcur_g.err) report_error(P, TSKV_ERR_SHORT_BLOCK, page);
-  }
+  if (VK == VK_GOR && have_item && n_rows != 0 && vcur_g.consumed_any() && !vcur_g.drain())  // float.rs:480-591
+    report_error(P, TSKV_ERR_SHORT_BLOCK, page);
   asm volatile("cp.async.wait_all;\n" ::: "memory");  // drain the rings before the next chunk reuses them
   n_points = __reduce_add_sync(FULL, n_points);
   n_inrange = __reduce_add_sync(FULL, n_inrange);
@@ -808,54 +877,28 @@ __device__ __noinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_b
   }
 }
 
-// Order in which the decode-kind bins are drained: longest tasks first (gorilla, generic, simple8b).
-__constant__ uint8_t c_bin_order[N_BINS] = {TK_S8B * N_VK + VK_GOR, TK_GEN * N_VK + VK_GOR, TK_RLE * N_VK + VK_GOR,
-                                            TK_S8B * N_VK + VK_GEN, TK_GEN * N_VK + VK_GEN, TK_RLE * N_VK + VK_GEN,
-                                            TK_S8B * N_VK + VK_S8B, TK_GEN * N_VK + VK_S8B, TK_RLE * N_VK + VK_S8B};
-
-// The fused decode -> filter -> bucket-reduce kernel. Persistent grid; each warp repeatedly grabs one
-// 32-item chunk (homogeneous in time codec x value codec) from a global counter and runs the matching
-// specialisation. SEL = the query asks for FIRST/LAST.
-template <bool SEL>
-__global__ void __launch_bounds__(256, 2) k_scan_aggregate(const __grid_constant__ ScanParams P) {
-  __shared__ __align__(16) uint64_t s_ring[8][2][RING_WORDS][32];  // 32 KB: per warp, per stream
-  __shared__ uint32_t s_cstart[N_BINS + 1], s_chunk_base[N_BINS + 1];
-  if (threadIdx.x == 0) {
-    for (int k = 0; k <= N_BINS; k++) s_cstart[k] = P.bin_cstart[k];
-    uint32_t base = 0;
-    for (int j = 0; j < N_BINS; j++) {
-      s_chunk_base[j] = base;
-      int b = c_bin_order[j];
-      base += (s_cstart[b + 1] - s_cstart[b] + 31) >> 5;
-    }
-    s_chunk_base[N_BINS] = base;
-  }
-  __syncthreads();
+// The fused decode -> filter -> bucket-reduce kernel, one instantiation per decode-kind bin (time codec x
+// value codec) and SEL (= the query asks for FIRST/LAST) so that each keeps its state in registers.
+// The bins' kernels run concurrently on separate streams, each with a persistent grid sized to its share
+// of the work; a warp repeatedly grabs one 32-item chunk of its bin from the bin's global counter.
+constexpr int SCAN_THREADS = 128;
+template <int TK, int VK, bool SEL>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_aggregate(const __grid_constant__ ScanParams P) {
+  __shared__ __align__(16) uint64_t s_ring[SCAN_THREADS / 32][2][RING_WORDS][32];  // per warp, per stream
+  constexpr int bin = TK * N_VK + VK;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0][0]);
-  const uint32_t n_chunks = s_chunk_base[N_BINS];
+  const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
+  const uint32_t n_chunks = (end0 - begin0 + 31) >> 5;
   for (;;) {
     uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(P.task_counter, 1u);
+    if (lane == 0) c = atomicAdd(P.task_counter + bin, 1u);
     c = __shfl_sync(FULL, c, 0);
     if (c >= n_chunks) break;
-    int j = 0;
-#pragma unroll
-    for (int k = 1; k < N_BINS; k++) j += (c >= s_chunk_base[k]) ? 1 : 0;
-    const int bin = c_bin_order[j];
-    const uint32_t begin = s_cstart[bin] + ((c - s_chunk_base[j]) << 5);
-    const uint32_t end = min(begin + 32, s_cstart[bin + 1]);
-    switch (bin) {
-      case TK_RLE * N_VK + VK_S8B: scan_chunk_seg<TK_RLE, VK_S8B, SEL>(P, begin, end, ring_base); break;
-      case TK_RLE * N_VK + VK_GOR: scan_chunk_seg<TK_RLE, VK_GOR, SEL>(P, begin, end, ring_base); break;
-      case TK_RLE * N_VK + VK_GEN: scan_chunk_seg<TK_RLE, VK_GEN, SEL>(P, begin, end, ring_base); break;
-      case TK_S8B * N_VK + VK_S8B: scan_chunk_seg<TK_S8B, VK_S8B, SEL>(P, begin, end, ring_base); break;
-      case TK_S8B * N_VK + VK_GOR: scan_chunk_seg<TK_S8B, VK_GOR, SEL>(P, begin, end, ring_base); break;
-      case TK_S8B * N_VK + VK_GEN: scan_chunk_seg<TK_S8B, VK_GEN, SEL>(P, begin, end, ring_base); break;
-      case TK_GEN * N_VK + VK_S8B: scan_chunk_rows<TK_GEN, VK_S8B, SEL>(P, begin, end, ring_base); break;
-      case TK_GEN * N_VK + VK_GOR: scan_chunk_rows<TK_GEN, VK_GOR, SEL>(P, begin, end, ring_base); break;
-      default: scan_chunk_rows<TK_GEN, VK_GEN, SEL>(P, begin, end, ring_base); break;
-    }
+    const uint32_t begin = begin0 + (c << 5);
+    const uint32_t end = min(begin + 32, end0);
+    if (TK == TK_GEN) scan_chunk_rows<TK, VK, SEL>(P, begin, end, ring_base);
+    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base);
   }
 }
 
@@ -1002,9 +1045,8 @@ __global__ void k_time_bounds(const uint8_t *arena, const tskv_page_desc *descs,
       if (cur.open(pv, d.reserved) == TSKV_OK) {
         for (uint32_t r = 0; r < d.num_values; r++) {
           if (!bits.next(r)) { if (r == 0) cur.skip_first_if_s8b_sc(); continue; }
-          bool ok = true;
-          long long t = (long long)cur.next(&ok);
-          if (!ok) break;
+          long long t = (long long)cur.next();
+          if (cur.exhausted) break;
           lo = t < lo ? t : lo;
           hi = t > hi ? t : hi;
         }
@@ -1051,9 +1093,8 @@ __global__ void k_decode_pages(const uint8_t *arena, const tskv_page_desc *descs
       bool valid = bits.next(r) && !allnull;
       uint64_t v = 0;
       if (valid) {
-        bool ok = true;
-        v = cur.next(&ok);
-        if (!ok) { st = cur.stream_error() ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH; break; }
+        v = cur.next();
+        if (cur.failed()) { st = cur.stream_error() ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH; break; }
         points++;
       } else if (r == 0 && !cur.is_gorilla) {
         cur.d.skip_first_if_s8b_sc();
@@ -1067,10 +1108,7 @@ __global__ void k_decode_pages(const uint8_t *arena, const tskv_page_desc *descs
       // zero the tail of the 8-byte-padded bitmap
       uint32_t words = ((n_rows + 63) / 64) * 2;
       for (uint32_t w = (n_rows + 31) / 32; w < words; w++) ob[w] = 0;
-      if (cur.is_gorilla && !cur.g.first) {
-        while (!cur.g.done) { if (!cur.g.advance()) cur.g.done = true; }
-        if (cur.g.err) st = TSKV_ERR_SHORT_BLOCK;
-      }
+      if (cur.is_gorilla && cur.g.consumed_any() && !cur.g.drain()) st = TSKV_ERR_SHORT_BLOCK;
     }
   }
   if (st != TSKV_OK) {

@@ -29,7 +29,9 @@ struct tskv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // boundaries of the per-bin fused kernels
+  cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // [0] fork, [N_BINS] join of the fused phase
+  cudaStream_t bin_stream[N_BINS] = {nullptr};  // the per-bin fused kernels run concurrently
+  cudaEvent_t ev_bin_start[N_BINS] = {nullptr}, ev_bin_done[N_BINS] = {nullptr};
   int sm_count = 148;
   std::mutex mu;
   std::string err;
@@ -91,7 +93,7 @@ struct tskv_scan {
   unsigned long long *d_counters = nullptr;  // [0] pages [1] bytes
   uint64_t *d_values = nullptr;
   uint8_t *d_validity = nullptr;
-  int grid = 0;
+  int grid[N_BINS] = {0};
   tskv_ctx *ctx = nullptr;
   uint32_t n_series_sel = 0;
   bool enqueued = false;
@@ -132,6 +134,27 @@ unsigned bits_for(uint64_t max_value) {  // bits needed to represent values in [
 }
 
 unsigned popc8(unsigned x) { return (unsigned)__builtin_popcount(x & TSKV_AGG_ALL); }
+
+typedef void (*scan_kernel_t)(const ScanParams);
+template <bool SEL>
+scan_kernel_t scan_kernel_for(int bin) {
+  switch (bin) {
+    case TK_RLE * N_VK + VK_S8B: return k_scan_aggregate<TK_RLE, VK_S8B, SEL>;
+    case TK_RLE * N_VK + VK_GOR: return k_scan_aggregate<TK_RLE, VK_GOR, SEL>;
+    case TK_RLE * N_VK + VK_GEN: return k_scan_aggregate<TK_RLE, VK_GEN, SEL>;
+    case TK_S8B * N_VK + VK_S8B: return k_scan_aggregate<TK_S8B, VK_S8B, SEL>;
+    case TK_S8B * N_VK + VK_GOR: return k_scan_aggregate<TK_S8B, VK_GOR, SEL>;
+    case TK_S8B * N_VK + VK_GEN: return k_scan_aggregate<TK_S8B, VK_GEN, SEL>;
+    case TK_GEN * N_VK + VK_S8B: return k_scan_aggregate<TK_GEN, VK_S8B, SEL>;
+    case TK_GEN * N_VK + VK_GOR: return k_scan_aggregate<TK_GEN, VK_GOR, SEL>;
+    default: return k_scan_aggregate<TK_GEN, VK_GEN, SEL>;
+  }
+}
+// relative cost of one item of a bin (sizes the bins' shares of the SMs)
+double bin_cost(int bin) {
+  static const double tk[N_TK] = {1.0, 1.5, 2.0}, vk[N_VK] = {1.0, 1.4, 1.6};
+  return tk[bin / N_VK] * vk[bin % N_VK];
+}
 
 tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_output_layout *out) {
   if (!pages || !q || !out || q->n_buckets == 0 || q->n_columns == 0 || !q->columns) return TSKV_ERR_INVALID_ARG;
@@ -202,6 +225,11 @@ tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
   for (int b = 0; b <= N_BINS; b++) cudaEventCreate(&ctx->ev_bin[b]);
+  for (int b = 0; b < N_BINS; b++) {
+    cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking);
+    cudaEventCreate(&ctx->ev_bin_start[b]);
+    cudaEventCreate(&ctx->ev_bin_done[b]);
+  }
   // per-scan buffers come from the stream-ordered pool; keep freed memory cached in the pool
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -223,6 +251,11 @@ void tskvgpu_ctx_destroy(tskv_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int b = 0; b <= N_BINS; b++)
     if (ctx->ev_bin[b]) cudaEventDestroy(ctx->ev_bin[b]);
+  for (int b = 0; b < N_BINS; b++) {
+    if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
+    if (ctx->ev_bin_start[b]) cudaEventDestroy(ctx->ev_bin_start[b]);
+    if (ctx->ev_bin_done[b]) cudaEventDestroy(ctx->ev_bin_done[b]);
+  }
   delete ctx;
 }
 
@@ -813,10 +846,28 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   P.rel_base = rel_base;
 
   {
-    int per_sm = 0;
-    if (s->has_sel) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_aggregate<true>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_aggregate<false>, 256, 0);
-    s->grid = std::max(1, per_sm) * ctx->sm_count;
+    // Static split of the resident thread blocks among the bins the arena contains, by estimated work.
+    double w[N_BINS], wsum = 0;
+    int per_sm = 4;
+    for (int b = 0; b < N_BINS; b++) {
+      uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
+      w[b] = n_bin * bin_cost(b);
+      wsum += w[b];
+      if (n_bin) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b),
+                                                      SCAN_THREADS, 0);
+        per_sm = std::min(per_sm, std::max(1, occ));
+      }
+    }
+    const int total = per_sm * ctx->sm_count;
+    for (int b = 0; b < N_BINS; b++) {
+      uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
+      if (!n_bin) continue;
+      int chunks = (int)((n_bin + 31) / 32);
+      int share = (int)(total * w[b] / wsum + 0.5);
+      s->grid[b] = std::max(1, std::min(share, (chunks + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32)));
+    }
   }
   ctx->counters.h2d_bytes = h2d;
   *out_scan = s;
@@ -861,12 +912,16 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
   k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
   launches++;
-  cudaEventRecord(ctx->ev_bin[0], ctx->stream);
-  if (n_items) {
-    // an upper bound of the work (the compacted list is a subset of the items) sizes the grid
-    uint32_t grid = std::min<uint32_t>((uint32_t)s->grid, std::max(1u, (n_items / 32 + 7) / 8));
-    if (s->has_sel) k_scan_aggregate<true><<<grid, 256, 0, ctx->stream>>>(s->params);
-    else k_scan_aggregate<false><<<grid, 256, 0, ctx->stream>>>(s->params);
+  cudaEventRecord(ctx->ev_bin[0], ctx->stream);  // fork
+  for (int b = 0; b < N_BINS; b++) {
+    if (!s->grid[b]) continue;
+    cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_bin[0], 0);
+    cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
+    void *args[] = {(void *)&s->params};
+    const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b));
+    CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, 0, ctx->bin_stream[b]));
+    cudaEventRecord(ctx->ev_bin_done[b], ctx->bin_stream[b]);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_bin_done[b], 0);  // join
     launches++;
   }
   cudaEventRecord(ctx->ev_bin[N_BINS], ctx->stream);
@@ -902,9 +957,19 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
   float fused = 0;
   cudaEventElapsedTime(&fused, ctx->ev_bin[0], ctx->ev_bin[N_BINS]);
   ctx->counters.elapsed_fused_ms = fused;
-  ctx->counters.dominant_kernel_ms = fused;          // one fused kernel per scan
-  ctx->counters.dominant_kernel_bytes = aux[3];
+  ctx->counters.dominant_kernel_ms = 0;
+  ctx->counters.dominant_kernel_bytes = 0;
   ctx->counters.dominant_kernel_bin = 0;
+  for (int b = 0; b < N_BINS; b++) {
+    if (!s->grid[b]) continue;
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev_bin_start[b], ctx->ev_bin_done[b]);
+    if (t > ctx->counters.dominant_kernel_ms) {
+      ctx->counters.dominant_kernel_ms = t;
+      ctx->counters.dominant_kernel_bytes = aux[4 + b];
+      ctx->counters.dominant_kernel_bin = (uint64_t)b;
+    }
+  }
   return TSKV_OK;
 }
 

@@ -4,7 +4,6 @@
 // last.rs semantics). TEST INFRASTRUCTURE ONLY (see tskv_oracle.h).
 #include <algorithm>
 #include <cstring>
-#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -52,9 +51,25 @@ struct ColumnGroup {
   uint64_t n_descs;     // incl. the time page
 };
 
+struct SeriesGroups {
+  uint32_t series;
+  uint32_t first_cg, n_cg;  // range in Index::cgs
+};
 struct Index {
-  std::vector<uint32_t> series;                 // sorted distinct ids
-  std::map<uint32_t, std::vector<ColumnGroup>> cgs;  // series -> column groups in arena order
+  std::vector<uint32_t> series;       // sorted distinct ids
+  std::vector<ColumnGroup> cgs;       // column groups, sorted by (series, arena order)
+  std::vector<SeriesGroups> by_series;  // sorted by series id
+  // column groups of one series (arena order), or an empty range
+  std::pair<const ColumnGroup *, const ColumnGroup *> find(uint32_t sid) const {
+    size_t lo = 0, hi = by_series.size();
+    while (lo < hi) {
+      size_t mid = (lo + hi) / 2;
+      if (by_series[mid].series < sid) lo = mid + 1; else hi = mid;
+    }
+    if (lo == by_series.size() || by_series[lo].series != sid) return {nullptr, nullptr};
+    const ColumnGroup *b = cgs.data() + by_series[lo].first_cg;
+    return {b, b + by_series[lo].n_cg};
+  }
 };
 
 tskv_status build_index(const tskv_page_desc *descs, uint64_t n, Index &ix) {
@@ -72,10 +87,22 @@ tskv_status build_index(const tskv_page_desc *descs, uint64_t n, Index &ix) {
       }
       j++;
     }
-    ix.cgs[descs[i].series_id].push_back(ColumnGroup{i, j - i});
+    ix.cgs.push_back(ColumnGroup{i, j - i});
     i = j;
   }
-  for (auto &kv : ix.cgs) ix.series.push_back(kv.first);
+  // group by series keeping the arena order inside a series (compacted files are already sorted)
+  auto sid = [&](const ColumnGroup &c) { return descs[c.first_desc].series_id; };
+  bool sorted = true;
+  for (size_t k = 1; k < ix.cgs.size() && sorted; k++) sorted = sid(ix.cgs[k - 1]) <= sid(ix.cgs[k]);
+  if (!sorted) std::stable_sort(ix.cgs.begin(), ix.cgs.end(), [&](const ColumnGroup &a, const ColumnGroup &b) { return sid(a) < sid(b); });
+  for (size_t k = 0; k < ix.cgs.size(); k++) {
+    uint32_t s = sid(ix.cgs[k]);
+    if (ix.by_series.empty() || ix.by_series.back().series != s) {
+      ix.by_series.push_back(SeriesGroups{s, (uint32_t)k, 0});
+      ix.series.push_back(s);
+    }
+    ix.by_series.back().n_cg++;
+  }
   return TSKV_OK;
 }
 
@@ -99,11 +126,12 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
   std::vector<uint64_t> ts, vals;
   std::vector<uint8_t> tvalid, vvalid;
   for (uint64_t slot = s0; slot < s1; slot++) {
-    auto it = S.ix->cgs.find(S.slots[slot]);
-    if (it == S.ix->cgs.end()) continue;  // selected id absent from this arena
+    auto range = S.ix->find(S.slots[slot]);
+    if (range.first == nullptr) continue;  // selected id absent from this arena
     uint64_t group = q.group_by_series ? slot : 0;
     (void)shared_table;
-    for (const ColumnGroup &cg : it->second) {
+    for (const ColumnGroup *cgp = range.first; cgp != range.second; cgp++) {
+      const ColumnGroup &cg = *cgp;
       const tskv_page_desc &td = S.descs[cg.first_desc];
       uint64_t n_rows = td.num_values;
       ts.assign(n_rows ? n_rows : 1, 0);

@@ -14,11 +14,28 @@ from cnosdb_b200.parallel import select_tag_subset  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--series", type=int, default=1_000_000)
 ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--kind", default="c4", help="c4 | i64 | f64a | f64b")
+ap.add_argument("--jitter", type=int, default=-1, help="permille of series with jittered timestamps")
+ap.add_argument("--aggs", default="count,sum,min,max,mean")
 a = ap.parse_args()
-g = bench.generate_shard(a.series, 0, 1)
+from cnosdb_b200 import cabi, datagen  # noqa: E402
+from cnosdb_b200.engine import PushedAggregate, QueryOption  # noqa: E402
+if a.kind == "c4":
+    g = bench.generate_shard(a.series, 0, 1)
+else:
+    kind = {"i64": datagen.I64_WALK, "f64a": datagen.F64_INT, "f64b": datagen.F64_NOISE}[a.kind]
+    g = datagen.generate(a.series, n_fields=1, n_points=1000, value_kind=kind, seed=4,
+                         jitter_permille=max(a.jitter, 0), jitter_max=999_999)
 eng = Engine(0)
 pages = eng.upload_pages(g.arena, g.descs, verify_crc=False)
-scan = eng.prepare(pages, bench.make_query(select_tag_subset(a.series, 10)))
+if a.kind == "c4":
+    q = bench.make_query(select_tag_subset(a.series, 10))
+else:
+    fbs, nb = bench.bucket_spec()
+    pt = cabi.TSKV_PT_I64 if a.kind == "i64" else cabi.TSKV_PT_F64
+    q = QueryOption([PushedAggregate(1, pt, a.aggs.split(","))], series_ids=select_tag_subset(a.series, 10),
+                    width=bench.W_NS, first_bucket_start=fbs, n_buckets=nb)
+scan = eng.prepare(pages, q)
 for _ in range(a.steps):
     scan.run()
 c = eng.counters()
