@@ -103,7 +103,8 @@ GPU_SYMBOLS = [
 
 
 def gpu_library_path():
-    return os.path.join(_PKG, "libtskv_gpu.so")
+    # TSKV_GPU_LIB: developer override to A/B alternative builds of the same library
+    return os.environ.get("TSKV_GPU_LIB") or os.path.join(_PKG, "libtskv_gpu.so")
 
 
 def hostgen_library_path():

@@ -37,6 +37,8 @@ struct ColState {
   uint64_t first_off;  // {i64 key, u64 val}[n_cells], 16B aligned  (FIRST)
   uint64_t last_off;   // {i64 key, u64 val}[n_cells], 16B aligned  (LAST)
   uint64_t sumhi_off;  // i64 high word of the exact 128-bit integer sum (MEAN on i64/u64 columns)
+  // word offsets of the same arrays inside the per-CTA shared-memory table (GROUP BY bucket only)
+  uint32_t s_count, s_sum, s_hi, s_min, s_max, s_pad;
   uint16_t column_id;
   uint8_t phys_type;
   uint8_t agg_mask;
@@ -72,6 +74,13 @@ struct ScanParams {
   uint32_t slot_bits;
   uint32_t slot_max;     // (1 << slot_bits) - 1
   int64_t rel_base;
+  // Per-CTA partial table in shared memory (count/sum/min/max of every (column, bucket) cell): all warps
+  // of the grid work on the same bucket at the same time, so flushing straight to global memory
+  // serialises every warp on a handful of L2 atomics. Used when GROUP BY bucket and the table fits.
+  uint32_t use_smem;
+  uint32_t smem_words;   // table size in 8-byte words
+  uint32_t n_cols;
+  uint32_t pad2;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -323,16 +332,32 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
 
 // Integer sum: the low word is the reference's wrapping i64/u64 SUM; with MEAN the carries go to a high
 // word so that mean = exact 128-bit sum / count (DataFusion's avg accumulates in f64 and never wraps).
-__device__ __forceinline__ void add_int_sum(uint64_t *st, const ColState &cs, uint64_t cell, uint8_t mask,
-                                            uint64_t lo, int64_t hi) {
-  unsigned long long *plo = reinterpret_cast<unsigned long long *>(st + cs.sum_off + cell);
+__device__ __forceinline__ void add_int_sum(uint64_t *sum_cell, uint64_t *hi_cell, uint8_t mask, uint64_t lo, int64_t hi) {
+  unsigned long long *plo = reinterpret_cast<unsigned long long *>(sum_cell);
   if (mask & TSKV_AGG_MEAN) {
     unsigned long long old = atomicAdd(plo, (unsigned long long)lo);
     hi += (old + lo < old) ? 1 : 0;
-    if (hi) atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.sumhi_off + cell), (unsigned long long)hi);
+    if (hi) atomicAdd(reinterpret_cast<unsigned long long *>(hi_cell), (unsigned long long)hi);
   } else {
     atomicAdd(plo, (unsigned long long)lo);
   }
+}
+
+// count / sum / min / max of one run into the partial table: `tab` is either the global state (offsets
+// *_off) or the CTA's shared-memory table (offsets s_*).
+__device__ __forceinline__ void table_update(const ScanParams &P, uint64_t *stab, const ColState &cs, uint64_t cell,
+                                             uint8_t mask, bool f64, uint32_t cnt, uint64_t sum, int64_t shi,
+                                             int64_t kmin, int64_t kmax) {
+  const bool sm = P.use_smem != 0;
+  uint64_t *tab = sm ? stab : P.state;
+  atomicAdd(reinterpret_cast<unsigned long long *>(tab + (sm ? cs.s_count : cs.count_off) + cell), (unsigned long long)cnt);
+  if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
+    uint64_t *sc = tab + (sm ? cs.s_sum : cs.sum_off) + cell;
+    if (f64) atomicAdd(reinterpret_cast<double *>(sc), __longlong_as_double((long long)sum));
+    else add_int_sum(sc, tab + (sm ? cs.s_hi : cs.sumhi_off) + cell, mask, sum, shi);
+  }
+  if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(tab + (sm ? cs.s_min : cs.min_off) + cell), (long long)kmin);
+  if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(tab + (sm ? cs.s_max : cs.max_off) + cell), (long long)kmax);
 }
 
 // Warp reductions on REDUX (one instruction per 32-bit word instead of a 5-step shuffle butterfly).
@@ -382,7 +407,7 @@ struct ScanCtx {
 // (the common lock-step case of GROUP BY bucket) the partials are combined with a butterfly first
 // and one lane issues the atomics.
 template <bool SEL>
-__device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uint32_t qcol,
+__device__ __forceinline__ void warp_flush(const ScanParams &P, uint64_t *stab, bool active, uint32_t qcol,
                                            uint64_t cell, int64_t bucket, uint8_t pt, uint8_t mask,
                                            RunAcc &a, uint32_t slot) {
   uint32_t m = __ballot_sync(FULL, active);
@@ -437,30 +462,14 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, bool active, uin
     if ((int)(threadIdx.x & 31) == leader) {
       const ColState &cs = P.cols[qcol];
       uint64_t *st = P.state;
-      if (tot) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.count_off + cell), (unsigned long long)tot);
-        if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
-          if (is_f64) atomicAdd(reinterpret_cast<double *>(st + cs.sum_off + cell), __longlong_as_double((long long)sum));
-          else add_int_sum(st, cs, cell, mask, sum, shi);
-        }
-        if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)kmin);
-        if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)kmax);
-      }
+      if (tot) table_update(P, stab, cs, cell, mask, is_f64, tot, sum, shi, kmin, kmax);
       if (SEL && (mask & TSKV_AGG_FIRST) && mf) atomic_select_pair<true>(st + cs.first_off + 2 * cell, fk, fv);
       if (SEL && (mask & TSKV_AGG_LAST) && ml) atomic_select_pair<false>(st + cs.last_off + 2 * cell, lk, lv);
     }
   } else if (active) {
     const ColState &cs = P.cols[qcol];
     uint64_t *st = P.state;
-    if (a.count) {
-      atomicAdd(reinterpret_cast<unsigned long long *>(st + cs.count_off + cell), (unsigned long long)a.count);
-      if (mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
-        if (own_f64) atomicAdd(reinterpret_cast<double *>(st + cs.sum_off + cell), __longlong_as_double((long long)a.sum));
-        else add_int_sum(st, cs, cell, mask, a.sum, a.sum_hi);
-      }
-      if (mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(st + cs.min_off + cell), (long long)a.kmin);
-      if (mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(st + cs.max_off + cell), (long long)a.kmax);
-    }
+    if (a.count) table_update(P, stab, cs, cell, mask, own_f64, a.count, a.sum, a.sum_hi, a.kmin, a.kmax);
     if (SEL && (mask & TSKV_AGG_FIRST) && a.first_ok) atomic_select_pair<true>(st + cs.first_off + 2 * cell, kf, a.first_val);
     if (SEL && (mask & TSKV_AGG_LAST) && a.last_ok) atomic_select_pair<false>(st + cs.last_off + 2 * cell, kl, a.last_val);
   }
@@ -530,7 +539,7 @@ __device__ __forceinline__ bool range_span(const ScanParams &P, int64_t t, int64
 // SEL: the query wants FIRST/LAST somewhere (tracks the (ts, value) of each run's end rows).
 template <int TK, int VK, bool SEL>
 __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
-                                             uint32_t ring_base) {
+                                             uint32_t ring_base, uint64_t *stab) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
@@ -630,7 +639,7 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
     } else {
       flush = have_run;
     }
-    warp_flush<SEL>(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+    warp_flush<SEL>(P, stab, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
     if (flush) have_run = false;
     if (has && inr) {
       if (newrun) {
@@ -708,7 +717,7 @@ struct ValueAcc {  // count / sum / min / max of one run; VK fixes the arithmeti
 
 template <int TK, int VK, bool SEL>
 __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
-                                               uint32_t ring_base) {
+                                               uint32_t ring_base, uint64_t *stab) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
@@ -805,7 +814,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     const bool flush = have_run && (newrun || !has);
     if (__any_sync(FULL, flush)) {
       acc.count = va.count; acc.sum = va.sum; acc.sum_hi = va.sum_hi; acc.kmin = va.kmin; acc.kmax = va.kmax;
-      warp_flush<SEL>(P, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+      warp_flush<SEL>(P, stab, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
     }
     if (flush) have_run = false;
     if (newrun) {
@@ -882,10 +891,26 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
 // The bins' kernels run concurrently on separate streams, each with a persistent grid sized to its share
 // of the work; a warp repeatedly grabs one 32-item chunk of its bin from the bin's global counter.
 constexpr int SCAN_THREADS = 128;
+#ifndef SCAN_MIN_BLOCKS
+#define SCAN_MIN_BLOCKS 4
+#endif
 template <int TK, int VK, bool SEL>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_aggregate(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS) k_scan_aggregate(const __grid_constant__ ScanParams P) {
   __shared__ __align__(16) uint64_t s_ring[SCAN_THREADS / 32][2][RING_WORDS][32];  // per warp, per stream
+  extern __shared__ __align__(16) uint64_t s_tab[];  // per-CTA partial table (P.smem_words words) or empty
   constexpr int bin = TK * N_VK + VK;
+  if (P.use_smem) {  // identities: 0 for counts / sums, +-inf keys for min / max
+    for (uint32_t i = threadIdx.x; i < P.smem_words; i += SCAN_THREADS) s_tab[i] = 0;
+    __syncthreads();
+    for (uint32_t c = 0; c < P.n_cols; c++) {
+      const ColState cs = P.cols[c];
+      for (uint32_t i = threadIdx.x; i < (uint32_t)P.n_cells; i += SCAN_THREADS) {
+        if (cs.agg_mask & TSKV_AGG_MIN) s_tab[cs.s_min + i] = 0x7fffffffffffffffull;
+        if (cs.agg_mask & TSKV_AGG_MAX) s_tab[cs.s_max + i] = 0x8000000000000000ull;
+      }
+    }
+    __syncthreads();
+  }
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0][0]);
   const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
@@ -897,8 +922,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_scan_aggregate(const __grid
     if (c >= n_chunks) break;
     const uint32_t begin = begin0 + (c << 5);
     const uint32_t end = min(begin + 32, end0);
-    if (TK == TK_GEN) scan_chunk_rows<TK, VK, SEL>(P, begin, end, ring_base);
-    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base);
+    if (TK == TK_GEN) scan_chunk_rows<TK, VK, SEL>(P, begin, end, ring_base, s_tab);
+    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base, s_tab);
+  }
+  if (P.use_smem) {  // merge this CTA's table into the global state, once
+    __syncthreads();
+    for (uint32_t c = 0; c < P.n_cols; c++) {
+      const ColState cs = P.cols[c];
+      const bool f64 = cs.phys_type == TSKV_PT_F64;
+      for (uint32_t i = threadIdx.x; i < (uint32_t)P.n_cells; i += SCAN_THREADS) {
+        const uint64_t cnt = s_tab[cs.s_count + i];
+        if (!cnt) continue;
+        atomicAdd(reinterpret_cast<unsigned long long *>(P.state + cs.count_off + i), (unsigned long long)cnt);
+        if (cs.agg_mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
+          const uint64_t sv = s_tab[cs.s_sum + i];
+          if (f64) atomicAdd(reinterpret_cast<double *>(P.state + cs.sum_off + i), __longlong_as_double((long long)sv));
+          else add_int_sum(P.state + cs.sum_off + i, P.state + cs.sumhi_off + i, cs.agg_mask, sv,
+                           (cs.agg_mask & TSKV_AGG_MEAN) ? (int64_t)s_tab[cs.s_hi + i] : 0);
+        }
+        if (cs.agg_mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(P.state + cs.min_off + i), (long long)s_tab[cs.s_min + i]);
+        if (cs.agg_mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(P.state + cs.max_off + i), (long long)s_tab[cs.s_max + i]);
+      }
+    }
   }
 }
 

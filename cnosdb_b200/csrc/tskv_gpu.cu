@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -803,7 +804,6 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   if (e == cudaSuccess) e = stream_alloc(ctx, reinterpret_cast<unsigned long long **>(&s->d_task_counter), 24);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_values, L.n_out * L.n_cells);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_validity, L.validity_bytes + 8);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_cols, cols.data(), cols.size() * sizeof(ColState), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_outs, outs.data(), outs.size() * sizeof(OutCol), cudaMemcpyHostToDevice, ctx->stream);
   h2d += cols.size() * sizeof(ColState) + outs.size() * sizeof(OutCol) + means.size() * sizeof(MeanExport) + sizeof(ScanParams);
   if (e != cudaSuccess) {
@@ -844,11 +844,33 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   P.slot_bits = slot_bits;
   P.slot_max = slot_bits ? (uint32_t)((1ull << slot_bits) - 1) : 0;
   P.rel_base = rel_base;
+  // per-CTA shared-memory partial table (GROUP BY bucket): count | sum | hi | min | max per column
+  {
+    uint32_t words = 0;
+    for (uint32_t c = 0; c < q->n_columns; c++) {
+      const uint8_t m = q->columns[c].agg_mask;
+      const bool is_int = q->columns[c].phys_type != TSKV_PT_F64;
+      cols[c].s_count = words; words += (uint32_t)n_cells;
+      if (m & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) { cols[c].s_sum = words; words += (uint32_t)n_cells; }
+      if ((m & TSKV_AGG_MEAN) && is_int) { cols[c].s_hi = words; words += (uint32_t)n_cells; }
+      if (m & TSKV_AGG_MIN) { cols[c].s_min = words; words += (uint32_t)n_cells; }
+      if (m & TSKV_AGG_MAX) { cols[c].s_max = words; words += (uint32_t)n_cells; }
+      if (n_cells > (1u << 20)) { words = UINT32_MAX / 2; break; }
+    }
+    P.use_smem = (!q->group_by_series && (uint64_t)words * 8 <= 32 * 1024) ? 1u : 0u;
+    P.smem_words = P.use_smem ? words : 0;
+    P.n_cols = q->n_columns;
+  }
+  if (cudaMemcpyAsync(s->d_cols, cols.data(), cols.size() * sizeof(ColState), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    ctx->set_error("scan_prepare: column table upload failed");
+    free_scan(s);
+    return TSKV_ERR_CUDA;
+  }
 
   {
     // Static split of the resident thread blocks among the bins the arena contains, by estimated work.
     double w[N_BINS], wsum = 0;
-    int per_sm = 4;
+    int per_sm = SCAN_MIN_BLOCKS;
     for (int b = 0; b < N_BINS; b++) {
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       w[b] = n_bin * bin_cost(b);
@@ -856,7 +878,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       if (n_bin) {
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b),
-                                                      SCAN_THREADS, 0);
+                                                      SCAN_THREADS, (size_t)P.smem_words * 8);
         per_sm = std::min(per_sm, std::max(1, occ));
       }
     }
@@ -919,7 +941,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
     cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
     void *args[] = {(void *)&s->params};
     const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b));
-    CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, 0, ctx->bin_stream[b]));
+    CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, (size_t)s->params.smem_words * 8, ctx->bin_stream[b]));
     cudaEventRecord(ctx->ev_bin_done[b], ctx->bin_stream[b]);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_bin_done[b], 0);  // join
     launches++;
@@ -964,6 +986,11 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
     if (!s->grid[b]) continue;
     float t = 0;
     cudaEventElapsedTime(&t, ctx->ev_bin_start[b], ctx->ev_bin_done[b]);
+    if (getenv("TSKV_DEBUG_BINS")) {
+      float t0 = 0;
+      cudaEventElapsedTime(&t0, ctx->ev_bin[0], ctx->ev_bin_start[b]);
+      fprintf(stderr, "[tskv] bin %d grid %d: start +%.3f ms, run %.3f ms, %llu bytes\n", b, s->grid[b], t0, t, aux[4 + b]);
+    }
     if (t > ctx->counters.dominant_kernel_ms) {
       ctx->counters.dominant_kernel_ms = t;
       ctx->counters.dominant_kernel_bytes = aux[4 + b];
