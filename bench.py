@@ -8,7 +8,7 @@
 Workload (config.workload): BASELINE config C4 — 1 000 000 series x 1 000 points, mixed i64 (Delta/simple8b)
 and f64 (Gorilla, full-mantissa) columns, 20 % of the series with jittered timestamps (simple8b time pages),
 1 % of the pages with 5 % nulls, tag predicate selecting 10 % of the series, GROUP BY 1-minute bucket with
-count/sum/min/max/mean. Series are sharded `id % N` over N GPUs (strong scaling: total work fixed); the
+count/sum/min/max/mean. Series are sharded in contiguous id ranges over N GPUs (strong scaling: total work fixed); the
 only collective is the all-reduce of the per-bucket partials.
 
 One JSON line on stdout (rank 0). A "step" is one full pass: series selection -> work list -> fused
@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 from cnosdb_b200 import cabi, datagen  # noqa: E402
 from cnosdb_b200.engine import PushedAggregate, QueryOption  # noqa: E402
-from cnosdb_b200.parallel import select_tag_subset  # noqa: E402
+from cnosdb_b200.parallel import select_tag_subset, shard_range  # noqa: E402
 
 METRIC = "decoded+aggregated points/s"
 W_NS = 60_000_000_000
@@ -63,9 +63,9 @@ def make_query(series_ids):
 
 
 def generate_shard(n_total, rank, world):
-    n_local = (n_total - rank + world - 1) // world
-    return datagen.generate(n_local, n_fields=1, n_points=1000, value_kind=datagen.MIXED, seed=4,
-                            first_series_id=rank, series_stride=world, jitter_permille=200, jitter_max=999_999,
+    lo, hi = shard_range(n_total, rank, world)
+    return datagen.generate(hi - lo, n_fields=1, n_points=1000, value_kind=datagen.MIXED, seed=4,
+                            first_series_id=lo, series_stride=1, jitter_permille=200, jitter_max=999_999,
                             null_page_permille=10, null_row_permille=50)
 
 
@@ -148,7 +148,7 @@ def main():
     sel_all = select_tag_subset(args.series, 10)
     config = {"workload": workload_name(args.series), "series_total": args.series, "points_per_series": 1000,
               "selectivity": 0.1, "selected_series": int(len(sel_all)), "buckets": bucket_spec()[1],
-              "aggregates": AGGS, "sharding": "series_id % n_gpus"}
+              "aggregates": AGGS, "sharding": "contiguous series-id ranges, one per GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -167,7 +167,7 @@ def main():
     import torch
     import torch.distributed as dist
     from cnosdb_b200.engine import Engine
-    from cnosdb_b200.parallel import allreduce_scan, scan_sections
+    from cnosdb_b200.parallel import GatherExchange
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
@@ -181,13 +181,13 @@ def main():
     pages = eng.upload_pages(g.arena, g.descs, verify_crc=True)
     q = make_query(sel_all)
     scan = eng.prepare(pages, q)
-    sections = scan_sections(scan, device) if world > 1 else None
+    exchange = GatherExchange(scan, eng, world) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def one_step():
         scan.enqueue()
         if world > 1:
-            allreduce_scan(scan, eng, sections)
+            exchange.run()
         scan.finalize_device()
 
     def barrier():
@@ -266,7 +266,7 @@ def main():
         s = eng.prepare(hp, q)
         s.enqueue()
         if world > 1:
-            allreduce_scan(s, eng)
+            GatherExchange(s, eng, world).run()
         res = s.finalize()
         s.sync()
         cc = eng.counters()

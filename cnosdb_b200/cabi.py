@@ -96,7 +96,7 @@ GPU_SYMBOLS = [
     "tskvgpu_get_counters", "tskvgpu_ctx_stream", "tskvgpu_upload_pages", "tskvgpu_pages_destroy",
     "tskvgpu_pages_series_count", "tskvgpu_decode_pages", "tskvgpu_query_output_layout",
     "tskvgpu_scan_aggregate", "tskvgpu_scan_prepare", "tskvgpu_scan_run", "tskvgpu_scan_enqueue",
-    "tskvgpu_scan_sync", "tskvgpu_scan_partials",
+    "tskvgpu_scan_sync", "tskvgpu_scan_partials", "tskvgpu_scan_exchange_view", "tskvgpu_scan_merge_gathered",
     "tskvgpu_scan_snapshot_keys", "tskvgpu_scan_mask_values", "tskvgpu_scan_finalize",
     "tskvgpu_scan_finalize_device", "tskvgpu_scan_destroy", "tskvgpu_version",
 ]
@@ -151,6 +151,8 @@ def load_gpu_library():
     lib.tskvgpu_scan_enqueue.argtypes = [vp, vp]
     lib.tskvgpu_scan_sync.argtypes = [vp, vp]
     lib.tskvgpu_scan_partials.argtypes = [vp, vp, C.POINTER(PartialsView)]
+    lib.tskvgpu_scan_exchange_view.argtypes = [vp, vp, u64p, u64p]
+    lib.tskvgpu_scan_merge_gathered.argtypes = [vp, vp, C.c_uint64, C.c_uint32]
     lib.tskvgpu_scan_snapshot_keys.argtypes = [vp, vp]
     lib.tskvgpu_scan_mask_values.argtypes = [vp, vp]
     lib.tskvgpu_scan_finalize.argtypes = [vp, vp, vp, vp]

@@ -1030,6 +1030,54 @@ __global__ void k_mask_values(uint64_t *state, StateLayout L) {
   }
 }
 
+// Multi-GPU: every rank all-gathers the exchange region state[0, exch_words) of all ranks (ONE collective)
+// and merges the copies locally, section by section: counts / integer sums wrap-add, f64 sums add in rank
+// order (deterministic), min / max keys, and for FIRST / LAST the value of the rank holding the best key.
+__global__ void k_merge_gathered(uint64_t *state, StateLayout L, const uint64_t *gathered, uint32_t n_ranks,
+                                 uint64_t exch_words) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t min_plain = L.first_keys_off - L.min_off, max_plain = L.last_keys_off - L.max_off;
+  for (uint64_t k = i; k < L.sum_i64_len; k += stride) {
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) acc += gathered[r * exch_words + L.sum_i64_off + k];
+    state[L.sum_i64_off + k] = acc;
+  }
+  for (uint64_t k = i; k < L.sum_f64_len; k += stride) {
+    double acc = 0.0;
+    for (uint32_t r = 0; r < n_ranks; r++) acc += __longlong_as_double((long long)gathered[r * exch_words + L.sum_f64_off + k]);
+    state[L.sum_f64_off + k] = (uint64_t)__double_as_longlong(acc);
+  }
+  for (uint64_t k = i; k < min_plain; k += stride) {
+    int64_t acc = INT64_MAX;
+    for (uint32_t r = 0; r < n_ranks; r++) { int64_t v = (int64_t)gathered[r * exch_words + L.min_off + k]; acc = v < acc ? v : acc; }
+    state[L.min_off + k] = (uint64_t)acc;
+  }
+  for (uint64_t k = i; k < max_plain; k += stride) {
+    int64_t acc = INT64_MIN;
+    for (uint32_t r = 0; r < n_ranks; r++) { int64_t v = (int64_t)gathered[r * exch_words + L.max_off + k]; acc = v > acc ? v : acc; }
+    state[L.max_off + k] = (uint64_t)acc;
+  }
+  for (uint64_t k = i; k < L.first_cells; k += stride) {
+    int64_t bk = INT64_MAX; uint64_t bv = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) {
+      int64_t key = (int64_t)gathered[r * exch_words + L.first_keys_off + k];
+      if (key < bk) { bk = key; bv = gathered[r * exch_words + L.selval_off + k]; }
+    }
+    state[L.first_keys_off + k] = (uint64_t)bk;
+    state[L.selval_off + k] = bv;
+  }
+  for (uint64_t k = i; k < L.last_cells; k += stride) {
+    int64_t bk = INT64_MIN; uint64_t bv = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) {
+      int64_t key = (int64_t)gathered[r * exch_words + L.last_keys_off + k];
+      if (key > bk) { bk = key; bv = gathered[r * exch_words + L.selval_off + L.first_cells + k]; }
+    }
+    state[L.last_keys_off + k] = (uint64_t)bk;
+    state[L.selval_off + L.first_cells + k] = bv;
+  }
+}
+
 // Per output column: which state arrays feed it.
 struct OutCol {
   uint64_t count_off;  // counts of the source column

@@ -1042,6 +1042,25 @@ tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *s, tskv_partials_vie
   return TSKV_OK;
 }
 
+tskv_status tskvgpu_scan_exchange_view(tskv_ctx *ctx, tskv_scan *s, uint64_t *out_dptr, uint64_t *out_words) {
+  if (!ctx || !s || !out_dptr || !out_words) return TSKV_ERR_INVALID_ARG;
+  *out_dptr = (uint64_t)(uintptr_t)s->d_state;
+  *out_words = s->sl.selval_off + s->sl.selval_len;  // sum_i64 | sum_f64 | min+first keys | max+last keys | values
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_merge_gathered(tskv_ctx *ctx, tskv_scan *s, uint64_t gathered_dptr, uint32_t n_ranks) {
+  if (!ctx || !s || !gathered_dptr || n_ranks == 0) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const uint64_t words = s->sl.selval_off + s->sl.selval_len;
+  uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, 2048);
+  k_merge_gathered<<<std::max(1u, blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl, reinterpret_cast<const uint64_t *>((uintptr_t)gathered_dptr),
+                                                                   n_ranks, words);
+  CU_TRY(ctx, cudaGetLastError());
+  return TSKV_OK;
+}
+
 tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *s) {
   if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);

@@ -155,6 +155,15 @@ class PreparedScan:
         self.engine._check(self.engine.lib.tskvgpu_scan_partials(self.engine.ctx, self.handle, C.byref(v)))
         return v
 
+    def exchange_view(self):
+        """(device pointer, length in 8-byte words) of the region a multi-GPU run all-gathers."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.engine._check(self.engine.lib.tskvgpu_scan_exchange_view(self.engine.ctx, self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def merge_gathered(self, gathered_ptr, n_ranks):
+        self.engine._check(self.engine.lib.tskvgpu_scan_merge_gathered(self.engine.ctx, self.handle, gathered_ptr, n_ranks))
+
     def snapshot_keys(self):
         self.engine._check(self.engine.lib.tskvgpu_scan_snapshot_keys(self.engine.ctx, self.handle))
 

@@ -28,9 +28,17 @@ def device_tensor(ptr, n, dtype, device):
     return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
 
 
-def shard_of(series_id, world_size):
-    """Series -> rank. `id % N`."""
-    return series_id % world_size
+def shard_range(n_series, rank, world_size):
+    """Contiguous series-id range [lo, hi) of a rank, like the reference's per-task series chunks
+    (tskv/src/reader/iterator.rs:232-235). (BASELINE's `id % N` would put all i64 series of the mixed C4
+    workload on the even ranks and all f64 series on the odd ones.)"""
+    per = (n_series + world_size - 1) // world_size
+    return min(n_series, rank * per), min(n_series, (rank + 1) * per)
+
+
+def shard_of(series_id, n_series, world_size):
+    per = (n_series + world_size - 1) // world_size
+    return series_id // per
 
 
 def select_tag_subset(n_series, keep_one_in=10):
@@ -96,3 +104,21 @@ def allreduce_scan(scan, engine, sections=None, group=None):
     with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream(), device=device)):
         allreduce_sections(sections, group=group)
     return sections
+
+
+class GatherExchange:
+    """The one collective of a multi-GPU scan: all-gather every rank's exchange region, merge locally
+    (tskvgpu_scan_merge_gathered). Buffers are allocated once per PreparedScan."""
+
+    def __init__(self, scan, engine, world_size, group=None):
+        self.scan, self.engine, self.world, self.group = scan, engine, world_size, group
+        self.device = torch.device("cuda", engine.device)
+        ptr, words = scan.exchange_view()
+        self.local = device_tensor(ptr, words, torch.int64, self.device)
+        self.gathered = torch.empty(world_size * words, dtype=torch.int64, device=self.device)
+        self.stream = torch.cuda.ExternalStream(engine.stream(), device=self.device)
+
+    def run(self):
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+        self.scan.merge_gathered(self.gathered.data_ptr(), self.world)

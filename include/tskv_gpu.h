@@ -249,6 +249,10 @@ tskv_status tskvgpu_scan_run(tskv_ctx *ctx, tskv_scan *scan);
 tskv_status tskvgpu_scan_enqueue(tskv_ctx *ctx, tskv_scan *scan);
 tskv_status tskvgpu_scan_sync(tskv_ctx *ctx, tskv_scan *scan);
 tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *scan, tskv_partials_view *out);
+/* Alternative with a single collective: all-gather the exchange region (device pointer + length in
+ * 8-byte words) of every rank into `gathered` (rank-major, n_ranks * words) and merge locally. */
+tskv_status tskvgpu_scan_exchange_view(tskv_ctx *ctx, tskv_scan *scan, uint64_t *out_dptr, uint64_t *out_words);
+tskv_status tskvgpu_scan_merge_gathered(tskv_ctx *ctx, tskv_scan *scan, uint64_t gathered_dptr, uint32_t n_ranks);
 /* Snapshot the local first/last keys before they are all-reduced in place (multi-GPU only). */
 tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *scan);
 /* Zero every first/last value whose local key (snapshot) lost the key all-reduce. */

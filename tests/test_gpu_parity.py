@@ -369,3 +369,41 @@ def test_query_validation_errors(engine):
     r = engine.scan_aggregate(pages, make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.array([77], dtype=np.uint32)))
     assert r.column(1, "count")[0][0, 0] == 0 and not r.column(1, "sum")[1][0, 0]
     pages.close()
+
+
+def test_two_shard_exchange_matches_whole_scan(engine):
+    """The multi-GPU exchange on one device: two contiguous series shards scanned separately with the
+    GLOBAL selection list, their exchange regions concatenated like an all-gather, merged with
+    tskvgpu_scan_merge_gathered -> identical to the oracle on the whole arena (incl. first/last ties)."""
+    import torch
+    from cnosdb_b200.parallel import device_tensor, select_tag_subset, shard_range
+    n = 3000
+    full = datagen.generate(n, n_fields=1, n_points=400, value_kind=datagen.MIXED, seed=31, jitter_permille=300,
+                            jitter_max=999, null_page_permille=100, null_row_permille=200)
+    sel = select_tag_subset(n, 3)
+    w = 60_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0 - 1000, datagen.TSBS_T0 + 399 * datagen.TSBS_STEP + 1000, w)
+    q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_I64, ALL_AGGS), PushedAggregate(2, cabi.TSKV_PT_F64, ALL_AGGS)],
+                    series_ids=sel, width=w, first_bucket_start=fbs, n_buckets=nb)
+    exp = orc.scan_aggregate(full.arena, full.descs, q)
+    dev = torch.device("cuda", engine.device)
+    scans, regions, keep = [], [], []
+    for r in range(2):
+        lo, hi = shard_range(n, r, 2)
+        g = datagen.generate(hi - lo, n_fields=1, n_points=400, value_kind=datagen.MIXED, seed=31, first_series_id=lo,
+                             jitter_permille=300, jitter_max=999, null_page_permille=100, null_row_permille=200)
+        pages = engine.upload_pages(g.arena, g.descs)
+        s = engine.prepare(pages, q)
+        s.run()
+        ptr, words = s.exchange_view()
+        regions.append(device_tensor(ptr, words, torch.int64, dev).clone())
+        scans.append(s)
+        keep.append((g, pages))
+    gathered = torch.cat(regions)
+    torch.cuda.synchronize()
+    for s in scans:  # every rank merges the same gathered buffer
+        s.merge_gathered(gathered.data_ptr(), 2)
+        assert_results_equal(s.finalize(), exp, what="2-shard exchange")
+        s.close()
+    for _, pages in keep:
+        pages.close()

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from cnosdb_b200 import cabi, datagen
 from cnosdb_b200.engine import PushedAggregate, QueryOption
-from cnosdb_b200.parallel import KEY_FIRST_IDENTITY, KEY_LAST_IDENTITY, allreduce_sections, select_tag_subset, shard_of
+from cnosdb_b200.parallel import KEY_FIRST_IDENTITY, KEY_LAST_IDENTITY, allreduce_sections, select_tag_subset, shard_range
 
 W = 60_000_000_000
 
@@ -69,10 +69,11 @@ def _worker(rank, world, port, out_dir):
     from oracle import pyoracle as orc
     n_series, n_first = 64, 40
     sel = select_tag_subset(n_series, 2)
-    # each rank generates only its shard (ids with id % world == rank), like bench.py does per GPU
-    g = datagen.generate((n_series - rank + world - 1) // world, n_fields=1, n_points=300, value_kind=datagen.MIXED,
-                         seed=21, first_series_id=rank, series_stride=world, null_page_permille=200, null_row_permille=100)
-    assert all(shard_of(int(s), world) == rank for s in g.descs["series_id"])
+    # each rank generates only its shard (a contiguous id range), like bench.py does per GPU
+    lo, hi = shard_range(n_series, rank, world)
+    g = datagen.generate(hi - lo, n_fields=1, n_points=300, value_kind=datagen.MIXED,
+                         seed=21, first_series_id=lo, null_page_permille=200, null_row_permille=100)
+    assert all(lo <= int(s) < hi for s in g.descs["series_id"])
     res = orc.scan_aggregate(g.arena, g.descs, _query(sel))   # global selection list, local pages
     rng = np.random.default_rng(100 + rank)
     sections, local_sel = _sections_from_oracle(res, rng, rank, n_first)
