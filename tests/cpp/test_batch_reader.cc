@@ -1,0 +1,124 @@
+// C++ test of the host-side BatchReader mirror (cnosdb_b200/csrc/host/batch_reader.h) over the C ABI, checked
+// against the CPU oracle. Reads like the reference's reader tests (tskv/src/reader/column_group/mod.rs:266-368):
+// build column groups, run the reader, compare the RecordBatch.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <vector>
+
+#include "../../cnosdb_b200/csrc/host/batch_reader.h"
+#include "../../cnosdb_b200/csrc/host/tsm_writer.h"
+#include "../../oracle/tskv_oracle.h"
+
+using namespace tskv::reader;
+
+#define CHECK(cond)                                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      return 1;                                                            \
+    }                                                                      \
+  } while (0)
+
+int main() {
+  // ---- 40 series x (time + i64 field 1 + f64 field 2), 500 rows, 10 s spacing ----------------------
+  const int n_series = 40, n = 500;
+  const int64_t t0 = 1640995200000000000ll, step = 10000000000ll, w = 60000000000ll;
+  tskv::Bytes arena;
+  std::vector<ColumnGroup> cgs;
+  std::vector<tskv_page_desc> descs;
+  uint64_t seed = 7;
+  auto rnd = [&]() { seed = seed * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(seed >> 33); };
+  for (int s = 0; s < n_series; s++) {
+    std::vector<int64_t> ts(n), iv(n);
+    std::vector<double> fv(n);
+    int64_t v = rnd() % 100;
+    for (int i = 0; i < n; i++) {
+      ts[i] = t0 + i * step + (s % 3 == 0 ? (int64_t)(rnd() % 1000) : 0);
+      v += (int64_t)(rnd() % 7) - 3;
+      iv[i] = v;
+      fv[i] = v * 0.5 + (rnd() % 1000) / 1024.0;
+    }
+    ColumnGroup cg(s, (SeriesId)(100 + s));
+    cg.time_range_merge(TimeRange{ts.front(), ts.back()});
+    auto add = [&](const tskv::Bytes &data, ColumnId id, const char *name, PhysicalDType pt) {
+      while (arena.size() & 15) arena.push_back(0);
+      uint64_t off = arena.size();
+      tskv::append_page(nullptr, n, data, arena);
+      cg.push(PageWriteSpec{off, arena.size() - off, PageMeta{(uint32_t)n, TableColumn{id, name, pt}}});
+      descs.push_back(tskv_page_desc{off, (uint32_t)(arena.size() - off), (uint32_t)n, (uint32_t)(100 + s), id, (uint8_t)pt, 0});
+    };
+    tskv::Bytes d;
+    tskv::encode_timestamps(ts.data(), n, d); add(d, 0, "time", PhysicalDType::Time);
+    d.clear(); tskv::encode_integers(iv.data(), n, d); add(d, 1, "usage_user", PhysicalDType::Integer);
+    d.clear(); tskv::encode_floats(fv.data(), n, d); add(d, 2, "usage_idle", PhysicalDType::Float);
+    cgs.push_back(cg);
+  }
+  // ---- the pushed-down scan: WHERE time BETWEEN .. AND series IN (..) GROUP BY time_window(1m) -------
+  QueryOption opt;
+  opt.time_ranges = {TimeRange{t0 + 95 * step, t0 + 400 * step}};
+  std::vector<SeriesId> sel;
+  for (int s = 0; s < n_series; s += 2) sel.push_back(100 + s);
+  opt.series_ids = sel;
+  opt.bucket = TimeBucket{0, w};
+  opt.table_columns = {TableColumn{1, "usage_user", PhysicalDType::Integer}, TableColumn{2, "usage_idle", PhysicalDType::Float}};
+  opt.aggregates = {{AggregateKind::Mean, 1}, {AggregateKind::Max, 1}, {AggregateKind::Count, 2}, {AggregateKind::Sum, 2},
+                    {AggregateKind::First, 2}, {AggregateKind::Last, 1}};
+  auto eng = GpuEngine::create(0);
+  CHECK(eng.ok());
+  GpuAggregateBatchReader reader(eng.value, arena.data(), arena.size(), cgs, opt);
+  std::ostringstream desc;
+  reader.fmt_as(desc);
+  CHECK(desc.str().find("GpuAggregateBatchReader") == 0 && reader.children().empty());
+  auto res = reader.process();
+  CHECK(res.ok());
+  CHECK(res.value.size() == 1);
+  const RecordBatch &b = res.value[0];
+  CHECK(b.columns.size() == 1 + opt.aggregates.size());
+  CHECK(b.columns[0].name == "time" && b.columns[1].name == "mean(usage_user)" && b.columns[5].name == "first(usage_idle)");
+  CHECK(reader.metrics().page_read_count == (uint64_t)(n_series / 2) * 3);
+
+  // ---- oracle on the same arena / equivalent tskv_query ------------------------------------------------
+  tskv_agg_column qcols[2] = {{1, TSKV_PT_I64, (uint8_t)(TSKV_AGG_MEAN | TSKV_AGG_MAX | TSKV_AGG_LAST)},
+                              {2, TSKV_PT_F64, (uint8_t)(TSKV_AGG_COUNT | TSKV_AGG_SUM | TSKV_AGG_FIRST)}};
+  tskv_time_range tr{opt.time_ranges[0].min_ts, opt.time_ranges[0].max_ts};
+  tskv_query q{};
+  q.series_ids = sel.data(); q.n_series = (uint32_t)sel.size();
+  q.time_ranges = &tr; q.n_time_ranges = 1;
+  q.origin = 0; q.width = w;
+  q.first_bucket_start = (int64_t)b.columns[0].values[0];
+  q.n_buckets = (uint32_t)b.num_rows;
+  q.columns = qcols; q.n_columns = 2;
+  tskv_output_layout L{};
+  CHECK(orc_query_output_layout(descs.data(), descs.size(), &q, &L) == TSKV_OK);
+  std::vector<uint64_t> ov(L.n_out * L.n_cells);
+  std::vector<uint8_t> ob(L.validity_bytes);
+  CHECK(orc_scan_aggregate(arena.data(), arena.size(), descs.data(), descs.size(), &q, 1, 1, ov.data(), ob.data(), nullptr) == TSKV_OK);
+  // oracle output order: col1 {max, mean, last}, col2 {count, sum, first}
+  struct Map { int batch_col; int oracle_col; bool approx; } maps[] = {{1, 1, true}, {2, 0, false}, {3, 3, false}, {4, 4, true}, {5, 5, false}, {6, 2, false}};
+  for (const Map &m : maps) {
+    const ArrayData &c = b.columns[m.batch_col];
+    for (size_t i = 0; i < b.num_rows; i++) {
+      bool ev = (ob[m.oracle_col * L.bitmap_stride + (i >> 3)] >> (i & 7)) & 1;
+      CHECK(c.is_valid(i) == ev);
+      if (!ev) continue;
+      uint64_t e = ov[m.oracle_col * L.n_cells + i], g = c.values[i];
+      if (m.approx) {
+        double ed, gd;
+        memcpy(&ed, &e, 8); memcpy(&gd, &g, 8);
+        CHECK(std::fabs(ed - gd) <= 1e-6 * std::fabs(ed));
+      } else {
+        CHECK(e == g);
+      }
+    }
+  }
+  // ---- error behaviour: a corrupted page surfaces TsmPageFileHashCheckFailed, not a crash ----------------
+  tskv::Bytes bad = arena;
+  bad[cgs[0].pages()[1].offset + cgs[0].pages()[1].size - 1] ^= 0x10;
+  GpuAggregateBatchReader bad_reader(eng.value, bad.data(), bad.size(), cgs, opt);
+  auto bad_res = bad_reader.process();
+  CHECK(!bad_res.ok() && bad_res.error.status == TSKV_ERR_CRC_MISMATCH && bad_res.error.page == 1);
+  printf("test_batch_reader ok: %zu buckets, %llu pages read\n", b.num_rows, (unsigned long long)reader.metrics().page_read_count);
+  return 0;
+}
