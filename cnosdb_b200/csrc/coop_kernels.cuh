@@ -1,0 +1,336 @@
+// coop_kernels.cuh — warp-cooperative scan of ONE page per warp (sm_100a), for the codecs that decode in
+// parallel: timestamps RLE / simple8b, values zig-zag simple8b (and the closed-form / raw kinds).
+//
+// The lane-per-page kernels (scan_kernels.cuh) are bounded by the serial decode latency of one page
+// (1000 rows x ~120 dependent instructions) no matter how many SMs or GPUs share the work. Here a warp
+//   A. decodes the time page into shared memory (skipped for RLE: closed form),
+//   B. decodes the value page into shared memory: 32 simple8b words per step with coalesced 8-byte loads,
+//      selector -> count LUT, warp exclusive scan for the output offsets, unpack, warp inclusive scan of the
+//      per-word delta sums for the running prefix (the carry crosses steps),
+//   C. computes per row (lane-per-row) the (selected, bucket) key with a multiply-high division by the
+//      invariant bucket width and compacts the segment heads,
+//   D. reduces lane-per-segment (a 1-minute bucket of a 10-second series is 6 rows) and updates the
+//      per-CTA shared-memory table / the global state once per segment and aggregate.
+// Same formats and semantics as cursors.cuh / scan_kernels.cuh (reference lines cited there).
+#pragma once
+#include "scan_kernels.cuh"
+
+namespace tskv {
+
+constexpr int COOP_TILE = 1024;              // pages with more rows use the lane-per-page kernels
+constexpr int COOP_PAD = COOP_TILE + COOP_TILE / 32 + 8;
+__host__ __device__ __forceinline__ uint32_t cpad(uint32_t i) { return i + (i >> 5); }
+
+template <bool HAS_TS>
+struct CoopSmem {
+  uint64_t vals[COOP_PAD];
+  uint64_t ts[HAS_TS ? COOP_PAD : 1];
+  uint16_t seg[COOP_TILE + 2];
+  uint32_t rank_base[COOP_TILE / 32 + 1];
+};
+
+__device__ __forceinline__ uint64_t load_be64_any(const uint8_t *p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint64_t *ap = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+  const uint32_t sh = (uint32_t)(a & 7) * 8;
+  const uint64_t lo = __ldg(ap), hi = __ldg(ap + 1);
+  return bswap64((lo >> sh) | ((hi << 1) << (63 - sh)));
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan_u32(uint32_t v, uint32_t *total) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  *total = __shfl_sync(FULL, x, 31);
+  return x - v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, o), hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), o);
+    if (lane >= (uint32_t)o) v += ((uint64_t)hi << 32) | lo;
+  }
+  return v;
+}
+
+// Cooperative simple8b delta decode (simple8b.rs:80-208 + timestamp.rs:261-299 / integer.rs:216-248):
+// dst[cpad(i)] = first + sum_{j<=i} d(u_j), d = zig-zag decode (ZZ) or u * scaler. Writes at most `cap`
+// values; returns how many values the stream holds (first value included).
+template <bool ZZ>
+__device__ __forceinline__ uint32_t coop_decode_s8b(const uint8_t *words, uint32_t n_words, uint64_t first,
+                                                    uint64_t scaler, uint64_t *dst, uint32_t cap) {
+  const uint32_t lane = threadIdx.x & 31;
+  if (lane == 0 && cap) dst[0] = first;
+  uint64_t carry = first;
+  uint32_t base = 1;
+  for (uint32_t w0 = 0; w0 < n_words; w0 += 32) {
+    const uint32_t wi = w0 + lane;
+    const bool have = wi < n_words;
+    const uint64_t word = have ? load_be64_any(words + 8ull * wi) : 0;
+    const uint32_t sel = (uint32_t)(word >> 60);
+    const uint32_t cnt = have ? c_s8b_count[sel] : 0;
+    const uint32_t bits = c_s8b_bits[sel];
+    const uint64_t mask = bits ? (~0ull >> (64 - bits)) : 0ull;
+    uint32_t total;
+    const uint32_t pos = base + warp_excl_scan_u32(cnt, &total);
+    // pass 1: sum of this word's deltas
+    uint64_t wsum = 0;
+    if (sel < 2) {
+      const uint64_t one = ZZ ? (uint64_t)zigzag_dec(1) : scaler;
+      wsum = one * cnt;
+    } else {
+      uint64_t x = word & 0x0fffffffffffffffull;
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint64_t u = x & mask;
+        x >>= bits;
+        wsum += ZZ ? (uint64_t)zigzag_dec(u) : u * scaler;
+      }
+    }
+    const uint64_t incl = warp_incl_scan_u64(wsum);
+    uint64_t run = carry + incl - wsum;
+    // pass 2: running prefix to shared memory
+    {
+      uint64_t x = word & 0x0fffffffffffffffull;
+      for (uint32_t k = 0; k < cnt; k++) {
+        const uint64_t u = sel < 2 ? 1ull : (x & mask);
+        x >>= bits;
+        run += ZZ ? (uint64_t)zigzag_dec(u) : u * scaler;
+        if (pos + k < cap) dst[cpad(pos + k)] = run;
+      }
+    }
+    carry += shfl_u64(incl, 31);
+    base += total;
+  }
+  return base;
+}
+
+// Multiply-high division of a non-negative dividend by the invariant bucket width (Granlund-Montgomery):
+// q = floor(x / d) for d >= 1 with m = floor(2^64 (2^l - d) / d) + 1, l = ceil(log2 d).
+struct MagicDiv {
+  uint64_t m;
+  uint32_t l;  // 0 => d == 1
+};
+__device__ __forceinline__ uint64_t magic_div(uint64_t x, MagicDiv md) {
+  if (md.l == 0) return x;
+  const uint64_t t = __umul64hi(md.m, x);
+  return (((x - t) >> 1) + t) >> (md.l - 1);
+}
+
+struct CoopParams {
+  MagicDiv div;        // by P.width
+  int64_t q0;          // quotient of first_bucket_start: bucket idx = q(t) - q0
+  uint32_t grid_ok;    // first_bucket_start lies on the bucket grid
+  uint32_t pad;
+};
+
+// (selected by the time ranges, bucket) of one timestamp as a 32-bit key; 0xffffffff = not selected.
+__device__ __forceinline__ uint32_t coop_row_key(const ScanParams &P, const CoopParams &C, int64_t t, bool *range_err) {
+  bool in = P.n_ranges == 0;
+#pragma unroll 1
+  for (uint32_t k = 0; k < P.n_ranges && !in; k++) in = t >= P.ranges[k].min_ts && t <= P.ranges[k].max_ts;
+  if (!in) return 0xffffffffu;
+  if (P.width <= 0) return 0;
+  const int64_t dividend = (int64_t)((uint64_t)t - (uint64_t)P.origin_mod + (uint64_t)P.width);
+  int64_t idx;
+  if (dividend >= 0 && C.grid_ok) {
+    idx = (int64_t)magic_div((uint64_t)dividend, C.div) - C.q0;
+  } else {  // the reference's truncating-% regime (time_window.rs:184-198): exact slow path
+    const int64_t start = (int64_t)((uint64_t)t - (uint64_t)(dividend % P.width));
+    const int64_t diff = (int64_t)((uint64_t)start - (uint64_t)P.first_bucket_start);
+    idx = (diff % P.width != 0) ? -1 : diff / P.width;
+  }
+  if (idx < 0 || idx >= (int64_t)P.n_buckets) {
+    *range_err = true;
+    return 0xffffffffu;
+  }
+  return (uint32_t)idx;
+}
+
+// One page per warp. TK in {TK_RLE, TK_S8B} (time page without nulls), VK = VK_S8B (zig-zag simple8b values).
+template <int TK, bool SEL>
+__device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopParams &C, uint32_t item,
+                                               CoopSmem<TK == TK_S8B> &S, uint64_t *stab) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t page = P.work_page[item];
+  const uint32_t slot = P.work_slot[item];
+  const uint32_t qcol = P.work_qcol[item] & 0x7f;
+  const tskv_page_desc vd = P.descs[page];
+  const uint32_t tpage = P.time_page_of[page];
+  const tskv_page_desc td = P.descs[tpage];
+  const ColState &cs = P.cols[qcol];
+  const uint8_t pt = cs.phys_type, mask = cs.agg_mask;
+  const uint32_t n_rows = vd.num_values;
+  PageView tpv, vpv;
+  tpv.open(P.arena, td);
+  vpv.open(P.arena, vd);
+
+  // ---- A. timestamps --------------------------------------------------------------------------------
+  uint64_t t_first = 0, t_delta = 0;
+  if (TK == TK_RLE) {  // timestamp.rs:226-259
+    uint64_t dl = 0;
+    const bool ok = decode_varint(tpv.data + 10, tpv.data_len - 10, &dl);
+    if (!ok) { if (lane == 0) report_error(P, TSKV_ERR_SHORT_BLOCK, tpage); return; }
+    t_delta = dl * pow10_u64(__ldg(tpv.data + 1) & 0xf);
+    t_first = load_be64_any(tpv.data + 2);
+  } else {             // timestamp.rs:261-299
+    const uint64_t scaler = pow10_u64(__ldg(tpv.data + 1) & 0xf);
+    const uint32_t got = coop_decode_s8b<false>(tpv.data + 10, (tpv.data_len - 10) >> 3, load_be64_any(tpv.data + 2),
+                                                scaler, S.ts, n_rows);
+    if (got < n_rows) { if (lane == 0) report_error(P, TSKV_ERR_BITSET_MISMATCH, tpage); return; }
+  }
+  // ---- B. values + validity ranks -------------------------------------------------------------------
+  const uint32_t *vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
+  const uint32_t n_bm = (n_rows + 31) >> 5;
+  uint32_t n_valid;
+  {
+    uint32_t w = 0;
+    if (lane < n_bm) {
+      w = __ldg(vbm + lane);
+      if (lane == n_bm - 1 && (n_rows & 31)) w &= (1u << (n_rows & 31)) - 1;
+    }
+    const uint32_t ex = warp_excl_scan_u32(__popc(w), &n_valid);
+    S.rank_base[lane] = ex;
+  }
+  const uint32_t got = coop_decode_s8b<true>(vpv.data + 10, (vpv.data_len - 10) >> 3,
+                                             (uint64_t)zigzag_dec(load_be64_any(vpv.data + 2)), 1, S.vals, n_valid);
+  if (got < n_valid) { if (lane == 0) report_error(P, TSKV_ERR_BITSET_MISMATCH, page); return; }
+  __syncwarp();
+  // ---- C. per-row keys -> segment heads ---------------------------------------------------------------
+  bool range_err = false;
+  uint32_t n_seg = 0, n_inrange = 0;
+  uint32_t prev_key = 0xfffffffeu;  // key of the row before this 32-row strip (lane 31 of the last strip)
+  for (uint32_t r0 = 0; r0 < n_rows; r0 += 32) {
+    const uint32_t r = r0 + lane;
+    uint32_t key = 0xfffffffeu;
+    if (r < n_rows) {
+      const int64_t t = TK == TK_RLE ? (int64_t)(t_first + (uint64_t)r * t_delta) : (int64_t)S.ts[cpad(r)];
+      key = coop_row_key(P, C, t, &range_err);
+    }
+    uint32_t left = __shfl_up_sync(FULL, key, 1);
+    if (lane == 0) left = prev_key;
+    const bool head = r < n_rows && key != left;
+    const uint32_t hm = __ballot_sync(FULL, head);
+    if (head) S.seg[n_seg + __popc(hm & ((1u << lane) - 1))] = (uint16_t)r;
+    n_seg += __popc(hm);
+    n_inrange += __popc(__ballot_sync(FULL, r < n_rows && key != 0xffffffffu));
+    prev_key = __shfl_sync(FULL, key, 31);
+  }
+  if (lane == 0) S.seg[n_seg] = (uint16_t)n_rows;
+  __syncwarp();
+  if (__any_sync(FULL, range_err)) {
+    if (lane == 0) report_error(P, TSKV_ERR_BUCKET_RANGE, page);
+    return;
+  }
+  // ---- D. lane-per-segment reduce ---------------------------------------------------------------------
+  const uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull : 0ull;
+  const bool mean_hi = (mask & TSKV_AGG_MEAN) != 0;
+  const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
+  for (uint32_t s0 = 0; s0 < n_seg; s0 += 32) {
+    const uint32_t s = s0 + lane;
+    if (s < n_seg) {
+      const uint32_t rb = S.seg[s], re = S.seg[s + 1];
+      const int64_t tb = TK == TK_RLE ? (int64_t)(t_first + (uint64_t)rb * t_delta) : (int64_t)S.ts[cpad(rb)];
+      bool dummy = false;
+      const uint32_t key = coop_row_key(P, C, tb, &dummy);
+      if (key != 0xffffffffu) {
+        ValueAcc<VK_S8B> va;
+        va.reset();
+        uint64_t first_v = 0, last_v = 0;
+        bool first_ok = false, last_ok = false;
+        for (uint32_t r = rb; r < re; r++) {
+          const uint32_t w = __ldg(vbm + (r >> 5));
+          const bool vv = (w >> (r & 31)) & 1;
+          uint64_t v = 0;
+          if (vv) {
+            v = S.vals[cpad(S.rank_base[r >> 5] + __popc(w & ((1u << (r & 31)) - 1)))];
+            va.count++;
+            va.add(v, pt, flip, mean_hi);
+          }
+          if (SEL) {
+            if (r == rb) { first_v = v; first_ok = vv; }
+            last_v = v;
+            last_ok = vv;
+          }
+        }
+        const uint64_t cell = group_base + key;
+        if (va.count) table_update(P, stab, cs, cell, mask, false, va.count, va.sum, va.sum_hi, va.kmin, va.kmax);
+        if (SEL) {
+          const int64_t te = TK == TK_RLE ? (int64_t)(t_first + (uint64_t)(re - 1) * t_delta) : (int64_t)S.ts[cpad(re - 1)];
+          int64_t kf = tb, kl = te;
+          if (P.slot_bits) {
+            const uint64_t kb = P.width > 0 ? (uint64_t)P.first_bucket_start + (uint64_t)((int64_t)key - 1) * (uint64_t)P.width
+                                            : (uint64_t)P.rel_base;
+            kf = (int64_t)((((uint64_t)tb - kb) << P.slot_bits) | slot);
+            kl = (int64_t)((((uint64_t)te - kb) << P.slot_bits) | (P.slot_max - slot));
+          }
+          if ((mask & TSKV_AGG_FIRST) && first_ok) atomic_select_pair<true>(P.state + cs.first_off + 2 * cell, kf, first_v);
+          if ((mask & TSKV_AGG_LAST) && last_ok) atomic_select_pair<false>(P.state + cs.last_off + 2 * cell, kl, last_v);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    atomicAdd(&P.stats[0], (unsigned long long)n_valid);
+    if (n_inrange) atomicAdd(&P.stats[1], (unsigned long long)n_inrange);
+  }
+}
+
+template <int TK, bool SEL>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) k_scan_coop(const __grid_constant__ ScanParams P,
+                                                               const __grid_constant__ CoopParams C, int bin) {
+  extern __shared__ __align__(16) uint64_t s_dyn[];  // [per-CTA table | per-warp CoopSmem]
+  uint64_t *s_tab = s_dyn;
+  if (P.use_smem) {
+    for (uint32_t i = threadIdx.x; i < P.smem_words; i += SCAN_THREADS) s_tab[i] = 0;
+    __syncthreads();
+    for (uint32_t c = 0; c < P.n_cols; c++) {
+      const ColState cs = P.cols[c];
+      for (uint32_t i = threadIdx.x; i < (uint32_t)P.n_cells; i += SCAN_THREADS) {
+        if (cs.agg_mask & TSKV_AGG_MIN) s_tab[cs.s_min + i] = 0x7fffffffffffffffull;
+        if (cs.agg_mask & TSKV_AGG_MAX) s_tab[cs.s_max + i] = 0x8000000000000000ull;
+      }
+    }
+    __syncthreads();
+  }
+  using Smem = CoopSmem<TK == TK_S8B>;
+  Smem &S = *reinterpret_cast<Smem *>(reinterpret_cast<uint8_t *>(s_dyn + ((P.smem_words + 1) & ~1u)) +
+                                      (threadIdx.x >> 5) * ((sizeof(Smem) + 15) & ~(size_t)15));
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(P.task_counter + bin, 1u);
+    i = __shfl_sync(FULL, i, 0);
+    if (begin0 + i >= end0) break;
+    scan_page_coop<TK, SEL>(P, C, begin0 + i, S, s_tab);
+    __syncwarp();
+  }
+  if (P.use_smem) {  // merge this CTA's table into the global state, once
+    __syncthreads();
+    for (uint32_t c = 0; c < P.n_cols; c++) {
+      const ColState cs = P.cols[c];
+      const bool f64 = cs.phys_type == TSKV_PT_F64;
+      for (uint32_t i = threadIdx.x; i < (uint32_t)P.n_cells; i += SCAN_THREADS) {
+        const uint64_t cnt = s_tab[cs.s_count + i];
+        if (!cnt) continue;
+        atomicAdd(reinterpret_cast<unsigned long long *>(P.state + cs.count_off + i), (unsigned long long)cnt);
+        if (cs.agg_mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN)) {
+          const uint64_t sv = s_tab[cs.s_sum + i];
+          if (f64) atomicAdd(reinterpret_cast<double *>(P.state + cs.sum_off + i), __longlong_as_double((long long)sv));
+          else add_int_sum(P.state + cs.sum_off + i, P.state + cs.sumhi_off + i, cs.agg_mask, sv,
+                           (cs.agg_mask & TSKV_AGG_MEAN) ? (int64_t)s_tab[cs.s_hi + i] : 0);
+        }
+        if (cs.agg_mask & TSKV_AGG_MIN) atomicMin(reinterpret_cast<long long *>(P.state + cs.min_off + i), (long long)s_tab[cs.s_min + i]);
+        if (cs.agg_mask & TSKV_AGG_MAX) atomicMax(reinterpret_cast<long long *>(P.state + cs.max_off + i), (long long)s_tab[cs.s_max + i]);
+      }
+    }
+  }
+}
+
+}  // namespace tskv

@@ -13,7 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "host_util.h"
-#include "scan_kernels.cuh"
+#include "coop_kernels.cuh"
 
 using namespace tskv;
 
@@ -95,6 +95,7 @@ struct tskv_scan {
   uint64_t *d_values = nullptr;
   uint8_t *d_validity = nullptr;
   int grid[N_BINS] = {0};
+  CoopParams coop{};
   tskv_ctx *ctx = nullptr;
   uint32_t n_series_sel = 0;
   bool enqueued = false;
@@ -154,7 +155,28 @@ scan_kernel_t scan_kernel_for(int bin) {
 // relative cost of one item of a bin (sizes the bins' shares of the SMs)
 double bin_cost(int bin) {
   static const double tk[N_TK] = {1.0, 1.5, 2.0}, vk[N_VK] = {1.0, 1.4, 1.6};
+  if (bin == BIN_COOP_RLE_S8B) return 0.5;
+  if (bin == BIN_COOP_S8B_S8B) return 0.8;
   return tk[bin / N_VK] * vk[bin % N_VK];
+}
+
+size_t coop_smem_bytes(int bin, uint32_t table_words) {
+  size_t per_warp = bin == BIN_COOP_S8B_S8B ? sizeof(CoopSmem<true>) : sizeof(CoopSmem<false>);
+  per_warp = (per_warp + 15) & ~(size_t)15;
+  return (size_t)((table_words + 1) & ~1u) * 8 + per_warp * (SCAN_THREADS / 32);
+}
+const void *coop_kernel_for(int bin, bool sel) {
+  if (bin == BIN_COOP_RLE_S8B) return sel ? (const void *)k_scan_coop<TK_RLE, true> : (const void *)k_scan_coop<TK_RLE, false>;
+  return sel ? (const void *)k_scan_coop<TK_S8B, true> : (const void *)k_scan_coop<TK_S8B, false>;
+}
+
+MagicDiv make_magic(uint64_t d) {  // d >= 1
+  MagicDiv md{0, 0};
+  uint32_t l = 0;
+  while (l < 64 && ((unsigned __int128)1 << l) < d) l++;
+  md.l = l;
+  if (l) md.m = (uint64_t)(((((unsigned __int128)1 << l) - d) << 64) / d) + 1;
+  return md;
 }
 
 tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_output_layout *out) {
@@ -392,6 +414,10 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
       const tskv_page_desc &td = pg->h_descs[time_page_of[item_page[k]]];
       int tclass = time_has_nulls[time_page_of[item_page[k]]] ? TK_GEN : time_class(td.reserved);
       uint64_t bin = (uint64_t)tclass * N_VK + value_class(vd.reserved);
+      // pages that decode in parallel go to the warp-cooperative kernels
+      static const bool no_coop = getenv("TSKV_NO_COOP") != nullptr;
+      if (!no_coop && vd.num_values <= COOP_TILE && vd.reserved == DK_S8B_ZZ && tclass != TK_GEN)
+        bin = tclass == TK_RLE ? BIN_COOP_RLE_S8B : BIN_COOP_S8B_S8B;
       key[k] = (bin << 48) | ((uint64_t)vd.column_id << 32) | k;
       order[k] = k;
     }
@@ -801,7 +827,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_state, sl.total);
   // aux block (8-byte units): [0..7] task counters (N_BINS x u32) | 8 status | 9 err_page | 10,11 stats
   //                           | 12 pages 13 bytes 14..22 per-bin bytes
-  if (e == cudaSuccess) e = stream_alloc(ctx, reinterpret_cast<unsigned long long **>(&s->d_task_counter), 24);
+  if (e == cudaSuccess) e = stream_alloc(ctx, reinterpret_cast<unsigned long long **>(&s->d_task_counter), 32);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_values, L.n_out * L.n_cells);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_validity, L.validity_bytes + 8);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_outs, outs.data(), outs.size() * sizeof(OutCol), cudaMemcpyHostToDevice, ctx->stream);
@@ -875,18 +901,28 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       w[b] = n_bin * bin_cost(b);
       wsum += w[b];
-      if (n_bin) {
+      if (n_bin && b < N_SERIAL_BINS) {
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b),
                                                       SCAN_THREADS, (size_t)P.smem_words * 8);
         per_sm = std::min(per_sm, std::max(1, occ));
+      } else if (n_bin) {
+        const void *fn = coop_kernel_for(b, s->has_sel);
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(b, P.smem_words));
       }
+    }
+    // bucket arithmetic of the cooperative kernels: multiply-high division by the invariant width
+    if (q->width > 0) {
+      s->coop.div = make_magic((uint64_t)q->width);
+      const int64_t d0 = (int64_t)((uint64_t)q->first_bucket_start - (uint64_t)P.origin_mod + (uint64_t)q->width);
+      s->coop.grid_ok = (d0 >= 0 && d0 % q->width == 0) ? 1u : 0u;
+      s->coop.q0 = s->coop.grid_ok ? d0 / q->width : 0;
     }
     const int total = per_sm * ctx->sm_count;
     for (int b = 0; b < N_BINS; b++) {
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       if (!n_bin) continue;
-      int chunks = (int)((n_bin + 31) / 32);
+      int chunks = b < N_SERIAL_BINS ? (int)((n_bin + 31) / 32) : (int)n_bin;  // coop: one page per warp task
       int share = (int)(total * w[b] / wsum + 0.5);
       s->grid[b] = std::max(1, std::min(share, (chunks + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32)));
     }
@@ -904,7 +940,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   const uint32_t n_items = pages->n_items;
   cudaEventRecord(ctx->ev0, ctx->stream);
   unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
-  CU_TRY(ctx, cudaMemsetAsync(aux, 0, 24 * 8, ctx->stream));
+  CU_TRY(ctx, cudaMemsetAsync(aux, 0, 32 * 8, ctx->stream));
   CU_TRY(ctx, cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream));
   uint64_t launches = 0;
   if (pages->n_cg) {
@@ -939,9 +975,16 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
     if (!s->grid[b]) continue;
     cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_bin[0], 0);
     cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
-    void *args[] = {(void *)&s->params};
-    const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b));
-    CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, (size_t)s->params.smem_words * 8, ctx->bin_stream[b]));
+    if (b < N_SERIAL_BINS) {
+      void *args[] = {(void *)&s->params};
+      const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b));
+      CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, (size_t)s->params.smem_words * 8, ctx->bin_stream[b]));
+    } else {
+      int bin = b;
+      void *args[] = {(void *)&s->params, (void *)&s->coop, (void *)&bin};
+      CU_TRY(ctx, cudaLaunchKernel(coop_kernel_for(b, s->has_sel), dim3(s->grid[b]), dim3(SCAN_THREADS), args,
+                                   coop_smem_bytes(b, s->params.smem_words), ctx->bin_stream[b]));
+    }
     cudaEventRecord(ctx->ev_bin_done[b], ctx->bin_stream[b]);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_bin_done[b], 0);  // join
     launches++;
@@ -967,8 +1010,8 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
     if (st == TSKV_ERR_INVALID_ARG) ctx->set_error("page type does not match the query column type", ctx->err_page);
     return st;
   }
-  unsigned long long aux[14] = {0};  // stats[2], pages, bytes, per-bin bytes[9] (+1 spare)
-  CU_TRY(ctx, cudaMemcpy(aux, s->d_stats, 13 * 8, cudaMemcpyDeviceToHost));
+  unsigned long long aux[4 + N_BINS + 1] = {0};  // stats[2], pages, bytes, per-bin bytes[N_BINS]
+  CU_TRY(ctx, cudaMemcpy(aux, s->d_stats, (4 + N_BINS) * 8, cudaMemcpyDeviceToHost));
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->counters.elapsed_scan_ms = ms;

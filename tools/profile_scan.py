@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Minimal driver for ncu: builds the bench workload and runs a few device-resident scan steps.
-   ncu --set full --clock-control none --import-source on -k regex:k_scan_aggregate -s 2 -c 1 \
+   ncu --set full --clock-control none --import-source on -k regex:k_scan_ -s 2 -c 1 \
        -o gpurun_out/prof python tools/profile_scan.py --series 1000000 --steps 4"""
 import argparse
 import os
