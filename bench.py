@@ -41,8 +41,8 @@ W_NS = 60_000_000_000
 AGGS = ["count", "sum", "min", "max", "mean"]
 BIN_NAMES = {0: "ts=RLE,val=simple8b", 1: "ts=RLE,val=gorilla", 2: "ts=RLE,val=generic", 3: "ts=simple8b,val=simple8b",
              4: "ts=simple8b,val=gorilla", 5: "ts=simple8b,val=generic", 6: "ts=generic,val=simple8b",
-             7: "ts=generic,val=gorilla", 8: "ts=generic,val=generic", 9: "coop ts=RLE,val=simple8b",
-             10: "coop ts=simple8b,val=simple8b"}
+             7: "ts=generic,val=gorilla", 8: "ts=generic,val=generic", 9: "ts=RLE,val=simple8b (<=1024 rows)",
+             10: "ts=simple8b,val=simple8b (<=1024 rows)"}
 
 
 def workload_name(n_series):
@@ -250,7 +250,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     dom_gbs = dom_bytes / (np.mean(dom_ms) * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": ("k_scan_coop<%s>" if int(dom_bin) >= 9 else "k_scan_aggregate<%s>") % BIN_NAMES[int(dom_bin)],
+    roofline = {"bound": "hbm", "kernel": "k_scan_aggregate<%s>" % BIN_NAMES[int(dom_bin)],
                 "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": None, "bytes_per_launch": int(dom_bytes), "ms_per_launch": float(np.mean(dom_ms)),

@@ -898,10 +898,9 @@ constexpr int SCAN_THREADS = 128;
 #define SCAN_MIN_BLOCKS 4
 #endif
 template <int TK, int VK, bool SEL>
-__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS) k_scan_aggregate(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS) k_scan_aggregate(const __grid_constant__ ScanParams P, int bin) {
   __shared__ __align__(16) uint64_t s_ring[SCAN_THREADS / 32][2][RING_WORDS][32];  // per warp, per stream
   extern __shared__ __align__(16) uint64_t s_tab[];  // per-CTA partial table (P.smem_words words) or empty
-  constexpr int bin = TK * N_VK + VK;
   if (P.use_smem) {  // identities: 0 for counts / sums, +-inf keys for min / max
     for (uint32_t i = threadIdx.x; i < P.smem_words; i += SCAN_THREADS) s_tab[i] = 0;
     __syncthreads();

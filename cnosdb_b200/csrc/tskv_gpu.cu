@@ -95,6 +95,7 @@ struct tskv_scan {
   uint64_t *d_values = nullptr;
   uint8_t *d_validity = nullptr;
   int grid[N_BINS] = {0};
+  bool use_coop[N_BINS] = {false};  // cooperative-eligible bins: which kernel family runs them
   CoopParams coop{};
   tskv_ctx *ctx = nullptr;
   uint32_t n_series_sel = 0;
@@ -137,7 +138,7 @@ unsigned bits_for(uint64_t max_value) {  // bits needed to represent values in [
 
 unsigned popc8(unsigned x) { return (unsigned)__builtin_popcount(x & TSKV_AGG_ALL); }
 
-typedef void (*scan_kernel_t)(const ScanParams);
+typedef void (*scan_kernel_t)(const ScanParams, int);
 template <bool SEL>
 scan_kernel_t scan_kernel_for(int bin) {
   switch (bin) {
@@ -153,11 +154,16 @@ scan_kernel_t scan_kernel_for(int bin) {
   }
 }
 // relative cost of one item of a bin (sizes the bins' shares of the SMs)
-double bin_cost(int bin) {
+// serial (lane-per-page) kernel bin whose code also handles a cooperative-eligible bin
+int serial_bin_of(int bin) {
+  if (bin == BIN_COOP_RLE_S8B) return TK_RLE * N_VK + VK_S8B;
+  if (bin == BIN_COOP_S8B_S8B) return TK_S8B * N_VK + VK_S8B;
+  return bin;
+}
+double bin_cost(int bin, bool coop) {
   static const double tk[N_TK] = {1.0, 1.5, 2.0}, vk[N_VK] = {1.0, 1.4, 1.6};
-  if (bin == BIN_COOP_RLE_S8B) return 0.5;
-  if (bin == BIN_COOP_S8B_S8B) return 0.8;
-  return tk[bin / N_VK] * vk[bin % N_VK];
+  const int sb = serial_bin_of(bin);
+  return tk[sb / N_VK] * vk[sb % N_VK] * (coop ? 1.8 : 1.0);
 }
 
 size_t coop_smem_bytes(int bin, uint32_t table_words) {
@@ -894,16 +900,27 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   }
 
   {
+    // Cooperative (one page per warp) vs lane-per-page for the eligible bins: lane-per-page needs fewer
+    // instructions per point but one page costs ~1 ms of serial latency, so it only pays when the selected
+    // pages can fill the machine (>= ~1/4 of the resident lanes); otherwise go cooperative.
+    const char *mode = getenv("TSKV_COOP");  // "0" never, "1" always, unset = auto
+    const double sel_frac = (q->series_ids && !pages->series.empty())
+                                ? std::min(1.0, (double)q->n_series / (double)pages->series.size()) : 1.0;
+    const double lanes = (double)ctx->sm_count * SCAN_MIN_BLOCKS * SCAN_THREADS;
+    const double est_total = (double)pages->n_items * sel_frac;  // selected field pages, all bins
+    for (int b = N_SERIAL_BINS; b < N_BINS; b++)
+      s->use_coop[b] = mode ? (mode[0] == '1') : (est_total < 0.25 * lanes);
     // Static split of the resident thread blocks among the bins the arena contains, by estimated work.
     double w[N_BINS], wsum = 0;
     int per_sm = SCAN_MIN_BLOCKS;
     for (int b = 0; b < N_BINS; b++) {
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
-      w[b] = n_bin * bin_cost(b);
+      w[b] = n_bin * bin_cost(b, s->use_coop[b]);
       wsum += w[b];
-      if (n_bin && b < N_SERIAL_BINS) {
+      if (n_bin && !s->use_coop[b]) {
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b),
+        const int sb = serial_bin_of(b);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb),
                                                       SCAN_THREADS, (size_t)P.smem_words * 8);
         per_sm = std::min(per_sm, std::max(1, occ));
       } else if (n_bin) {
@@ -922,7 +939,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     for (int b = 0; b < N_BINS; b++) {
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       if (!n_bin) continue;
-      int chunks = b < N_SERIAL_BINS ? (int)((n_bin + 31) / 32) : (int)n_bin;  // coop: one page per warp task
+      int chunks = s->use_coop[b] ? (int)n_bin : (int)((n_bin + 31) / 32);  // coop: one page per warp task
       int share = (int)(total * w[b] / wsum + 0.5);
       s->grid[b] = std::max(1, std::min(share, (chunks + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32)));
     }
@@ -975,12 +992,13 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
     if (!s->grid[b]) continue;
     cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_bin[0], 0);
     cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
-    if (b < N_SERIAL_BINS) {
-      void *args[] = {(void *)&s->params};
-      const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(b) : scan_kernel_for<false>(b));
+    int bin = b;
+    if (!s->use_coop[b]) {
+      const int sb = serial_bin_of(b);
+      void *args[] = {(void *)&s->params, (void *)&bin};
+      const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb));
       CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, (size_t)s->params.smem_words * 8, ctx->bin_stream[b]));
     } else {
-      int bin = b;
       void *args[] = {(void *)&s->params, (void *)&s->coop, (void *)&bin};
       CU_TRY(ctx, cudaLaunchKernel(coop_kernel_for(b, s->has_sel), dim3(s->grid[b]), dim3(SCAN_THREADS), args,
                                    coop_smem_bytes(b, s->params.smem_words), ctx->bin_stream[b]));
@@ -1032,7 +1050,8 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
     if (getenv("TSKV_DEBUG_BINS")) {
       float t0 = 0;
       cudaEventElapsedTime(&t0, ctx->ev_bin[0], ctx->ev_bin_start[b]);
-      fprintf(stderr, "[tskv] bin %d grid %d: start +%.3f ms, run %.3f ms, %llu bytes\n", b, s->grid[b], t0, t, aux[4 + b]);
+      fprintf(stderr, "[tskv] bin %d%s grid %d: start +%.3f ms, run %.3f ms, %llu bytes\n", b, s->use_coop[b] ? " (coop)" : "",
+              s->grid[b], t0, t, aux[4 + b]);
     }
     if (t > ctx->counters.dominant_kernel_ms) {
       ctx->counters.dominant_kernel_ms = t;

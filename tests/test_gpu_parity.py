@@ -407,3 +407,23 @@ def test_two_shard_exchange_matches_whole_scan(engine):
         s.close()
     for _, pages in keep:
         pages.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_both_kernel_families_agree_with_oracle(engine, mode, monkeypatch):
+    """TSKV_COOP=0 forces the lane-per-page kernels, =1 the warp-cooperative ones, for the eligible pages
+    (zig-zag simple8b values, RLE / simple8b timestamps, <= 1024 rows). Default is chosen per scan."""
+    monkeypatch.setenv("TSKV_COOP", mode)
+    g = datagen.generate(3000, n_fields=2, n_points=777, value_kind=datagen.I64_WALK, seed=77, jitter_permille=400,
+                         jitter_max=999_999, null_page_permille=300, null_row_permille=150)
+    pages = engine.upload_pages(g.arena, g.descs)
+    w = 60_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0 - 1_000_000, datagen.TSBS_T0 + 776 * datagen.TSBS_STEP + 1_000_000, w)
+    sel = np.arange(0, 3000, 3, dtype=np.uint32)
+    for gbs in (False, True):
+        q = QueryOption([PushedAggregate(c, cabi.TSKV_PT_I64, ALL_AGGS) for c in (1, 2)], series_ids=sel,
+                        time_ranges=[(datagen.TSBS_T0 + 7 * datagen.TSBS_STEP, datagen.TSBS_T0 + 700 * datagen.TSBS_STEP)],
+                        width=w, first_bucket_start=fbs, n_buckets=nb, group_by_series=gbs)
+        assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=4),
+                             what="coop=%s gbs=%s" % (mode, gbs))
+    pages.close()
