@@ -897,8 +897,10 @@ constexpr int SCAN_THREADS = 128;
 #ifndef SCAN_MIN_BLOCKS
 #define SCAN_MIN_BLOCKS 4
 #endif
+// RLE-timestamp variants without FIRST/LAST need < 102 registers: 5 blocks per SM, the others 4.
+__host__ __device__ constexpr int scan_min_blocks(int tk, bool sel) { return (tk == TK_RLE && !sel) ? SCAN_MIN_BLOCKS + 1 : SCAN_MIN_BLOCKS; }
 template <int TK, int VK, bool SEL>
-__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS) k_scan_aggregate(const __grid_constant__ ScanParams P, int bin) {
+__global__ void __launch_bounds__(SCAN_THREADS, scan_min_blocks(TK, SEL)) k_scan_aggregate(const __grid_constant__ ScanParams P, int bin) {
   __shared__ __align__(16) uint64_t s_ring[SCAN_THREADS / 32][2][RING_WORDS][32];  // per warp, per stream
   extern __shared__ __align__(16) uint64_t s_tab[];  // per-CTA partial table (P.smem_words words) or empty
   if (P.use_smem) {  // identities: 0 for counts / sums, +-inf keys for min / max

@@ -910,23 +910,39 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     const double est_total = (double)pages->n_items * sel_frac;  // selected field pages, all bins
     for (int b = N_SERIAL_BINS; b < N_BINS; b++)
       s->use_coop[b] = mode ? (mode[0] == '1') : (est_total < 0.25 * lanes);
-    // Static split of the resident thread blocks among the bins the arena contains, by estimated work.
-    double w[N_BINS], wsum = 0;
-    int per_sm = SCAN_MIN_BLOCKS;
+    // Grid sizes. Every kernel is persistent (warps pull tasks from their bin's counter). If the resident
+    // capacity allows, each bin gets one warp per estimated task (a single round: the makespan of a bin is
+    // quantised in units of one task = one page's serial decode); otherwise the blocks are split by cost.
+    double w[N_BINS], wsum = 0, need_sum = 0, occ_weighted = 0;
+    int need[N_BINS] = {0};
     for (int b = 0; b < N_BINS; b++) {
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       w[b] = n_bin * bin_cost(b, s->use_coop[b]);
       wsum += w[b];
-      if (n_bin && !s->use_coop[b]) {
-        int occ = 0;
+      if (!n_bin) continue;
+      int occ = 0;
+      if (!s->use_coop[b]) {
         const int sb = serial_bin_of(b);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb),
                                                       SCAN_THREADS, (size_t)P.smem_words * 8);
-        per_sm = std::min(per_sm, std::max(1, occ));
-      } else if (n_bin) {
+      } else {
         const void *fn = coop_kernel_for(b, s->has_sel);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(b, P.smem_words));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, SCAN_THREADS, coop_smem_bytes(b, P.smem_words));
       }
+      occ = std::max(1, occ);
+      const double est_items = n_bin * sel_frac * 1.02 + 32;
+      const double tasks = s->use_coop[b] ? est_items : est_items / 32.0;
+      need[b] = (int)(tasks / (SCAN_THREADS / 32)) + 1;
+      need[b] = std::min(need[b], (int)((s->use_coop[b] ? n_bin : (n_bin + 31) / 32) + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32));
+      need_sum += need[b];
+      occ_weighted += (double)need[b] * occ;
+    }
+    const double capacity = need_sum > 0 ? (occ_weighted / need_sum) * ctx->sm_count : 0;  // resident blocks, mixed kernels
+    for (int b = 0; b < N_BINS; b++) {
+      if (!need[b]) continue;
+      if (need_sum <= capacity) s->grid[b] = std::max(1, need[b]);
+      else s->grid[b] = std::max(1, std::min(need[b], (int)(capacity * w[b] / wsum + 0.5)));
     }
     // bucket arithmetic of the cooperative kernels: multiply-high division by the invariant width
     if (q->width > 0) {
@@ -934,14 +950,6 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       const int64_t d0 = (int64_t)((uint64_t)q->first_bucket_start - (uint64_t)P.origin_mod + (uint64_t)q->width);
       s->coop.grid_ok = (d0 >= 0 && d0 % q->width == 0) ? 1u : 0u;
       s->coop.q0 = s->coop.grid_ok ? d0 / q->width : 0;
-    }
-    const int total = per_sm * ctx->sm_count;
-    for (int b = 0; b < N_BINS; b++) {
-      uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
-      if (!n_bin) continue;
-      int chunks = s->use_coop[b] ? (int)n_bin : (int)((n_bin + 31) / 32);  // coop: one page per warp task
-      int share = (int)(total * w[b] / wsum + 0.5);
-      s->grid[b] = std::max(1, std::min(share, (chunks + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32)));
     }
   }
   ctx->counters.h2d_bytes = h2d;
