@@ -249,16 +249,26 @@ def main():
     except (OSError, ValueError):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom_gbs = dom_bytes / (np.mean(dom_ms) * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_scan_aggregate<%s>" % BIN_NAMES[int(dom_bin)],
-                "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
-                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None, "bytes_per_launch": int(dom_bytes), "ms_per_launch": float(np.mean(dom_ms)),
-                "fused_phase": {"bytes": int(algo_bytes), "ms": float(np.mean(fused_ms)),
-                                "GBps": algo_bytes / (np.mean(fused_ms) * 1e-3) / 1e9,
-                                "frac": algo_bytes / (np.mean(fused_ms) * 1e-3) / 1e9 / peak,
-                                "decoded_equivalent_frac": 16 * points_local / (np.mean(fused_ms) * 1e-3) / 1e9 / peak},
-                "step_ms": float(np.mean(scan_ms)), "bound_note": "instruction/latency-bound lane-serial decode; see DESIGN.md"}
+    # The dominant kernel is the fused decode/filter/reduce kernel k_scan_aggregate: one template, launched
+    # once per decode-kind bin present (C4: 4 instantiations) on concurrent streams. `achieved` = the
+    # algorithmic bytes of one step / the CUDA-event time from the fork to the join of those launches.
+    fused_s = float(np.mean(fused_ms)) * 1e-3
+    traffic = None
+    try:  # DRAM bytes of the same launches from the committed `ncu --set full` capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_scan_ncu_summary.json")))["step_dram_traffic_bytes"]
+        traffic = int(traffic * page_bytes / 565936507) if world > 1 else traffic
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_scan_aggregate<TK,VK,SEL> (fused decode+filter+bucket-reduce; %d concurrent bin launches)" % 4,
+                "achieved": algo_bytes / fused_s / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo_bytes / fused_s / 1e9 / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": traffic, "bytes_per_launch": int(algo_bytes), "ms_per_launch": fused_s * 1e3,
+                "decoded_equivalent_frac": 16 * points_local / fused_s / 1e9 / peak,
+                "slowest_bin": {"kernel": "k_scan_aggregate<%s>" % BIN_NAMES[int(dom_bin)], "ms": float(np.mean(dom_ms)),
+                                "page_bytes": int(dom_bytes)},
+                "step_ms": float(np.mean(scan_ms)),
+                "bound_note": "issue/latency-bound lane-serial decode (ncu: issue-active 19-37%, DRAM 1.1x algorithmic bytes); see DESIGN.md section 5"}
 
     # ---- end to end: pages in host memory, PCIe gather inside the timed region ---------------------
     hp = eng.upload_pages(g.arena, g.descs, verify_crc=False, host_resident=True)

@@ -63,7 +63,10 @@ struct tskv_pages {
   uint32_t h_bin_start[N_BINS + 1]{};
   uint32_t *d_bin_start = nullptr;
   std::vector<uint32_t> series;  // sorted distinct ids
-  int64_t ts_min = INT64_MAX, ts_max = INT64_MIN;  // arena-wide time bounds (k_time_bounds)
+  // arena-wide time bounds, computed on first use by k_time_bounds (the reference keeps them in
+  // PageMeta.statistics); only unbucketed first/last across series needs them
+  mutable bool bounds_known = false;
+  mutable int64_t ts_min = INT64_MIN, ts_max = INT64_MAX;
 };
 
 struct tskv_scan {
@@ -183,6 +186,24 @@ MagicDiv make_magic(uint64_t d) {  // d >= 1
   md.l = l;
   if (l) md.m = (uint64_t)(((((unsigned __int128)1 << l) - d) << 64) / d) + 1;
   return md;
+}
+
+// Lazily computes the arena's min / max timestamp on the device (one lane per time page).
+void ensure_time_bounds(tskv_ctx *ctx, const tskv_pages *pg) {
+  if (pg->bounds_known || pg->n_cg == 0) return;
+  long long *d_bounds = nullptr;
+  if (cudaMalloc(reinterpret_cast<void **>(&d_bounds), 16) != cudaSuccess) return;
+  long long b[2] = {INT64_MAX, INT64_MIN};
+  cudaMemcpyAsync(d_bounds, b, sizeof(b), cudaMemcpyHostToDevice, ctx->stream);
+  k_time_bounds<<<(pg->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pg->h_mapped ? pg->h_mapped : pg->d_arena, pg->d_descs,
+                                                                pg->d_cg_time_page, pg->n_cg, d_bounds);
+  if (cudaMemcpyAsync(b, d_bounds, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+      cudaStreamSynchronize(ctx->stream) == cudaSuccess && b[0] <= b[1]) {
+    pg->ts_min = b[0];
+    pg->ts_max = b[1];
+  }
+  pg->bounds_known = true;
+  cudaFree(d_bounds);
 }
 
 tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_output_layout *out) {
@@ -472,24 +493,6 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
   cudaEventRecord(ctx->ev1, ctx->stream);
-  // arena-wide timestamp bounds (device pass over the time pages)
-  long long *d_bounds = nullptr;
-  if (e == cudaSuccess) e = dev_alloc(&d_bounds, 2);
-  if (e == cudaSuccess) {
-    long long init[2] = {INT64_MAX, INT64_MIN};
-    e = cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && pg->n_cg) {
-      k_time_bounds<<<(pg->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pg->h_mapped ? pg->h_mapped : pg->d_arena, pg->d_descs,
-                                                                    pg->d_cg_time_page, pg->n_cg, d_bounds);
-      e = cudaGetLastError();
-    }
-    long long b[2] = {INT64_MAX, INT64_MIN};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(b, d_bounds, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    pg->ts_min = b[0];
-    pg->ts_max = b[1];
-  }
-  cudaFree(d_bounds);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     ctx->set_error(std::string("upload: ") + cudaGetErrorString(e));
@@ -656,7 +659,8 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       if (q->width < (int64_t)1 << 61) rel_bits = bits_for(2 * (uint64_t)q->width);
     } else {
       // unbucketed: rel = t - (lower bound of every in-range timestamp); the arena's own time
-      // bounds (upload-time statistics) tighten unbounded / loose query ranges
+      // bounds tighten unbounded / loose query ranges
+      ensure_time_bounds(ctx, pages);
       int64_t lo = pages->ts_min, hi = pages->ts_max;
       if (q->n_time_ranges > 0) {
         int64_t qlo = q->time_ranges[0].min_ts, qhi = q->time_ranges[0].max_ts;
