@@ -177,11 +177,11 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_p
 // file reads of TsmReader::read_adjacent_pages (tsm/reader.rs:236-264).
 __global__ void k_gather_pages(const uint8_t *host_arena, uint8_t *dev_arena, const tskv_page_desc *descs,
                                const uint32_t *time_page_of, const uint32_t *work_page,
-                               const uint8_t *work_qcol, const uint32_t *total) {
-  const uint32_t n = *total;
+                               const uint8_t *work_qcol, const uint32_t *bin_cstart, int bin) {
+  const uint32_t w0 = bin_cstart[bin], n = bin_cstart[bin + 1];  // the bin's range of the work list
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+  for (uint32_t w = w0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < n; w += warps) {
     const uint32_t page = work_page[w];
     const bool with_time = work_qcol[w] & 0x80;
     for (int pass = 0; pass < (with_time ? 2 : 1); pass++) {
@@ -446,8 +446,9 @@ __device__ __forceinline__ void warp_flush(const ScanParams &P, uint64_t *stab, 
         sum = warp_sum_u64(sum, &carry);
         shi = (int64_t)(int32_t)__reduce_add_sync(FULL, (uint32_t)shi) + carry;  // |per-lane hi| < 2^26
       }
-      kmin = warp_min_i64((active && a.count) ? a.kmin : INT64_MAX);
-      kmax = warp_max_i64((active && a.count) ? a.kmax : INT64_MIN);
+      const uint32_t lmask = __shfl_sync(FULL, (uint32_t)mask, leader);  // same cell => same column => same mask
+      if (lmask & TSKV_AGG_MIN) kmin = warp_min_i64((active && a.count) ? a.kmin : INT64_MAX);
+      if (lmask & TSKV_AGG_MAX) kmax = warp_max_i64((active && a.count) ? a.kmax : INT64_MIN);
     }
     if (SEL) {
       fk = warp_min_i64((active && a.first_ok) ? kf : INT64_MAX);
@@ -522,6 +523,13 @@ __device__ __forceinline__ bool range_span(const ScanParams &P, int64_t t, int64
   lo = INT64_MIN;
   hi = INT64_MAX;
   if (P.n_ranges == 0) return true;
+  if (P.n_ranges == 1) {  // the common single BETWEEN
+    const int64_t a = P.ranges[0].min_ts, b = P.ranges[0].max_ts;
+    if (t < a) { hi = a - 1; return false; }
+    if (t > b) { lo = b + 1; return false; }
+    lo = a; hi = b;
+    return true;
+  }
   bool in = false;
 #pragma unroll 1
   for (uint32_t k = 0; k < P.n_ranges; k++) {

@@ -989,12 +989,6 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
                                                            s->d_work_page, s->d_work_slot, s->d_work_qcol,
                                                            s->d_bin_cstart, s->d_bin_cstart + N_BINS + 1);
     launches += 3;
-    if (pages->h_mapped) {
-      k_gather_pages<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(pages->h_mapped, pages->d_arena, pages->d_descs,
-                                                                 pages->d_time_page_of, s->d_work_page, s->d_work_qcol,
-                                                                 s->d_bin_cstart + N_BINS + 1);
-      launches++;
-    }
   }
   uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
   k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
@@ -1003,8 +997,18 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   for (int b = 0; b < N_BINS; b++) {
     if (!s->grid[b]) continue;
     cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_bin[0], 0);
-    cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
     int bin = b;
+    if (pages->h_mapped) {
+      // host-resident pages: pull this bin's selected pages over PCIe on the bin's own stream, so that the
+      // other bins' scans overlap with the copy
+      uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
+      uint32_t gblocks = std::max(1u, std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (n_bin + 7) / 8));
+      k_gather_pages<<<gblocks, 256, 0, ctx->bin_stream[b]>>>(pages->h_mapped, pages->d_arena, pages->d_descs,
+                                                              pages->d_time_page_of, s->d_work_page, s->d_work_qcol,
+                                                              s->d_bin_cstart, bin);
+      launches++;
+    }
+    cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
     if (!s->use_coop[b]) {
       const int sb = serial_bin_of(b);
       void *args[] = {(void *)&s->params, (void *)&bin};
