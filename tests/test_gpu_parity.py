@@ -427,3 +427,62 @@ def test_both_kernel_families_agree_with_oracle(engine, mode, monkeypatch):
         assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q, n_threads=4),
                              what="coop=%s gbs=%s" % (mode, gbs))
     pages.close()
+
+
+def test_maximum_and_minimum_page_sizes(engine):
+    """Column groups are capped at max_datablock_size = 102 400 rows (config/src/tskv/storage_config.rs:136-138);
+    the other extreme is a single row. Every codec, decode + scan."""
+    rng = np.random.default_rng(102400)
+    n = 102_400
+    b = datagen.ArenaBuilder()
+    ts_reg = datagen.TSBS_T0 + np.arange(n, dtype=np.int64) * 1_000_000
+    ts_jit = ts_reg + rng.integers(0, 999, n)
+    valid = rng.random(n) > 0.03
+    b.add_column_group(1, ts_reg, [(1, cabi.TSKV_PT_I64, np.cumsum(rng.integers(-9, 10, n)), None),
+                                   (2, cabi.TSKV_PT_F64, np.cumsum(rng.integers(-2, 3, n)) + rng.random(n), valid),
+                                   (3, cabi.TSKV_PT_U64, np.cumsum(rng.integers(0, 3, n)).astype(np.uint64), None)])
+    b.add_column_group(2, ts_jit, [(1, cabi.TSKV_PT_I64, rng.integers(-2**62, 2**62, n), valid),      # raw deltas
+                                   (2, cabi.TSKV_PT_F64, np.cumsum(rng.integers(-2, 3, n)).astype(np.float64), None),
+                                   (3, cabi.TSKV_PT_U64, np.full(n, 7, dtype=np.uint64), None)])         # RLE
+    b.add_column_group(3, np.array([datagen.TSBS_T0 + 5]), [(1, cabi.TSKV_PT_I64, np.array([-42]), None),
+                                                            (2, cabi.TSKV_PT_F64, np.array([2.5]), None),
+                                                            (3, cabi.TSKV_PT_U64, np.array([9], dtype=np.uint64), None)])
+    arena, descs = b.finish()
+    check_decode(engine, arena, descs)
+    pages = engine.upload_pages(arena, descs)
+    w = 1_000_000_000
+    fbs, nb = bucket_spec(int(ts_reg[0]), int(ts_jit[-1]), w)
+    for gbs in (False, True):
+        q = make_query(SCAN_FIELDS, time_ranges=[(int(ts_reg[100]), int(ts_reg[-100]))], width=w,
+                       first_bucket_start=fbs, n_buckets=nb, group_by_series=gbs)
+        assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q, n_threads=3),
+                             what="max page gbs=%s" % gbs)
+    pages.close()
+
+
+def test_many_ranges_many_buckets_and_empty_inputs(engine):
+    g = datagen.generate(300, n_fields=1, n_points=500, value_kind=datagen.I64_WALK, seed=5, jitter_permille=500, jitter_max=5000)
+    pages = engine.upload_pages(g.arena, g.descs)
+    t0, step = datagen.TSBS_T0, datagen.TSBS_STEP
+    ranges = [(t0 + k * 60 * step, t0 + (k * 60 + 25) * step) for k in range(8)]    # 8 disjoint ranges (the ABI maximum)
+    w = 7 * step + 3
+    fbs, nb = bucket_spec(t0 - 5000, t0 + 499 * step + 5000, w, origin=11)
+    q = make_query([(1, cabi.TSKV_PT_I64)], time_ranges=ranges, origin=11, width=w, first_bucket_start=fbs, n_buckets=nb)
+    assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(g.arena, g.descs, q), what="8 ranges")
+    # overlapping + unsorted ranges behave like their union
+    q2 = make_query([(1, cabi.TSKV_PT_I64)], time_ranges=[ranges[3], (ranges[1][0], ranges[2][1]), ranges[1]], origin=11,
+                    width=w, first_bucket_start=fbs, n_buckets=nb)
+    assert_results_equal(engine.scan_aggregate(pages, q2), orc.scan_aggregate(g.arena, g.descs, q2), what="overlapping ranges")
+    # a range that selects nothing / an empty selection list / a column no page has
+    for q3 in (make_query([(1, cabi.TSKV_PT_I64)], time_ranges=[(0, 5)]),
+               make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.zeros(0, dtype=np.uint32)),
+               make_query([(9, cabi.TSKV_PT_F64)])):
+        r = engine.scan_aggregate(pages, q3)
+        assert_results_equal(r, orc.scan_aggregate(g.arena, g.descs, q3), what="empty")
+        assert r.validity[1:].sum() == 0 and r.values[0].sum() == 0
+    pages.close()
+    # an arena without pages
+    empty = engine.upload_pages(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=cabi.PAGE_DESC_DTYPE))
+    r = engine.scan_aggregate(empty, make_query([(1, cabi.TSKV_PT_I64)]))
+    assert r.column(1, "count")[0][0, 0] == 0
+    empty.close()
