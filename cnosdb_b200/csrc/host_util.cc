@@ -22,6 +22,11 @@ inline uint32_t rd32be(const uint8_t *p) {
 }
 }  // namespace
 
+const uint32_t *crc32_tables() {
+  std::call_once(g_once, init_tables);
+  return &g_tab[0][0];
+}
+
 uint32_t crc32_ieee(const uint8_t *p, size_t len) {
   std::call_once(g_once, init_tables);
   uint32_t crc = ~0u;

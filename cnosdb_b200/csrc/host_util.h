@@ -12,6 +12,8 @@ namespace tskv {
 
 // CRC-32/IEEE (crc32fast semantics), slicing-by-8.
 uint32_t crc32_ieee(const uint8_t *data, size_t len);
+// The slicing-by-8 tables ([8][256]), for the device-side verifier.
+const uint32_t *crc32_tables();
 
 struct PageHeader {
   uint32_t bitset_len;

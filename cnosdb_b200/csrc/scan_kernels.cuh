@@ -271,6 +271,57 @@ __global__ void k_scatter_items(const uint32_t *item_page, const uint32_t *item_
   }
 }
 
+// Page::crc_validation on the device (tskv/src/tsm/page.rs:58-76): CRC-32/IEEE of the data part of every page
+// a scan is about to read, checked against the page header. One lane per work item (its field page, plus the
+// column group's time page when the item carries it), slicing-by-4 with the tables in shared memory.
+// Host-resident arenas run it after the PCIe gather, i.e. on every read like the reference.
+__device__ __forceinline__ uint32_t crc_step8(const uint32_t (*t)[256], uint32_t crc, uint32_t lo, uint32_t hi) {
+  lo ^= crc;
+  return t[7][lo & 0xff] ^ t[6][(lo >> 8) & 0xff] ^ t[5][(lo >> 16) & 0xff] ^ t[4][lo >> 24] ^ t[3][hi & 0xff] ^
+         t[2][(hi >> 8) & 0xff] ^ t[1][(hi >> 16) & 0xff] ^ t[0][hi >> 24];
+}
+
+__global__ void __launch_bounds__(256)
+k_verify_crc(const uint8_t *arena, const tskv_page_desc *descs, const uint32_t *time_page_of,
+             const uint32_t *work_page, const uint8_t *work_qcol, const uint32_t *bin_cstart, int bin,
+             const uint32_t *crc_tables /* [8][256] */, int32_t *status, unsigned long long *err_page) {
+  __shared__ uint32_t s_t[8][256];
+  for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s_t[i >> 8][i & 255] = crc_tables[i];
+  __syncthreads();
+  const uint32_t w0 = bin_cstart[bin], n = bin_cstart[bin + 1];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x; w < n; w += stride) {
+    const uint32_t page = work_page[w];
+    const bool with_time = work_qcol[w] & 0x80;
+    for (int pass = 0; pass < (with_time ? 2 : 1); pass++) {
+      const uint32_t pg = pass == 0 ? page : time_page_of[page];
+      const tskv_page_desc d = descs[pg];
+      if (d.size < 16) continue;  // framing errors are reported by the decode kinds
+      const uint8_t *p = arena + d.offset;
+      const uint32_t bitset_len = load_be32_aligned(p);
+      const uint32_t want = load_be32_aligned(p + 12);
+      if (16ull + bitset_len > d.size) continue;
+      const uint8_t *q = p + 16 + bitset_len;
+      uint32_t len = d.size - 16 - bitset_len;
+      uint32_t crc = 0xffffffffu;
+      while (len && (reinterpret_cast<uintptr_t>(q) & 15)) {  // head bytes up to 16-byte alignment
+        crc = (crc >> 8) ^ s_t[0][(crc ^ __ldg(q)) & 0xff];
+        q++;
+        len--;
+      }
+      for (; len >= 16; len -= 16, q += 16) {  // one 16-byte load per half sector, slicing-by-8 twice
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(q));
+        crc = crc_step8(s_t, crc, v.x, v.y);
+        crc = crc_step8(s_t, crc, v.z, v.w);
+      }
+      for (; len; len--, q++) crc = (crc >> 8) ^ s_t[0][(crc ^ __ldg(q)) & 0xff];
+      if ((crc ^ 0xffffffffu) != want) {
+        if (atomicCAS(status, 0, (int)TSKV_ERR_CRC_MISMATCH) == 0) *err_page = pg;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused scan
 // ------------------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@ struct tskv_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // [0] fork, [N_BINS] join of the fused phase
   cudaStream_t bin_stream[N_BINS] = {nullptr};  // the per-bin fused kernels run concurrently
-  cudaEvent_t ev_bin_start[N_BINS] = {nullptr}, ev_bin_done[N_BINS] = {nullptr};
+  cudaEvent_t ev_bin_start[N_BINS] = {nullptr}, ev_bin_done[N_BINS] = {nullptr}, ev_gather[N_BINS] = {nullptr};
   int sm_count = 148;
   std::mutex mu;
   std::string err;
@@ -48,6 +48,8 @@ struct tskv_pages {
   tskv_ctx *ctx = nullptr;
   uint8_t *d_arena = nullptr;       // device copy (or, host-resident mode: gather target)
   const uint8_t *h_mapped = nullptr; // host-resident mode: device-visible alias of the caller's arena
+  bool verify_on_read = false;       // host-resident + VERIFY_CRC: CRC32 checked on the device on every scan
+  uint32_t *d_crc_tables = nullptr;
   void *h_registered = nullptr;      // range this library page-locked (unregistered on destroy)
   uint64_t arena_len = 0;
   tskv_page_desc *d_descs = nullptr;
@@ -61,6 +63,7 @@ struct tskv_pages {
   uint32_t *d_item_page = nullptr;
   uint32_t *d_item_cg = nullptr;
   uint32_t h_bin_start[N_BINS + 1]{};
+  uint64_t h_bin_bytes[N_BINS]{};    // field-page bytes per bin (orders the PCIe gathers of host-resident scans)
   uint32_t *d_bin_start = nullptr;
   std::vector<uint32_t> series;  // sorted distinct ids
   // arena-wide time bounds, computed on first use by k_time_bounds (the reference keeps them in
@@ -113,7 +116,7 @@ const char *status_text(tskv_status st) {
     case TSKV_ERR_INVALID_ARG: return "invalid argument";
     case TSKV_ERR_BAD_ENCODING: return "invalid block encoding";
     case TSKV_ERR_SHORT_BLOCK: return "not enough data to decode / unexpected end of block";
-    case TSKV_ERR_CRC_MISMATCH: return "page crc32 mismatch";
+    case TSKV_ERR_CRC_MISMATCH: return "TsmPageFileHashCheckFailed: page crc32 mismatch";
     case TSKV_ERR_BITSET_MISMATCH: return "Mismatch between bit set and decoded values";
     case TSKV_ERR_UNSUPPORTED: return "unsupported encoding or query shape";
     case TSKV_ERR_BUCKET_RANGE: return "row outside the requested bucket range";
@@ -279,6 +282,7 @@ tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
     cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking);
     cudaEventCreate(&ctx->ev_bin_start[b]);
     cudaEventCreate(&ctx->ev_bin_done[b]);
+    cudaEventCreateWithFlags(&ctx->ev_gather[b], cudaEventDisableTiming);
   }
   // per-scan buffers come from the stream-ordered pool; keep freed memory cached in the pool
   cudaMemPool_t pool;
@@ -305,6 +309,7 @@ void tskvgpu_ctx_destroy(tskv_ctx *ctx) {
     if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
     if (ctx->ev_bin_start[b]) cudaEventDestroy(ctx->ev_bin_start[b]);
     if (ctx->ev_bin_done[b]) cudaEventDestroy(ctx->ev_bin_done[b]);
+    if (ctx->ev_gather[b]) cudaEventDestroy(ctx->ev_gather[b]);
   }
   delete ctx;
 }
@@ -363,7 +368,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
         d.reserved = DK_BAD_PAGE;
         continue;
       }
-      if ((flags & TSKV_UPLOAD_VERIFY_CRC) && crc32_ieee(h.data, h.data_len) != h.crc) {
+      if ((flags & TSKV_UPLOAD_VERIFY_CRC) && !(flags & TSKV_UPLOAD_HOST_RESIDENT) && crc32_ieee(h.data, h.data_len) != h.crc) {
         fail(TSKV_ERR_CRC_MISMATCH, (int64_t)i);
         return;
       }
@@ -456,6 +461,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
       ip[k] = item_page[src];
       ic[k] = item_cg[src];
       counts[key[k] >> 48]++;
+      pg->h_bin_bytes[key[k] >> 48] += pg->h_descs[item_page[src]].size;
     }
     item_page.swap(ip);
     item_cg.swap(ic);
@@ -492,6 +498,10 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   if (e == cudaSuccess) e = up(&pg->d_item_page, item_page.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
+  if (e == cudaSuccess && (flags & TSKV_UPLOAD_VERIFY_CRC) && (flags & TSKV_UPLOAD_HOST_RESIDENT)) {
+    pg->verify_on_read = true;  // like the reference: every read of a page re-checks its CRC (device side)
+    e = up(&pg->d_crc_tables, crc32_tables(), 2048);
+  }
   cudaEventRecord(ctx->ev1, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
@@ -520,6 +530,7 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_item_page);
   cudaFree(pg->d_item_cg);
   cudaFree(pg->d_bin_start);
+  cudaFree(pg->d_crc_tables);
   delete pg;
 }
 
@@ -1001,19 +1012,36 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
   launches++;
   cudaEventRecord(ctx->ev_bin[0], ctx->stream);  // fork
-  for (int b = 0; b < N_BINS; b++) {
+  // Host-resident pages: one bin's gather already saturates PCIe, so the gathers are chained largest bin first
+  // (an event per bin); each bin's CRC check and scan then overlap the next bins' transfers and only the smallest
+  // bin's tail is exposed after the last byte has arrived.
+  int order[N_BINS];
+  for (int b = 0; b < N_BINS; b++) order[b] = b;
+  static const bool gather_concurrent = getenv("TSKV_GATHER_CONCURRENT") != nullptr;
+  if (pages->h_mapped && !gather_concurrent)
+    std::stable_sort(order, order + N_BINS, [&](int a, int b) { return pages->h_bin_bytes[a] > pages->h_bin_bytes[b]; });
+  int prev_gather = -1;
+  for (int oi = 0; oi < N_BINS; oi++) {
+    const int b = order[oi];
     if (!s->grid[b]) continue;
     cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_bin[0], 0);
     int bin = b;
     if (pages->h_mapped) {
-      // host-resident pages: pull this bin's selected pages over PCIe on the bin's own stream, so that the
-      // other bins' scans overlap with the copy
+      if (prev_gather >= 0 && !gather_concurrent) cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_gather[prev_gather], 0);
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       uint32_t gblocks = std::max(1u, std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (n_bin + 7) / 8));
       k_gather_pages<<<gblocks, 256, 0, ctx->bin_stream[b]>>>(pages->h_mapped, pages->d_arena, pages->d_descs,
                                                               pages->d_time_page_of, s->d_work_page, s->d_work_qcol,
                                                               s->d_bin_cstart, bin);
       launches++;
+      cudaEventRecord(ctx->ev_gather[b], ctx->bin_stream[b]);
+      prev_gather = b;
+      if (pages->verify_on_read) {
+        k_verify_crc<<<gblocks, 256, 0, ctx->bin_stream[b]>>>(pages->d_arena, pages->d_descs, pages->d_time_page_of,
+                                                              s->d_work_page, s->d_work_qcol, s->d_bin_cstart, bin,
+                                                              pages->d_crc_tables, s->d_status, s->d_err_page);
+        launches++;
+      }
     }
     cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
     if (!s->use_coop[b]) {

@@ -192,7 +192,9 @@ enum {
    * `arena` alive and unchanged until tskvgpu_pages_destroy) and let every scan pull only the
    * selected pages over PCIe — the analogue of the reference reading pages of the selected series
    * from the page cache on each query. Descriptor tables still live on the device (TsmReader
-   * metadata is cached in the reference too: tsfamily/version.rs:158-172). */
+   * metadata is cached in the reference too: tsfamily/version.rs:158-172). Combined with
+   * TSKV_UPLOAD_VERIFY_CRC the CRC32 of every page a scan reads is re-checked on the device after the
+   * transfer, i.e. on every read like Page::crc_validation (tsm/reader.rs:259,492). */
   TSKV_UPLOAD_HOST_RESIDENT = 2u
 };
 tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t arena_len,

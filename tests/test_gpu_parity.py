@@ -486,3 +486,25 @@ def test_many_ranges_many_buckets_and_empty_inputs(engine):
     r = engine.scan_aggregate(empty, make_query([(1, cabi.TSKV_PT_I64)]))
     assert r.column(1, "count")[0][0, 0] == 0
     empty.close()
+
+
+def test_host_resident_pages_verify_crc_on_every_read(engine):
+    """HOST_RESIDENT | VERIFY_CRC: the device re-checks the CRC32 of every page a scan pulls over PCIe
+    (Page::crc_validation on each read, tsm/reader.rs:259). Corruption after the upload is caught by the next scan."""
+    g = datagen.generate(400, n_fields=2, n_points=300, value_kind=datagen.MIXED, seed=12, jitter_permille=300, jitter_max=999)
+    arena = g.arena.copy()
+    q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_I64, ["count", "sum"]), PushedAggregate(3, cabi.TSKV_PT_F64, ["count", "max"])],
+                    series_ids=np.arange(0, 400, 2, dtype=np.uint32).repeat(1)[:150])
+    hp = engine.upload_pages(arena, g.descs, verify_crc=True, host_resident=True)
+    assert_results_equal(engine.scan_aggregate(hp, q), orc.scan_aggregate(arena, g.descs, q), what="host-resident verified")
+    victim = next(i for i, d in enumerate(g.descs) if d["phys_type"] == cabi.TSKV_PT_I64 and d["series_id"] == 4 and d["column_id"] == 1)
+    arena[int(g.descs[victim]["offset"]) + int(g.descs[victim]["size"]) - 3] ^= 0x21
+    with pytest.raises(TskvError) as e:
+        engine.scan_aggregate(hp, q)
+    assert e.value.status == cabi.TSKV_ERR_CRC_MISMATCH and e.value.page == victim
+    # pages of series that are not selected are not read, so their corruption goes unnoticed (like the reference)
+    arena[int(g.descs[victim]["offset"]) + int(g.descs[victim]["size"]) - 3] ^= 0x21
+    other = next(i for i, d in enumerate(g.descs) if d["series_id"] == 399 and d["phys_type"] != cabi.TSKV_PT_TIME)
+    arena[int(g.descs[other]["offset"]) + 40] ^= 0xff
+    engine.scan_aggregate(hp, q)
+    hp.close()

@@ -17,6 +17,7 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--kind", default="c4", help="c4 | c3 | i64 | f64a | f64b")
 ap.add_argument("--jitter", type=int, default=-1, help="permille of series with jittered timestamps")
 ap.add_argument("--aggs", default="count,sum,min,max,mean")
+ap.add_argument("--host-resident", type=int, default=0, help="1: pages stay in host memory; 2: + CRC on every read")
 a = ap.parse_args()
 from cnosdb_b200 import cabi, datagen  # noqa: E402
 from cnosdb_b200.engine import PushedAggregate, QueryOption  # noqa: E402
@@ -29,7 +30,7 @@ else:
     g = datagen.generate(a.series, n_fields=1, n_points=1000, value_kind=kind, seed=4,
                          jitter_permille=max(a.jitter, 0), jitter_max=999_999)
 eng = Engine(0)
-pages = eng.upload_pages(g.arena, g.descs, verify_crc=False)
+pages = eng.upload_pages(g.arena, g.descs, verify_crc=a.host_resident == 2, host_resident=a.host_resident > 0)
 if a.kind == "c4":
     q = bench.make_query(select_tag_subset(a.series, 10))
 elif a.kind == "c3":
