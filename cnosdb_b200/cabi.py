@@ -42,6 +42,19 @@ PAGE_DESC_DTYPE = np.dtype(
      ("column_id", "<u2"), ("phys_type", "u1"), ("reserved", "u1")], align=False)
 assert PAGE_DESC_DTYPE.itemsize == 24
 
+# numpy view of tskv_tombstone (24 bytes); series_id / column_id = TSKV_TOMB_ALL: see include/tskv_gpu.h
+TSKV_TOMB_ALL = 0xFFFFFFFF
+TOMBSTONE_DTYPE = np.dtype([("series_id", "<u4"), ("column_id", "<u4"), ("min_ts", "<i8"), ("max_ts", "<i8")], align=False)
+assert TOMBSTONE_DTYPE.itemsize == 24
+
+
+def tombstones(entries):
+    """[(series_id | None, column_id | None, min_ts, max_ts), ...] -> TOMBSTONE_DTYPE array (None = TSKV_TOMB_ALL)."""
+    a = np.zeros(len(entries), dtype=TOMBSTONE_DTYPE)
+    for i, (s, c, lo, hi) in enumerate(entries):
+        a[i] = (TSKV_TOMB_ALL if s is None else s, TSKV_TOMB_ALL if c is None else c, lo, hi)
+    return a
+
 
 class PageDesc(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("size", C.c_uint32), ("num_values", C.c_uint32),
@@ -94,7 +107,7 @@ class PartialsView(C.Structure):
 GPU_SYMBOLS = [
     "tskvgpu_ctx_create", "tskvgpu_ctx_destroy", "tskvgpu_last_error", "tskvgpu_last_error_page",
     "tskvgpu_get_counters", "tskvgpu_ctx_stream", "tskvgpu_upload_pages", "tskvgpu_pages_destroy",
-    "tskvgpu_pages_series_count", "tskvgpu_decode_pages", "tskvgpu_query_output_layout",
+    "tskvgpu_pages_series_count", "tskvgpu_pages_set_tombstones", "tskvgpu_decode_pages", "tskvgpu_query_output_layout",
     "tskvgpu_scan_aggregate", "tskvgpu_scan_prepare", "tskvgpu_scan_run", "tskvgpu_scan_enqueue",
     "tskvgpu_scan_sync", "tskvgpu_scan_partials", "tskvgpu_scan_exchange_view", "tskvgpu_scan_merge_gathered",
     "tskvgpu_scan_snapshot_keys", "tskvgpu_scan_mask_values", "tskvgpu_scan_finalize",
@@ -143,6 +156,7 @@ def load_gpu_library():
     lib.tskvgpu_pages_destroy.restype = None
     lib.tskvgpu_pages_series_count.argtypes = [vp]
     lib.tskvgpu_pages_series_count.restype = C.c_uint64
+    lib.tskvgpu_pages_set_tombstones.argtypes = [vp, vp, vp, C.c_uint64]
     lib.tskvgpu_decode_pages.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
     lib.tskvgpu_query_output_layout.argtypes = [vp, C.POINTER(Query), C.POINTER(OutputLayout)]
     lib.tskvgpu_scan_aggregate.argtypes = [vp, vp, C.POINTER(Query), vp, vp]

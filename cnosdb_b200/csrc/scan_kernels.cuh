@@ -48,6 +48,8 @@ struct ColState {
   uint32_t pad;
 };
 
+constexpr int SCAN_THREADS = 128;  // threads per CTA of the fused scan kernels
+
 struct ScanParams {
   const uint8_t *arena;
   const tskv_page_desc *descs;   // device copy; .reserved = DK_* kind
@@ -83,7 +85,15 @@ struct ScanParams {
   uint32_t use_smem;
   uint32_t smem_words;   // table size in 8-byte words
   uint32_t n_cols;
-  uint32_t pad2;
+  // TsmTombstone ranges of the page set (tskvgpu_pages_set_tombstones): ranges [0, n_tomb_global) drop rows of every
+  // series; sorted keys (series << 32 | column, column = TSKV_TOMB_ALL: drop rows of the series, else: the
+  // column reads as NULL) index the rest through the CSR offsets.
+  uint32_t has_tomb;
+  const uint64_t *tomb_keys;
+  const uint32_t *tomb_off;
+  const tskv_time_range *tomb_ranges;
+  uint32_t n_tomb_keys;
+  uint32_t n_tomb_global;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -595,6 +605,49 @@ __device__ __forceinline__ bool range_span(const ScanParams &P, int64_t t, int64
   return in;
 }
 
+// Like range_span for a tombstone list: is t inside one of the n closed ranges, and narrow [lo, hi] to an interval
+// around t over which that answer holds.
+__device__ __forceinline__ bool tomb_span(const tskv_time_range *r, uint32_t n, int64_t t, int64_t &lo, int64_t &hi) {
+  bool in = false;
+  int64_t l = INT64_MIN, h = INT64_MAX;
+#pragma unroll 1
+  for (uint32_t k = 0; k < n; k++) {
+    const int64_t a = r[k].min_ts, b = r[k].max_ts;
+    if (a > b) continue;
+    if (t >= a && t <= b) {
+      if (!in) { l = a; h = b; in = true; }
+    } else if (!in) {
+      if (a > t && a - 1 < h) h = a - 1;
+      if (b < t && b + 1 > l) l = b + 1;
+    }
+  }
+  lo = lo > l ? lo : l;
+  hi = hi < h ? hi : h;
+  return in;
+}
+
+// Tombstone lists of one field page: .x/.y = offset/count of the series' row-drop ranges, .z/.w = of the
+// (series, column) null-mask ranges (binary search in the sorted keys, once per page).
+__device__ __forceinline__ uint4 tomb_lookup(const ScanParams &P, uint32_t series, uint32_t column) {
+  uint4 out = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const uint64_t key = ((uint64_t)series << 32) | (pass == 0 ? (uint64_t)TSKV_TOMB_ALL : (uint64_t)column);
+    uint32_t lo = 0, hi = P.n_tomb_keys;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(P.tomb_keys + mid) < key) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < P.n_tomb_keys && __ldg(P.tomb_keys + lo) == key) {
+      const uint32_t a = __ldg(P.tomb_off + lo), b = __ldg(P.tomb_off + lo + 1);
+      if (pass == 0) { out.x = a; out.y = b - a; }
+      else { out.z = a; out.w = b - a; }
+    }
+  }
+  return out;
+}
+
 // One chunk of <= 32 work items, one lane per field page. The whole warp stays converged; lanes
 // without a page (or past their last row) idle through the loop. `ring_base` = shared-space address of
 // this warp's 2 x RING_WORDS x 256 B prefetch rings (time stream, value stream).
@@ -611,6 +664,7 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
   uint8_t pt = TSKV_PT_I64, mask = 0;
   PageView tpv, vpv;
   BitCursor tbits, vbits;
+  __shared__ uint4 s_tomb[SCAN_THREADS];  // per lane tombstone lists (only touched when the page set has any)
   DeltaCursor<TK == TK_RLE ? DK_RLE_SC : TK == TK_S8B ? DK_S8B_SC : -1, RingStream> tcur;
   DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, RingStream> vcur_d;
   GorillaCursor<RingStream> vcur_g;
@@ -625,6 +679,7 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
     const tskv_page_desc td = P.descs[tpage];
     pt = P.cols[qcol].phys_type;
     mask = P.cols[qcol].agg_mask;
+    if (P.has_tomb) s_tomb[threadIdx.x] = tomb_lookup(P, vd.series_id, vd.column_id);
     tskv_status st = kind_status(td.reserved);
     if (st == TSKV_OK) st = kind_status(vd.reserved);
     if (st != TSKV_OK) {
@@ -685,6 +740,12 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
         inr = P.n_ranges == 0;
 #pragma unroll 1
         for (uint32_t k = 0; k < P.n_ranges && !inr; k++) inr = t >= P.ranges[k].min_ts && t <= P.ranges[k].max_ts;
+        if (P.has_tomb && inr) {  // decode_pages' tombstone handling, row by row (reader.rs:507-551)
+          const uint4 tl = s_tomb[threadIdx.x];
+          int64_t lo = INT64_MIN, hi = INT64_MAX;
+          if (tomb_span(P.tomb_ranges, P.n_tomb_global, t, lo, hi) || tomb_span(P.tomb_ranges + tl.x, tl.y, t, lo, hi)) inr = false;
+          else if (tomb_span(P.tomb_ranges + tl.z, tl.w, t, lo, hi)) vv = false;
+        }
       }
       if (inr) {
         n_inrange++;
@@ -794,12 +855,14 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   const uint32_t *vbm = nullptr;  // value validity bitmap, 32 rows per word
   bool allnull = false;
   int64_t pend_t = 0;  // timestamp of row `row`
+  __shared__ uint4 s_tomb[SCAN_THREADS];  // per lane tombstone lists (only touched when the page set has any)
 
   if (have_item) {
     page = P.work_page[item];
     slot = P.work_slot[item];
     qcol = P.work_qcol[item] & 0x7f;
     const tskv_page_desc vd = P.descs[page];
+    if (P.has_tomb) s_tomb[threadIdx.x] = tomb_lookup(P, vd.series_id, vd.column_id);
     const uint32_t tpage = P.time_page_of[page];
     const tskv_page_desc td = P.descs[tpage];
     if (VK != VK_GOR) pt = P.cols[qcol].phys_type;
@@ -845,10 +908,18 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     // ---- 1. next segment: rows [row, row + n) share (selected, bucket) --------------------------
     uint32_t n = 0;
     bool seg_in = false;
+    bool seg_masked = false;  // tombstoned column range: the rows stay, their values read as NULL
     int64_t seg_first_t = pend_t, seg_last_t = pend_t;
     if (has) {
       int64_t lim_lo, lim_hi;
       seg_in = range_span(P, pend_t, lim_lo, lim_hi);
+      if (P.has_tomb) {  // decode_pages' tombstone handling (reader.rs:507-551) as two more segment attributes
+        const uint4 tl = s_tomb[threadIdx.x];
+        const bool dropped = tomb_span(P.tomb_ranges, P.n_tomb_global, pend_t, lim_lo, lim_hi) |
+                             tomb_span(P.tomb_ranges + tl.x, tl.y, pend_t, lim_lo, lim_hi);
+        seg_masked = tomb_span(P.tomb_ranges + tl.z, tl.w, pend_t, lim_lo, lim_hi);
+        if (dropped) seg_in = false;
+      }
       if (seg_in) {
         if (!(bk.valid && pend_t >= bk.lo && pend_t <= bk.hi) && !locate_bucket(P, pend_t, bk)) {
           report_error(P, TSKV_ERR_BUCKET_RANGE, page);
@@ -899,7 +970,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
         uint32_t m = allnull ? 0u : ((vword >> off) & want);
         n_points += __popc(m);
         uint64_t v = 0;
-        if (!SEL && seg_in) {
+        if (!SEL && seg_in && !seg_masked) {
           va.count += __popc(m);
           if (m == want) {
 #pragma unroll 1
@@ -917,8 +988,9 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
           for (uint32_t c = __popc(m); c; c--) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
         } else {            // FIRST / LAST wanted: per-row, the run's end rows keep (ts, value, valid)
           for (uint32_t j = 0; j < span; j++) {
-            const bool vv = (m >> j) & 1;
+            bool vv = (m >> j) & 1;
             if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+            vv = vv && !seg_masked;
             if (seg_in) {
               if (r + j == row && newrun) { acc.first_ts = seg_first_t; acc.first_val = vv ? v : 0; acc.first_ok = vv; }
               if (r + j == rend - 1) { acc.last_ts = seg_last_t; acc.last_val = vv ? v : 0; acc.last_ok = vv; }
@@ -952,7 +1024,6 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
 // value codec) and SEL (= the query asks for FIRST/LAST) so that each keeps its state in registers.
 // The bins' kernels run concurrently on separate streams, each with a persistent grid sized to its share
 // of the work; a warp repeatedly grabs one 32-item chunk of its bin from the bin's global counter.
-constexpr int SCAN_THREADS = 128;
 #ifndef SCAN_MIN_BLOCKS
 #define SCAN_MIN_BLOCKS 4
 #endif

@@ -65,6 +65,12 @@ struct tskv_pages {
   uint32_t h_bin_start[N_BINS + 1]{};
   uint64_t h_bin_bytes[N_BINS]{};    // field-page bytes per bin (orders the PCIe gathers of host-resident scans)
   uint32_t *d_bin_start = nullptr;
+  // tombstones (tskvgpu_pages_set_tombstones); the epoch invalidates scans prepared before a change
+  uint64_t *d_tomb_keys = nullptr;
+  uint32_t *d_tomb_off = nullptr;
+  tskv_time_range *d_tomb_ranges = nullptr;
+  uint32_t n_tomb_keys = 0, n_tomb_global = 0, n_tomb_ranges = 0;
+  uint64_t tomb_epoch = 0;
   std::vector<uint32_t> series;  // sorted distinct ids
   // arena-wide time bounds, computed on first use by k_time_bounds (the reference keeps them in
   // PageMeta.statistics); only unbucketed first/last across series needs them
@@ -74,6 +80,7 @@ struct tskv_pages {
 
 struct tskv_scan {
   const tskv_pages *pages = nullptr;
+  uint64_t tomb_epoch = 0;
   tskv_output_layout layout{};
   StateLayout sl{};
   ScanParams params{};
@@ -531,10 +538,65 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_item_cg);
   cudaFree(pg->d_bin_start);
   cudaFree(pg->d_crc_tables);
+  cudaFree(pg->d_tomb_keys);
+  cudaFree(pg->d_tomb_off);
+  cudaFree(pg->d_tomb_ranges);
   delete pg;
 }
 
 uint64_t tskvgpu_pages_series_count(const tskv_pages *pages) { return pages ? pages->series.size() : 0; }
+
+// TsmTombstone cache -> device tables: the all-series ranges first, then one CSR row per (series, column) key.
+tskv_status tskvgpu_pages_set_tombstones(tskv_ctx *ctx, tskv_pages *pg, const tskv_tombstone *tombs, uint64_t n_tombs) {
+  if (!ctx || !pg || (n_tombs && !tombs) || n_tombs > 0x7fffffffull) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_error("");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<tskv_time_range> ranges;
+  std::vector<std::pair<uint64_t, tskv_time_range>> keyed;
+  for (uint64_t i = 0; i < n_tombs; i++) {
+    const tskv_tombstone &tb = tombs[i];
+    if (tb.series_id == TSKV_TOMB_ALL && tb.column_id != TSKV_TOMB_ALL) {
+      ctx->set_error("tombstone: series_id = TSKV_TOMB_ALL needs column_id = TSKV_TOMB_ALL", -1);
+      return TSKV_ERR_INVALID_ARG;
+    }
+    if (tb.min_ts > tb.max_ts) continue;  // empty range
+    if (tb.series_id == TSKV_TOMB_ALL) ranges.push_back({tb.min_ts, tb.max_ts});
+    else keyed.push_back({((uint64_t)tb.series_id << 32) | tb.column_id, {tb.min_ts, tb.max_ts}});
+  }
+  std::stable_sort(keyed.begin(), keyed.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+  const uint32_t n_global = (uint32_t)ranges.size();
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> off;
+  for (const auto &kr : keyed) {
+    if (keys.empty() || keys.back() != kr.first) {
+      keys.push_back(kr.first);
+      off.push_back((uint32_t)ranges.size());
+    }
+    ranges.push_back(kr.second);
+  }
+  off.push_back((uint32_t)ranges.size());
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // no scan of this page set may be in flight
+  cudaFree(pg->d_tomb_keys);
+  cudaFree(pg->d_tomb_off);
+  cudaFree(pg->d_tomb_ranges);
+  pg->d_tomb_keys = nullptr;
+  pg->d_tomb_off = nullptr;
+  pg->d_tomb_ranges = nullptr;
+  pg->n_tomb_keys = (uint32_t)keys.size();
+  pg->n_tomb_global = n_global;
+  pg->n_tomb_ranges = (uint32_t)ranges.size();
+  pg->tomb_epoch++;
+  if (!ranges.empty()) {
+    CU_TRY(ctx, cudaMalloc(&pg->d_tomb_ranges, ranges.size() * sizeof(tskv_time_range)));
+    CU_TRY(ctx, cudaMemcpy(pg->d_tomb_ranges, ranges.data(), ranges.size() * sizeof(tskv_time_range), cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMalloc(&pg->d_tomb_keys, std::max<size_t>(keys.size(), 1) * 8));
+    if (!keys.empty()) CU_TRY(ctx, cudaMemcpy(pg->d_tomb_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMalloc(&pg->d_tomb_off, off.size() * 4));
+    CU_TRY(ctx, cudaMemcpy(pg->d_tomb_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return TSKV_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 tskv_status tskvgpu_decode_pages(tskv_ctx *ctx, const tskv_pages *pages, uint64_t first_page,
@@ -911,6 +973,13 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     P.use_smem = (!q->group_by_series && (uint64_t)words * 8 <= limit) ? 1u : 0u;
     P.smem_words = P.use_smem ? words : 0;
     P.n_cols = q->n_columns;
+    P.has_tomb = pages->n_tomb_ranges ? 1u : 0u;
+    P.tomb_keys = pages->d_tomb_keys;
+    P.tomb_off = pages->d_tomb_off;
+    P.tomb_ranges = pages->d_tomb_ranges;
+    P.n_tomb_keys = pages->n_tomb_keys;
+    P.n_tomb_global = pages->n_tomb_global;
+    s->tomb_epoch = pages->tomb_epoch;
   }
   if (cudaMemcpyAsync(s->d_cols, cols.data(), cols.size() * sizeof(ColState), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
     ctx->set_error("scan_prepare: column table upload failed");
@@ -928,7 +997,8 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     const double lanes = (double)ctx->sm_count * SCAN_MIN_BLOCKS * SCAN_THREADS;
     const double est_total = (double)pages->n_items * sel_frac;  // selected field pages, all bins
     for (int b = N_SERIAL_BINS; b < N_BINS; b++)
-      s->use_coop[b] = mode ? (mode[0] == '1') : (est_total < 0.25 * lanes);
+      s->use_coop[b] = pages->n_tomb_ranges ? false  // tombstones are handled by the lane-per-page kernels
+                                            : mode ? (mode[0] == '1') : (est_total < 0.25 * lanes);
     // Grid sizes. Every kernel is persistent (warps pull tasks from their bin's counter). If the resident
     // capacity allows, each bin gets one warp per estimated task (a single round: the makespan of a bin is
     // quantised in units of one task = one page's serial decode); otherwise the blocks are split by cost.
@@ -985,6 +1055,10 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
 static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   const tskv_pages *pages = s->pages;
   const uint32_t n_items = pages->n_items;
+  if (s->tomb_epoch != pages->tomb_epoch) {
+    ctx->set_error("the page set's tombstones changed after this scan was prepared", -1);
+    return TSKV_ERR_INVALID_ARG;
+  }
   cudaEventRecord(ctx->ev0, ctx->stream);
   unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
   CU_TRY(ctx, cudaMemsetAsync(aux, 0, 32 * 8, ctx->stream));

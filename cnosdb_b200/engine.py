@@ -124,6 +124,15 @@ class PageSet:
         self.handle = handle
         self.n_pages = n_pages
 
+    def set_tombstones(self, tombs):
+        """Attach the TsmTombstone ranges (cabi.TOMBSTONE_DTYPE array or cabi.tombstones([...]) input);
+        replaces the previous set, an empty one clears it. Applies to every later scan of this page set."""
+        if not isinstance(tombs, np.ndarray):
+            tombs = cabi.tombstones(list(tombs))
+        tombs = np.ascontiguousarray(tombs, dtype=cabi.TOMBSTONE_DTYPE)
+        self.engine._check(self.engine.lib.tskvgpu_pages_set_tombstones(
+            self.engine.ctx, self.handle, tombs.ctypes.data if len(tombs) else None, len(tombs)))
+
     def close(self):
         if self.handle:
             self.engine.lib.tskvgpu_pages_destroy(self.engine.ctx, self.handle)

@@ -204,6 +204,28 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pages);
 /* Number of distinct series in the arena. */
 uint64_t tskvgpu_pages_series_count(const tskv_pages *pages);
 
+/* ---- tombstones ------------------------------------------------------------------------------
+ * Replaces the tombstone half of decode_pages (tskv/src/tsm/reader.rs:507-551,634-656) with the
+ * TsmTombstone cache as its source (tsm/tombstone.rs:417-550). One entry = one closed time range:
+ *   series_id = s, column_id = c      rows of (s, c) whose time lies in the range read as NULL
+ *                                     (column_excluded: update_nullbits_by_time_range + updated_nullbuffer)
+ *   series_id = TSKV_TOMB_ALL         the range is in the file's `all_excluded` set: those ROWS are dropped
+ *     (column_id = TSKV_TOMB_ALL)     for every series of this page set (filter_record_batch, reader.rs:546-550)
+ *   series_id = s, column_id = TSKV_TOMB_ALL   same, scoped to one series (for page sets assembled from
+ *                                     several TSM files, whose `all_excluded` sets differ)
+ * The reference locates the rows with a binary search over the page's time values; time pages are strictly
+ * increasing (tsm/chunk.rs:100-110), for which that equals the row-wise test min_ts <= t <= max_ts used here.
+ * The call replaces the page set's previous tombstones (n = 0 clears them) and must not overlap a scan
+ * of the same page set. Tombstones apply to scans; tskvgpu_decode_pages stays Page::to_arrow_array. */
+#define TSKV_TOMB_ALL 0xffffffffu
+typedef struct tskv_tombstone {
+  uint32_t series_id;
+  uint32_t column_id;
+  int64_t min_ts, max_ts; /* closed */
+} tskv_tombstone;
+tskv_status tskvgpu_pages_set_tombstones(tskv_ctx *ctx, tskv_pages *pages, const tskv_tombstone *tombs,
+                                         uint64_t n_tombs);
+
 /* ---- decode only ---------------------------------------------------------------------------
  * Replaces Page::to_arrow_array / data_buf_to_arrow_array (tskv/src/tsm/reader.rs:658-731) for
  * pages [first_page, first_page + n_pages): row r of page p lands at out_values[row_offsets[p]+r]

@@ -48,6 +48,9 @@ def lib():
         L.orc_scan_aggregate.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.POINTER(cabi.Query), C.c_int, C.c_int,
                                          vp, vp, C.POINTER(C.c_uint64)]
         L.orc_scan_aggregate.restype = C.c_int32
+        L.orc_scan_aggregate_tomb.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.POINTER(cabi.Query), vp, C.c_uint64,
+                                              C.c_int, C.c_int, vp, vp, C.POINTER(C.c_uint64)]
+        L.orc_scan_aggregate_tomb.restype = C.c_int32
         L.orc_last_error.restype = C.c_char_p
         _lib = L
     return _lib
@@ -146,8 +149,9 @@ def decode_pages(arena, descs, first_page=0, n_pages=None, verify_crc=True):
     return out
 
 
-def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_points=False):
-    """Same inputs / ScanResult as cnosdb_b200.engine.Engine.scan_aggregate, computed on the CPU."""
+def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_points=False, tombstones=None):
+    """Same inputs / ScanResult as cnosdb_b200.engine.Engine.scan_aggregate, computed on the CPU.
+    tombstones: cabi.TOMBSTONE_DTYPE array, what PageSet.set_tombstones takes."""
     if isinstance(arena, tuple):
         aptr, alen = arena
     else:
@@ -162,9 +166,11 @@ def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_poi
     values = np.zeros(max(int(L.n_out * L.n_cells), 1), dtype=np.uint64)
     bitmaps = np.zeros(max(int(L.validity_bytes), 1), dtype=np.uint8)
     pts = C.c_uint64(0)
-    st = lib().orc_scan_aggregate(aptr, alen, descs.ctypes.data, len(descs), C.byref(q),
-                                  1 if verify_crc else 0, n_threads, values.ctypes.data, bitmaps.ctypes.data,
-                                  C.byref(pts))
+    tombs = np.ascontiguousarray(tombstones if tombstones is not None else [], dtype=cabi.TOMBSTONE_DTYPE)
+    st = lib().orc_scan_aggregate_tomb(aptr, alen, descs.ctypes.data, len(descs), C.byref(q),
+                                       tombs.ctypes.data if len(tombs) else None, len(tombs),
+                                       1 if verify_crc else 0, n_threads, values.ctypes.data, bitmaps.ctypes.data,
+                                       C.byref(pts))
     if st != 0:
         raise OracleError(st, lib().orc_last_error().decode())
     res = ScanResult(query, L, values[: int(L.n_out * L.n_cells)], bitmaps[: int(L.validity_bytes)])

@@ -117,14 +117,41 @@ struct Scan {
   const Index *ix;
   std::vector<uint32_t> slots;  // slot -> series id
   uint64_t n_cells;
+  const tskv_tombstone *tombs = nullptr;
+  uint64_t n_tombs = 0;
 };
+
+// update_nullbits_by_time_range (tsm/reader.rs:634-656): binary search over the page's time VALUES (the raw
+// value buffer, nulls included) for [min_ts, max_ts]; clears bits start..end.
+void clear_bits_by_time_range(const std::vector<uint64_t> &ts, uint64_t n_rows, int64_t min_ts, int64_t max_ts,
+                              std::vector<uint8_t> &bits) {
+  auto lower = [&](int64_t x, bool *found) {  // slice::binary_search: Ok(i) if found else Err(insertion point)
+    uint64_t lo = 0, hi = n_rows;
+    *found = false;
+    while (lo < hi) {
+      uint64_t mid = lo + (hi - lo) / 2;
+      int64_t v = (int64_t)ts[mid];
+      if (v == x) { *found = true; return mid; }
+      if (v < x) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  bool f;
+  uint64_t start = lower(min_ts, &f);
+  uint64_t end = lower(max_ts, &f);
+  if (f) end += 1;
+  for (uint64_t i = start; i < end && i < n_rows; i++) bits[i] = 0;
+}
 
 // One worker: slots [s0, s1) into `cells` (n_columns * n_cells). Returns status.
 tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, bool shared_table,
                        uint64_t *points) {
   const tskv_query &q = *S.q;
   std::vector<uint64_t> ts, vals;
-  std::vector<uint8_t> tvalid, vvalid;
+  std::vector<uint8_t> tvalid, vvalid, keep;
+  bool have_keep = false;
+  int64_t page_min = 0, page_max = 0;
   for (uint64_t slot = s0; slot < s1; slot++) {
     auto range = S.ix->find(S.slots[slot]);
     if (range.first == nullptr) continue;  // selected id absent from this arena
@@ -158,6 +185,24 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
           if (st != TSKV_OK) return st;
           if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
           time_decoded = true;
+          // decode_pages with a tombstone (reader.rs:507-524): the all-fields excluded ranges that overlap the
+          // page's time range clear bits of the TIME page's null bitset; the result filters the rows.
+          keep.assign(n_rows ? n_rows : 1, 1);
+          have_keep = false;
+          if (S.n_tombs && n_rows) {
+            int64_t pmin = INT64_MAX, pmax = INT64_MIN;  // PageStatistics min/max of the time column
+            for (uint64_t r = 0; r < n_rows; r++)
+              if (tvalid[r]) { pmin = std::min(pmin, (int64_t)ts[r]); pmax = std::max(pmax, (int64_t)ts[r]); }
+            page_min = pmin; page_max = pmax;
+            for (uint64_t k = 0; k < S.n_tombs; k++) {
+              const tskv_tombstone &tb = S.tombs[k];
+              if (tb.column_id != TSKV_TOMB_ALL) continue;
+              if (tb.series_id != TSKV_TOMB_ALL && tb.series_id != td.series_id) continue;
+              if (!(tb.min_ts <= pmax && tb.max_ts >= pmin)) continue;  // TimeRange::overlaps
+              if (!have_keep) { keep = tvalid; have_keep = true; }
+              clear_bits_by_time_range(ts, n_rows, tb.min_ts, tb.max_ts, keep);
+            }
+          }
         }
         vals.assign(n_rows ? n_rows : 1, 0);
         vvalid.assign(n_rows ? n_rows : 1, 0);
@@ -167,6 +212,13 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
                                          vals.data(), vvalid.data(), n_rows, &nr);
         if (st != TSKV_OK) return st;
         if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
+        // per-column tombstones (reader.rs:531-542): clear the value validity of the excluded rows
+        for (uint64_t k = 0; k < S.n_tombs && n_rows; k++) {
+          const tskv_tombstone &tb = S.tombs[k];
+          if (tb.column_id == TSKV_TOMB_ALL || tb.series_id != fd->series_id || tb.column_id != fd->column_id) continue;
+          if (!(tb.min_ts <= page_max && tb.max_ts >= page_min)) continue;
+          clear_bits_by_time_range(ts, n_rows, tb.min_ts, tb.max_ts, vvalid);
+        }
         const uint8_t pt = qc.phys_type;
         Cell *ccells = cells + (uint64_t)c * S.n_cells + group * q.n_buckets;
         // Run state for first/last: the rows of one (page, bucket) form one DataFusion group slice;
@@ -197,6 +249,7 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
         };
         for (uint64_t r = 0; r < n_rows; r++) {
           if (vvalid[r] && points) (*points)++;
+          if (have_keep && !keep[r]) continue;  // filter_record_batch(&record_batch, time_null_bits) (reader.rs:546-550)
           if (!tvalid[r]) continue;  // is_not_null(time) (transform_time_window.rs:313)
           int64_t t = (int64_t)ts[r];
           bool in = q.n_time_ranges == 0;
@@ -357,6 +410,15 @@ tskv_status orc_scan_aggregate(const uint8_t *arena, uint64_t arena_len,
                                const tskv_page_desc *descs, uint64_t n_descs, const tskv_query *q,
                                int verify_crc, int n_threads, uint64_t *out_values,
                                uint8_t *out_validity, uint64_t *out_points) {
+  return orc_scan_aggregate_tomb(arena, arena_len, descs, n_descs, q, nullptr, 0, verify_crc, n_threads, out_values,
+                                 out_validity, out_points);
+}
+
+tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
+                                    const tskv_page_desc *descs, uint64_t n_descs, const tskv_query *q,
+                                    const tskv_tombstone *tombs, uint64_t n_tombs,
+                                    int verify_crc, int n_threads, uint64_t *out_values,
+                                    uint8_t *out_validity, uint64_t *out_points) {
   g_err.clear();
   tskv_output_layout L;
   tskv_status st = orc_query_output_layout(descs, n_descs, q, &L);
@@ -365,6 +427,8 @@ tskv_status orc_scan_aggregate(const uint8_t *arena, uint64_t arena_len,
   st = build_index(descs, n_descs, ix);
   if (st != TSKV_OK) return st;
   Scan S{arena, arena_len, descs, q, verify_crc, &ix, {}, L.n_cells};
+  S.tombs = tombs;
+  S.n_tombs = n_tombs;
   if (q->series_ids) {
     for (uint32_t i = 0; i < q->n_series; i++) {
       if (i && q->series_ids[i] <= q->series_ids[i - 1]) {

@@ -73,6 +73,13 @@ tskv_status orc_scan_aggregate(const uint8_t *arena, uint64_t arena_len,
                                const tskv_page_desc *descs, uint64_t n_descs, const tskv_query *q,
                                int verify_crc, int n_threads, uint64_t *out_values,
                                uint8_t *out_validity, uint64_t *out_points /* may be NULL */);
+/* Same with a TsmTombstone attached (tsm/reader.rs:507-551): entries as in include/tskv_gpu.h. Rows are located
+ * the reference's way, by binary search over the page's time values (reader.rs:634-656). */
+tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
+                                    const tskv_page_desc *descs, uint64_t n_descs, const tskv_query *q,
+                                    const tskv_tombstone *tombs, uint64_t n_tombs,
+                                    int verify_crc, int n_threads, uint64_t *out_values,
+                                    uint8_t *out_validity, uint64_t *out_points /* may be NULL */);
 const char *orc_last_error(void);
 
 #ifdef __cplusplus

@@ -508,3 +508,93 @@ def test_host_resident_pages_verify_crc_on_every_read(engine):
     arena[int(g.descs[other]["offset"]) + 40] ^= 0xff
     engine.scan_aggregate(hp, q)
     hp.close()
+
+
+def random_tombstones(rng, descs, t_lo, t_hi, n=60):
+    """Column masks, series-scoped row drops and a few page-set-wide row drops over random sub-ranges."""
+    fields = descs[descs["phys_type"] != cabi.TSKV_PT_TIME]
+    out = []
+    for _ in range(n):
+        d = fields[int(rng.integers(0, len(fields)))]
+        a = int(rng.integers(t_lo, t_hi))
+        b = a + int(rng.integers(0, (t_hi - t_lo) // 6))
+        kind = rng.random()
+        if kind < 0.6:
+            out.append((int(d["series_id"]), int(d["column_id"]), a, b))
+        elif kind < 0.9:
+            out.append((int(d["series_id"]), None, a, b))
+        else:
+            out.append((None, None, a, a + (b - a) // 8))
+    out.append((int(fields[0]["series_id"]), int(fields[0]["column_id"]), t_hi, t_lo))  # empty range: ignored
+    return cabi.tombstones(out)
+
+
+@pytest.mark.parametrize("variant", ["plain", "nulls", "jitter", "multi_cg", "raw"])
+def test_scan_with_tombstones_matches_decode_pages_semantics(engine, variant):
+    """TsmTombstone ranges through the fused scan (tsm/reader.rs:507-551): dropped rows, nulled column values, and
+    the first()/last() consequences, against the oracle's binary-search restatement."""
+    rng = np.random.default_rng(1000 + len(variant))
+    kw = dict(n_series=70, n_points=333, fields=SCAN_FIELDS)
+    if variant == "nulls":
+        kw["null_frac"] = 0.2
+    if variant == "jitter":
+        kw["jitter"] = 300
+    if variant == "multi_cg":
+        kw.update(multi_cg=True, null_frac=0.05)
+    if variant == "raw":
+        kw["raw_frac"] = 0.5
+    arena, descs, _ = random_arena(rng, **kw)
+    pages = engine.upload_pages(arena, descs)
+    t_lo, t_hi = 1_000_000 - 400, 1_000_000 + 700_000
+    tombs = random_tombstones(rng, descs, t_lo, 1_000_000 + 340_000)
+    pages.set_tombstones(tombs)
+    fbs, nb = bucket_spec(t_lo, t_hi, 17_000, origin=3)
+    sel = np.array(sorted(rng.choice(np.arange(80), 45, replace=False)), dtype=np.uint32)
+    for group_by_series in (False, True):
+        for series_ids in (sel, None):
+            for ranges in ([(t_lo + 30_000, t_lo + 250_000)], []):
+                q = make_query(SCAN_FIELDS, series_ids=series_ids, time_ranges=ranges, origin=3, width=17_000,
+                               first_bucket_start=fbs, n_buckets=nb, group_by_series=group_by_series)
+                got = engine.scan_aggregate(pages, q)
+                exp = orc.scan_aggregate(arena, descs, q, tombstones=tombs)
+                assert_results_equal(got, exp, what="tomb %s gbs=%s %s" % (variant, group_by_series, ranges))
+        q = make_query(SCAN_FIELDS, series_ids=sel, group_by_series=group_by_series)  # unbucketed
+        assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q, tombstones=tombs), what="tomb unbucketed")
+    q_plain = make_query(SCAN_FIELDS, aggs=("count", "sum"), series_ids=sel)
+    with_t = engine.scan_aggregate(pages, q_plain)
+    pages.set_tombstones([])  # cleared: back to the plain result
+    without = engine.scan_aggregate(pages, q_plain)
+    assert_results_equal(without, orc.scan_aggregate(arena, descs, q_plain), what="tombstones cleared")
+    assert int(with_t.column(1, "count")[0].sum()) < int(without.column(1, "count")[0].sum())
+    pages.close()
+
+
+def test_tombstones_golden_generic_time_pages_and_api_rules(engine):
+    b = datagen.ArenaBuilder()
+    for ts, vals in (([1], [111]), ([2, 3, 4], [212, 213, 214]), ([4, 5, 6], [314, 315, 316]), ([8, 9], [418, 419])):
+        b.add_column_group(1, np.array(ts, dtype=np.int64), [(1, cabi.TSKV_PT_I64, np.array(vals, dtype=np.int64), None)])
+    # a raw-encoded time page (one delta > 2^60 - 1) goes through the row-wise kernel
+    ts = np.concatenate([-(2**62) + np.arange(40, dtype=np.int64) * 1000, [2**61]]).astype(np.int64)
+    b.add_column_group(2, ts, [(1, cabi.TSKV_PT_I64, np.arange(41, dtype=np.int64), None),
+                               (2, cabi.TSKV_PT_F64, np.arange(41, dtype=np.float64), None)])
+    arena, descs = b.finish()
+    pages = engine.upload_pages(arena, descs)
+    q = make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.array([1], dtype=np.uint32))
+    prepared = engine.prepare(pages, q)
+    tombs = cabi.tombstones([(1, 1, 2, 6), (2, 1, -(2**62) + 5000, -(2**62) + 9000), (2, None, 2**61, 2**61),
+                             (None, None, -(2**62), -(2**62) + 1500)])
+    pages.set_tombstones(tombs)
+    with pytest.raises(TskvError) as e:  # prepared before the change: refused, not silently stale
+        prepared.run()
+    assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
+    prepared.close()
+    got = engine.scan_aggregate(pages, q)  # compact_test.rs:421-521: [111, None x5, 418, 419]
+    assert int(got.column(1, "count")[0][0, 0]) == 3 and int(got.column(1, "sum")[0][0, 0].view(np.int64)) == 948
+    q2 = make_query([(1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64)], group_by_series=True)
+    got, exp = engine.scan_aggregate(pages, q2), orc.scan_aggregate(arena, descs, q2, tombstones=tombs)
+    assert_results_equal(got, exp, what="raw time page + tombstones")
+    assert int(got.column(1, "count")[0][1, 0]) == 41 - 5 - 1 - 2 and int(got.column(2, "count")[0][1, 0]) == 41 - 1 - 2
+    with pytest.raises(TskvError) as e:
+        pages.set_tombstones(cabi.tombstones([(None, 1, 0, 10)]))
+    assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
+    pages.close()

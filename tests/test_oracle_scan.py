@@ -193,3 +193,57 @@ def test_bucket_range_error_and_bad_args():
     with pytest.raises(orc.OracleError) as e:
         orc.scan_aggregate(arena, descs, q)
     assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
+
+
+def test_tombstone_golden_compaction_3():
+    """compaction/compact/compact_test.rs:421-521 (test_compaction_3): a column tombstone (series 1, column 1) over
+    [2, 6] on the files holding t = 2..6 turns those values into NULL and keeps the rows:
+    expected [111, None x5, 418, 419] at t = [1, 2, 3, 4, 5, 6, 8, 9]."""
+    b = datagen.ArenaBuilder()
+    for ts, vals in (([1], [111]), ([2, 3, 4], [212, 213, 214]), ([4, 5, 6], [314, 315, 316]), ([8, 9], [418, 419])):
+        b.add_column_group(1, np.array(ts, dtype=np.int64), [(1, cabi.TSKV_PT_I64, np.array(vals, dtype=np.int64), None)])
+    arena, descs = b.finish()
+    q = make_query([(1, cabi.TSKV_PT_I64)])
+    res = orc.scan_aggregate(arena, descs, q, tombstones=cabi.tombstones([(1, 1, 2, 6)]))
+    assert int(res.column(1, "count")[0][0, 0]) == 3
+    assert int(res.column(1, "sum")[0][0, 0].view(np.int64)) == 111 + 418 + 419
+    assert int(res.column(1, "min")[0][0, 0].view(np.int64)) == 111
+    assert int(res.column(1, "max")[0][0, 0].view(np.int64)) == 419
+    assert int(res.column(1, "first")[0][0, 0].view(np.int64)) == 111
+    assert int(res.column(1, "last")[0][0, 0].view(np.int64)) == 419
+    # per-bucket: the rows survive as NULLs, so buckets [2,3], [4,5] have no values at all
+    q = make_query([(1, cabi.TSKV_PT_I64)], aggs=("count", "sum"), width=2, first_bucket_start=0, n_buckets=5)
+    res = orc.scan_aggregate(arena, descs, q, tombstones=cabi.tombstones([(1, 1, 2, 6)]))
+    assert res.column(1, "count")[0][0].tolist() == [1, 0, 0, 0, 2]
+
+
+def test_tombstone_semantics_restated_from_decode_pages():
+    """tsm/reader.rs:507-551: all-fields ranges drop ROWS (filter_record_batch), column ranges null the VALUES
+    (updated_nullbuffer); first()/last() then see a NULL at the run's end row and skip the run (first.rs:91-94)."""
+    b = datagen.ArenaBuilder()
+    ts = np.arange(10, dtype=np.int64) * 10
+    b.add_column_group(7, ts, [(1, cabi.TSKV_PT_I64, np.arange(1, 11, dtype=np.int64), None),
+                               (2, cabi.TSKV_PT_F64, np.arange(1, 11, dtype=np.float64) / 2, None)])
+    b.add_column_group(8, ts, [(1, cabi.TSKV_PT_I64, np.arange(101, 111, dtype=np.int64), None)])
+    arena, descs = b.finish()
+    q = make_query([(1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64)], series_ids=np.array([7], dtype=np.uint32))
+
+    def scan(tombs, query=q):
+        return orc.scan_aggregate(arena, descs, query, tombstones=cabi.tombstones(tombs))
+
+    r = scan([(7, 1, 20, 40)])  # values at t = 20, 30, 40 of column 1 are NULL; column 2 untouched
+    assert int(r.column(1, "count")[0][0, 0]) == 7 and int(r.column(1, "sum")[0][0, 0].view(np.int64)) == 55 - 12
+    assert int(r.column(2, "count")[0][0, 0]) == 10
+    r = scan([(7, 1, 20, 40), (None, None, 65, 75)])  # + the row t = 70 is dropped from every column
+    assert int(r.column(1, "count")[0][0, 0]) == 6 and int(r.column(1, "sum")[0][0, 0].view(np.int64)) == 43 - 8
+    assert int(r.column(2, "count")[0][0, 0]) == 9
+    r = scan([(7, None, 0, 5)])  # series-scoped row drop: first() moves to t = 10
+    assert int(r.column(1, "first")[0][0, 0].view(np.int64)) == 2
+    r = scan([(7, 1, 0, 0)])  # NULL at the min-time row: first() has no value for this run, last() unaffected
+    assert not r.column(1, "first")[1][0, 0]
+    assert r.column(1, "last")[1][0, 0] and int(r.column(1, "last")[0][0, 0].view(np.int64)) == 10
+    r = scan([(8, 1, 0, 1000), (9, None, 0, 1000)])  # other series' tombstones do not apply
+    assert int(r.column(1, "count")[0][0, 0]) == 10
+    both = make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.array([7, 8], dtype=np.uint32), group_by_series=True)
+    r = scan([(None, None, 0, 49)], both)
+    assert r.column(1, "count")[0][:, 0].tolist() == [5, 5]
