@@ -131,6 +131,14 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
     out.error = engine_->last_error(st);
     return out;
   }
+  if (!tombstones_.empty()) {
+    st = tskvgpu_pages_set_tombstones(ctx, pages, tombstones_.data(), tombstones_.size());
+    if (st != TSKV_OK) {
+      out.error = engine_->last_error(st);
+      tskvgpu_pages_destroy(ctx, pages);
+      return out;
+    }
+  }
   tskv_output_layout L{};
   st = tskvgpu_query_output_layout(pages, &q, &L);
   std::vector<uint64_t> values(L.n_out * L.n_cells);

@@ -157,6 +157,9 @@ class GpuAggregateBatchReader : public BatchReader {
   void fmt_as(std::ostream &f) const override;
   std::vector<BatchReaderRef> children() const override { return {}; }
   const tskv_counters &metrics() const { return counters_; }  // page_read_count/bytes, elapsed_* (column_group/mod.rs:141-193)
+  // The TsmTombstone of the file(s) behind the arena (ColumnGroupReader carries `tomb`, column_group/mod.rs:25-45;
+  // applied by decode_pages, tsm/reader.rs:507-551). Entries as in include/tskv_gpu.h.
+  void set_tombstones(std::vector<tskv_tombstone> tombs) { tombstones_ = std::move(tombs); }
 
  private:
   std::shared_ptr<GpuEngine> engine_;
@@ -165,6 +168,7 @@ class GpuAggregateBatchReader : public BatchReader {
   std::vector<ColumnGroup> column_groups_;
   QueryOption option_;
   bool verify_crc_;
+  std::vector<tskv_tombstone> tombstones_;
   tskv_counters counters_{};
 };
 

@@ -113,6 +113,37 @@ int main() {
       }
     }
   }
+  // ---- with a TsmTombstone attached (ColumnGroupReader's `tomb`, decode_pages reader.rs:507-551) -----------
+  std::vector<tskv_tombstone> tombs = {{100, 1, t0 + 100 * step, t0 + 180 * step},             // (series 100, usage_user) reads NULL
+                                       {102, TSKV_TOMB_ALL, t0 + 200 * step, t0 + 260 * step},  // rows of series 102 dropped
+                                       {TSKV_TOMB_ALL, TSKV_TOMB_ALL, t0 + 300 * step, t0 + 310 * step}};
+  GpuAggregateBatchReader tomb_reader(eng.value, arena.data(), arena.size(), cgs, opt);
+  tomb_reader.set_tombstones(tombs);
+  auto tres = tomb_reader.process();
+  CHECK(tres.ok() && tres.value.size() == 1 && tres.value[0].num_rows == b.num_rows);
+  std::vector<uint64_t> tv(L.n_out * L.n_cells);
+  std::vector<uint8_t> tb(L.validity_bytes);
+  CHECK(orc_scan_aggregate_tomb(arena.data(), arena.size(), descs.data(), descs.size(), &q, tombs.data(), tombs.size(), 1, 1,
+                                tv.data(), tb.data(), nullptr) == TSKV_OK);
+  bool differs = false;
+  for (const Map &m : maps) {
+    const ArrayData &c = tres.value[0].columns[m.batch_col];
+    for (size_t i = 0; i < b.num_rows; i++) {
+      bool ev = (tb[m.oracle_col * L.bitmap_stride + (i >> 3)] >> (i & 7)) & 1;
+      CHECK(c.is_valid(i) == ev);
+      if (!ev) continue;
+      uint64_t e = tv[m.oracle_col * L.n_cells + i], g = c.values[i];
+      differs |= e != ov[m.oracle_col * L.n_cells + i];
+      if (m.approx) {
+        double ed, gd;
+        memcpy(&ed, &e, 8); memcpy(&gd, &g, 8);
+        CHECK(std::fabs(ed - gd) <= 1e-6 * std::fabs(ed));
+      } else {
+        CHECK(e == g);
+      }
+    }
+  }
+  CHECK(differs);  // the tombstones did change the answer
   // ---- error behaviour: a corrupted page surfaces TsmPageFileHashCheckFailed, not a crash ----------------
   tskv::Bytes bad = arena;
   bad[cgs[0].pages()[1].offset + cgs[0].pages()[1].size - 1] ^= 0x10;
