@@ -42,7 +42,8 @@ AGGS = ["count", "sum", "min", "max", "mean"]
 BIN_NAMES = {0: "ts=RLE,val=simple8b", 1: "ts=RLE,val=gorilla", 2: "ts=RLE,val=generic", 3: "ts=simple8b,val=simple8b",
              4: "ts=simple8b,val=gorilla", 5: "ts=simple8b,val=generic", 6: "ts=generic,val=simple8b",
              7: "ts=generic,val=gorilla", 8: "ts=generic,val=generic", 9: "ts=RLE,val=simple8b (<=1024 rows)",
-             10: "ts=simple8b,val=simple8b (<=1024 rows)"}
+             10: "ts=simple8b,val=simple8b (<=1024 rows)", 11: "ts=RLE,val=gorilla (<=1024 rows)",
+             12: "ts=simple8b,val=gorilla (<=1024 rows)"}
 
 
 def workload_name(n_series):

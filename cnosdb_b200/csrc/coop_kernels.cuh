@@ -1,5 +1,5 @@
 // coop_kernels.cuh — warp-cooperative scan of ONE page per warp (sm_100a), for the codecs that decode in
-// parallel: timestamps RLE / simple8b, values zig-zag simple8b (and the closed-form / raw kinds).
+// parallel: timestamps RLE / simple8b, values zig-zag simple8b — and, split in two phases, gorilla values.
 //
 // The lane-per-page kernels (scan_kernels.cuh) are bounded by the serial decode latency of one page
 // (1000 rows x ~120 dependent instructions) no matter how many SMs or GPUs share the work. Here a warp
@@ -11,6 +11,13 @@
 //      invariant bucket width and compacts the segment heads,
 //   D. reduces lane-per-segment (a 1-minute bucket of a 10-second series is 6 rows) and updates the
 //      per-CTA shared-memory table / the global state once per segment and aggregate.
+// Gorilla (float.rs:418-606) is bit-serial only in its STRUCTURE (where each value's XOR window starts depends on
+// the control bits before it), so its pages are decoded in two phases by the same warp, a group of G pages at a time:
+//   1. lane g parses the control bits of page g (13 bits per element, ~20 dependent instructions) and writes one
+//      32-bit record per element {mantissa bit offset, meaningful bits, trailing zeros} to a global scratch row;
+//   2. the warp takes the G pages one by one: lane-per-value mantissa extraction from the records, a warp XOR scan
+//      for the running value, then steps C and D as for the integer pages.
+// G is chosen by the host so that the selected pages make about one task per resident warp.
 // Same formats and semantics as cursors.cuh / scan_kernels.cuh (reference lines cited there).
 #pragma once
 #include "scan_kernels.cuh"
@@ -21,12 +28,28 @@ constexpr int COOP_TILE = 1024;              // pages with more rows use the lan
 constexpr int COOP_PAD = COOP_TILE + COOP_TILE / 32 + 8;
 __host__ __device__ __forceinline__ uint32_t cpad(uint32_t i) { return i + (i >> 5); }
 
-template <bool HAS_TS>
+constexpr uint32_t GOR_REC_STRIDE = COOP_TILE + 8;  // u32 records per page row in the scratch
+constexpr uint64_t GOR_SENTINEL = 0x7ff80000000000ffull;  // float.rs:16
+
+// Phase-1 result of one gorilla page (lane g of the group wrote entry g).
+struct GorGroup {
+  uint32_t n_valid[32];   // valid rows = values the bitset asks for
+  uint32_t n_parsed[32];  // elements 1..n_parsed parsed inside the block (< n_valid: element n_parsed + 1 overran it)
+  uint32_t endpos[32];    // stream bit position after the last parsed element
+  uint8_t meaningful[32], trailing[32];  // window state after the last parsed element
+};
+
+struct NoGorGroup {};
+template <bool GOR> struct GorGroupSel { using type = GorGroup; };
+template <> struct GorGroupSel<false> { using type = NoGorGroup; };
+
+template <bool HAS_TS, bool GOR>
 struct CoopSmem {
   uint64_t vals[COOP_PAD];
   uint64_t ts[HAS_TS ? COOP_PAD : 1];
   uint16_t seg[COOP_TILE + 2];
   uint32_t rank_base[COOP_TILE / 32 + 1];
+  typename GorGroupSel<GOR>::type gor;
 };
 
 __device__ __forceinline__ uint64_t load_be64_any(const uint8_t *p) {
@@ -47,6 +70,15 @@ __device__ __forceinline__ uint32_t warp_excl_scan_u32(uint32_t v, uint32_t *tot
   }
   *total = __shfl_sync(FULL, x, 31);
   return x - v;
+}
+__device__ __forceinline__ uint64_t warp_incl_xor_scan_u64(uint64_t v) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t lo = __shfl_up_sync(FULL, (uint32_t)v, o), hi = __shfl_up_sync(FULL, (uint32_t)(v >> 32), o);
+    if (lane >= (uint32_t)o) v ^= ((uint64_t)hi << 32) | lo;
+  }
+  return v;
 }
 __device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
   const uint32_t lane = threadIdx.x & 31;
@@ -109,6 +141,72 @@ __device__ __forceinline__ uint32_t coop_decode_s8b(const uint8_t *words, uint32
   return base;
 }
 
+// ---- gorilla, phase 1 and bit helpers -------------------------------------------------------------------------
+// MSB-first bit stream addressed through 4-byte aligned words: `wp` = aligned pointer at or below the stream start,
+// `abs` = bit offset from wp. Reads may run <= 12 bytes past the page (arena slack).
+__device__ __forceinline__ uint32_t gor_peek32(const uint32_t *wp, uint32_t abs) {
+  const uint32_t wi = abs >> 5;
+  const uint32_t a = __byte_perm(__ldg(wp + wi), 0, 0x0123), b = __byte_perm(__ldg(wp + wi + 1), 0, 0x0123);
+  return __funnelshift_l(b, a, abs & 31);
+}
+__device__ __forceinline__ uint64_t gor_peek64(const uint32_t *wp, uint32_t abs) {
+  const uint32_t wi = abs >> 5, sh = abs & 31;
+  const uint32_t a = __byte_perm(__ldg(wp + wi), 0, 0x0123), b = __byte_perm(__ldg(wp + wi + 1), 0, 0x0123),
+                 c = __byte_perm(__ldg(wp + wi + 2), 0, 0x0123);
+  return ((uint64_t)__funnelshift_l(b, a, sh) << 32) | __funnelshift_l(c, b, sh);
+}
+// One element's control bits (float.rs:480-560, cursors.cuh GorillaCursor::advance): returns the control length,
+// sets `sig` = XOR-window width (0: repeat the previous value) and updates the (meaningful, trailing) window state.
+__device__ __forceinline__ uint32_t gor_parse_ctrl(uint32_t x13, uint32_t &meaningful, uint32_t &trailing, uint32_t &sig) {
+  if (!(x13 & 0x1000)) { sig = 0; return 1; }
+  if (!(x13 & 0x0800)) { sig = meaningful; return 2; }
+  const uint32_t leading = (x13 >> 6) & 0x1f, m = x13 & 0x3f;
+  if (m > 0) { meaningful = m; trailing = (64 - leading - m) & 0xff; }  // u8 arithmetic like the reference
+  else { meaningful = 64; trailing = 0; }
+  sig = meaningful;
+  return 13;
+}
+__device__ __forceinline__ void gor_stream(const PageView &vpv, const uint32_t *&wp, uint32_t &base_bits, uint32_t &total_bits) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(vpv.data + 10);  // id | 0x10 | first(8) | bit stream
+  wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+  base_bits = (uint32_t)(a & 3) * 8;
+  total_bits = (vpv.data_len - 10) * 8;
+}
+
+// Phase 1, one lane per page: records[e] for the elements e = 1..n_valid (element n_valid is the one that has to be
+// the sentinel); stops at the first element that runs past the block.
+__device__ __forceinline__ void gor_parse_page(const ScanParams &P, uint32_t item, uint32_t *records, GorGroup &G, uint32_t g) {
+  const uint32_t page = P.work_page[item];
+  const tskv_page_desc vd = P.descs[page];
+  PageView vpv;
+  vpv.open(P.arena, vd);
+  const uint32_t n_rows = vd.num_values;
+  const uint32_t *vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
+  uint32_t n_valid = 0;
+  for (uint32_t w = 0; w < (n_rows + 31) >> 5; w++) {
+    uint32_t bits = __ldg(vbm + w);
+    if (w == (n_rows >> 5)) bits &= (1u << (n_rows & 31)) - 1;
+    n_valid += __popc(bits);
+  }
+  const uint32_t *wp;
+  uint32_t base_bits, total_bits;
+  gor_stream(vpv, wp, base_bits, total_bits);
+  uint32_t bitpos = 0, meaningful = 64, trailing = 0, e = 1;
+#pragma unroll 1
+  for (; e <= n_valid; e++) {
+    uint32_t sig;
+    const uint32_t len = gor_parse_ctrl(gor_peek32(wp, base_bits + bitpos) >> 19, meaningful, trailing, sig);
+    records[e] = (bitpos + len) | (sig << 17) | ((trailing & 63) << 24);
+    bitpos += len + sig;
+    if (bitpos > total_bits) break;  // "unexpected end of block" (bits_used > bits_total in the serial cursor)
+  }
+  G.n_valid[g] = n_valid;
+  G.n_parsed[g] = e - 1;
+  G.endpos[g] = bitpos;
+  G.meaningful[g] = (uint8_t)meaningful;
+  G.trailing[g] = (uint8_t)trailing;
+}
+
 // Multiply-high division of a non-negative dividend by the invariant bucket width (Granlund-Montgomery):
 // q = floor(x / d) for d >= 1 with m = floor(2^64 (2^l - d) / d) + 1, l = ceil(log2 d).
 struct MagicDiv {
@@ -125,7 +223,8 @@ struct CoopParams {
   MagicDiv div;        // by P.width
   int64_t q0;          // quotient of first_bucket_start: bucket idx = q(t) - q0
   uint32_t grid_ok;    // first_bucket_start lies on the bucket grid
-  uint32_t pad;
+  uint32_t gor_group;  // gorilla bins: pages per warp task (1..32)
+  uint32_t *gor_scratch[2];  // per gorilla bin: [warps of the grid][gor_group][GOR_REC_STRIDE] element records
 };
 
 // (selected by the time ranges, bucket) of one timestamp as a 32-bit key; 0xffffffff = not selected.
@@ -151,10 +250,12 @@ __device__ __forceinline__ uint32_t coop_row_key(const ScanParams &P, const Coop
   return (uint32_t)idx;
 }
 
-// One page per warp. TK in {TK_RLE, TK_S8B} (time page without nulls), VK = VK_S8B (zig-zag simple8b values).
-template <int TK, bool SEL>
+// One page per warp. TK in {TK_RLE, TK_S8B} (time page without nulls), VK = VK_S8B (zig-zag simple8b values) or
+// VK_GOR (gorilla values; `records` / entry `g` of S.gor = phase 1's output for this page).
+template <int TK, int VK, bool SEL>
 __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopParams &C, uint32_t item,
-                                               CoopSmem<TK == TK_S8B> &S, uint64_t *stab) {
+                                               CoopSmem<TK == TK_S8B, VK == VK_GOR> &S, uint64_t *stab,
+                                               const uint32_t *records = nullptr, uint32_t g = 0) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t page = P.work_page[item];
   const uint32_t slot = P.work_slot[item];
@@ -196,9 +297,59 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
     const uint32_t ex = warp_excl_scan_u32(__popc(w), &n_valid);
     S.rank_base[lane] = ex;
   }
-  const uint32_t got = coop_decode_s8b<true>(vpv.data + 10, (vpv.data_len - 10) >> 3,
-                                             (uint64_t)zigzag_dec(load_be64_any(vpv.data + 2)), 1, S.vals, n_valid);
-  if (got < n_valid) { if (lane == 0) report_error(P, TSKV_ERR_BITSET_MISMATCH, page); return; }
+  if (VK == VK_S8B) {
+    const uint32_t got = coop_decode_s8b<true>(vpv.data + 10, (vpv.data_len - 10) >> 3,
+                                               (uint64_t)zigzag_dec(load_be64_any(vpv.data + 2)), 1, S.vals, n_valid);
+    if (got < n_valid) { if (lane == 0) report_error(P, TSKV_ERR_BITSET_MISMATCH, page); return; }
+  } else if (n_valid) {  // gorilla, phase 2: value i = first ^ xor of the elements' deltas 1..i
+    const GorGroup &G = *reinterpret_cast<const GorGroup *>(&S.gor);
+    const uint32_t n_parsed = G.n_parsed[g];  // < n_valid: element n_parsed + 1 ran past the block
+    const uint32_t *wp;
+    uint32_t base_bits, total_bits;
+    gor_stream(vpv, wp, base_bits, total_bits);
+    uint64_t carry = load_be64_any(vpv.data + 2);
+    uint32_t first_sentinel = 0xffffffffu;  // lowest value index < n_valid (and before the overrun) holding the sentinel
+    uint64_t v_end = 0;                     // value n_valid (has to be the sentinel)
+    bool end_ok = false;
+    for (uint32_t i0 = 0; i0 <= n_parsed; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      uint64_t delta = 0;
+      uint32_t sig = 0;  // 0: the first value or a "repeat" element - both are pushed without a sentinel test
+      if (i >= 1 && i <= n_parsed) {
+        const uint32_t rec = __ldcg(records + i);  // written by this kernel (phase 1): not through the read-only path
+        sig = (rec >> 17) & 0x7f;
+        if (sig) delta = (gor_peek64(wp, base_bits + (rec & 0x1ffff)) >> (64 - sig)) << (rec >> 24);
+      }
+      const uint64_t x = warp_incl_xor_scan_u64(delta) ^ carry;
+      if (i < n_valid && i <= n_parsed) S.vals[cpad(i)] = x;
+      const bool is_end = sig != 0 && x == GOR_SENTINEL;  // float.rs:585-589
+      const uint32_t sm = __ballot_sync(FULL, i < n_valid && is_end);
+      if (sm && first_sentinel == 0xffffffffu) first_sentinel = i0 + __ffs(sm) - 1;
+      if (n_valid - i0 < 32 && n_parsed == n_valid) {
+        v_end = shfl_u64(x, n_valid - i0);
+        end_ok = __shfl_sync(FULL, (int)is_end, n_valid - i0) != 0;
+      }
+      carry = shfl_u64(x, 31);
+    }
+    // the serial cursor's outcomes (cursors.cuh GorillaCursor): a sentinel before the bitset is served =
+    // "Mismatch between bit set and decoded values"; running past the block = "unexpected end of block"
+    if (first_sentinel != 0xffffffffu) { if (lane == 0) report_error(P, TSKV_ERR_BITSET_MISMATCH, page); return; }
+    if (n_parsed < n_valid) { if (lane == 0) report_error(P, TSKV_ERR_SHORT_BLOCK, page); return; }
+    if (!end_ok) {
+      // more elements than valid rows: the reference decodes on to the sentinel (float.rs:480-591). Rare; every
+      // lane walks the rest of the stream redundantly.
+      uint32_t bitpos = G.endpos[g], meaningful = G.meaningful[g], trailing = G.trailing[g];
+      uint64_t val = v_end;
+      for (;;) {
+        uint32_t sig;
+        const uint32_t len = gor_parse_ctrl(gor_peek32(wp, base_bits + bitpos) >> 19, meaningful, trailing, sig);
+        if (sig) val ^= (gor_peek64(wp, base_bits + bitpos + len) >> (64 - sig)) << (trailing & 63);
+        bitpos += len + sig;
+        if (bitpos > total_bits) { if (lane == 0) report_error(P, TSKV_ERR_SHORT_BLOCK, page); return; }
+        if (sig && val == GOR_SENTINEL) break;
+      }
+    }
+  }
   __syncwarp();
   // ---- C. per-row keys -> segment heads ---------------------------------------------------------------
   bool range_err = false;
@@ -238,7 +389,7 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
       bool dummy = false;
       const uint32_t key = coop_row_key(P, C, tb, &dummy);
       if (key != 0xffffffffu) {
-        ValueAcc<VK_S8B> va;
+        ValueAcc<VK> va;
         va.reset();
         uint64_t first_v = 0, last_v = 0;
         bool first_ok = false, last_ok = false;
@@ -258,7 +409,7 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
           }
         }
         const uint64_t cell = group_base + key;
-        if (va.count) table_update(P, stab, cs, cell, mask, false, va.count, va.sum, va.sum_hi, va.kmin, va.kmax);
+        if (va.count) table_update(P, stab, cs, cell, mask, VK == VK_GOR, va.count, va.sum, va.sum_hi, va.kmin, va.kmax);
         if (SEL) {
           const int64_t te = TK == TK_RLE ? (int64_t)(t_first + (uint64_t)(re - 1) * t_delta) : (int64_t)S.ts[cpad(re - 1)];
           int64_t kf = tb, kl = te;
@@ -281,7 +432,7 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
   }
 }
 
-template <int TK, bool SEL>
+template <int TK, int VK, bool SEL>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) k_scan_coop(const __grid_constant__ ScanParams P,
                                                                const __grid_constant__ CoopParams C, int bin) {
   extern __shared__ __align__(16) uint64_t s_dyn[];  // [per-CTA table | per-warp CoopSmem]
@@ -298,18 +449,39 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) k_scan_coop(const __grid_cons
     }
     __syncthreads();
   }
-  using Smem = CoopSmem<TK == TK_S8B>;
+  using Smem = CoopSmem<TK == TK_S8B, VK == VK_GOR>;
   Smem &S = *reinterpret_cast<Smem *>(reinterpret_cast<uint8_t *>(s_dyn + ((P.smem_words + 1) & ~1u)) +
                                       (threadIdx.x >> 5) * ((sizeof(Smem) + 15) & ~(size_t)15));
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
-  for (;;) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(P.task_counter + bin, 1u);
-    i = __shfl_sync(FULL, i, 0);
-    if (begin0 + i >= end0) break;
-    scan_page_coop<TK, SEL>(P, C, begin0 + i, S, s_tab);
-    __syncwarp();
+  if (VK != VK_GOR) {
+    for (;;) {
+      uint32_t i = 0;
+      if (lane == 0) i = atomicAdd(P.task_counter + bin, 1u);
+      i = __shfl_sync(FULL, i, 0);
+      if (begin0 + i >= end0) break;
+      scan_page_coop<TK, VK, SEL>(P, C, begin0 + i, S, s_tab);
+      __syncwarp();
+    }
+  } else {
+    const uint32_t group = C.gor_group;
+    uint32_t *rows = C.gor_scratch[bin == BIN_COOP_RLE_GOR ? 0 : 1] +
+                     (size_t)(blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5)) * group * GOR_REC_STRIDE;
+    GorGroup &G = *reinterpret_cast<GorGroup *>(&S.gor);
+    for (;;) {
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(P.task_counter + bin, 1u);
+      t = __shfl_sync(FULL, t, 0);
+      const uint64_t first = (uint64_t)begin0 + (uint64_t)t * group;
+      if (first >= end0) break;
+      const uint32_t cnt = min(group, end0 - (uint32_t)first);
+      if (lane < cnt) gor_parse_page(P, (uint32_t)first + lane, rows + lane * GOR_REC_STRIDE, G, lane);  // phase 1
+      __syncwarp();
+      for (uint32_t g = 0; g < cnt; g++) {                                                            // phase 2
+        scan_page_coop<TK, VK, SEL>(P, C, (uint32_t)first + g, S, s_tab, rows + g * GOR_REC_STRIDE, g);
+        __syncwarp();
+      }
+    }
   }
   if (P.use_smem) {  // merge this CTA's table into the global state, once
     __syncthreads();

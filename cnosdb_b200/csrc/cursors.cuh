@@ -358,7 +358,12 @@ struct GorillaCursor {
   __device__ __forceinline__ bool advance() {
     const uint32_t x = (uint32_t)(peek() >> 51);  // 13 bits: c0 c1 lead[5] sig[6]
     if (!(x & 0x1000)) {
-      skip(1);  // repeat previous value
+      skip(1);  // repeat previous value: pushed without a sentinel test (float.rs:493-497), like the first value
+      if (bits_used > bits_total) {
+        err = true;
+        return false;
+      }
+      return true;
     } else {
       if (!(x & 0x0800)) {
         skip(2);  // reuse the previous (leading, trailing) window

@@ -17,9 +17,11 @@ constexpr int MAX_RANGES = 8;
 constexpr int N_TK = 3;  // time-cursor specialisations: RLE, S8B scaled, generic
 constexpr int N_VK = 3;  // value-cursor specialisations: S8B zig-zag, gorilla, generic
 constexpr int N_SERIAL_BINS = N_TK * N_VK;  // lane-per-page kernels (scan_kernels.cuh)
-// + warp-cooperative kernels (coop_kernels.cuh): zig-zag simple8b values with RLE / simple8b timestamps
-enum { BIN_COOP_RLE_S8B = N_SERIAL_BINS, BIN_COOP_S8B_S8B = N_SERIAL_BINS + 1 };
-constexpr int N_BINS = N_SERIAL_BINS + 2;
+// + warp-cooperative kernels (coop_kernels.cuh): zig-zag simple8b or gorilla values (<= COOP_TILE rows) with
+// RLE / simple8b timestamps
+enum { BIN_COOP_RLE_S8B = N_SERIAL_BINS, BIN_COOP_S8B_S8B = N_SERIAL_BINS + 1, BIN_COOP_RLE_GOR = N_SERIAL_BINS + 2,
+       BIN_COOP_S8B_GOR = N_SERIAL_BINS + 3 };
+constexpr int N_BINS = N_SERIAL_BINS + 4;
 
 enum { TK_RLE = 0, TK_S8B = 1, TK_GEN = 2 };
 enum { VK_S8B = 0, VK_GOR = 1, VK_GEN = 2 };

@@ -95,6 +95,7 @@ struct tskv_scan {
   uint32_t *d_work_page = nullptr, *d_work_slot = nullptr;
   uint8_t *d_work_qcol = nullptr;
   uint32_t *d_bin_cstart = nullptr;  // [N_BINS+1] then [1] total
+  uint32_t *d_gor_scratch[2] = {nullptr, nullptr};  // element records of the cooperative gorilla bins
   ColState *d_cols = nullptr;
   OutCol *d_outs = nullptr;
   MeanExport *d_means = nullptr;
@@ -171,8 +172,11 @@ scan_kernel_t scan_kernel_for(int bin) {
 int serial_bin_of(int bin) {
   if (bin == BIN_COOP_RLE_S8B) return TK_RLE * N_VK + VK_S8B;
   if (bin == BIN_COOP_S8B_S8B) return TK_S8B * N_VK + VK_S8B;
+  if (bin == BIN_COOP_RLE_GOR) return TK_RLE * N_VK + VK_GOR;
+  if (bin == BIN_COOP_S8B_GOR) return TK_S8B * N_VK + VK_GOR;
   return bin;
 }
+bool is_gor_coop_bin(int bin) { return bin == BIN_COOP_RLE_GOR || bin == BIN_COOP_S8B_GOR; }
 double bin_cost(int bin, bool coop) {
   static const double tk[N_TK] = {1.0, 1.5, 2.0}, vk[N_VK] = {1.0, 1.4, 1.6};
   const int sb = serial_bin_of(bin);
@@ -180,13 +184,20 @@ double bin_cost(int bin, bool coop) {
 }
 
 size_t coop_smem_bytes(int bin, uint32_t table_words) {
-  size_t per_warp = bin == BIN_COOP_S8B_S8B ? sizeof(CoopSmem<true>) : sizeof(CoopSmem<false>);
+  size_t per_warp = bin == BIN_COOP_S8B_S8B   ? sizeof(CoopSmem<true, false>)
+                    : bin == BIN_COOP_RLE_S8B ? sizeof(CoopSmem<false, false>)
+                    : bin == BIN_COOP_S8B_GOR ? sizeof(CoopSmem<true, true>)
+                                              : sizeof(CoopSmem<false, true>);
   per_warp = (per_warp + 15) & ~(size_t)15;
   return (size_t)((table_words + 1) & ~1u) * 8 + per_warp * (SCAN_THREADS / 32);
 }
 const void *coop_kernel_for(int bin, bool sel) {
-  if (bin == BIN_COOP_RLE_S8B) return sel ? (const void *)k_scan_coop<TK_RLE, true> : (const void *)k_scan_coop<TK_RLE, false>;
-  return sel ? (const void *)k_scan_coop<TK_S8B, true> : (const void *)k_scan_coop<TK_S8B, false>;
+  switch (bin) {
+    case BIN_COOP_RLE_S8B: return sel ? (const void *)k_scan_coop<TK_RLE, VK_S8B, true> : (const void *)k_scan_coop<TK_RLE, VK_S8B, false>;
+    case BIN_COOP_S8B_S8B: return sel ? (const void *)k_scan_coop<TK_S8B, VK_S8B, true> : (const void *)k_scan_coop<TK_S8B, VK_S8B, false>;
+    case BIN_COOP_RLE_GOR: return sel ? (const void *)k_scan_coop<TK_RLE, VK_GOR, true> : (const void *)k_scan_coop<TK_RLE, VK_GOR, false>;
+    default: return sel ? (const void *)k_scan_coop<TK_S8B, VK_GOR, true> : (const void *)k_scan_coop<TK_S8B, VK_GOR, false>;
+  }
 }
 
 MagicDiv make_magic(uint64_t d) {  // d >= 1
@@ -239,7 +250,7 @@ void free_scan(tskv_scan *s) {
   cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
   void *bufs[] = {s->d_series, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
                   s->d_work_qcol, s->d_bin_cstart, s->d_cols, s->d_outs, s->d_means, s->d_state,
-                  s->d_task_counter, s->d_values, s->d_validity};
+                  s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1]};
   for (void *b : bufs)
     if (b) cudaFreeAsync(b, st);
   delete s;
@@ -457,6 +468,8 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
       static const bool no_coop = getenv("TSKV_NO_COOP") != nullptr;
       if (!no_coop && vd.num_values <= COOP_TILE && vd.reserved == DK_S8B_ZZ && tclass != TK_GEN)
         bin = tclass == TK_RLE ? BIN_COOP_RLE_S8B : BIN_COOP_S8B_S8B;
+      if (!no_coop && vd.num_values <= COOP_TILE && vd.reserved == DK_GORILLA && tclass != TK_GEN)
+        bin = tclass == TK_RLE ? BIN_COOP_RLE_GOR : BIN_COOP_S8B_GOR;
       key[k] = (bin << 48) | ((uint64_t)vd.column_id << 32) | k;
       order[k] = k;
     }
@@ -1002,6 +1015,18 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     // Grid sizes. Every kernel is persistent (warps pull tasks from their bin's counter). If the resident
     // capacity allows, each bin gets one warp per estimated task (a single round: the makespan of a bin is
     // quantised in units of one task = one page's serial decode); otherwise the blocks are split by cost.
+    // Gorilla coop bins: pages per warp task (phase 1 parses them lane-per-page) so that the selected pages make
+    // about one task per resident warp; TSKV_GOR_GROUP overrides.
+    uint32_t gor_group = 1;
+    {
+      double est_gor = 0;
+      for (int b = N_SERIAL_BINS; b < N_BINS; b++)
+        if (is_gor_coop_bin(b) && s->use_coop[b]) est_gor += (pages->h_bin_start[b + 1] - pages->h_bin_start[b]) * sel_frac;
+      const double resident_warps = (double)ctx->sm_count * 2 * (SCAN_THREADS / 32);
+      while (gor_group < 32 && est_gor / gor_group > resident_warps) gor_group *= 2;
+      if (const char *g = getenv("TSKV_GOR_GROUP")) gor_group = (uint32_t)std::min(32, std::max(1, atoi(g)));
+      s->coop.gor_group = gor_group;
+    }
     double w[N_BINS], wsum = 0, need_sum = 0, occ_weighted = 0;
     int need[N_BINS] = {0};
     for (int b = 0; b < N_BINS; b++) {
@@ -1024,17 +1049,49 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       }
       occ = std::max(1, occ);
       const double est_items = n_bin * sel_frac * 1.02 + 32;
-      const double tasks = s->use_coop[b] ? est_items : est_items / 32.0;
+      const uint32_t per_task = !s->use_coop[b] ? 32u : is_gor_coop_bin(b) ? gor_group : 1u;  // pages per warp task
+      const double tasks = est_items / per_task;
       need[b] = (int)(tasks / (SCAN_THREADS / 32)) + 1;
-      need[b] = std::min(need[b], (int)((s->use_coop[b] ? n_bin : (n_bin + 31) / 32) + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32));
+      need[b] = std::min(need[b], (int)((n_bin + per_task - 1) / per_task + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32));
       need_sum += need[b];
       occ_weighted += (double)need[b] * occ;
     }
     const double capacity = need_sum > 0 ? (occ_weighted / need_sum) * ctx->sm_count : 0;  // resident blocks, mixed kernels
-    for (int b = 0; b < N_BINS; b++) {
-      if (!need[b]) continue;
-      if (need_sum <= capacity) s->grid[b] = std::max(1, need[b]);
-      else s->grid[b] = std::max(1, std::min(need[b], (int)(capacity * w[b] / wsum + 0.5)));
+    if (need_sum <= capacity) {
+      for (int b = 0; b < N_BINS; b++)
+        if (need[b]) s->grid[b] = std::max(1, need[b]);
+    } else {
+      // water-filling: bins that need less than their cost share keep their need, the rest split what is left
+      bool fixed[N_BINS] = {false};
+      double cap_left = capacity, w_left = 0;
+      for (int b = 0; b < N_BINS; b++) w_left += need[b] ? w[b] : 0;
+      for (int round = 0; round < N_BINS; round++) {
+        bool changed = false;
+        for (int b = 0; b < N_BINS; b++) {
+          if (!need[b] || fixed[b]) continue;
+          if (need[b] <= cap_left * w[b] / w_left) {
+            s->grid[b] = std::max(1, need[b]);
+            fixed[b] = true;
+            cap_left -= s->grid[b];
+            w_left -= w[b];
+            changed = true;
+          }
+        }
+        if (!changed) break;
+      }
+      for (int b = 0; b < N_BINS; b++)
+        if (need[b] && !fixed[b]) s->grid[b] = std::max(1, std::min(need[b], (int)(cap_left * w[b] / w_left + 0.5)));
+    }
+    for (int b = N_SERIAL_BINS; b < N_BINS; b++) {
+      if (!is_gor_coop_bin(b) || !s->use_coop[b] || !s->grid[b]) continue;
+      const int k = b == BIN_COOP_RLE_GOR ? 0 : 1;
+      const size_t words = (size_t)s->grid[b] * (SCAN_THREADS / 32) * gor_group * GOR_REC_STRIDE;
+      if (stream_alloc(ctx, &s->d_gor_scratch[k], words) != cudaSuccess) {
+        ctx->set_error("scan_prepare: out of memory for the gorilla record scratch");
+        free_scan(s);
+        return TSKV_ERR_OOM;
+      }
+      s->coop.gor_scratch[k] = s->d_gor_scratch[k];
     }
     // bucket arithmetic of the cooperative kernels: multiply-high division by the invariant width
     if (q->width > 0) {

@@ -598,3 +598,77 @@ def test_tombstones_golden_generic_time_pages_and_api_rules(engine):
         pages.set_tombstones(cabi.tombstones([(None, 1, 0, 10)]))
     assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
     pages.close()
+
+
+@pytest.mark.parametrize("group", ["1", "4", "32"])
+def test_gorilla_two_phase_cooperative_scan(engine, group, monkeypatch):
+    """Gorilla pages through the warp-cooperative kernels (phase 1: lane-per-page control-bit parse of a group of
+    pages, phase 2: warp-per-page extraction + XOR scan), for several group sizes, against the oracle and against the
+    lane-per-page kernels."""
+    monkeypatch.setenv("TSKV_GOR_GROUP", group)
+    g = datagen.generate(1500, n_fields=2, n_points=1000, value_kind=datagen.MIXED, seed=int(group) + 5, jitter_permille=300,
+                         jitter_max=999_999, null_page_permille=300, null_row_permille=120)
+    pages = engine.upload_pages(g.arena, g.descs)
+    w = 60_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0 - 1_000_000, datagen.TSBS_T0 + 999 * datagen.TSBS_STEP + 1_000_000, w)
+    sel = np.arange(0, 1500, 2, dtype=np.uint32)
+    cols = [PushedAggregate(1, cabi.TSKV_PT_I64, ALL_AGGS), PushedAggregate(3, cabi.TSKV_PT_F64, ALL_AGGS),
+            PushedAggregate(4, cabi.TSKV_PT_F64, ("count", "sum", "first"))]
+    for gbs in (False, True):
+        q = QueryOption(cols, series_ids=sel, time_ranges=[(datagen.TSBS_T0 + 7 * datagen.TSBS_STEP, datagen.TSBS_T0 + 900 * datagen.TSBS_STEP)],
+                        width=w, first_bucket_start=fbs, n_buckets=nb, group_by_series=gbs)
+        exp = orc.scan_aggregate(g.arena, g.descs, q, n_threads=4)
+        for mode in ("1", "0"):
+            monkeypatch.setenv("TSKV_COOP", mode)
+            assert_results_equal(engine.scan_aggregate(pages, q), exp, what="gorilla coop=%s group=%s gbs=%s" % (mode, group, gbs))
+    pages.close()
+
+
+@pytest.mark.parametrize("case,status", [("extra_values", 0), ("early_sentinel", cabi.TSKV_ERR_BITSET_MISMATCH),
+                                         ("truncated", cabi.TSKV_ERR_SHORT_BLOCK), ("sentinel_valued_data", 0),
+                                         ("first_value_only", cabi.TSKV_ERR_SHORT_BLOCK)])
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_gorilla_stream_end_cases_in_both_kernel_families(engine, case, status, mode, monkeypatch):
+    """The end of a gorilla stream (float.rs:480-591): more values than valid rows are decoded and ignored, a
+    sentinel before the bitset is served is a mismatch, a stream without sentinel is an unexpected end of block."""
+    monkeypatch.setenv("TSKV_COOP", mode)
+    n = 200
+    vals = np.cumsum(np.arange(n) % 5).astype(np.float64) * 0.37 + 1.5
+    ts = datagen.TSBS_T0 + np.arange(n, dtype=np.int64) * datagen.TSBS_STEP
+    b = datagen.ArenaBuilder()
+    b.add_page(datagen.build_page(datagen.encode_timestamps(ts), n), 5, 0, cabi.TSKV_PT_TIME, n)
+    if case == "extra_values":    # 230 encoded values for 200 rows
+        data = datagen.encode_floats(np.concatenate([vals, np.arange(30) * 3.25]))
+    elif case == "early_sentinel":  # 150 encoded values for 200 valid rows
+        data = datagen.encode_floats(vals[:150])
+    elif case == "truncated":     # cut inside the stream: no sentinel
+        data = datagen.encode_floats(vals)[:-24]
+    elif case == "sentinel_valued_data":  # the first value and "repeat" elements are pushed without a sentinel test
+        # the encoder refuses the sentinel (float.rs:58), so the stream is written by hand: first = sentinel, 6 x "repeat",
+        # one full-width element giving 2.5, the terminator; 8 rows
+        sent, v25 = 0x7FF80000000000FF, int(np.float64(2.5).view(np.uint64))
+        bits = "0" * 6 + "11" + "00000" + "000000" + format(sent ^ v25, "064b") + "11" + "00000" + "000000" + format(v25 ^ sent, "064b")
+        data = np.frombuffer(bytes([6, 0x10]) + sent.to_bytes(8, "big") + int(bits, 2).to_bytes(len(bits) // 8, "big"), dtype=np.uint8)
+        n = 8
+        ts = ts[:n]
+        b = datagen.ArenaBuilder()
+        b.add_page(datagen.build_page(datagen.encode_timestamps(ts), n), 5, 0, cabi.TSKV_PT_TIME, n)
+    else:                         # nothing after the first value: refill_cache fails (float.rs:447-466)
+        data = np.frombuffer(bytes([6, 0x10]) + (0x7FF80000000000FF).to_bytes(8, "big"), dtype=np.uint8)
+    b.add_page(datagen.build_page(data, n), 5, 1, cabi.TSKV_PT_F64, n)
+    b.add_column_group(6, ts, [(1, cabi.TSKV_PT_F64, np.arange(n) * 0.5, None)])
+    arena, descs = b.finish()
+    aggs = ("count", "first", "last") if case == "sentinel_valued_data" else ALL_AGGS  # (no NaN into sum/min/max)
+    q = QueryOption([PushedAggregate(1, cabi.TSKV_PT_F64, aggs)], group_by_series=True,
+                    time_ranges=[(int(ts[0]), int(ts[6]))] if case == "sentinel_valued_data" else [])
+    pages = engine.upload_pages(arena, descs)
+    if status == 0:
+        assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q), what=case)
+    else:
+        with pytest.raises(orc.OracleError) as oe:
+            orc.scan_aggregate(arena, descs, q)
+        assert oe.value.status == status
+        with pytest.raises(TskvError) as ge:
+            engine.scan_aggregate(pages, q)
+        assert ge.value.status == status and ge.value.page == 1
+    pages.close()
