@@ -20,6 +20,8 @@
 // G is chosen by the host so that the selected pages make about one task per resident warp.
 // Same formats and semantics as cursors.cuh / scan_kernels.cuh (reference lines cited there).
 #pragma once
+#include <cstddef>
+
 #include "scan_kernels.cuh"
 
 namespace tskv {
@@ -158,13 +160,16 @@ __device__ __forceinline__ uint64_t gor_peek64(const uint32_t *wp, uint32_t abs)
 // One element's control bits (float.rs:480-560, cursors.cuh GorillaCursor::advance): returns the control length,
 // sets `sig` = XOR-window width (0: repeat the previous value) and updates the (meaningful, trailing) window state.
 __device__ __forceinline__ uint32_t gor_parse_ctrl(uint32_t x13, uint32_t &meaningful, uint32_t &trailing, uint32_t &sig) {
-  if (!(x13 & 0x1000)) { sig = 0; return 1; }
-  if (!(x13 & 0x0800)) { sig = meaningful; return 2; }
+  // branch-free: the lanes of a warp parse different pages and would diverge on every element
+  const bool c0 = x13 & 0x1000, c1 = x13 & 0x0800;
   const uint32_t leading = (x13 >> 6) & 0x1f, m = x13 & 0x3f;
-  if (m > 0) { meaningful = m; trailing = (64 - leading - m) & 0xff; }  // u8 arithmetic like the reference
-  else { meaningful = 64; trailing = 0; }
-  sig = meaningful;
-  return 13;
+  const uint32_t new_mean = m ? m : 64u;
+  const uint32_t new_trail = m ? ((64u - leading - m) & 0xffu) : 0u;  // u8 arithmetic like the reference
+  const bool fresh = c0 && c1;
+  meaningful = fresh ? new_mean : meaningful;
+  trailing = fresh ? new_trail : trailing;
+  sig = c0 ? meaningful : 0u;
+  return c0 ? (c1 ? 13u : 2u) : 1u;
 }
 __device__ __forceinline__ void gor_stream(const PageView &vpv, const uint32_t *&wp, uint32_t &base_bits, uint32_t &total_bits) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(vpv.data + 10);  // id | 0x10 | first(8) | bit stream
@@ -191,20 +196,76 @@ __device__ __forceinline__ void gor_parse_page(const ScanParams &P, uint32_t ite
   const uint32_t *wp;
   uint32_t base_bits, total_bits;
   gor_stream(vpv, wp, base_bits, total_bits);
-  uint32_t bitpos = 0, meaningful = 64, trailing = 0, e = 1;
+  uint32_t bitpos = 0, meaningful = 64, trailing = 0, e = 1, first_over = 0;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 32));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));
 #pragma unroll 1
   for (; e <= n_valid; e++) {
     uint32_t sig;
-    const uint32_t len = gor_parse_ctrl(gor_peek32(wp, base_bits + bitpos) >> 19, meaningful, trailing, sig);
+    // the walk is one dependent chain: without this the chain stalls on a DRAM round trip at every new sector
+    const uint32_t rp = base_bits + min(bitpos, total_bits);  // (after an overrun the walk goes on, reading at the block's end)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (rp >> 5) + 96));
+    const uint32_t len = gor_parse_ctrl(gor_peek32(wp, rp) >> 19, meaningful, trailing, sig);
     records[e] = (bitpos + len) | (sig << 17) | ((trailing & 63) << 24);
     bitpos += len + sig;
-    if (bitpos > total_bits) break;  // "unexpected end of block" (bits_used > bits_total in the serial cursor)
+    // "unexpected end of block" (bits_used > bits_total in the serial cursor): remembered, not branched on - the
+    // loop's back edge must not wait for the end of the dependent chain. (bitpos <= 77 * 1024: reads stay in the slack.)
+    first_over = (bitpos > total_bits && first_over == 0) ? e : first_over;
   }
+  if (first_over) e = first_over;
   G.n_valid[g] = n_valid;
   G.n_parsed[g] = e - 1;
   G.endpos[g] = bitpos;
   G.meaningful[g] = (uint8_t)meaningful;
   G.trailing[g] = (uint8_t)trailing;
+}
+
+// Phase 1 for a group of ONE page: the warp first copies the page's bit stream into its shared memory (byte-swapped
+// words, coalesced), then lane 0 walks the control bits from there: the dependent chain per element is two LDS + ~12
+// ALU operations instead of global-memory round trips. `stage` overlays the warp's CoopSmem (free until phase 2).
+__device__ __forceinline__ void gor_parse_page_staged(const ScanParams &P, uint32_t item, uint32_t *records, GorGroup &G,
+                                                      uint32_t *stage, uint32_t stage_words) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t page = P.work_page[item];
+  const tskv_page_desc vd = P.descs[page];
+  PageView vpv;
+  vpv.open(P.arena, vd);
+  const uint32_t *wp;
+  uint32_t base_bits, total_bits;
+  gor_stream(vpv, wp, base_bits, total_bits);
+  const uint32_t n_words = ((base_bits + total_bits + 31) >> 5) + 2;  // + the look-ahead words of the last peek
+  if (n_words > stage_words) {  // does not fit (cannot happen for <= 1024 reference-written rows): parse from global memory
+    if (lane == 0) gor_parse_page(P, item, records, G, 0);
+    return;
+  }
+  for (uint32_t w = lane; w < n_words; w += 32) stage[w] = __byte_perm(__ldg(wp + w), 0, 0x0123);
+  const uint32_t n_rows = vd.num_values;
+  const uint32_t *vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
+  uint32_t bits = 0;
+  if (lane < ((n_rows + 31) >> 5)) {
+    bits = __ldg(vbm + lane);
+    if (lane == (n_rows >> 5)) bits &= (1u << (n_rows & 31)) - 1;
+  }
+  const uint32_t n_valid = __reduce_add_sync(FULL, __popc(bits));
+  __syncwarp();
+  if (lane == 0) {
+    uint32_t bitpos = 0, meaningful = 64, trailing = 0, e = 1;
+#pragma unroll 1
+    for (; e <= n_valid; e++) {
+      const uint32_t abs = base_bits + bitpos, wi = abs >> 5;
+      uint32_t sig;
+      const uint32_t len = gor_parse_ctrl(__funnelshift_l(stage[wi + 1], stage[wi], abs & 31) >> 19, meaningful, trailing, sig);
+      records[e] = (bitpos + len) | (sig << 17) | ((trailing & 63) << 24);
+      bitpos += len + sig;
+      if (bitpos > total_bits) break;
+    }
+    G.n_valid[0] = n_valid;
+    G.n_parsed[0] = e - 1;
+    G.endpos[0] = bitpos;
+    G.meaningful[0] = (uint8_t)meaningful;
+    G.trailing[0] = (uint8_t)trailing;
+  }
 }
 
 // Multiply-high division of a non-negative dividend by the invariant bucket width (Granlund-Montgomery):
@@ -311,14 +372,34 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
     uint32_t first_sentinel = 0xffffffffu;  // lowest value index < n_valid (and before the overrun) holding the sentinel
     uint64_t v_end = 0;                     // value n_valid (has to be the sentinel)
     bool end_ok = false;
+    // records were written by this kernel (phase 1): read them from L2, not through the read-only path. The loop is
+    // software-pipelined: the record of tile t+2 and the window bits of tile t+1 are in flight during tile t's scan
+    // (raw words of tile t+1 are loaded during tile t and only byte-swapped / shifted one iteration later)
+    uint32_t rec_cur = (lane >= 1 && lane <= n_parsed) ? __ldcg(records + lane) : 0u;
+    uint32_t rec_next = (lane + 32 <= n_parsed) ? __ldcg(records + lane + 32) : 0u;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+    {
+      const uint32_t wi = (base_bits + (rec_cur & 0x1ffff)) >> 5;
+      if (rec_cur) { w0 = __ldg(wp + wi); w1 = __ldg(wp + wi + 1); w2 = __ldg(wp + wi + 2); }
+    }
     for (uint32_t i0 = 0; i0 <= n_parsed; i0 += 32) {
       const uint32_t i = i0 + lane;
+      // issue the next tile's loads first
+      const uint32_t rec_n1 = rec_next;
+      rec_next = (i + 64 <= n_parsed) ? __ldcg(records + i + 64) : 0u;
+      uint32_t n0 = 0, n1 = 0, n2 = 0;
+      {
+        const uint32_t wi = (base_bits + (rec_n1 & 0x1ffff)) >> 5;
+        if (rec_n1) { n0 = __ldg(wp + wi); n1 = __ldg(wp + wi + 1); n2 = __ldg(wp + wi + 2); }
+      }
+      // this tile: window bits -> delta (sig == 0: the first value or a "repeat" element, pushed without a sentinel test)
+      const uint32_t sig = (rec_cur >> 17) & 0x7f;
       uint64_t delta = 0;
-      uint32_t sig = 0;  // 0: the first value or a "repeat" element - both are pushed without a sentinel test
-      if (i >= 1 && i <= n_parsed) {
-        const uint32_t rec = __ldcg(records + i);  // written by this kernel (phase 1): not through the read-only path
-        sig = (rec >> 17) & 0x7f;
-        if (sig) delta = (gor_peek64(wp, base_bits + (rec & 0x1ffff)) >> (64 - sig)) << (rec >> 24);
+      if (sig) {
+        const uint32_t sh = (base_bits + (rec_cur & 0x1ffff)) & 31;
+        const uint32_t a = __byte_perm(w0, 0, 0x0123), b = __byte_perm(w1, 0, 0x0123), cc = __byte_perm(w2, 0, 0x0123);
+        const uint64_t win = ((uint64_t)__funnelshift_l(b, a, sh) << 32) | __funnelshift_l(cc, b, sh);
+        delta = (win >> (64 - sig)) << (rec_cur >> 24);
       }
       const uint64_t x = warp_incl_xor_scan_u64(delta) ^ carry;
       if (i < n_valid && i <= n_parsed) S.vals[cpad(i)] = x;
@@ -330,6 +411,7 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
         end_ok = __shfl_sync(FULL, (int)is_end, n_valid - i0) != 0;
       }
       carry = shfl_u64(x, 31);
+      rec_cur = rec_n1; w0 = n0; w1 = n1; w2 = n2;
     }
     // the serial cursor's outcomes (cursors.cuh GorillaCursor): a sentinel before the bitset is served =
     // "Mismatch between bit set and decoded values"; running past the block = "unexpected end of block"
@@ -475,7 +557,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) k_scan_coop(const __grid_cons
       const uint64_t first = (uint64_t)begin0 + (uint64_t)t * group;
       if (first >= end0) break;
       const uint32_t cnt = min(group, end0 - (uint32_t)first);
-      if (lane < cnt) gor_parse_page(P, (uint32_t)first + lane, rows + lane * GOR_REC_STRIDE, G, lane);  // phase 1
+      // phase 1
+      if (group == 1) gor_parse_page_staged(P, (uint32_t)first, rows, G, reinterpret_cast<uint32_t *>(&S), (uint32_t)(offsetof(Smem, gor) / 4));
+      else if (lane < cnt) gor_parse_page(P, (uint32_t)first + lane, rows + lane * GOR_REC_STRIDE, G, lane);
       __syncwarp();
       for (uint32_t g = 0; g < cnt; g++) {                                                            // phase 2
         scan_page_coop<TK, VK, SEL>(P, C, (uint32_t)first + g, S, s_tab, rows + g * GOR_REC_STRIDE, g);

@@ -1022,8 +1022,13 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       double est_gor = 0;
       for (int b = N_SERIAL_BINS; b < N_BINS; b++)
         if (is_gor_coop_bin(b) && s->use_coop[b]) est_gor += (pages->h_bin_start[b + 1] - pages->h_bin_start[b]) * sel_frac;
-      const double resident_warps = (double)ctx->sm_count * 2 * (SCAN_THREADS / 32);
-      while (gor_group < 32 && est_gor / gor_group > resident_warps) gor_group *= 2;
+      int gocc = 0;  // resident CTAs per SM of the gorilla cooperative kernel (shared memory bound)
+      const void *gfn = coop_kernel_for(BIN_COOP_RLE_GOR, s->has_sel);
+      cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(BIN_COOP_RLE_GOR, P.smem_words));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gfn, SCAN_THREADS, coop_smem_bytes(BIN_COOP_RLE_GOR, P.smem_words));
+      const double resident_warps = (double)ctx->sm_count * std::max(1, gocc) * (SCAN_THREADS / 32);
+      // smallest group that fits the tasks in ~3/4 of the resident warps (measured best on 1/8 of C4: G = 4)
+      while (gor_group < 32 && est_gor / gor_group > 0.75 * resident_warps) gor_group *= 2;
       if (const char *g = getenv("TSKV_GOR_GROUP")) gor_group = (uint32_t)std::min(32, std::max(1, atoi(g)));
       s->coop.gor_group = gor_group;
     }
