@@ -1062,9 +1062,16 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       occ_weighted += (double)need[b] * occ;
     }
     const double capacity = need_sum > 0 ? (occ_weighted / need_sum) * ctx->sm_count : 0;  // resident blocks, mixed kernels
+    bool any_coop = false;
+    for (int b = N_SERIAL_BINS; b < N_BINS; b++) any_coop |= s->use_coop[b] && need[b];
     if (need_sum <= capacity) {
       for (int b = 0; b < N_BINS; b++)
         if (need[b]) s->grid[b] = std::max(1, need[b]);
+    } else if (!any_coop) {
+      // lane-per-page kernels only (long tasks): plain cost shares, leaving the slack of the bins that need less than
+      // their share unused - an over-subscribed persistent grid would queue whole blocks behind ~1 ms tasks
+      for (int b = 0; b < N_BINS; b++)
+        if (need[b]) s->grid[b] = std::max(1, std::min(need[b], (int)(capacity * w[b] / wsum + 0.5)));
     } else {
       // water-filling: bins that need less than their cost share keep their need, the rest split what is left
       bool fixed[N_BINS] = {false};
