@@ -72,16 +72,37 @@ def generate_shard(n_total, rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The region is
+    ~20 ms long, so NVML is polled from a thread every millisecond (what nvidia-smi reads, without its 100 ms period);
+    `nvidia-smi -lms` is the fallback when pynvml is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                   0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.handle, self.stop_flag = index, [], None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
 
     def start(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -90,11 +111,39 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.perf_counter(), float(sm), float(mx), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin / t_end (time.perf_counter): host-side bounds of the timed region; NVML samples outside are dropped."""
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            rows = [r for r in self.rows if (t_begin is None or r[0] >= t_begin) and (t_end is None or r[0] <= t_end)]
+            if not rows:
+                rows = self.rows[-3:]
+            reasons = sorted({name for r in rows for bit, name in self.REASON_BITS.items() if r[4] & bit})
+            return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                    "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                    "power_w_max": max(r[3] for r in rows) if rows else None, "reasons": reasons, "samples": len(rows),
+                    "source": "nvml, 1 ms period, inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -105,7 +154,7 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_arm(arena, descs, sel_all, steps, warmup, target_s=12.0):
@@ -210,6 +259,7 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
+    t_region = time.perf_counter()
     with torch.cuda.stream(stream):
         for a, b in ev:
             flush.zero_()          # evict the previous step's pages from L2 (outside the timed interval)
@@ -218,7 +268,7 @@ def main():
             b.record(stream)
     scan.sync()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region, time.perf_counter()) if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, float(points_local)], dtype=torch.float64, device=device)
     if world > 1:

@@ -1005,8 +1005,14 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     // instructions per point but one page costs ~1 ms of serial latency, so it only pays when the selected
     // pages can fill the machine (>= ~1/4 of the resident lanes); otherwise go cooperative.
     const char *mode = getenv("TSKV_COOP");  // "0" never, "1" always, unset = auto
-    const double sel_frac = (q->series_ids && !pages->series.empty())
-                                ? std::min(1.0, (double)q->n_series / (double)pages->series.size()) : 1.0;
+    // Expected fraction of this arena's series the query selects. The id list may cover more than this arena (a
+    // multi-GPU caller passes the whole selection to every shard): only the ids inside the arena's id range count.
+    double sel_frac = 1.0;
+    if (q->series_ids && !pages->series.empty()) {
+      const uint32_t *ib = q->series_ids, *ie = q->series_ids + q->n_series;
+      const size_t in_range = (size_t)(std::upper_bound(ib, ie, pages->series.back()) - std::lower_bound(ib, ie, pages->series.front()));
+      sel_frac = std::min(1.0, (double)in_range / (double)pages->series.size());
+    }
     const double lanes = (double)ctx->sm_count * SCAN_MIN_BLOCKS * SCAN_THREADS;
     const double est_total = (double)pages->n_items * sel_frac;  // selected field pages, all bins
     for (int b = N_SERIAL_BINS; b < N_BINS; b++)
