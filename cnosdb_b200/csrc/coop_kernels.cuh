@@ -179,7 +179,7 @@ __device__ __forceinline__ void gor_stream(const PageView &vpv, const uint32_t *
 }
 
 // Phase 1, one lane per page: records[e] for the elements e = 1..n_valid (element n_valid is the one that has to be
-// the sentinel); stops at the first element that runs past the block.
+// the sentinel); remembers the first element that runs past the block (n_parsed = the elements before it).
 __device__ __forceinline__ void gor_parse_page(const ScanParams &P, uint32_t item, uint32_t *records, GorGroup &G, uint32_t g) {
   const uint32_t page = P.work_page[item];
   const tskv_page_desc vd = P.descs[page];
@@ -197,20 +197,21 @@ __device__ __forceinline__ void gor_parse_page(const ScanParams &P, uint32_t ite
   uint32_t base_bits, total_bits;
   gor_stream(vpv, wp, base_bits, total_bits);
   uint32_t bitpos = 0, meaningful = 64, trailing = 0, e = 1, first_over = 0;
+  const uint32_t last_word = (base_bits + total_bits) >> 5;  // prefetches stay inside the page
   asm volatile("prefetch.global.L1 [%0];" ::"l"(wp));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 32));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + 64));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + min(32u, last_word)));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + min(64u, last_word)));
 #pragma unroll 1
   for (; e <= n_valid; e++) {
     uint32_t sig;
     // the walk is one dependent chain: without this the chain stalls on a DRAM round trip at every new sector
     const uint32_t rp = base_bits + min(bitpos, total_bits);  // (after an overrun the walk goes on, reading at the block's end)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (rp >> 5) + 96));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + min((rp >> 5) + 96, last_word)));
     const uint32_t len = gor_parse_ctrl(gor_peek32(wp, rp) >> 19, meaningful, trailing, sig);
     records[e] = (bitpos + len) | (sig << 17) | ((trailing & 63) << 24);
     bitpos += len + sig;
     // "unexpected end of block" (bits_used > bits_total in the serial cursor): remembered, not branched on - the
-    // loop's back edge must not wait for the end of the dependent chain. (bitpos <= 77 * 1024: reads stay in the slack.)
+    // loop's back edge must not wait for the end of the dependent chain (the reads are clamped to the block's end).
     first_over = (bitpos > total_bits && first_over == 0) ? e : first_over;
   }
   if (first_over) e = first_over;
