@@ -1,6 +1,7 @@
 // host_util.cc — see host_util.h.
 #include "host_util.h"
 
+#include <algorithm>
 #include <mutex>
 
 namespace tskv {
@@ -42,6 +43,23 @@ uint32_t crc32_ieee(const uint8_t *p, size_t len) {
   }
   while (len--) crc = (crc >> 8) ^ g_tab[0][(crc ^ *p++) & 0xff];
   return ~crc;
+}
+
+double plan_selected_fraction(const uint32_t *arena_series, uint64_t n_arena, const uint32_t *sel, uint64_t n_sel) {
+  if (!sel || n_arena == 0) return 1.0;
+  const uint32_t *ie = sel + n_sel;
+  const uint64_t in_range = (uint64_t)(std::upper_bound(sel, ie, arena_series[n_arena - 1]) - std::lower_bound(sel, ie, arena_series[0]));
+  return std::min(1.0, (double)in_range / (double)n_arena);
+}
+
+bool plan_use_cooperative(double est_selected_pages, int sm_count, int min_blocks_per_sm, int threads_per_block) {
+  return est_selected_pages < 0.25 * (double)sm_count * min_blocks_per_sm * threads_per_block;
+}
+
+uint32_t plan_gorilla_group(double est_gorilla_pages, double resident_warps) {
+  uint32_t g = 1;
+  while (g < 32 && est_gorilla_pages / g > 0.75 * resident_warps) g *= 2;
+  return g;
 }
 
 bool parse_page(const uint8_t *page, uint64_t size, PageHeader *h) {

@@ -30,6 +30,18 @@ bool parse_page(const uint8_t *page, uint64_t size, PageHeader *out);
 
 // Decode kind (DK_* of cursors.cuh) of a page of physical type `phys_type`; error kinds encode the
 // reference's decode errors so that they surface when (and only when) the page is read.
+// ---- scan planning heuristics (host only; exercised on the CPU by tests/test_scan_planning.py) -------------------
+// Expected fraction of an arena's series a query selects. The id list may cover more than this arena (a multi-GPU
+// caller hands the whole selection to every shard): only ids inside the arena's id range can match.
+// Both lists sorted ascending; n_sel == 0 with sel == nullptr means "all series".
+double plan_selected_fraction(const uint32_t *arena_series, uint64_t n_arena, const uint32_t *sel, uint64_t n_sel);
+// Cooperative (warp-per-page) kernels for the eligible bins when the selected pages cannot fill the machine with
+// lane-per-page work (>= ~1/4 of the resident lanes), where one page's serial decode (~1 ms) would be the makespan.
+bool plan_use_cooperative(double est_selected_pages, int sm_count, int min_blocks_per_sm, int threads_per_block);
+// Pages per warp task of the cooperative gorilla bins: the smallest power of two that fits the tasks in 3/4 of the
+// resident warps (measured best on 1/8 of C4: 4).
+uint32_t plan_gorilla_group(double est_gorilla_pages, double resident_warps);
+
 uint8_t classify_page(const PageHeader &h, uint8_t phys_type);
 
 }  // namespace tskv

@@ -1005,19 +1005,12 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     // instructions per point but one page costs ~1 ms of serial latency, so it only pays when the selected
     // pages can fill the machine (>= ~1/4 of the resident lanes); otherwise go cooperative.
     const char *mode = getenv("TSKV_COOP");  // "0" never, "1" always, unset = auto
-    // Expected fraction of this arena's series the query selects. The id list may cover more than this arena (a
-    // multi-GPU caller passes the whole selection to every shard): only the ids inside the arena's id range count.
-    double sel_frac = 1.0;
-    if (q->series_ids && !pages->series.empty()) {
-      const uint32_t *ib = q->series_ids, *ie = q->series_ids + q->n_series;
-      const size_t in_range = (size_t)(std::upper_bound(ib, ie, pages->series.back()) - std::lower_bound(ib, ie, pages->series.front()));
-      sel_frac = std::min(1.0, (double)in_range / (double)pages->series.size());
-    }
-    const double lanes = (double)ctx->sm_count * SCAN_MIN_BLOCKS * SCAN_THREADS;
+    const double sel_frac = plan_selected_fraction(pages->series.data(), pages->series.size(), q->series_ids, q->n_series);
     const double est_total = (double)pages->n_items * sel_frac;  // selected field pages, all bins
     for (int b = N_SERIAL_BINS; b < N_BINS; b++)
       s->use_coop[b] = pages->n_tomb_ranges ? false  // tombstones are handled by the lane-per-page kernels
-                                            : mode ? (mode[0] == '1') : (est_total < 0.25 * lanes);
+                       : mode             ? (mode[0] == '1')
+                                          : plan_use_cooperative(est_total, ctx->sm_count, SCAN_MIN_BLOCKS, SCAN_THREADS);
     // Grid sizes. Every kernel is persistent (warps pull tasks from their bin's counter). If the resident
     // capacity allows, each bin gets one warp per estimated task (a single round: the makespan of a bin is
     // quantised in units of one task = one page's serial decode); otherwise the blocks are split by cost.
@@ -1033,8 +1026,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(BIN_COOP_RLE_GOR, P.smem_words));
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gfn, SCAN_THREADS, coop_smem_bytes(BIN_COOP_RLE_GOR, P.smem_words));
       const double resident_warps = (double)ctx->sm_count * std::max(1, gocc) * (SCAN_THREADS / 32);
-      // smallest group that fits the tasks in ~3/4 of the resident warps (measured best on 1/8 of C4: G = 4)
-      while (gor_group < 32 && est_gor / gor_group > 0.75 * resident_warps) gor_group *= 2;
+      gor_group = plan_gorilla_group(est_gor, resident_warps);
       if (const char *g = getenv("TSKV_GOR_GROUP")) gor_group = (uint32_t)std::min(32, std::max(1, atoi(g)));
       s->coop.gor_group = gor_group;
     }

@@ -1,0 +1,53 @@
+"""Host-side scan planning heuristics (cnosdb_b200/csrc/host_util.cc), exercised through the host library: which kernel
+family a scan gets and how gorilla pages are grouped, for the shard sizes of the C4 strong-scaling run. No GPU needed."""
+import ctypes as C
+
+import numpy as np
+
+from cnosdb_b200 import cabi
+from cnosdb_b200.parallel import select_tag_subset, shard_range
+
+
+def lib():
+    L = cabi.load_hostgen_library()
+    L.tskvplan_selected_fraction.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.tskvplan_selected_fraction.restype = C.c_double
+    L.tskvplan_use_cooperative.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int]
+    L.tskvplan_use_cooperative.restype = C.c_int
+    L.tskvplan_gorilla_group.argtypes = [C.c_double, C.c_double]
+    L.tskvplan_gorilla_group.restype = C.c_uint32
+    return L
+
+
+def frac(arena_ids, sel):
+    a = np.ascontiguousarray(arena_ids, dtype=np.uint32)
+    if sel is None:
+        return lib().tskvplan_selected_fraction(a.ctypes.data, len(a), None, 0)
+    s = np.ascontiguousarray(sel, dtype=np.uint32)
+    return lib().tskvplan_selected_fraction(a.ctypes.data, len(a), s.ctypes.data, len(s))
+
+
+def test_selected_fraction_counts_only_ids_inside_the_shard():
+    n = 1_000_000
+    sel = select_tag_subset(n, 10)  # the global 10 % selection every rank is handed
+    for world in (1, 2, 4, 8):
+        for rank in (0, world - 1):
+            lo, hi = shard_range(n, rank, world)
+            f = frac(np.arange(lo, hi), sel)
+            assert abs(f - 0.1) < 0.005, (world, rank, f)   # not 0.1 * world
+    assert frac(np.arange(100, 200), None) == 1.0
+    assert frac(np.arange(100, 200), np.array([5, 7, 300])) == 0.0
+    assert frac(np.arange(100, 200), np.arange(0, 1000)) == 1.0
+
+
+def test_kernel_family_and_group_size_for_the_c4_shards():
+    """148 SMs x 4 CTAs x 128 lanes: lane-per-page kernels down to 1/4 of C4 per GPU, cooperative kernels on the
+    8-GPU shards, where the gorilla pages go in groups of 4 (measured best)."""
+    L = lib()
+    selected_pages = {1: 100_000, 2: 50_000, 4: 25_000, 8: 12_500}  # 10 % of 1 M series, one field page each
+    family = {w: bool(L.tskvplan_use_cooperative(float(p), 148, 4, 128)) for w, p in selected_pages.items()}
+    assert family == {1: False, 2: False, 4: False, 8: True}
+    resident_warps = 148 * 4 * 4
+    assert L.tskvplan_gorilla_group(6250.0, float(resident_warps)) == 4
+    assert L.tskvplan_gorilla_group(100.0, float(resident_warps)) == 1
+    assert L.tskvplan_gorilla_group(1e9, float(resident_warps)) == 32
