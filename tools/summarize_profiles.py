@@ -62,7 +62,10 @@ json.dump({"source": "ncu --set full --clock-control none --import-source on, to
                      "one step of the C4 workload; ncu serialises them)" % tag,
            "units": {"gpu__time_duration.sum": "us", "dram__bytes_*": "MB"}, "kernels": kernels,
            "totals": {"dram_MB": sum(k.get("dram__bytes_read.sum", 0) + k.get("dram__bytes_write.sum", 0) for k in kernels),
-                      "warp_instructions": sum(k.get("smsp__inst_executed.sum", 0) for k in kernels)}},
+                      "warp_instructions": sum(k.get("smsp__inst_executed.sum", 0) for k in kernels)},
+           # read by bench.py as roofline.traffic (per fused phase = per "launch" of the roofline object)
+           "step_dram_traffic_bytes": int(round(1e6 * sum(k.get("dram__bytes_read.sum", 0) + k.get("dram__bytes_write.sum", 0) for k in kernels))),
+           "step_dram_traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the fused kernels of one C4 step"},
           open(dst + "scan_ncu_summary.json", "w"), indent=1)
 print(open(dst + "launches_summary.txt").read())
 for k in kernels:
