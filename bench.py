@@ -316,7 +316,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": traffic, "bytes_per_launch": int(algo_bytes), "ms_per_launch": fused_s * 1e3,
                 "decoded_equivalent_frac": 16 * points_local / fused_s / 1e9 / peak,
-                "slowest_bin": {"kernel": "k_scan_aggregate<%s>" % BIN_NAMES[int(dom_bin)], "ms": float(np.mean(dom_ms)),
+                "slowest_bin": {"kernel": "fused scan kernel of bin <%s> (k_scan_aggregate, or k_scan_coop on small scans)" % BIN_NAMES[int(dom_bin)], "ms": float(np.mean(dom_ms)),
                                 "page_bytes": int(dom_bytes)},
                 "step_ms": float(np.mean(scan_ms)),
                 "bound_note": "issue/latency-bound lane-serial decode (ncu: issue-active 19-37%, DRAM 1.1x algorithmic bytes); see DESIGN.md section 5"}
