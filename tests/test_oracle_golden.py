@@ -160,3 +160,18 @@ def test_page_roundtrip_with_nulls():  # page.rs:334-345 + :58-94
     with pytest.raises(orc.OracleError) as e:
         orc.decode_pages(page, descs)
     assert e.value.status == cabi.TSKV_ERR_CRC_MISMATCH
+
+
+def test_crc32_matches_an_independent_implementation():
+    """crc32fast (page.rs:62-65, test page.rs:651-690 over b"hello world") is CRC-32/IEEE: zlib's is the same polynomial.
+    Every tail length of the slicing-by-8 loop, plus the reference test's page bytes."""
+    import zlib
+    rng = np.random.default_rng(32)
+    for n in list(range(0, 40)) + [255, 256, 257, 4095, 7001]:
+        buf = rng.integers(0, 256, n, dtype=np.uint8)
+        assert orc.crc32(buf) == zlib.crc32(buf.tobytes()), n
+    hello = np.frombuffer(b"hello world", dtype=np.uint8)
+    assert orc.crc32(hello) == zlib.crc32(b"hello world") == 0x0D4A1185
+    # create_test_page(): bitset_len 0 | rows 1 | crc | (no bitset) | data
+    page = np.frombuffer((0).to_bytes(4, "big") + (1).to_bytes(8, "big") + (0x0D4A1185).to_bytes(4, "big") + b"hello world", dtype=np.uint8)
+    assert int.from_bytes(page[12:16].tobytes(), "big") == orc.crc32(page[16:])

@@ -247,3 +247,33 @@ def test_tombstone_semantics_restated_from_decode_pages():
     both = make_query([(1, cabi.TSKV_PT_I64)], series_ids=np.array([7, 8], dtype=np.uint32), group_by_series=True)
     r = scan([(None, None, 0, 49)], both)
     assert r.column(1, "count")[0][:, 0].tolist() == [5, 5]
+
+
+def test_reference_reader_tables():
+    """The tables of the reference's own reader tests, through the writer and the oracle.
+    reader/column_group/mod.rs:266-368: time [1,3,5,7] with u64 / f64 fields written to a TSM file and read back;
+    reader/filter.rs:160-253: `time > 2` (normalised to the closed range [3, i64::MAX], predicate/domain.rs:41-57)
+    over the rows time = [-1, 2, 4, 18, 8] keeps 4, 18 and 8 (the field comparisons of that test are outside the path)."""
+    b = datagen.ArenaBuilder()
+    b.add_column_group(1, np.array([1, 3, 5, 7], dtype=np.int64), [
+        (1, cabi.TSKV_PT_U64, np.array([1, 3, 5, 7], dtype=np.uint64), None),
+        (2, cabi.TSKV_PT_F64, np.array([1.0, 3.0, 5.0, 7.0]), None)])
+    arena, descs = b.finish()
+    (t, tv), (c1, v1), (c2, v2) = orc.decode_pages(arena, descs)
+    assert tv.all() and v1.all() and v2.all()
+    assert t.view(np.int64).tolist() == [1, 3, 5, 7] and c1.tolist() == [1, 3, 5, 7]
+    assert c2.view(np.float64).tolist() == [1.0, 3.0, 5.0, 7.0]
+    r = orc.scan_aggregate(arena, descs, make_query([(1, cabi.TSKV_PT_U64), (2, cabi.TSKV_PT_F64)]))
+    assert int(r.column(1, "sum")[0][0, 0]) == 16 and float(r.column(2, "mean")[0][0, 0]) == 4.0
+    assert int(r.column(1, "first")[0][0, 0]) == 1 and float(r.column(2, "last")[0][0, 0]) == 7.0
+
+    b = datagen.ArenaBuilder()
+    for i, (ts, c1v, c2v) in enumerate(zip([-1, 2, 4, 18, 8], [1, 2, 4, 18, 8], [1.0, 2.0, 4.0, 18.0, 8.0])):  # unsorted rows: one page each
+        b.add_column_group(1, np.array([ts], dtype=np.int64), [(1, cabi.TSKV_PT_U64, np.array([c1v], dtype=np.uint64), None),
+                                                                  (2, cabi.TSKV_PT_F64, np.array([c2v]), None)])
+    arena, descs = b.finish()
+    q = make_query([(1, cabi.TSKV_PT_U64), (2, cabi.TSKV_PT_F64)], aggs=("count", "sum", "min", "max"),
+                   time_ranges=[(3, np.iinfo(np.int64).max)])
+    r = orc.scan_aggregate(arena, descs, q)
+    assert int(r.column(1, "count")[0][0, 0]) == 3 and int(r.column(1, "sum")[0][0, 0]) == 30
+    assert float(r.column(2, "min")[0][0, 0]) == 4.0 and float(r.column(2, "max")[0][0, 0]) == 18.0
