@@ -63,7 +63,15 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
   // ---- descriptor table: column group by column group, time page first (column_group.rs:9-17) --------
   std::vector<tskv_page_desc> descs;
   TimeRange data_range = TimeRange::none();
+  pruned_column_groups_ = 0;
   for (const ColumnGroup &cg : column_groups_) {
+    // filter_column_groups (reader/chunk.rs:12-50) for the time predicate: a column group whose time range
+    // (PageMeta statistics) misses every query range is never read
+    if (!option_.time_ranges.empty() &&
+        std::none_of(option_.time_ranges.begin(), option_.time_ranges.end(), [&](const TimeRange &r) { return cg.time_range().overlaps(r); })) {
+      pruned_column_groups_++;
+      continue;
+    }
     data_range.merge(cg.time_range());
     for (const PageWriteSpec &p : cg.pages()) {
       tskv_page_desc d{};
@@ -75,6 +83,10 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
       d.phys_type = (uint8_t)p.meta.column.column_type;
       descs.push_back(d);
     }
+  }
+  if (descs.empty()) {  // nothing left to read: an empty stream, like a reader tree without chunks
+    counters_ = tskv_counters{};
+    return out;
   }
   // ---- query: one tskv_agg_column per referenced column, aggregates OR-ed into its mask ---------------
   std::vector<tskv_agg_column> cols;

@@ -160,6 +160,8 @@ class GpuAggregateBatchReader : public BatchReader {
   // The TsmTombstone of the file(s) behind the arena (ColumnGroupReader carries `tomb`, column_group/mod.rs:25-45;
   // applied by decode_pages, tsm/reader.rs:507-551). Entries as in include/tskv_gpu.h.
   void set_tombstones(std::vector<tskv_tombstone> tombs) { tombstones_ = std::move(tombs); }
+  // Column groups skipped by the statistics pruning of the last process() (filter_column_groups, reader/chunk.rs:12-50).
+  uint64_t pruned_column_groups() const { return pruned_column_groups_; }
 
  private:
   std::shared_ptr<GpuEngine> engine_;
@@ -170,6 +172,7 @@ class GpuAggregateBatchReader : public BatchReader {
   bool verify_crc_;
   std::vector<tskv_tombstone> tombstones_;
   tskv_counters counters_{};
+  uint64_t pruned_column_groups_ = 0;
 };
 
 }  // namespace reader

@@ -144,6 +144,17 @@ int main() {
     }
   }
   CHECK(differs);  // the tombstones did change the answer
+  // ---- statistics pruning (filter_column_groups, reader/chunk.rs:12-50): a query range that misses a column group's
+  //      time range keeps it from being read at all -----------------------------------------------------------------
+  {
+    QueryOption late = opt;
+    late.time_ranges = {TimeRange{t0 + 600 * step, t0 + 900 * step}};  // after every row
+    GpuAggregateBatchReader none_reader(eng.value, arena.data(), arena.size(), cgs, late);
+    auto nres = none_reader.process();
+    CHECK(nres.ok() && nres.value.empty());  // an empty stream; the library is not even called
+    CHECK(none_reader.pruned_column_groups() == (uint64_t)n_series && none_reader.metrics().page_read_count == 0);
+    CHECK(reader.pruned_column_groups() == 0);
+  }
   // ---- error behaviour: a corrupted page surfaces TsmPageFileHashCheckFailed, not a crash ----------------
   tskv::Bytes bad = arena;
   bad[cgs[0].pages()[1].offset + cgs[0].pages()[1].size - 1] ^= 0x10;
