@@ -1,0 +1,11 @@
+#!/bin/bash
+# Run on the GPU box (gpurun): compute-sanitizer over the parity tests that exercise the newest device code
+# (cooperative gorilla decode, tombstones, device CRC, error paths). memcheck slows kernels 10-50x, the selected
+# tests use small arenas. Usage: gpurun --timeout 900 -- 'bash tools/sanitize.sh [memcheck|racecheck|initcheck]'
+TOOL=${1:-memcheck}
+mkdir -p gpurun_out
+compute-sanitizer --tool "$TOOL" --error-exitcode 1 --print-limit 20 \
+  python -m pytest tests -m gpu -x -q -k "gorilla or tombstone or small or errors or crc or empty or maximum" \
+  > gpurun_out/sanitize_${TOOL}.log 2>&1
+echo "exit $?"
+grep -E "ERROR SUMMARY|passed|failed|Invalid|Race" gpurun_out/sanitize_${TOOL}.log | tail -20
