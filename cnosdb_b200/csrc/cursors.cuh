@@ -19,6 +19,11 @@
 
 namespace tskv {
 
+// Bytes allocated (and zeroed) after the last page of a device arena: streaming loads read whole aligned words /
+// 16-byte chunks and may run past the end of the last page (compute-sanitizer memcheck, round 2: the 64 bytes of
+// round 1 were less than its 72-byte look-ahead).
+constexpr uint32_t ARENA_SLACK = 256;
+
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) {
   uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
   return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
@@ -29,21 +34,20 @@ __device__ __forceinline__ int64_t zigzag_dec(uint64_t v) {
 
 // Streams an arbitrarily aligned byte range as big-endian u64 words. Two implementations with the
 // same interface:
-//   BeStream      aligned 8-byte global loads (one per word; previous word kept and funnel-shifted).
-//   RingStream    the same words, prefetched RING_WORDS ahead into a per-lane shared-memory ring with
-//                 cp.async (LDGSTS): a lane-serial decoder otherwise exposes a full HBM/L2 round trip on
-//                 every word it consumes.
-// Both may read up to RING_WORDS*8+8 bytes past the end of the page: the arena carries 128 bytes of slack.
+//   BeStream      aligned 8-byte global loads (one per word; previous word kept and funnel-shifted). Reads up to
+//                 15 bytes past the end of the range (the arena carries ARENA_SLACK bytes after the last page).
+//   SeqStream     the same words staged through a per-lane shared-memory ring of 16-byte cp.async chunks (below).
 struct BeStream {
   const uint64_t *ap;  // next aligned word
   uint64_t cur;        // last aligned word, little-endian
   uint32_t sh;         // misalignment in bits
-  __device__ __forceinline__ void init(const uint8_t *p, uint32_t /*smem_slot*/ = 0) {
+  __device__ __forceinline__ void init(const uint8_t *p, uint32_t /*smem_slot*/ = 0, const uint8_t * /*end*/ = nullptr) {
     uintptr_t a = reinterpret_cast<uintptr_t>(p);
     sh = (uint32_t)(a & 7) * 8;
     ap = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
     cur = __ldg(ap++);
   }
+  __device__ __forceinline__ void reset(uint32_t /*lane_slot*/ = 0) {}
   __device__ __forceinline__ uint64_t next() {
     uint64_t nxt = __ldg(ap++);
     uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
@@ -52,50 +56,91 @@ struct BeStream {
   }
 };
 
-constexpr int RING_WORDS = 8;  // 64 bytes of lookahead per stream per lane
+// ------------------------------------------------------------------------------------------------
+// Shared-memory staging of a lane's byte stream (round 2). One lane owns one page, so a warp reads 32 different
+// pages: each lane stages ITS stream through a ring of RING_CHUNKS 16-byte chunks filled by 128-bit cp.async
+// (LDGSTS.128, L2 -> shared memory without a register round trip). Chunk c of lane l lives at
+//   ring + ((c mod RING_CHUNKS) * 32 + l) * 16        (lane-interleaved: a warp-wide LDS hits 32 different 16-byte slots)
+// A decoder calls step(c) once per element / word BEFORE reading, c = the chunk its read window starts in; a window
+// never spans more than chunks c and c + 1, and c advances by at most one per step (an element is <= 77 bits, a word
+// 64). step() issues at most one new chunk - branch-free, a predicated LDGSTS - commits exactly one group and waits
+// until at most RING_CHUNKS - 2 groups are pending: chunk c + 1 was issued when the window first reached chunk
+// c + 2 - RING_CHUNKS, i.e. at least RING_CHUNKS - 2 steps (= groups) ago, so it has landed; the RING_CHUNKS - 2
+// chunks behind it (96 bytes, ~12 full-mantissa gorilla values) stay in flight and hide the HBM / L2 latency.
+// The initial fill is one group the caller waits for once per page (ring_drain) before the first step.
+// A chunk may extend <= 15 bytes past its page (next page or arena slack); chunks past the page are never issued and a
+// decoder that runs into them reads stale shared memory, which its own end-of-stream accounting turns into an error.
+#ifndef TSKV_RING_CHUNKS
+#define TSKV_RING_CHUNKS 8
+#endif
+constexpr int RING_CHUNKS = TSKV_RING_CHUNKS;
+constexpr uint32_t RING_BYTES_PER_WARP = RING_CHUNKS * 32 * 16;  // one stream of one warp
+static_assert((RING_CHUNKS & (RING_CHUNKS - 1)) == 0 && RING_CHUNKS >= 4, "ring size must be a power of two >= 4");
 
-// Ring layout: word k of lane l lives at slot_base + k * 256 + l * 8 (shared space): whatever ring
-// position each lane is at, lane l always hits banks 2l, 2l+1 => conflict-free 64-bit LDS.
-struct RingStream {
-  const uint64_t *gp;  // next aligned global word to prefetch
-  uint32_t sbase;      // shared-space address of this lane's word 0
-  uint32_t rd;         // ring position of the next word to consume
-  uint64_t cur;
-  uint32_t sh;
-  __device__ __forceinline__ void prefetch(uint32_t slot) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;\n"
-                 :: "r"(sbase + slot * 256u), "l"(gp) : "memory");
-    gp++;
+struct ChunkRing {
+  const uint8_t *gnext;  // global address of the next chunk to issue (16-byte aligned)
+  uint32_t sbase;        // shared-space address of this lane's slot of ring position 0
+  uint32_t n_chunks;     // chunks that intersect [start, end)
+  uint32_t issued;       // chunks handed to cp.async so far
+  __device__ __forceinline__ void issue_one() {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                 :: "r"(sbase + ((issued & (RING_CHUNKS - 1)) << 9)), "l"(gnext) : "memory");
+    gnext += 16;
+    issued++;
   }
-  __device__ __forceinline__ uint64_t pop() {
-    // every consumed word was followed by exactly one newer commit group, so at most RING_WORDS - 1
-    // groups may still be in flight when the oldest one is needed
-    asm volatile("cp.async.wait_group %0;\n" :: "n"(RING_WORDS - 2) : "memory");
-    uint64_t v;
-    asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(sbase + rd * 256u) : "memory");
-    // refill the slot consumed by the PREVIOUS pop (its read retired long ago)
-    prefetch((rd + RING_WORDS - 1) & (RING_WORDS - 1));
-    rd = (rd + 1) & (RING_WORDS - 1);
+  __device__ __forceinline__ void init(const uint8_t *start, const uint8_t *end, uint32_t lane_slot) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15;
+    gnext = reinterpret_cast<const uint8_t *>(a);
+    const uintptr_t e = reinterpret_cast<uintptr_t>(end);
+    n_chunks = e > a ? (uint32_t)((e - a + 15) >> 4) : 0u;
+    sbase = lane_slot;
+    issued = 0;
+#pragma unroll
+    for (int i = 0; i < RING_CHUNKS; i++)
+      if (issued < n_chunks) issue_one();
+  }
+  // One decoder step whose read window starts in chunk c (see above).
+  __device__ __forceinline__ void step(uint32_t c) {
+    if (issued < c + RING_CHUNKS && issued < n_chunks) issue_one();
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group %0;\n" :: "n"(RING_CHUNKS - 2) : "memory");
+  }
+  // An empty ring: steps issue nothing, reads return stale shared memory (lanes without a page / kinds without a stream).
+  __device__ __forceinline__ void reset(uint32_t lane_slot) { gnext = nullptr; sbase = lane_slot; n_chunks = 0; issued = 0; }
+  // 64-bit word k of the stream (8-byte units from the aligned start), as stored (little-endian load of stream bytes)
+  __device__ __forceinline__ uint2 word(uint32_t k) const {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n"
+                 : "=r"(v.x), "=r"(v.y) : "r"(sbase + (((k >> 1) & (RING_CHUNKS - 1)) << 9) + ((k & 1) << 3)) : "memory");
     return v;
   }
-  // `slot_base`: shared-space address reserved for this stream of this lane (see scan_chunk)
-  __device__ __forceinline__ void init(const uint8_t *p, uint32_t slot_base) {
-    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+};
+// Commits the initial fills of the lane's rings and waits for them (once per page, before the first step).
+__device__ __forceinline__ void ring_drain() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;\n" ::: "memory"); }
+
+// Sequential big-endian u64 words of an arbitrarily aligned byte range through a ChunkRing (simple8b / raw pages).
+// Same interface as BeStream.
+struct SeqStream {
+  ChunkRing ring;
+  uint32_t k;    // index of the last aligned word loaded
+  uint32_t sh;   // misalignment in bits
+  uint64_t cur;  // last aligned word, little-endian
+  __device__ __forceinline__ void init(const uint8_t *p, uint32_t lane_slot, const uint8_t *end) {
+    ring.init(p, end, lane_slot);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     sh = (uint32_t)(a & 7) * 8;
-    gp = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
-    sbase = slot_base;
-    rd = 0;
-    // fill slots 0 .. RING_WORDS-2; slot RING_WORDS-1 is refilled by the first pop
-#pragma unroll
-    for (int k = 0; k < RING_WORDS - 1; k++) prefetch(k);
-    cur = pop();
+    k = (uint32_t)(a & 15) >> 3;
+    cur = __ldg(reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7));  // the first word straight from global memory
   }
   __device__ __forceinline__ uint64_t next() {
-    uint64_t nxt = pop();
-    uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
+    k++;
+    ring.step(k >> 1);
+    const uint2 w = ring.word(k);
+    const uint64_t nxt = ((uint64_t)w.y << 32) | w.x;
+    const uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
     cur = nxt;
     return bswap64(raw);
   }
+  __device__ __forceinline__ void reset(uint32_t lane_slot = 0) { ring.reset(lane_slot); k = 0; sh = 0; cur = 0; }
 };
 
 __device__ __forceinline__ uint64_t load_be64(const uint8_t *p) {
@@ -148,6 +193,18 @@ struct BitCursor {
 
 __constant__ uint8_t c_s8b_count[16] = {240, 120, 60, 30, 20, 15, 12, 10, 8, 7, 6, 5, 4, 3, 2, 1};
 __constant__ uint8_t c_s8b_bits[16] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 20, 30, 60};
+// The same tables (simple8b.rs:17-50) as byte-permute lookups: lanes of a warp decode different pages and hold
+// different selectors, and a divergent index into constant memory is replayed once per distinct value.
+__device__ __forceinline__ void s8b_lut(uint32_t sel, uint32_t &count, uint32_t &bits) {
+  const uint32_t i = sel & 7;
+  const uint32_t c_lo = __byte_perm(0x1e3c78f0u, 0x0a0c0f14u, i);  // 240 120 60 30 | 20 15 12 10
+  const uint32_t c_hi = __byte_perm(0x05060708u, 0x01020304u, i);  //   8   7  6  5 |  4  3  2  1
+  const uint32_t b_lo = __byte_perm(0x02010000u, 0x06050403u, i);  //   0   0  1  2 |  3  4  5  6
+  const uint32_t b_hi = __byte_perm(0x0c0a0807u, 0x3c1e140fu, i);  //   7   8 10 12 | 15 20 30 60
+  const bool hi = sel & 8;
+  count = (hi ? c_hi : c_lo) & 0xff;
+  bits = (hi ? b_hi : b_lo) & 0xff;
+}
 
 // LEB128 (integer-encoding 4.0.2 decode_var); returns false when the slice ends first.
 __device__ inline bool decode_varint(const uint8_t *p, uint32_t len, uint64_t *out) {
@@ -201,6 +258,7 @@ struct DeltaCursor {
   // classified the page, so lengths needed by the fixed header are guaranteed.
   __device__ inline tskv_status open(const PageView &pv, uint8_t kind_, uint32_t smem_slot = 0) {
     kind = KIND >= 0 ? (uint8_t)KIND : kind_;
+    bs.reset(smem_slot);
     exhausted = false;
     v = 0;
     delta = 0;
@@ -229,24 +287,24 @@ struct DeltaCursor {
       }
       case DK_S8B_SC:  // timestamp.rs:261-299
         scaler = pow10_u64(__ldg(d + 1) & 0xf);
-        bs.init(d + 2, smem_slot);
-        v = bs.next();
+        v = load_be64(d + 2);  // header fields come straight from global memory; the stream covers the packed words
+        bs.init(d + 10, smem_slot, d + pv.data_len);
         words_left = (pv.data_len - 10) >> 3;
         in_word = 1;  // fake zero delta in front of the packed ones
         break;
       case DK_S8B_ZZ:  // integer.rs:216-248
-        bs.init(d + 2, smem_slot);
-        v = (uint64_t)zigzag_dec(bs.next());
+        v = (uint64_t)zigzag_dec(load_be64(d + 2));
+        bs.init(d + 10, smem_slot, d + pv.data_len);
         words_left = (pv.data_len - 10) >> 3;
         in_word = 1;
         break;
       case DK_RAW_SC:  // timestamp.rs:201-224
       case DK_RAW_ZZ:  // integer.rs:165-184
-        bs.init(d + 2, smem_slot);
+        bs.init(d + 2, smem_slot, d + pv.data_len);
         words_left = (pv.data_len - 2) >> 3;
         break;
       case DK_RAWBE:  // timestamp.rs:301-323
-        bs.init(d + 1, smem_slot);
+        bs.init(d + 1, smem_slot, d + pv.data_len);
         words_left = (pv.data_len - 1) >> 3;
         break;
       default:
@@ -265,8 +323,7 @@ struct DeltaCursor {
     words_left--;
     w = bs.next();
     const uint32_t sel = (uint32_t)(w >> 60);
-    in_word = c_s8b_count[sel];
-    bits = c_s8b_bits[sel];
+    s8b_lut(sel, in_word, bits);
     ones = sel < 2 ? 1u : 0u;
     mask = bits ? (~0ull >> (64 - bits)) : 0ull;
   }
@@ -329,7 +386,7 @@ struct GorillaCursor {
     trailing = 0;
     meaningful = 64;
     const uint8_t *d = pv.data;
-    bs.init(d + 2, smem_slot);
+    bs.init(d + 2, smem_slot, d + pv.data_len);
     val = bs.next();
     hi = 0;  // its last bit is the fake control bit 0 = "repeat the previous value"
     lo = bs.next();
@@ -401,6 +458,92 @@ struct GorillaCursor {
       if (!advance()) done = true;
     }
     return !err;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Gorilla cursor of the fused scan (float.rs:418-606), round 2: same results as GorillaCursor above, different
+// mechanics. The bit stream is staged through a ChunkRing and addressed by absolute bit position: one element is
+//   three 8-byte LDS (a 128-bit window at `pos`), a branch-free parse of the 13 control bits
+//   (c0 c1 leading[5] meaningful[6]), two funnel shifts for the XOR payload, pos += len + sig
+// with no per-lane branches: the 32 lanes of a warp decode 32 different pages and would diverge on every element.
+// The cursor runs ONE ELEMENT AHEAD: next() returns the value decoded by the previous call and decodes the following
+// element, so the first call needs no special case and the caller's arithmetic overlaps the next element's dependent
+// chain. `cur_ok` says whether the value about to be returned is a real one (not the sentinel 0x7ff8_0000_0000_00ff,
+// float.rs:16, and inside the block); asking for a value that is not sets the sticky `done` like the serial cursor.
+// ------------------------------------------------------------------------------------------------
+struct GorillaRing {
+  ChunkRing ring;
+  uint64_t val;         // value the next call returns
+  uint32_t pos;         // bit position of the next element, from the ring's aligned start
+  uint32_t end_pos;     // bit position of the end of the block
+  uint32_t meaningful, trailing;
+  bool cur_ok;          // `val` is a real value (not the terminating sentinel)
+  bool done;            // a value was asked for after the sentinel
+  bool any;
+
+  __device__ __forceinline__ void open(const PageView &pv, uint32_t lane_slot) {
+    const uint8_t *d = pv.data;  // id | 0x10 | first(8) | bit stream
+    val = load_be64(d + 2);
+    ring.init(d + 10, d + pv.data_len, lane_slot);
+    pos = (uint32_t)(reinterpret_cast<uintptr_t>(d + 10) & 15) * 8;
+    end_pos = pos + (pv.data_len - 10) * 8;
+    meaningful = 64;
+    trailing = 0;
+    cur_ok = true;  // the first value is pushed without a sentinel test (float.rs:445-460)
+    done = any = false;
+  }
+  __device__ __forceinline__ void reset(uint32_t lane_slot) {
+    ring.reset(lane_slot);
+    val = 0; pos = 0; end_pos = 0; meaningful = 64; trailing = 0;
+    cur_ok = false; done = any = false;
+  }
+  __device__ __forceinline__ bool consumed_any() const { return any; }
+  // "unexpected end of block" (float.rs:462): an element ran past the block. `pos` only grows and stops growing at the
+  // sentinel, so this one comparison, made when the caller checks, stands for the serial cursor's per-element test: an
+  // overrun BEFORE the sentinel leaves pos > end_pos, a sentinel inside the block freezes pos <= end_pos.
+  __device__ __forceinline__ bool overran() const { return pos > end_pos; }
+  // Asked for more values than the stream holds, or the stream is truncated.
+  __device__ __forceinline__ bool failed() const { return done || overran(); }
+
+  // Decodes the element at `pos` into `val`.
+  __device__ __forceinline__ void step() {
+    ring.step(pos >> 7);
+    const uint32_t k = pos >> 6;
+    const uint2 w0 = ring.word(k), w1 = ring.word(k + 1), w2 = ring.word(k + 2);
+    const bool up = pos & 32;  // the window starts in the upper half of w0
+    const uint32_t a0 = __byte_perm(up ? w0.y : w0.x, 0, 0x0123), a1 = __byte_perm(up ? w1.x : w0.y, 0, 0x0123),
+                   a2 = __byte_perm(up ? w1.y : w1.x, 0, 0x0123), a3 = __byte_perm(up ? w2.x : w1.y, 0, 0x0123);
+    const uint32_t s = pos & 31;
+    const uint32_t H = __funnelshift_l(a1, a0, s), M = __funnelshift_l(a2, a1, s), L = __funnelshift_l(a3, a2, s);
+    const uint32_t x = H >> 19;  // 13 bits: c0 c1 leading[5] meaningful[6]
+    const bool c0 = x & 0x1000, c1 = x & 0x0800;
+    const uint32_t leading = (x >> 6) & 0x1f, m = x & 0x3f;
+    const bool fresh = c0 && c1;
+    meaningful = fresh ? (m ? m : 64u) : meaningful;
+    trailing = fresh ? (m ? ((64u - leading - m) & 0xffu) : 0u) : trailing;  // u8 arithmetic like the reference
+    const uint32_t len = c0 ? (c1 ? 13u : 2u) : 1u;
+    const uint32_t sig = c0 ? meaningful : 0u;
+    const uint64_t payload = ((uint64_t)__funnelshift_l(M, H, len) << 32) | __funnelshift_l(L, M, len);
+    const uint64_t delta = (payload >> ((64u - sig) & 63u)) << (trailing & 63u);
+    val ^= c0 ? delta : 0ull;
+    pos += cur_ok ? len + sig : 0u;  // frozen once the sentinel has been seen (the lane keeps re-reading it, harmlessly)
+    // the sentinel ends the stream (float.rs:585-589); repeats are pushed without the test (float.rs:493-497)
+    cur_ok = cur_ok && !(c0 && val == 0x7ff80000000000ffull);
+  }
+  // Value for the next VALID row; sets `done` when the stream ended before the bitset did.
+  __device__ __forceinline__ uint64_t next() {
+    const uint64_t r = val;
+    done = done || !cur_ok;
+    any = true;
+    step();
+    return r;
+  }
+  // The reference decodes to the sentinel (float.rs:480-591): a stream without one is an error even when enough
+  // values were produced. Returns false on "unexpected end of block".
+  __device__ __forceinline__ bool drain() {
+    while (!done && cur_ok && !overran()) step();
+    return !overran();
   }
 };
 

@@ -651,25 +651,25 @@ __device__ __forceinline__ uint4 tomb_lookup(const ScanParams &P, uint32_t serie
 }
 
 // One chunk of <= 32 work items, one lane per field page. The whole warp stays converged; lanes
-// without a page (or past their last row) idle through the loop. `ring_base` = shared-space address of
-// this warp's 2 x RING_WORDS x 256 B prefetch rings (time stream, value stream).
+// without a page (or past their last row) idle through the loop. Generic path (time pages with NULLs or raw / unusual
+// time encodings - nothing the reference's writer produces): row by row, streams read straight from global memory.
 // SEL: the query wants FIRST/LAST somewhere (tracks the (ts, value) of each run's end rows).
 template <int TK, int VK, bool SEL>
 __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
-                                             uint32_t ring_base, uint64_t *stab) {
+                                             uint32_t /*ring_base*/, uint64_t *stab) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
-  const uint32_t tslot = ring_base + lane * 8, vslot = ring_base + RING_WORDS * 256 + lane * 8;
+  const uint32_t tslot = 0, vslot = 0;
 
   uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
   uint8_t pt = TSKV_PT_I64, mask = 0;
   PageView tpv, vpv;
   BitCursor tbits, vbits;
   __shared__ uint4 s_tomb[SCAN_THREADS];  // per lane tombstone lists (only touched when the page set has any)
-  DeltaCursor<TK == TK_RLE ? DK_RLE_SC : TK == TK_S8B ? DK_S8B_SC : -1, RingStream> tcur;
-  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, RingStream> vcur_d;
-  GorillaCursor<RingStream> vcur_g;
+  DeltaCursor<TK == TK_RLE ? DK_RLE_SC : TK == TK_S8B ? DK_S8B_SC : -1, BeStream> tcur;
+  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, BeStream> vcur_d;
+  GorillaCursor<BeStream> vcur_g;
   bool allnull = false;
 
   if (have_item) {
@@ -797,8 +797,6 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
   // without one is an error even when enough values were produced.
   if (VK == VK_GOR && have_item && n_rows != 0 && vcur_g.consumed_any() && !vcur_g.drain())
     report_error(P, TSKV_ERR_SHORT_BLOCK, page);
-  // drain the prefetch rings before the next chunk reuses them
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
   // statistics
   n_points = __reduce_add_sync(FULL, n_points);
   n_inrange = __reduce_add_sync(FULL, n_inrange);
@@ -840,25 +838,134 @@ struct ValueAcc {  // count / sum / min / max of one run; VK fixes the arithmeti
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Staged flush (GROUP BY bucket, no FIRST/LAST). The 32 pages of a warp usually cross a bucket boundary at the same
+// row (TSBS-aligned timestamps), so all lanes finish a run for the SAME cell at the same time. Combining 32 partials
+// with warp reductions (REDUX / butterflies) and then updating the shared table with CAS-loop atomics costs ~230
+// instructions per 6-row segment. Instead every lane parks its partial in a per-warp staging area
+//   stage[slot][quantity][lane]          (one conflict-free STS.64 per quantity)
+// and every FLUSH_SLOTS flushes the warp reduces the parked partials TRANSPOSED: lane j owns slot j % FLUSH_SLOTS and
+// sums the partials of source lanes 4 * (j / FLUSH_SLOTS) .. + 3 serially (every lane does useful work on every
+// instruction), three xor-shuffle steps combine the 8 lane groups, and FLUSH_SLOTS lanes update the CTA table.
+// ------------------------------------------------------------------------------------------------
+constexpr int FLUSH_SLOTS = 4;
+constexpr int FLUSH_Q = 5;  // count | sum | sum_hi | min key | max key
+constexpr uint32_t FLUSH_STAGE_WORDS = FLUSH_SLOTS * FLUSH_Q * 32 + FLUSH_SLOTS;  // + one meta word per slot
+constexpr uint32_t FLUSH_STAGE_BYTES = FLUSH_STAGE_WORDS * 8;
+
+template <int VK>
+__device__ __forceinline__ void reduce_staged(const ScanParams &P, uint64_t *stab, uint64_t *stage, uint32_t n_slots) {
+  __syncwarp();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t s = lane & (FLUSH_SLOTS - 1), g = lane / FLUSH_SLOTS;
+  const uint64_t meta = stage[FLUSH_SLOTS * FLUSH_Q * 32 + s];  // (query column << 32) | cell
+  const uint32_t qcol = (uint32_t)(meta >> 32);
+  const ColState &cs = P.cols[s < n_slots ? qcol : 0];
+  const bool is_f64 = VK == VK_GOR || (VK == VK_GEN && cs.phys_type == TSKV_PT_F64);
+  uint64_t cnt = 0, sum = 0;
+  int64_t hi = 0, kmin = INT64_MAX, kmax = INT64_MIN;
+  const uint64_t *base = stage + (size_t)s * FLUSH_Q * 32;
+#pragma unroll
+  for (int i = 0; i < 32 / (32 / FLUSH_SLOTS); i++) {  // 4 source lanes per group, rotated by the slot: conflict-free
+    const uint32_t src = g * 4 + ((i + s) & 3);
+    const uint64_t c = base[src], v = base[32 + src];
+    cnt += c;
+    if (is_f64) {
+      sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)v));
+    } else {
+      sum += v;
+      if (VK != VK_GOR) hi += (int64_t)base[64 + src] + (sum < v ? 1 : 0);
+    }
+    const int64_t a = (int64_t)base[96 + src], b = (int64_t)base[128 + src];
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+#pragma unroll
+  for (int o = FLUSH_SLOTS; o < 32; o <<= 1) {  // lanes j, j ^ o own the same slot
+    cnt += shfl_xor_u64(cnt, o);
+    const uint64_t v = shfl_xor_u64(sum, o);
+    if (is_f64) {
+      sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)v));
+    } else {
+      sum += v;
+      if (VK != VK_GOR) hi += (int64_t)shfl_xor_u64((uint64_t)hi, o) + (sum < v ? 1 : 0);
+    }
+    const int64_t a = (int64_t)shfl_xor_u64((uint64_t)kmin, o), b = (int64_t)shfl_xor_u64((uint64_t)kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+  if (lane < n_slots && cnt)
+    table_update(P, stab, cs, (uint64_t)(uint32_t)meta, cs.agg_mask, is_f64, (uint32_t)cnt, sum, hi, kmin, kmax);
+  __syncwarp();
+}
+
+// Flush of one finished run per flushing lane (no FIRST/LAST). `seq` = staged slots in use (warp-uniform).
+template <int VK>
+__device__ __forceinline__ void flush_runs(const ScanParams &P, uint64_t *stab, uint64_t *stage, uint32_t &seq, bool active,
+                                           uint32_t qcol, uint64_t cell, uint8_t pt, uint8_t mask, const ValueAcc<VK> &va) {
+  const uint32_t m = __ballot_sync(FULL, active);
+  if (m == 0) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t gcell = ((uint64_t)qcol << 32) | (uint32_t)cell;
+  const int leader = __ffs(m) - 1;
+  const uint64_t lcell = shfl_u64(gcell, leader);
+  const bool same = P.use_smem && __all_sync(FULL, !active || gcell == lcell);
+  if (same) {
+    uint64_t *q = stage + (size_t)seq * FLUSH_Q * 32 + lane;
+    const bool live = active && va.count;
+    q[0] = live ? va.count : 0;
+    q[32] = live ? va.sum : 0;  // 0 bits == +0.0
+    if (VK != VK_GOR) q[64] = live ? (uint64_t)va.sum_hi : 0;
+    q[96] = live ? (uint64_t)va.kmin : (uint64_t)INT64_MAX;
+    q[128] = live ? (uint64_t)va.kmax : (uint64_t)INT64_MIN;
+    if ((int)lane == leader) stage[FLUSH_SLOTS * FLUSH_Q * 32 + seq] = lcell;
+    if (++seq == FLUSH_SLOTS) {
+      reduce_staged<VK>(P, stab, stage, seq);
+      seq = 0;
+    }
+  } else if (active && va.count) {  // lanes on different cells (GROUP BY series, unaligned pages): one update each
+    table_update(P, stab, P.cols[qcol], cell, mask, VK == VK_GOR || (VK == VK_GEN && pt == TSKV_PT_F64), va.count, va.sum,
+                 va.sum_hi, va.kmin, va.kmax);
+  }
+}
+
+// Rows of an RLE time page that stay inside [t, t + d] when stepping by delta > 0 from t: min(left, floor(d / delta) + 1),
+// with the quotient estimated in double precision (inv = 1.0 / delta, one division per page) and corrected exactly.
+__device__ __forceinline__ uint32_t rle_rows_within(uint64_t d, uint64_t delta, double inv, uint32_t left) {
+  const double e = (double)d * inv;
+  if (e >= (double)left) return left;  // floor(d / delta) >= left - 1 (relative error 2^-51, left < 2^32)
+  uint64_t q = (uint64_t)e;            // < 2^32, off by at most one
+  if (__umul64hi(q, delta) != 0 || q * delta > d) q--;
+  else if (d - q * delta >= delta) q++;
+  return (uint32_t)min((uint64_t)left, q + 1);
+}
+
 template <int TK, int VK, bool SEL>
 __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
-                                               uint32_t ring_base, uint64_t *stab) {
+                                               uint32_t ring_base, uint64_t *stab, uint64_t *stage) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
-  const uint32_t tslot = ring_base + lane * 8, vslot = ring_base + RING_WORDS * 256 + lane * 8;
+  // this lane's slots in the warp's staging rings: [time ring (simple8b timestamps only)] [value ring]
+  const uint32_t tslot = ring_base + lane * 16;
+  const uint32_t vslot = ring_base + (TK == TK_S8B ? RING_BYTES_PER_WARP : 0) + lane * 16;
 
   uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
   uint8_t pt = VK == VK_GOR ? TSKV_PT_F64 : TSKV_PT_I64, mask = 0;
   PageView tpv, vpv;
-  DeltaCursor<TK == TK_RLE ? DK_RLE_SC : DK_S8B_SC, RingStream> tcur;
-  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, RingStream> vcur_d;
-  GorillaCursor<RingStream> vcur_g;
+  DeltaCursor<DK_S8B_SC, SeqStream> tcur;     // TK_S8B: timestamps staged through the time ring
+  uint64_t rle_t0 = 0, rle_delta = 0;          // TK_RLE: t(row) = rle_t0 + row * rle_delta (wrapping), closed form
+  double rle_inv = 0.0;
+  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, SeqStream> vcur_d;
+  GorillaRing vcur_g;
   const uint32_t *vbm = nullptr;  // value validity bitmap, 32 rows per word
   bool allnull = false;
   int64_t pend_t = 0;  // timestamp of row `row`
   __shared__ uint4 s_tomb[SCAN_THREADS];  // per lane tombstone lists (only touched when the page set has any)
 
+  if (TK == TK_S8B) tcur.bs.reset(tslot);
+  if (VK == VK_GOR) vcur_g.reset(vslot);
+  else vcur_d.bs.reset(vslot);
   if (have_item) {
     page = P.work_page[item];
     slot = P.work_slot[item];
@@ -877,18 +984,30 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
       vpv.open(P.arena, vd);
       n_rows = vd.num_values;
       vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
-      st = tcur.open(tpv, td.reserved, tslot);
+      if (TK == TK_RLE) {  // timestamp.rs:226-259
+        DeltaCursor<DK_RLE_SC, BeStream> rc;
+        st = rc.open(tpv, td.reserved);
+        rle_delta = rc.delta;
+        rle_t0 = rc.v + rc.delta;
+        if ((int64_t)rle_delta > 0) rle_inv = 1.0 / (double)rle_delta;
+      } else {
+        st = tcur.open(tpv, td.reserved, tslot);
+      }
       if (st == TSKV_OK) {
-        if (VK == VK_GOR) st = vcur_g.open(vpv, vslot);
+        if (VK == VK_GOR) vcur_g.open(vpv, vslot);
         else { st = vcur_d.open(vpv, vd.reserved, vslot); allnull = vd.reserved == DK_ALLNULL; }
       }
       if (st == TSKV_OK && n_rows) {
-        pend_t = (int64_t)tcur.next();
-        if (tcur.exhausted) st = TSKV_ERR_BITSET_MISMATCH;
+        if (TK == TK_RLE) pend_t = (int64_t)rle_t0;
+        else {
+          pend_t = (int64_t)tcur.next();  // the first value: no ring access (cursors.cuh)
+          if (tcur.exhausted) st = TSKV_ERR_BITSET_MISMATCH;
+        }
       }
       if (st != TSKV_OK) { report_error(P, st, st == TSKV_ERR_BITSET_MISMATCH ? tpage : page); n_rows = 0; }
     }
   }
+  ring_drain();  // the rings' initial fills have landed before the first step (once per page)
 
   ValueAcc<VK> va;
   va.reset();
@@ -903,7 +1022,157 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   const bool mean_hi = VK != VK_GOR && pt != TSKV_PT_F64 && (mask & TSKV_AGG_MEAN);
   const uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull : 0ull;
   const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
+  uint32_t staged = 0;  // staged flush slots in use (warp-uniform)
 
+  // Finished runs of the flushing lanes -> partial tables.
+  auto flush_now = [&](bool flush) {
+    if (SEL) {
+      if (__any_sync(FULL, flush)) {
+        acc.count = va.count; acc.sum = va.sum; acc.sum_hi = va.sum_hi; acc.kmin = va.kmin; acc.kmax = va.kmax;
+        warp_flush<SEL>(P, stab, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
+      }
+    } else {
+      flush_runs<VK>(P, stab, stage, staged, flush, qcol, group_base + run_idx, pt, mask, va);
+    }
+  };
+  // Values of the segment rows [row, row + n), one bitmap word at a time. Every valid row is decoded - rows outside the
+  // time ranges too, the streams are sequential - and accumulated when the segment is selected. One loop for dense and
+  // sparse bitmaps: a warp holds pages of both kinds and would otherwise run both variants.
+  auto seg_values = [&](uint32_t n, bool seg_in, bool seg_masked, bool newrun, int64_t seg_first_t, int64_t seg_last_t) {
+    uint32_t r = row;
+    const uint32_t rend = row + n;
+    const bool accumulate = seg_in && !seg_masked;
+    while (r < rend) {
+      if ((r & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
+        vword = vahead;
+        vahead = __ldg(vbm + (r >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
+      }
+      const uint32_t off = r & 31;
+      const uint32_t span = min(32u - off, rend - r);
+      const uint32_t m = allnull ? 0u : ((vword >> off) & (0xffffffffu >> (32 - span)));
+      n_points += __popc(m);
+      if (!SEL) {
+        if (accumulate) va.count += __popc(m);
+#pragma unroll 1
+        for (uint32_t j = 0; j < span; j++) {
+          if ((m >> j) & 1) {
+            const uint64_t v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+            if (accumulate) va.add(v, pt, flip, mean_hi);
+          }
+        }
+      } else {  // FIRST / LAST wanted: the run's end rows keep (ts, value, valid)
+        for (uint32_t j = 0; j < span; j++) {
+          bool vv = (m >> j) & 1;
+          uint64_t v = 0;
+          if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+          vv = vv && !seg_masked;
+          if (seg_in) {
+            if (r + j == row && newrun) { acc.first_ts = seg_first_t; acc.first_val = vv ? v : 0; acc.first_ok = vv; }
+            if (r + j == rend - 1) { acc.last_ts = seg_last_t; acc.last_val = vv ? v : 0; acc.last_ok = vv; }
+            if (vv) { va.count++; va.add(v, pt, flip, mean_hi); }
+          }
+        }
+      }
+      r += span;
+    }
+    const bool bad = VK == VK_GOR ? vcur_g.failed() : vcur_d.exhausted;
+    if (bad) {
+      report_error(P, (VK == VK_GOR && vcur_g.overran()) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
+      n_rows = 0;
+      have_run = false;
+    }
+    row = rend;
+  };
+
+  // ---- RLE timestamps, increasing, at most one time range, no tombstones: the segment structure is arithmetic in the
+  // ROW index. Rows [ra, rb1) are inside the range; bucket edges advance by q or q + 1 rows (w = q * delta + rem, the
+  // offset e of a bucket's first row inside it decides), so a segment costs a handful of 32-bit operations instead of
+  // 64-bit interval arithmetic per segment. Anything else (wrapping / constant timestamps, several ranges, tombstones,
+  // the reference's truncating-% regime for negative dividends, values near the i64 limits) takes the general loop.
+  uint32_t ra = 0, rb1 = 0, nb = 0xffffffffu, q32 = 0, bidx = 0;
+  uint64_t e_off = 0, w_rem = 0;
+  bool fast = false;
+  if (TK == TK_RLE) {
+    bool elig = P.n_ranges <= 1 && !P.has_tomb;
+    if (elig && n_rows) {
+      const uint64_t span_t = (uint64_t)(n_rows - 1) * rle_delta;
+      elig = (int64_t)rle_delta > 0 && __umul64hi((uint64_t)(n_rows - 1), rle_delta) == 0 && span_t < (1ull << 62) &&
+             rle_t0 + (1ull << 62) < (1ull << 63) && P.width < ((int64_t)1 << 61);
+      if (elig) {
+        const int64_t t0 = (int64_t)rle_t0;
+        ra = 0;
+        rb1 = n_rows;
+        if (P.n_ranges == 1) {  // rows with t < a, rows with t <= b
+          const int64_t a = P.ranges[0].min_ts, b = P.ranges[0].max_ts;
+          ra = a <= t0 ? 0u : rle_rows_within((uint64_t)(a - 1) - rle_t0, rle_delta, rle_inv, n_rows);
+          rb1 = b < t0 ? 0u : rle_rows_within((uint64_t)b - rle_t0, rle_delta, rle_inv, n_rows);
+        }
+        if (P.width > 0 && ra < rb1) {
+          const int64_t tr = (int64_t)(rle_t0 + (uint64_t)ra * rle_delta);
+          if ((int64_t)((uint64_t)tr - (uint64_t)P.origin_mod + (uint64_t)P.width) < 0) {
+            elig = false;  // truncating-% regime (time_window.rs:184-198): general loop
+          } else if (!locate_bucket(P, tr, bk)) {
+            report_error(P, TSKV_ERR_BUCKET_RANGE, page);
+            n_rows = 0;
+          } else {
+            bidx = bk.idx;
+            nb = rle_rows_within((uint64_t)bk.hi - (uint64_t)tr, rle_delta, rle_inv, 0xffffffffu);
+            e_off = (uint64_t)tr + (uint64_t)nb * rle_delta - ((uint64_t)bk.hi + 1);
+            q32 = rle_rows_within((uint64_t)P.width, rle_delta, rle_inv, 0xffffffffu) - 1;
+            w_rem = (uint64_t)P.width - (uint64_t)q32 * rle_delta;
+          }
+        }
+      }
+    }
+    fast = __all_sync(FULL, elig);
+  }
+
+  if (TK == TK_RLE && fast) {
+    for (;;) {
+      const bool has = row < n_rows;
+      if (!__any_sync(FULL, has || have_run)) break;
+      uint32_t n = 0;
+      bool seg_in = false;
+      if (has) {
+        if (row < ra) n = ra - row;
+        else if (row >= rb1) n = n_rows - row;
+        else {
+          seg_in = true;
+          while (nb == 0) {  // next bucket (one narrower than the step may hold no row at all)
+            bidx++;
+            nb = q32 + (e_off < w_rem ? 1u : 0u);
+            e_off = e_off + (uint64_t)nb * rle_delta - (uint64_t)P.width;
+          }
+          if (bidx >= P.n_buckets) {
+            report_error(P, TSKV_ERR_BUCKET_RANGE, page);
+            seg_in = false;
+            n_rows = row;
+          } else {
+            n = min(nb, rb1 - row);
+            if (P.width > 0) nb -= n;
+          }
+        }
+      }
+      if (seg_in) n_inrange += n;
+      const bool newrun = seg_in && (!have_run || bidx != run_idx);
+      const bool flush = have_run && (newrun || !has);
+      flush_now(flush);
+      if (flush) have_run = false;
+      if (newrun) {
+        have_run = true;
+        run_idx = bidx;
+        va.reset();
+      }
+      if (n) {
+        int64_t ft = 0, lt = 0;
+        if (SEL) {
+          ft = (int64_t)(rle_t0 + (uint64_t)row * rle_delta);
+          lt = (int64_t)(rle_t0 + (uint64_t)(row + n - 1) * rle_delta);
+        }
+        seg_values(n, seg_in, false, newrun, ft, lt);
+      }
+    }
+  } else {
   for (;;) {
     const bool has = row < n_rows;
     if (!__any_sync(FULL, has || have_run)) break;
@@ -912,8 +1181,8 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     bool seg_in = false;
     bool seg_masked = false;  // tombstoned column range: the rows stay, their values read as NULL
     int64_t seg_first_t = pend_t, seg_last_t = pend_t;
+    int64_t lim_lo = pend_t, lim_hi = pend_t;
     if (has) {
-      int64_t lim_lo, lim_hi;
       seg_in = range_span(P, pend_t, lim_lo, lim_hi);
       if (P.has_tomb) {  // decode_pages' tombstone handling (reader.rs:507-551) as two more segment attributes
         const uint4 tl = s_tomb[threadIdx.x];
@@ -934,86 +1203,53 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
         }
       }
       const uint32_t left = n_rows - row;
-      int64_t t = pend_t;
-      do {  // look ahead: t = timestamp of row + n
-        n++;
-        seg_last_t = t;
-        t = (int64_t)tcur.next();
-      } while (n < left && t >= lim_lo && t <= lim_hi);
-      pend_t = t;  // (past the last row: the next() above ran one value too far - harmless, see below)
-      if (tcur.exhausted && n < left) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row + n; }
-      if (seg_in) n_inrange += n;
+      if (TK == TK_RLE) {
+        if ((int64_t)rle_delta > 0) {  // increasing: the segment ends where t passes lim_hi - closed form
+          n = rle_rows_within((uint64_t)lim_hi - (uint64_t)pend_t, rle_delta, rle_inv, left);
+          seg_last_t = (int64_t)((uint64_t)pend_t + (uint64_t)(n - 1) * rle_delta);
+          pend_t = (int64_t)((uint64_t)seg_last_t + rle_delta);
+        } else {  // constant or wrapping ("descending") timestamps: walk the rows
+          int64_t t = pend_t;
+          do {
+            n++;
+            seg_last_t = t;
+            t = (int64_t)((uint64_t)t + rle_delta);
+          } while (n < left && t >= lim_lo && t <= lim_hi);
+          pend_t = t;
+        }
+      } else {  // look ahead through the time ring: t = timestamp of row + n
+        int64_t t = pend_t;
+        do {
+          n++;
+          seg_last_t = t;
+          t = (int64_t)tcur.next();
+        } while (n < left && t >= lim_lo && t <= lim_hi);
+        pend_t = t;  // (past the last row: the next() above ran one value too far - harmless)
+        if (tcur.exhausted && n < left) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row + n; }
+      }
     }
+    if (seg_in) n_inrange += n;
     // ---- 2. flush the finished run (warp-converged) ----------------------------------------------
     const bool newrun = has && seg_in && (!have_run || bk.idx != run_idx);
     const bool flush = have_run && (newrun || !has);
-    if (__any_sync(FULL, flush)) {
-      acc.count = va.count; acc.sum = va.sum; acc.sum_hi = va.sum_hi; acc.kmin = va.kmin; acc.kmax = va.kmax;
-      warp_flush<SEL>(P, stab, flush, qcol, group_base + run_idx, (int64_t)run_idx, pt, mask, acc, slot);
-    }
+    flush_now(flush);
     if (flush) have_run = false;
     if (newrun) {
       have_run = true;
       run_idx = bk.idx;
       va.reset();
     }
-    // ---- 3. values of the segment, one bitmap word at a time --------------------------------------
-    if (has) {
-      uint32_t r = row;
-      const uint32_t rend = row + n;
-      while (r < rend) {
-        if ((r & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
-          vword = vahead;
-          vahead = __ldg(vbm + (r >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
-        }
-        const uint32_t off = r & 31;
-        const uint32_t span = min(32u - off, rend - r);
-        const uint32_t want = span == 32 ? 0xffffffffu : ((1u << span) - 1);
-        uint32_t m = allnull ? 0u : ((vword >> off) & want);
-        n_points += __popc(m);
-        uint64_t v = 0;
-        if (!SEL && seg_in && !seg_masked) {
-          va.count += __popc(m);
-          if (m == want) {
-#pragma unroll 1
-            for (uint32_t j = 0; j < span; j++) {
-              v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-              va.add(v, pt, flip, mean_hi);
-            }
-          } else {
-            for (; m; m &= m - 1) {
-              v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-              va.add(v, pt, flip, mean_hi);
-            }
-          }
-        } else if (!SEL) {  // rows outside the time ranges: decode (the streams are sequential), drop
-          for (uint32_t c = __popc(m); c; c--) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-        } else {            // FIRST / LAST wanted: per-row, the run's end rows keep (ts, value, valid)
-          for (uint32_t j = 0; j < span; j++) {
-            bool vv = (m >> j) & 1;
-            if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-            vv = vv && !seg_masked;
-            if (seg_in) {
-              if (r + j == row && newrun) { acc.first_ts = seg_first_t; acc.first_val = vv ? v : 0; acc.first_ok = vv; }
-              if (r + j == rend - 1) { acc.last_ts = seg_last_t; acc.last_val = vv ? v : 0; acc.last_ok = vv; }
-              if (vv) { va.count++; va.add(v, pt, flip, mean_hi); }
-            }
-          }
-        }
-        r += span;
-      }
-      const bool bad = VK == VK_GOR ? vcur_g.done : vcur_d.exhausted;
-      if (bad) {
-        report_error(P, (VK == VK_GOR && vcur_g.err) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
-        n_rows = 0;
-        have_run = false;
-      }
-      row = rend;
-    }
+    // ---- 3. values of the segment ------------------------------------------------------------------
+    if (has) seg_values(n, seg_in, seg_masked, newrun, seg_first_t, seg_last_t);
+  }
+  }
+  if (!SEL && staged) {  // partials still parked in the staging area
+    reduce_staged<VK>(P, stab, stage, staged);
+    staged = 0;
   }
   if (VK == VK_GOR && have_item && n_rows != 0 && vcur_g.consumed_any() && !vcur_g.drain())  // float.rs:480-591
     report_error(P, TSKV_ERR_SHORT_BLOCK, page);
-  asm volatile("cp.async.wait_all;\n" ::: "memory");  // drain the rings before the next chunk reuses them
+  ring_drain();  // nothing in flight when the next chunk reuses the rings
   n_points = __reduce_add_sync(FULL, n_points);
   n_inrange = __reduce_add_sync(FULL, n_inrange);
   if (lane == 0) {
@@ -1031,10 +1267,19 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
 #endif
 // RLE-timestamp variants without FIRST/LAST need < 102 registers: 5 blocks per SM, the others 4.
 __host__ __device__ constexpr int scan_min_blocks(int tk, bool sel) { return (tk == TK_RLE && !sel) ? SCAN_MIN_BLOCKS + 1 : SCAN_MIN_BLOCKS; }
+// staging-ring bytes one warp of the fused kernel needs (generic time pages read from global memory)
+__host__ __device__ constexpr uint32_t scan_ring_bytes_per_warp(int tk) {
+  return tk == TK_RLE ? RING_BYTES_PER_WARP : tk == TK_S8B ? 2 * RING_BYTES_PER_WARP : 0;
+}
+// per-warp shared memory of the fused kernel: staging rings + the staged-flush area
+__host__ __device__ constexpr uint32_t scan_warp_bytes(int tk) {
+  return tk == TK_GEN ? 0 : scan_ring_bytes_per_warp(tk) + FLUSH_STAGE_BYTES;
+}
 template <int TK, int VK, bool SEL>
 __global__ void __launch_bounds__(SCAN_THREADS, scan_min_blocks(TK, SEL)) k_scan_aggregate(const __grid_constant__ ScanParams P, int bin) {
-  __shared__ __align__(16) uint64_t s_ring[SCAN_THREADS / 32][2][RING_WORDS][32];  // per warp, per stream
-  extern __shared__ __align__(16) uint64_t s_tab[];  // per-CTA partial table (P.smem_words words) or empty
+  // dynamic shared memory: [per-CTA partial table, P.smem_words 8-byte words (or empty)] [staging rings, per warp:
+  // a value ring, preceded by a time ring when the timestamps are simple8b]
+  extern __shared__ __align__(16) uint64_t s_tab[];
   if (P.use_smem) {  // identities: 0 for counts / sums, +-inf keys for min / max
     for (uint32_t i = threadIdx.x; i < P.smem_words; i += SCAN_THREADS) s_tab[i] = 0;
     __syncthreads();
@@ -1048,7 +1293,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, scan_min_blocks(TK, SEL)) k_scan
     __syncthreads();
   }
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0][0]);
+  uint64_t *warp_area = s_tab + ((P.smem_words + 1) & ~1u) + (size_t)(threadIdx.x >> 5) * (scan_warp_bytes(TK) / 8);
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(warp_area);
+  uint64_t *stage = warp_area + scan_ring_bytes_per_warp(TK) / 8;
   const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
   const uint32_t n_chunks = (end0 - begin0 + 31) >> 5;
   for (;;) {
@@ -1059,7 +1306,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, scan_min_blocks(TK, SEL)) k_scan
     const uint32_t begin = begin0 + (c << 5);
     const uint32_t end = min(begin + 32, end0);
     if (TK == TK_GEN) scan_chunk_rows<TK, VK, SEL>(P, begin, end, ring_base, s_tab);
-    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base, s_tab);
+    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base, s_tab, stage);
   }
   if (P.use_smem) {  // merge this CTA's table into the global state, once
     __syncthreads();

@@ -183,6 +183,10 @@ double bin_cost(int bin, bool coop) {
   return tk[sb / N_VK] * vk[sb % N_VK] * (coop ? 1.8 : 1.0);
 }
 
+// dynamic shared memory of a lane-per-page kernel: the per-CTA table + the warps' staging rings
+size_t serial_smem_bytes(int serial_bin, uint32_t table_words) {
+  return (size_t)((table_words + 1) & ~1u) * 8 + (size_t)scan_warp_bytes(serial_bin / N_VK) * (SCAN_THREADS / 32);
+}
 size_t coop_smem_bytes(int bin, uint32_t table_words) {
   size_t per_warp = bin == BIN_COOP_S8B_S8B   ? sizeof(CoopSmem<true, false>)
                     : bin == BIN_COOP_RLE_S8B ? sizeof(CoopSmem<false, false>)
@@ -497,8 +501,8 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
     if (n) e = cudaMemcpyAsync(*dptr, src, n * sizeof(**dptr), cudaMemcpyHostToDevice, ctx->stream);
     return e;
   };
-  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&pg->d_arena), arena_len + 64);
-  if (e == cudaSuccess) e = cudaMemsetAsync(pg->d_arena + arena_len, 0, 64, ctx->stream);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&pg->d_arena), arena_len + ARENA_SLACK);
+  if (e == cudaSuccess) e = cudaMemsetAsync(pg->d_arena + arena_len, 0, ARENA_SLACK, ctx->stream);
   if (e == cudaSuccess && arena_len && (flags & TSKV_UPLOAD_HOST_RESIDENT)) {
     // pages stay in (page-locked) host memory like the reference's page cache; each scan pulls the
     // selected pages over PCIe itself (k_gather_pages)
@@ -1041,10 +1045,9 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       if (!s->use_coop[b]) {
         const int sb = serial_bin_of(b);
         const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb));
-        if ((size_t)P.smem_words * 8 > 32 * 1024)
-          cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)P.smem_words * 8));
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)serial_smem_bytes(sb, P.smem_words));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb),
-                                                      SCAN_THREADS, (size_t)P.smem_words * 8);
+                                                      SCAN_THREADS, serial_smem_bytes(sb, P.smem_words));
       } else {
         const void *fn = coop_kernel_for(b, s->has_sel);
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(b, P.smem_words));
@@ -1189,7 +1192,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
       const int sb = serial_bin_of(b);
       void *args[] = {(void *)&s->params, (void *)&bin};
       const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb));
-      CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, (size_t)s->params.smem_words * 8, ctx->bin_stream[b]));
+      CU_TRY(ctx, cudaLaunchKernel(fn, dim3(s->grid[b]), dim3(SCAN_THREADS), args, serial_smem_bytes(sb, s->params.smem_words), ctx->bin_stream[b]));
     } else {
       void *args[] = {(void *)&s->params, (void *)&s->coop, (void *)&bin};
       CU_TRY(ctx, cudaLaunchKernel(coop_kernel_for(b, s->has_sel), dim3(s->grid[b]), dim3(SCAN_THREADS), args,

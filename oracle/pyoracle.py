@@ -51,6 +51,12 @@ def lib():
         L.orc_scan_aggregate_tomb.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.POINTER(cabi.Query), vp, C.c_uint64,
                                               C.c_int, C.c_int, vp, vp, C.POINTER(C.c_uint64)]
         L.orc_scan_aggregate_tomb.restype = C.c_int32
+        L.orc_open.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_int, C.POINTER(vp)]
+        L.orc_open.restype = C.c_int32
+        L.orc_scan.argtypes = [vp, C.POINTER(cabi.Query), vp, C.c_uint64, C.c_int, vp, vp, C.POINTER(C.c_uint64)]
+        L.orc_scan.restype = C.c_int32
+        L.orc_close.argtypes = [vp]
+        L.orc_close.restype = None
         L.orc_last_error.restype = C.c_char_p
         _lib = L
     return _lib
@@ -175,6 +181,50 @@ def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_poi
         raise OracleError(st, lib().orc_last_error().decode())
     res = ScanResult(query, L, values[: int(L.n_out * L.n_cells)], bitmaps[: int(L.validity_bytes)])
     return (res, int(pts.value)) if return_points else res
+
+
+class OpenPages:
+    """An opened page set (orc_open): series index built once, persistent worker pool — what the reference's cached
+    TsmReader metadata + live runtime threads amount to. scan() = one query, same results as scan_aggregate()."""
+
+    def __init__(self, arena, descs, n_threads=1):
+        self.arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        self.descs = np.ascontiguousarray(descs, dtype=cabi.PAGE_DESC_DTYPE)
+        self.n_threads = n_threads
+        h = C.c_void_p()
+        st = lib().orc_open(self.arena.ctypes.data, self.arena.size, self.descs.ctypes.data, len(self.descs),
+                            n_threads, C.byref(h))
+        if st != 0:
+            raise OracleError(st, lib().orc_last_error().decode())
+        self.h = h
+
+    def scan(self, query, verify_crc=True, return_points=False, tombstones=None):
+        q = query.to_c()
+        L = cabi.OutputLayout()
+        st = lib().orc_query_output_layout(self.descs.ctypes.data, len(self.descs), C.byref(q), C.byref(L))
+        if st != 0:
+            raise OracleError(st)
+        values = np.zeros(max(int(L.n_out * L.n_cells), 1), dtype=np.uint64)
+        bitmaps = np.zeros(max(int(L.validity_bytes), 1), dtype=np.uint8)
+        pts = C.c_uint64(0)
+        tombs = np.ascontiguousarray(tombstones if tombstones is not None else [], dtype=cabi.TOMBSTONE_DTYPE)
+        st = lib().orc_scan(self.h, C.byref(q), tombs.ctypes.data if len(tombs) else None, len(tombs),
+                            1 if verify_crc else 0, values.ctypes.data, bitmaps.ctypes.data, C.byref(pts))
+        if st != 0:
+            raise OracleError(st, lib().orc_last_error().decode())
+        res = ScanResult(query, L, values[: int(L.n_out * L.n_cells)], bitmaps[: int(L.validity_bytes)])
+        return (res, int(pts.value)) if return_points else res
+
+    def close(self):
+        if self.h and _lib is not None:
+            _lib.orc_close(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
 
 def sliding_window(t, window, slide, start_time, i=0):

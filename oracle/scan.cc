@@ -3,7 +3,10 @@
 // -> bucket key (transform_time_window.rs:251-296) -> aggregates (DataFusion builtins + first.rs /
 // last.rs semantics). TEST INFRASTRUCTURE ONLY (see tskv_oracle.h).
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -414,19 +417,136 @@ tskv_status orc_scan_aggregate(const uint8_t *arena, uint64_t arena_len,
                                  out_validity, out_points);
 }
 
+}  // extern "C"
+
+namespace {
+
+// An opened page set: the series index is built ONCE here, like the reference's cached TsmReader metadata
+// (tskv/src/tsm/reader.rs:120-168 loaded on open, kept by the version's reader cache, tsfamily/version.rs:158-172),
+// and a persistent pool of worker threads stands in for the tokio/rayon workers the reference keeps alive.
+struct Pool {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::function<void(uint64_t)> job;
+  uint64_t n_jobs = 0, next = 0, done = 0, epoch = 0;
+  bool stop = false;
+  explicit Pool(unsigned n) {
+    for (unsigned i = 0; i < n; i++) workers.emplace_back([this]() { loop(); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      stop = true;
+    }
+    cv_go.notify_all();
+    for (auto &t : workers) t.join();
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> l(mu);
+      cv_go.wait(l, [&]() { return stop || (epoch != seen && next < n_jobs); });
+      if (stop) return;
+      while (next < n_jobs) {
+        uint64_t k = next++;
+        l.unlock();
+        job(k);
+        l.lock();
+        if (++done == n_jobs) cv_done.notify_all();
+      }
+      seen = epoch;
+    }
+  }
+  void run(uint64_t n, std::function<void(uint64_t)> f) {
+    std::unique_lock<std::mutex> l(mu);
+    job = std::move(f);
+    n_jobs = n;
+    next = 0;
+    done = 0;
+    epoch++;
+    cv_go.notify_all();
+    cv_done.wait(l, [&]() { return done == n_jobs; });
+  }
+};
+
+}  // namespace
+
+struct orc_handle {
+  const uint8_t *arena;
+  uint64_t arena_len;
+  const tskv_page_desc *descs;
+  uint64_t n_descs;
+  Index ix;
+  int n_threads;
+  Pool *pool;
+  std::vector<std::vector<Cell>> priv;  // per-chunk partial tables, kept between scans
+};
+
+namespace {
+
+tskv_status scan_with(orc_handle *H, const tskv_query *q, const tskv_tombstone *tombs, uint64_t n_tombs,
+                      int verify_crc, uint64_t *out_values, uint8_t *out_validity, uint64_t *out_points);
+
+}  // namespace
+
+extern "C" {
+
+tskv_status orc_open(const uint8_t *arena, uint64_t arena_len, const tskv_page_desc *descs, uint64_t n_descs,
+                     int n_threads, orc_handle **out) {
+  g_err.clear();
+  if (!out) return TSKV_ERR_INVALID_ARG;
+  orc_handle *H = new orc_handle{arena, arena_len, descs, n_descs, Index{}, n_threads, nullptr, {}};
+  tskv_status st = build_index(descs, n_descs, H->ix);
+  if (st != TSKV_OK) {
+    delete H;
+    return st;
+  }
+  if (n_threads > 1) H->pool = new Pool((unsigned)n_threads);
+  *out = H;
+  return TSKV_OK;
+}
+
+void orc_close(orc_handle *H) {
+  if (!H) return;
+  delete H->pool;
+  delete H;
+}
+
+tskv_status orc_scan(orc_handle *H, const tskv_query *q, const tskv_tombstone *tombs, uint64_t n_tombs, int verify_crc,
+                     uint64_t *out_values, uint8_t *out_validity, uint64_t *out_points) {
+  if (!H) return TSKV_ERR_INVALID_ARG;
+  return scan_with(H, q, tombs, n_tombs, verify_crc, out_values, out_validity, out_points);
+}
+
 tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
                                     const tskv_page_desc *descs, uint64_t n_descs, const tskv_query *q,
                                     const tskv_tombstone *tombs, uint64_t n_tombs,
                                     int verify_crc, int n_threads, uint64_t *out_values,
                                     uint8_t *out_validity, uint64_t *out_points) {
+  orc_handle *H = nullptr;
+  tskv_status st = orc_open(arena, arena_len, descs, n_descs, n_threads, &H);
+  if (st != TSKV_OK) return st;
+  st = orc_scan(H, q, tombs, n_tombs, verify_crc, out_values, out_validity, out_points);
+  orc_close(H);
+  return st;
+}
+
+}  // extern "C"
+
+namespace {
+
+tskv_status scan_with(orc_handle *H, const tskv_query *q, const tskv_tombstone *tombs, uint64_t n_tombs,
+                      int verify_crc, uint64_t *out_values, uint8_t *out_validity, uint64_t *out_points) {
   g_err.clear();
+  const tskv_page_desc *descs = H->descs;
+  const uint64_t n_descs = H->n_descs;
+  const Index &ix = H->ix;
+  const int n_threads = H->n_threads;
   tskv_output_layout L;
   tskv_status st = orc_query_output_layout(descs, n_descs, q, &L);
   if (st != TSKV_OK) return st;
-  Index ix;
-  st = build_index(descs, n_descs, ix);
-  if (st != TSKV_OK) return st;
-  Scan S{arena, arena_len, descs, q, verify_crc, &ix, {}, L.n_cells};
+  Scan S{H->arena, H->arena_len, descs, q, verify_crc, &ix, {}, L.n_cells};
   S.tombs = tombs;
   S.n_tombs = n_tombs;
   if (q->series_ids) {
@@ -435,8 +555,8 @@ tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
         g_err = "series_ids must be sorted ascending and unique";
         return TSKV_ERR_INVALID_ARG;
       }
-      S.slots.push_back(q->series_ids[i]);
     }
+    S.slots.assign(q->series_ids, q->series_ids + q->n_series);
   } else {
     S.slots = ix.series;
   }
@@ -444,7 +564,7 @@ tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
   uint64_t table = (uint64_t)q->n_columns * L.n_cells;
   std::vector<Cell> cells(table);
   uint64_t points = 0;
-  if (n_threads <= 1 || n_slots < 2) {
+  if (n_threads <= 1 || n_slots < 2 || !H->pool) {
     st = scan_slots(S, 0, n_slots, cells.data(), true, &points);
     if (st != TSKV_OK) return st;
   } else {
@@ -455,17 +575,17 @@ tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
     std::vector<tskv_status> sts(n_chunks, TSKV_OK);
     std::vector<uint64_t> pts(n_chunks, 0);
     std::vector<std::string> errs(n_chunks);
-    std::vector<std::vector<Cell>> priv;
-    if (!q->group_by_series) priv.assign(n_chunks, std::vector<Cell>(table));
-    std::vector<std::thread> th;
-    for (uint64_t k = 0; k < n_chunks; k++) {
-      th.emplace_back([&, k]() {
-        Cell *dst = q->group_by_series ? cells.data() : priv[k].data();  // disjoint cells per slot
-        sts[k] = scan_slots(S, k * cs, std::min(n_slots, (k + 1) * cs), dst, false, &pts[k]);
-        errs[k] = g_err;
-      });
+    std::vector<std::vector<Cell>> &priv = H->priv;
+    if (!q->group_by_series) {
+      if (priv.size() < n_chunks) priv.resize(n_chunks);
+      for (uint64_t k = 0; k < n_chunks; k++) priv[k].assign(table, Cell{});
     }
-    for (auto &t : th) t.join();
+    H->pool->run(n_chunks, [&](uint64_t k) {
+      g_err.clear();
+      Cell *dst = q->group_by_series ? cells.data() : priv[k].data();  // disjoint cells per slot
+      sts[k] = scan_slots(S, k * cs, std::min(n_slots, (k + 1) * cs), dst, false, &pts[k]);
+      errs[k] = g_err;
+    });
     for (uint64_t k = 0; k < n_chunks; k++) {
       if (sts[k] != TSKV_OK) {
         g_err = errs[k];
@@ -541,4 +661,4 @@ tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
   return TSKV_OK;
 }
 
-}  // extern "C"
+}  // namespace

@@ -80,6 +80,16 @@ tskv_status orc_scan_aggregate_tomb(const uint8_t *arena, uint64_t arena_len,
                                     const tskv_tombstone *tombs, uint64_t n_tombs,
                                     int verify_crc, int n_threads, uint64_t *out_values,
                                     uint8_t *out_validity, uint64_t *out_points /* may be NULL */);
+/* Handle API used by bench.py's CPU arms: `orc_open` builds the series index once (the reference keeps the
+ * TsmReader's chunk metadata cached after open: tsm/reader.rs:120-168, tsfamily/version.rs:158-172) and starts a
+ * persistent pool of n_threads workers; `orc_scan` is one query over the opened pages (same semantics and results
+ * as orc_scan_aggregate_tomb, which is now open + scan + close). The caller keeps arena / descs alive. */
+typedef struct orc_handle orc_handle;
+tskv_status orc_open(const uint8_t *arena, uint64_t arena_len, const tskv_page_desc *descs, uint64_t n_descs,
+                     int n_threads, orc_handle **out);
+tskv_status orc_scan(orc_handle *h, const tskv_query *q, const tskv_tombstone *tombs, uint64_t n_tombs,
+                     int verify_crc, uint64_t *out_values, uint8_t *out_validity, uint64_t *out_points);
+void orc_close(orc_handle *h);
 const char *orc_last_error(void);
 
 #ifdef __cplusplus
