@@ -35,6 +35,7 @@ TSKV_AGG_MEAN, TSKV_AGG_FIRST, TSKV_AGG_LAST, TSKV_AGG_ALL = 16, 32, 64, 0x7F
 AGG_NAMES = {1: "count", 2: "sum", 4: "min", 8: "max", 16: "mean", 32: "first", 64: "last"}
 TSKV_UPLOAD_VERIFY_CRC = 1
 TSKV_UPLOAD_HOST_RESIDENT = 2
+TSKV_UPLOAD_VERIFY_ON_READ = 4
 
 # numpy view of tskv_page_desc (24 bytes)
 PAGE_DESC_DTYPE = np.dtype(
@@ -44,6 +45,7 @@ assert PAGE_DESC_DTYPE.itemsize == 24
 
 # numpy view of tskv_tombstone (24 bytes); series_id / column_id = TSKV_TOMB_ALL: see include/tskv_gpu.h
 TSKV_TOMB_ALL = 0xFFFFFFFF
+TSKV_QUERY_MULTI_RANK = 1
 TOMBSTONE_DTYPE = np.dtype([("series_id", "<u4"), ("column_id", "<u4"), ("min_ts", "<i8"), ("max_ts", "<i8")], align=False)
 assert TOMBSTONE_DTYPE.itemsize == 24
 

@@ -492,6 +492,7 @@ __device__ __forceinline__ void scan_page_coop(const ScanParams &P, const CoopPa
           }
         }
         const uint64_t cell = group_base + key;
+        va.fold(pt);
         if (va.count) table_update(P, stab, cs, cell, mask, VK == VK_GOR, va.count, va.sum, va.sum_hi, va.kmin, va.kmax);
         if (SEL) {
           const int64_t te = TK == TK_RLE ? (int64_t)(t_first + (uint64_t)(re - 1) * t_delta) : (int64_t)S.ts[cpad(re - 1)];

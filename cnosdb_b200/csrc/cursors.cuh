@@ -80,38 +80,53 @@ static_assert((RING_CHUNKS & (RING_CHUNKS - 1)) == 0 && RING_CHUNKS >= 4, "ring 
 struct ChunkRing {
   const uint8_t *gnext;  // global address of the next chunk to issue (16-byte aligned)
   uint32_t sbase;        // shared-space address of this lane's slot of ring position 0
-  uint32_t n_chunks;     // chunks that intersect [start, end)
-  uint32_t issued;       // chunks handed to cp.async so far
+  uint32_t snext;        // ring offset (bytes) of the slot the next chunk goes to
+  uint32_t trig;         // the next chunk is issued once the read window reaches chunk `trig` (0xffffffff: page fully issued)
+  uint32_t left;         // chunks of the page not yet issued
   __device__ __forceinline__ void issue_one() {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                 :: "r"(sbase + ((issued & (RING_CHUNKS - 1)) << 9)), "l"(gnext) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sbase + snext), "l"(gnext) : "memory");
     gnext += 16;
-    issued++;
+    snext = (snext + 512) & (RING_CHUNKS * 512 - 1);
+    left--;
   }
   __device__ __forceinline__ void init(const uint8_t *start, const uint8_t *end, uint32_t lane_slot) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15;
     gnext = reinterpret_cast<const uint8_t *>(a);
     const uintptr_t e = reinterpret_cast<uintptr_t>(end);
-    n_chunks = e > a ? (uint32_t)((e - a + 15) >> 4) : 0u;
+    left = e > a ? (uint32_t)((e - a + 15) >> 4) : 0u;
     sbase = lane_slot;
-    issued = 0;
+    snext = 0;
 #pragma unroll
     for (int i = 0; i < RING_CHUNKS; i++)
-      if (issued < n_chunks) issue_one();
+      if (left) issue_one();
+    trig = left ? 1u : 0xffffffffu;  // chunk RING_CHUNKS goes out when the window reaches chunk 1
   }
   // One decoder step whose read window starts in chunk c (see above).
   __device__ __forceinline__ void step(uint32_t c) {
-    if (issued < c + RING_CHUNKS && issued < n_chunks) issue_one();
+    if (c >= trig) {
+      issue_one();
+      trig = left ? trig + 1 : 0xffffffffu;
+    }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group %0;\n" :: "n"(RING_CHUNKS - 2) : "memory");
   }
   // An empty ring: steps issue nothing, reads return stale shared memory (lanes without a page / kinds without a stream).
-  __device__ __forceinline__ void reset(uint32_t lane_slot) { gnext = nullptr; sbase = lane_slot; n_chunks = 0; issued = 0; }
-  // 64-bit word k of the stream (8-byte units from the aligned start), as stored (little-endian load of stream bytes)
-  __device__ __forceinline__ uint2 word(uint32_t k) const {
+  __device__ __forceinline__ void reset(uint32_t lane_slot) { gnext = nullptr; sbase = lane_slot; snext = 0; trig = 0xffffffffu; left = 0; }
+  // shared-space address of the chunk holding 64-bit word k (8-byte units from the aligned start)
+  __device__ __forceinline__ uint32_t chunk_addr(uint32_t k) const { return sbase + ((k & (2 * RING_CHUNKS - 2)) << 8); }
+  static __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n"
-                 : "=r"(v.x), "=r"(v.y) : "r"(sbase + (((k >> 1) & (RING_CHUNKS - 1)) << 9) + ((k & 1) << 3)) : "memory");
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
+  }
+  // 64-bit word k of the stream, as stored (little-endian load of stream bytes)
+  __device__ __forceinline__ uint2 word(uint32_t k) const { return lds64(chunk_addr(k) + ((k & 1) << 3)); }
+  // words k, k + 1, k + 2 (they span two chunks)
+  __device__ __forceinline__ void words3(uint32_t k, uint2 &w0, uint2 &w1, uint2 &w2) const {
+    const uint32_t c0 = chunk_addr(k), c1 = chunk_addr(k + 2);
+    const bool odd = k & 1;
+    w0 = lds64(odd ? c0 + 8 : c0);
+    w1 = lds64(odd ? c1 : c0 + 8);
+    w2 = lds64(odd ? c1 + 8 : c1);
   }
 };
 // Commits the initial fills of the lane's rings and waits for them (once per page, before the first step).
@@ -121,26 +136,31 @@ __device__ __forceinline__ void ring_drain() { asm volatile("cp.async.commit_gro
 // Same interface as BeStream.
 struct SeqStream {
   ChunkRing ring;
-  uint32_t k;    // index of the last aligned word loaded
-  uint32_t sh;   // misalignment in bits
-  uint64_t cur;  // last aligned word, little-endian
+  uint32_t k;     // index of the last aligned word loaded
+  uint32_t psel;  // byte-permute selector: the big-endian word at the stream's (constant) byte misalignment
+  bool high;      // the misalignment is >= 4 bytes
+  uint2 cur;      // last aligned word, as stored
   __device__ __forceinline__ void init(const uint8_t *p, uint32_t lane_slot, const uint8_t *end) {
     ring.init(p, end, lane_slot);
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    sh = (uint32_t)(a & 7) * 8;
+    const uint32_t o = (uint32_t)(a & 7), q = o & 3;
+    high = o >= 4;
+    psel = (q + 3) | ((q + 2) << 4) | ((q + 1) << 8) | (q << 12);  // result byte 3 (most significant) = stream byte q
     k = (uint32_t)(a & 15) >> 3;
-    cur = __ldg(reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7));  // the first word straight from global memory
+    const uint64_t w = __ldg(reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7));  // the first word straight from global memory
+    cur = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
   }
   __device__ __forceinline__ uint64_t next() {
     k++;
     ring.step(k >> 1);
-    const uint2 w = ring.word(k);
-    const uint64_t nxt = ((uint64_t)w.y << 32) | w.x;
-    const uint64_t raw = (cur >> sh) | ((nxt << 1) << (63 - sh));
+    const uint2 nxt = ring.word(k);
+    // bytes o .. o + 7 of (cur, nxt), most significant first: two byte permutes over three of the four 32-bit words
+    const uint32_t a = high ? cur.y : cur.x, b = high ? nxt.x : cur.y, c = high ? nxt.y : nxt.x;
+    const uint32_t hi = __byte_perm(a, b, psel), lo = __byte_perm(b, c, psel);
     cur = nxt;
-    return bswap64(raw);
+    return ((uint64_t)hi << 32) | lo;
   }
-  __device__ __forceinline__ void reset(uint32_t lane_slot = 0) { ring.reset(lane_slot); k = 0; sh = 0; cur = 0; }
+  __device__ __forceinline__ void reset(uint32_t lane_slot = 0) { ring.reset(lane_slot); k = 0; psel = 0x0123; high = false; cur = make_uint2(0, 0); }
 };
 
 __device__ __forceinline__ uint64_t load_be64(const uint8_t *p) {
@@ -510,7 +530,8 @@ struct GorillaRing {
   __device__ __forceinline__ void step() {
     ring.step(pos >> 7);
     const uint32_t k = pos >> 6;
-    const uint2 w0 = ring.word(k), w1 = ring.word(k + 1), w2 = ring.word(k + 2);
+    uint2 w0, w1, w2;
+    ring.words3(k, w0, w1, w2);
     const bool up = pos & 32;  // the window starts in the upper half of w0
     const uint32_t a0 = __byte_perm(up ? w0.y : w0.x, 0, 0x0123), a1 = __byte_perm(up ? w1.x : w0.y, 0, 0x0123),
                    a2 = __byte_perm(up ? w1.y : w1.x, 0, 0x0123), a3 = __byte_perm(up ? w2.x : w1.y, 0, 0x0123);

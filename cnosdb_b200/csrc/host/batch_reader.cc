@@ -8,6 +8,8 @@ namespace tskv {
 namespace reader {
 
 namespace {
+// dense results above this many buckets are refused (2^24 buckets x 8 bytes per output column)
+constexpr uint64_t kMaxBuckets = 1ull << 24;
 const char *agg_name(AggregateKind k) {
   switch (k) {
     case AggregateKind::Count: return "count";
@@ -123,12 +125,19 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
   q.time_ranges = ranges.data();
   q.n_time_ranges = (uint32_t)ranges.size();
   q.n_buckets = 1;
-  if (option_.bucket && option_.bucket->width > 0 && scan_range.min_ts <= scan_range.max_ts) {
+  if (scan_range.min_ts > scan_range.max_ts) return out;  // the query ranges miss the data: an empty stream, like the pruned path
+  if (option_.bucket && option_.bucket->width > 0) {
     q.origin = option_.bucket->origin;
     q.width = option_.bucket->width;
     q.first_bucket_start = window_start(scan_range.min_ts, q.width, q.origin);
-    int64_t last = window_start(scan_range.max_ts, q.width, q.origin);
-    q.n_buckets = (uint32_t)((last - q.first_bucket_start) / q.width + 1);
+    const int64_t last = window_start(scan_range.max_ts, q.width, q.origin);
+    // bucket count in 128-bit arithmetic: (last - first) can exceed the i64 range, the count the u32 of the ABI
+    const __int128 n = ((__int128)last - (__int128)q.first_bucket_start) / q.width + 1;
+    if (n < 1 || n > (__int128)kMaxBuckets) {
+      out.error = {TSKV_ERR_INVALID_ARG, "bucket expression yields too many buckets for a dense result", -1};
+      return out;
+    }
+    q.n_buckets = (uint32_t)n;
   }
   q.group_by_series = option_.group_by_series ? 1 : 0;
   q.columns = cols.data();

@@ -2,6 +2,8 @@
 #include "host_util.h"
 
 #include <algorithm>
+#include <cmath>
+#include <vector>
 #include <mutex>
 
 namespace tskv {
@@ -60,6 +62,37 @@ uint32_t plan_gorilla_group(double est_gorilla_pages, double resident_warps) {
   uint32_t g = 1;
   while (g < 32 && est_gorilla_pages / g > 0.75 * resident_warps) g *= 2;
   return g;
+}
+
+void plan_serial_grids(int n_bins, const double *chunks, const double *t_chunk, const int *occ, int sm_count,
+                       int warps_per_block, int *grid_out) {
+  std::vector<double> cand;
+  for (int b = 0; b < n_bins; b++) {
+    grid_out[b] = 0;
+    if (chunks[b] <= 0) continue;
+    for (int k = 1; k <= 64; k++) cand.push_back(k * t_chunk[b]);
+  }
+  if (cand.empty()) return;
+  std::sort(cand.begin(), cand.end());
+  auto blocks_for = [&](int b, double T) -> double {
+    const double rounds = std::floor(T / t_chunk[b] + 1e-9);
+    if (rounds < 1) return -1;
+    return std::ceil(chunks[b] / (rounds * warps_per_block));
+  };
+  double best = cand.back();
+  for (double T : cand) {
+    double sm_used = 0;
+    bool ok = true;
+    for (int b = 0; b < n_bins && ok; b++) {
+      if (chunks[b] <= 0) continue;
+      const double n = blocks_for(b, T);
+      if (n < 0) ok = false;
+      else sm_used += n / std::max(1, occ[b]);
+    }
+    if (ok && sm_used <= sm_count) { best = T; break; }
+  }
+  for (int b = 0; b < n_bins; b++)
+    if (chunks[b] > 0) grid_out[b] = std::max(1, (int)std::max(1.0, blocks_for(b, best)));
 }
 
 bool parse_page(const uint8_t *page, uint64_t size, PageHeader *h) {

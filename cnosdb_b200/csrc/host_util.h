@@ -41,6 +41,14 @@ bool plan_use_cooperative(double est_selected_pages, int sm_count, int min_block
 // Pages per warp task of the cooperative gorilla bins: the smallest power of two that fits the tasks in 3/4 of the
 // resident warps (measured best on 1/8 of C4: 4).
 uint32_t plan_gorilla_group(double est_gorilla_pages, double resident_warps);
+// Grid sizes of the lane-per-page kernels of one scan (one persistent kernel per decode-kind bin, all launched
+// concurrently; a warp repeatedly takes a chunk of 32 pages of its bin). A chunk is ONE serial task of t_chunk[b]
+// (relative units: rows x cost of the bin's codec pair), so a bin finishes after ceil(chunks / warps) rounds of
+// t_chunk: the makespan is quantised. Picks the smallest makespan T for which giving every bin
+// ceil(chunks_b / (floor(T / t_b) * warps_per_block)) blocks fits the machine, sum_b blocks_b / occ_b <= sm_count
+// (a block of bin b takes 1/occ_b of an SM). Bins with chunks[b] == 0 get 0 blocks.
+void plan_serial_grids(int n_bins, const double *chunks, const double *t_chunk, const int *occ, int sm_count,
+                       int warps_per_block, int *grid_out);
 
 uint8_t classify_page(const PageHeader &h, uint8_t phys_type);
 

@@ -6,7 +6,7 @@
 //       (replaces ColumnGroupReader::read + decode_pages + DataFilter + the DataFusion
 //        projection/AggregateExec above the scan; SURVEY.md §3.1 hot loops A, B and C)
 //   k_export_pairs / k_mask_values / k_finalize : partial state -> dense Arrow-style result
-//   k_decode_pages : decode-only (Page::to_arrow_array, tsm/reader.rs:658-731)
+//   (decode-only, Page::to_arrow_array: decode_kernels.cuh)
 #pragma once
 #include "cursors.cuh"
 
@@ -156,13 +156,22 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_p
       } else {
         sel = true;
         unsigned long long bytes = d.size, pages = 1;
-        // the time page of a column group is read once: charge it to the group's first selected
-        // field page (field pages of a group are contiguous after the time page)
+        // The time page of a column group is brought along (PCIe gather, CRC check, byte counters) by the first selected
+        // field page of the group IN EACH DECODE-KIND BIN: the bins' gathers and fused kernels run on different streams,
+        // so a bin must not rely on another bin having copied the time page (a series with an i64 and an f64 field
+        // selected together lands in two bins). Field pages of a group are contiguous after the time page and share its
+        // time class, so "same bin" is "same value class".
+        // The reader metrics (page_read_count / page_read_bytes) count the time page once per column group.
         uint32_t tp = cg_time_page[cg];
         first_sel = true;
+        bool first_in_group = true;
+        const int vclass = value_class(d.reserved);
         for (uint32_t q = tp + 1; q < p; q++)
-          if (find_qcol(cols, n_cols, descs[q].column_id) >= 0) { first_sel = false; break; }
-        if (first_sel) { bytes += descs[tp].size; pages += 1; }
+          if (find_qcol(cols, n_cols, descs[q].column_id) >= 0) {
+            first_in_group = false;
+            if (value_class(descs[q].reserved) == vclass) { first_sel = false; break; }
+          }
+        if (first_in_group) { bytes += descs[tp].size; pages += 1; }
         int bin = 0;
         for (int k = 1; k < N_BINS; k++) bin += (i >= bin_start[k]) ? 1 : 0;
         atomicAdd(&s_bytes[bin], bytes);
@@ -818,23 +827,34 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
 template <int VK>
 struct ValueAcc {  // count / sum / min / max of one run; VK fixes the arithmetic at compile time
   uint32_t count;
-  uint64_t sum;
-  int64_t sum_hi;
+  uint64_t sum;    // f64: the sum's bits. Integers, while accumulating: sum of the values' LOW 32-bit halves
+  int64_t sum_hi;  // integers, while accumulating: sum of the HIGH halves (sign- / zero-extended); see fold()
   int64_t kmin, kmax;
   __device__ __forceinline__ void reset() { count = 0; sum = 0; sum_hi = 0; kmin = INT64_MAX; kmax = INT64_MIN; }
-  // pt / flip / mean_hi are per-lane constants (flip = okey's xor mask for integer columns)
-  __device__ __forceinline__ void add(uint64_t v, uint8_t pt, uint64_t flip, bool mean_hi) {
+  // pt / flip are per-lane constants (flip = okey's xor mask for integer columns).
+  // Integer sums are kept as two 64-bit accumulators of 32-bit halves: exact for 2^32 rows without any carry
+  // bookkeeping per value (the wrapping SUM and the exact 128-bit sum MEAN needs both fall out of fold()).
+  __device__ __forceinline__ void add(uint64_t v, uint8_t pt, uint64_t flip, bool /*mean_hi*/ = false) {
     int64_t key;
     if (VK == VK_GOR || (VK == VK_GEN && pt == TSKV_PT_F64)) {
       sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)v));
       key = (int64_t)(v ^ (uint64_t)(((int64_t)v >> 63) & 0x7fffffffffffffffll));
     } else {
-      sum += v;
-      if (mean_hi) sum_hi += (sum < v ? 1 : 0) + (pt == TSKV_PT_I64 ? ((int64_t)v >> 63) : 0);
+      sum += (uint32_t)v;
+      sum_hi += pt == TSKV_PT_I64 ? (int64_t)(int32_t)(v >> 32) : (int64_t)(v >> 32);
       key = (int64_t)(v ^ flip);
     }
     kmin = key < kmin ? key : kmin;
     kmax = key > kmax ? key : kmax;
+  }
+  // End of the run: integers -> (sum, sum_hi) = low / high word of the exact 128-bit sum (sum = the reference's wrapping
+  // i64 / u64 SUM). Call once, right before the partial is handed to a flush.
+  __device__ __forceinline__ void fold(uint8_t pt) {
+    if (VK == VK_GOR || (VK == VK_GEN && pt == TSKV_PT_F64)) return;
+    const uint64_t x = (uint64_t)sum_hi << 32;
+    const uint64_t lo = x + sum;
+    sum_hi = (pt == TSKV_PT_I64 ? (sum_hi >> 32) : (int64_t)((uint64_t)sum_hi >> 32)) + (lo < x ? 1 : 0);
+    sum = lo;
   }
 };
 
@@ -865,8 +885,9 @@ __device__ __forceinline__ void reduce_staged(const ScanParams &P, uint64_t *sta
   uint64_t cnt = 0, sum = 0;
   int64_t hi = 0, kmin = INT64_MAX, kmax = INT64_MIN;
   const uint64_t *base = stage + (size_t)s * FLUSH_Q * 32;
+  static_assert(FLUSH_SLOTS == 4, "reduce_staged: 8 lane groups x 4 source lanes");
 #pragma unroll
-  for (int i = 0; i < 32 / (32 / FLUSH_SLOTS); i++) {  // 4 source lanes per group, rotated by the slot: conflict-free
+  for (int i = 0; i < 4; i++) {  // 4 source lanes per group, rotated by the slot: conflict-free
     const uint32_t src = g * 4 + ((i + s) & 3);
     const uint64_t c = base[src], v = base[32 + src];
     cnt += c;
@@ -884,11 +905,13 @@ __device__ __forceinline__ void reduce_staged(const ScanParams &P, uint64_t *sta
   for (int o = FLUSH_SLOTS; o < 32; o <<= 1) {  // lanes j, j ^ o own the same slot
     cnt += shfl_xor_u64(cnt, o);
     const uint64_t v = shfl_xor_u64(sum, o);
+    // (every shuffle outside the is_f64 branch: slots of a generic-kind warp can hold columns of different types)
+    const int64_t vh = VK != VK_GOR ? (int64_t)shfl_xor_u64((uint64_t)hi, o) : 0;
     if (is_f64) {
       sum = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sum) + __longlong_as_double((long long)v));
     } else {
       sum += v;
-      if (VK != VK_GOR) hi += (int64_t)shfl_xor_u64((uint64_t)hi, o) + (sum < v ? 1 : 0);
+      if (VK != VK_GOR) hi += vh + (sum < v ? 1 : 0);
     }
     const int64_t a = (int64_t)shfl_xor_u64((uint64_t)kmin, o), b = (int64_t)shfl_xor_u64((uint64_t)kmax, o);
     kmin = a < kmin ? a : kmin;
@@ -1019,13 +1042,13 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   uint32_t row = 0;
   uint32_t n_points = 0, n_inrange = 0;
   uint32_t vword = 0, vahead = vbm ? __ldg(vbm) : 0;  // bitmap word of `row`, and the next one (prefetched)
-  const bool mean_hi = VK != VK_GOR && pt != TSKV_PT_F64 && (mask & TSKV_AGG_MEAN);
   const uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull : 0ull;
   const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
   uint32_t staged = 0;  // staged flush slots in use (warp-uniform)
 
   // Finished runs of the flushing lanes -> partial tables.
   auto flush_now = [&](bool flush) {
+    if (flush) va.fold(pt);
     if (SEL) {
       if (__any_sync(FULL, flush)) {
         acc.count = va.count; acc.sum = va.sum; acc.sum_hi = va.sum_hi; acc.kmin = va.kmin; acc.kmax = va.kmax;
@@ -1035,60 +1058,36 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
       flush_runs<VK>(P, stab, stage, staged, flush, qcol, group_base + run_idx, pt, mask, va);
     }
   };
-  // Values of the segment rows [row, row + n), one bitmap word at a time. Every valid row is decoded - rows outside the
-  // time ranges too, the streams are sequential - and accumulated when the segment is selected. One loop for dense and
-  // sparse bitmaps: a warp holds pages of both kinds and would otherwise run both variants.
-  auto seg_values = [&](uint32_t n, bool seg_in, bool seg_masked, bool newrun, int64_t seg_first_t, int64_t seg_last_t) {
-    uint32_t r = row;
-    const uint32_t rend = row + n;
-    const bool accumulate = seg_in && !seg_masked;
-    while (r < rend) {
-      if ((r & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
-        vword = vahead;
-        vahead = __ldg(vbm + (r >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
-      }
-      const uint32_t off = r & 31;
-      const uint32_t span = min(32u - off, rend - r);
-      const uint32_t m = allnull ? 0u : ((vword >> off) & (0xffffffffu >> (32 - span)));
-      n_points += __popc(m);
-      if (!SEL) {
-        if (accumulate) va.count += __popc(m);
-#pragma unroll 1
-        for (uint32_t j = 0; j < span; j++) {
-          if ((m >> j) & 1) {
-            const uint64_t v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-            if (accumulate) va.add(v, pt, flip, mean_hi);
-          }
-        }
-      } else {  // FIRST / LAST wanted: the run's end rows keep (ts, value, valid)
-        for (uint32_t j = 0; j < span; j++) {
-          bool vv = (m >> j) & 1;
-          uint64_t v = 0;
-          if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-          vv = vv && !seg_masked;
-          if (seg_in) {
-            if (r + j == row && newrun) { acc.first_ts = seg_first_t; acc.first_val = vv ? v : 0; acc.first_ok = vv; }
-            if (r + j == rend - 1) { acc.last_ts = seg_last_t; acc.last_val = vv ? v : 0; acc.last_ok = vv; }
-            if (vv) { va.count++; va.add(v, pt, flip, mean_hi); }
-          }
-        }
-      }
-      r += span;
+  // One row's value: validity bit, decode (every valid row is decoded - rows outside the time ranges too, the streams
+  // are sequential), accumulate when the segment is selected. Returns the value; `vv` = the row holds one.
+  auto row_value = [&](bool accumulate, bool &vv) -> uint64_t {
+    if ((row & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
+      vword = vahead;
+      vahead = __ldg(vbm + (row >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
     }
+    vv = ((vword >> (row & 31)) & 1) && !allnull;
+    uint64_t v = 0;
+    if (vv) {
+      v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+      n_points++;
+      if (accumulate) { va.count++; va.add(v, pt, flip); }
+    }
+    return v;
+  };
+  auto check_values = [&]() {
     const bool bad = VK == VK_GOR ? vcur_g.failed() : vcur_d.exhausted;
     if (bad) {
       report_error(P, (VK == VK_GOR && vcur_g.overran()) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
       n_rows = 0;
       have_run = false;
     }
-    row = rend;
   };
 
   // ---- RLE timestamps, increasing, at most one time range, no tombstones: the segment structure is arithmetic in the
   // ROW index. Rows [ra, rb1) are inside the range; bucket edges advance by q or q + 1 rows (w = q * delta + rem, the
   // offset e of a bucket's first row inside it decides), so a segment costs a handful of 32-bit operations instead of
   // 64-bit interval arithmetic per segment. Anything else (wrapping / constant timestamps, several ranges, tombstones,
-  // the reference's truncating-% regime for negative dividends, values near the i64 limits) takes the general loop.
+  // the reference's truncating-% regime for negative dividends, values near the i64 limits) takes the general logic.
   uint32_t ra = 0, rb1 = 0, nb = 0xffffffffu, q32 = 0, bidx = 0;
   uint64_t e_off = 0, w_rem = 0;
   bool fast = false;
@@ -1110,7 +1109,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
         if (P.width > 0 && ra < rb1) {
           const int64_t tr = (int64_t)(rle_t0 + (uint64_t)ra * rle_delta);
           if ((int64_t)((uint64_t)tr - (uint64_t)P.origin_mod + (uint64_t)P.width) < 0) {
-            elig = false;  // truncating-% regime (time_window.rs:184-198): general loop
+            elig = false;  // truncating-% regime (time_window.rs:184-198): general logic
           } else if (!locate_bucket(P, tr, bk)) {
             report_error(P, TSKV_ERR_BUCKET_RANGE, page);
             n_rows = 0;
@@ -1127,15 +1126,29 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     fast = __all_sync(FULL, elig);
   }
 
-  if (TK == TK_RLE && fast) {
-    for (;;) {
-      const bool has = row < n_rows;
-      if (!__any_sync(FULL, has || have_run)) break;
-      uint32_t n = 0;
-      bool seg_in = false;
-      if (has) {
-        if (row < ra) n = ra - row;
-        else if (row >= rb1) n = n_rows - row;
+  // The warp walks its 32 pages SEGMENT by segment (a segment = rows of one page sharing (selected, bucket)), and for
+  // GROUP BY bucket it keeps the lanes aligned on the BUCKET: in every iteration only the lanes whose next selected
+  // segment lies in the smallest pending bucket go ahead (the others keep their segment pending, at most an iteration
+  // or two). Pages whose first row falls just before a bucket edge would otherwise run one segment ahead of their
+  // neighbours for the whole page, no two lanes would ever finish a run for the same cell in the same iteration, and
+  // every flush would degenerate into 32 contended atomics instead of one staged store per lane.
+  const bool align = P.width > 0 && !P.group_by_series;
+  bool pending = false;
+  uint32_t seg_n = 0, seg_b = 0;  // pending segment: rows (RLE pages), bucket
+  bool seg_in = false, seg_masked = false;
+  int64_t lim_lo = 0, lim_hi = 0;  // pending segment (simple8b timestamps): closed interval its rows stay in
+  for (;;) {
+    const bool has = row < n_rows;
+    if (!__any_sync(FULL, has || have_run)) break;
+    // ---- 1. attributes of the next segment ------------------------------------------------------------
+    if (has && !pending) {
+      pending = true;
+      seg_in = false;
+      seg_masked = false;
+      seg_n = 0;
+      if (TK == TK_RLE && fast) {
+        if (row < ra) seg_n = ra - row;
+        else if (row >= rb1) seg_n = n_rows - row;
         else {
           seg_in = true;
           while (nb == 0) {  // next bucket (one narrower than the step may hold no row at all)
@@ -1147,101 +1160,144 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
             report_error(P, TSKV_ERR_BUCKET_RANGE, page);
             seg_in = false;
             n_rows = row;
+            pending = false;
           } else {
-            n = min(nb, rb1 - row);
-            if (P.width > 0) nb -= n;
+            seg_n = min(nb, rb1 - row);
+            seg_b = bidx;
+            if (P.width > 0) nb -= seg_n;
+          }
+        }
+      } else {
+        lim_lo = lim_hi = pend_t;
+        seg_in = range_span(P, pend_t, lim_lo, lim_hi);
+        if (P.has_tomb) {  // decode_pages' tombstone handling (reader.rs:507-551) as two more segment attributes
+          const uint4 tl = s_tomb[threadIdx.x];
+          const bool dropped = tomb_span(P.tomb_ranges, P.n_tomb_global, pend_t, lim_lo, lim_hi) |
+                               tomb_span(P.tomb_ranges + tl.x, tl.y, pend_t, lim_lo, lim_hi);
+          seg_masked = tomb_span(P.tomb_ranges + tl.z, tl.w, pend_t, lim_lo, lim_hi);
+          if (dropped) seg_in = false;
+        }
+        if (seg_in) {
+          if (!(bk.valid && pend_t >= bk.lo && pend_t <= bk.hi) && !locate_bucket(P, pend_t, bk)) {
+            report_error(P, TSKV_ERR_BUCKET_RANGE, page);
+            seg_in = false;
+            bk.valid = false;
+            lim_lo = lim_hi = pend_t;
+          } else {
+            lim_lo = lim_lo > bk.lo ? lim_lo : bk.lo;
+            lim_hi = lim_hi < bk.hi ? lim_hi : bk.hi;
+            seg_b = bk.idx;
+          }
+        }
+        if (TK == TK_RLE) {  // the segment's row count: closed form, or a walk for constant / wrapping timestamps
+          const uint32_t left = n_rows - row;
+          if ((int64_t)rle_delta > 0) {
+            seg_n = rle_rows_within((uint64_t)lim_hi - (uint64_t)pend_t, rle_delta, rle_inv, left);
+          } else {
+            int64_t t = pend_t;
+            do {
+              seg_n++;
+              t = (int64_t)((uint64_t)t + rle_delta);
+            } while (seg_n < left && t >= lim_lo && t <= lim_hi);
           }
         }
       }
-      if (seg_in) n_inrange += n;
-      const bool newrun = seg_in && (!have_run || bidx != run_idx);
-      const bool flush = have_run && (newrun || !has);
-      flush_now(flush);
-      if (flush) have_run = false;
-      if (newrun) {
-        have_run = true;
-        run_idx = bidx;
-        va.reset();
-      }
-      if (n) {
-        int64_t ft = 0, lt = 0;
-        if (SEL) {
-          ft = (int64_t)(rle_t0 + (uint64_t)row * rle_delta);
-          lt = (int64_t)(rle_t0 + (uint64_t)(row + n - 1) * rle_delta);
-        }
-        seg_values(n, seg_in, false, newrun, ft, lt);
-      }
     }
-  } else {
-  for (;;) {
-    const bool has = row < n_rows;
-    if (!__any_sync(FULL, has || have_run)) break;
-    // ---- 1. next segment: rows [row, row + n) share (selected, bucket) --------------------------
-    uint32_t n = 0;
-    bool seg_in = false;
-    bool seg_masked = false;  // tombstoned column range: the rows stay, their values read as NULL
-    int64_t seg_first_t = pend_t, seg_last_t = pend_t;
-    int64_t lim_lo = pend_t, lim_hi = pend_t;
-    if (has) {
-      seg_in = range_span(P, pend_t, lim_lo, lim_hi);
-      if (P.has_tomb) {  // decode_pages' tombstone handling (reader.rs:507-551) as two more segment attributes
-        const uint4 tl = s_tomb[threadIdx.x];
-        const bool dropped = tomb_span(P.tomb_ranges, P.n_tomb_global, pend_t, lim_lo, lim_hi) |
-                             tomb_span(P.tomb_ranges + tl.x, tl.y, pend_t, lim_lo, lim_hi);
-        seg_masked = tomb_span(P.tomb_ranges + tl.z, tl.w, pend_t, lim_lo, lim_hi);
-        if (dropped) seg_in = false;
-      }
-      if (seg_in) {
-        if (!(bk.valid && pend_t >= bk.lo && pend_t <= bk.hi) && !locate_bucket(P, pend_t, bk)) {
-          report_error(P, TSKV_ERR_BUCKET_RANGE, page);
-          seg_in = false;
-          bk.valid = false;
-          lim_lo = lim_hi = pend_t;
-        } else {
-          lim_lo = lim_lo > bk.lo ? lim_lo : bk.lo;
-          lim_hi = lim_hi < bk.hi ? lim_hi : bk.hi;
-        }
-      }
-      const uint32_t left = n_rows - row;
-      if (TK == TK_RLE) {
-        if ((int64_t)rle_delta > 0) {  // increasing: the segment ends where t passes lim_hi - closed form
-          n = rle_rows_within((uint64_t)lim_hi - (uint64_t)pend_t, rle_delta, rle_inv, left);
-          seg_last_t = (int64_t)((uint64_t)pend_t + (uint64_t)(n - 1) * rle_delta);
-          pend_t = (int64_t)((uint64_t)seg_last_t + rle_delta);
-        } else {  // constant or wrapping ("descending") timestamps: walk the rows
-          int64_t t = pend_t;
-          do {
-            n++;
-            seg_last_t = t;
-            t = (int64_t)((uint64_t)t + rle_delta);
-          } while (n < left && t >= lim_lo && t <= lim_hi);
-          pend_t = t;
-        }
-      } else {  // look ahead through the time ring: t = timestamp of row + n
-        int64_t t = pend_t;
-        do {
-          n++;
-          seg_last_t = t;
-          t = (int64_t)tcur.next();
-        } while (n < left && t >= lim_lo && t <= lim_hi);
-        pend_t = t;  // (past the last row: the next() above ran one value too far - harmless)
-        if (tcur.exhausted && n < left) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row + n; }
-      }
+    // ---- 2. bucket alignment, run bookkeeping, flush ------------------------------------------------------
+    bool go = pending;
+    if (align) {
+      const uint32_t bmin = __reduce_min_sync(FULL, (pending && seg_in) ? seg_b : 0xffffffffu);
+      go = pending && (!seg_in || seg_b == bmin);
     }
-    if (seg_in) n_inrange += n;
-    // ---- 2. flush the finished run (warp-converged) ----------------------------------------------
-    const bool newrun = has && seg_in && (!have_run || bk.idx != run_idx);
+    const bool newrun = go && seg_in && (!have_run || seg_b != run_idx);
     const bool flush = have_run && (newrun || !has);
     flush_now(flush);
     if (flush) have_run = false;
     if (newrun) {
       have_run = true;
-      run_idx = bk.idx;
+      run_idx = seg_b;
       va.reset();
     }
-    // ---- 3. values of the segment ------------------------------------------------------------------
-    if (has) seg_values(n, seg_in, seg_masked, newrun, seg_first_t, seg_last_t);
-  }
+    // ---- 3. the segment's rows --------------------------------------------------------------------------
+    if (go) {
+      pending = false;
+      const bool accumulate = seg_in && !seg_masked;
+      if (TK == TK_RLE) {
+        // the row count is known: values one bitmap word at a time (no per-row timestamp, no per-row bitmap fetch)
+        const uint32_t rend = row + seg_n, row0 = row;
+        if (seg_in) n_inrange += seg_n;
+        uint32_t r = row;
+        while (r < rend) {
+          if ((r & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
+            vword = vahead;
+            vahead = __ldg(vbm + (r >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
+          }
+          const uint32_t off = r & 31;
+          const uint32_t span = min(32u - off, rend - r);
+          const uint32_t m = allnull ? 0u : ((vword >> off) & (0xffffffffu >> (32 - span)));
+          n_points += __popc(m);
+          if (!SEL) {  // one loop for dense and sparse bitmaps: a warp holds pages of both kinds
+            if (accumulate) va.count += __popc(m);
+#pragma unroll 1
+            for (uint32_t j = 0; j < span; j++) {
+              if ((m >> j) & 1) {
+                const uint64_t v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+                if (accumulate) va.add(v, pt, flip);
+              }
+            }
+          } else {  // FIRST / LAST wanted: the run's end rows keep (ts, value, valid)
+            for (uint32_t j = 0; j < span; j++) {
+              bool vv = (m >> j) & 1;
+              uint64_t v = 0;
+              if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
+              vv = vv && !seg_masked;
+              if (seg_in) {
+                if (r + j == row0 && newrun) {
+                  acc.first_ts = (int64_t)(rle_t0 + (uint64_t)row0 * rle_delta);
+                  acc.first_val = vv ? v : 0;
+                  acc.first_ok = vv;
+                }
+                if (r + j == rend - 1) {
+                  acc.last_ts = (int64_t)(rle_t0 + (uint64_t)(rend - 1) * rle_delta);
+                  acc.last_val = vv ? v : 0;
+                  acc.last_ok = vv;
+                }
+                if (vv) { va.count++; va.add(v, pt, flip); }
+              }
+            }
+          }
+          r += span;
+        }
+        row = rend;
+        if (!(TK == TK_RLE && fast)) pend_t = (int64_t)(rle_t0 + (uint64_t)rend * rle_delta);
+      } else {
+        // simple8b timestamps: ONE loop decodes the row's value and the NEXT row's timestamp - two independent dependent
+        // chains in flight per lane - and stops at the first timestamp outside the segment's interval
+        int64_t t = pend_t;
+        bool first_row = newrun;
+        const uint64_t span = (uint64_t)lim_hi - (uint64_t)lim_lo;
+        bool more;
+#pragma unroll 1
+        do {
+          bool vv;
+          const uint64_t v = row_value(accumulate, vv);
+          if (SEL && seg_in) {
+            const bool ok = vv && !seg_masked;
+            if (first_row) { acc.first_ts = t; acc.first_val = ok ? v : 0; acc.first_ok = ok; first_row = false; }
+            acc.last_ts = t;
+            acc.last_val = ok ? v : 0;
+            acc.last_ok = ok;
+          }
+          if (seg_in) n_inrange++;
+          row++;
+          t = (int64_t)tcur.next();  // (past the last row this runs one value too far - harmless)
+          more = row < n_rows && (uint64_t)t - (uint64_t)lim_lo <= span;
+        } while (more);
+        pend_t = t;
+        if (tcur.exhausted && row < n_rows) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row; }
+      }
+      check_values();
+    }
   }
   if (!SEL && staged) {  // partials still parked in the staging area
     reduce_staged<VK>(P, stab, stage, staged);
@@ -1265,8 +1321,9 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
 #ifndef SCAN_MIN_BLOCKS
 #define SCAN_MIN_BLOCKS 4
 #endif
-// RLE-timestamp variants without FIRST/LAST need < 102 registers: 5 blocks per SM, the others 4.
-__host__ __device__ constexpr int scan_min_blocks(int tk, bool sel) { return (tk == TK_RLE && !sel) ? SCAN_MIN_BLOCKS + 1 : SCAN_MIN_BLOCKS; }
+// 4 blocks of 4 warps per SM: the per-CTA shared memory (table + rings + flush staging) allows no more, and 128
+// registers keep every variant free of spills.
+__host__ __device__ constexpr int scan_min_blocks(int /*tk*/, bool /*sel*/) { return SCAN_MIN_BLOCKS; }
 // staging-ring bytes one warp of the fused kernel needs (generic time pages read from global memory)
 __host__ __device__ constexpr uint32_t scan_ring_bytes_per_warp(int tk) {
   return tk == TK_RLE ? RING_BYTES_PER_WARP : tk == TK_S8B ? 2 * RING_BYTES_PER_WARP : 0;
@@ -1538,59 +1595,6 @@ __global__ void k_time_bounds(const uint8_t *arena, const tskv_page_desc *descs,
     atomicMin(bounds, lo);
     atomicMax(bounds + 1, hi);
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// decode only: one lane per page, values + validity bitmap to HBM
-// ------------------------------------------------------------------------------------------------
-__global__ void k_decode_pages(const uint8_t *arena, const tskv_page_desc *descs, uint64_t first_page,
-                               uint32_t n_pages, const uint64_t *row_off, const uint64_t *bm_off,
-                               uint64_t *out_values, uint8_t *out_validity, int32_t *status,
-                               unsigned long long *err_page, unsigned long long *stats) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pages) return;
-  const uint32_t page = (uint32_t)first_page + i;
-  const tskv_page_desc d = descs[page];
-  tskv_status st = kind_status(d.reserved);
-  uint64_t *ov = out_values + row_off[i];
-  uint32_t *ob = reinterpret_cast<uint32_t *>(out_validity + bm_off[i]);
-  const uint32_t n_rows = d.num_values;
-  unsigned long long points = 0;
-  if (st == TSKV_OK) {
-    PageView pv;
-    pv.open(arena, d);
-    BitCursor bits;
-    bits.init(pv.bitset);
-    AnyCursor<> cur;
-    st = cur.open(pv, d.reserved);
-    const bool allnull = d.reserved == DK_ALLNULL;
-    uint32_t wbits = 0;
-    for (uint32_t r = 0; r < n_rows && st == TSKV_OK; r++) {
-      bool valid = bits.next(r) && !allnull;
-      uint64_t v = 0;
-      if (valid) {
-        v = cur.next();
-        if (cur.failed()) { st = cur.stream_error() ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH; break; }
-        points++;
-      } else if (r == 0 && !cur.is_gorilla) {
-        cur.d.skip_first_if_s8b_sc();
-      }
-      ov[r] = v;
-      wbits |= (valid ? 1u : 0u) << (r & 31);
-      if ((r & 31) == 31) { ob[r >> 5] = wbits; wbits = 0; }
-    }
-    if (st == TSKV_OK) {
-      if (n_rows & 31) ob[n_rows >> 5] = wbits;
-      // zero the tail of the 8-byte-padded bitmap
-      uint32_t words = ((n_rows + 63) / 64) * 2;
-      for (uint32_t w = (n_rows + 31) / 32; w < words; w++) ob[w] = 0;
-      if (cur.is_gorilla && cur.g.consumed_any() && !cur.g.drain()) st = TSKV_ERR_SHORT_BLOCK;
-    }
-  }
-  if (st != TSKV_OK) {
-    if (atomicCAS(status, 0, (int)st) == 0) *err_page = page;
-  }
-  if (points) atomicAdd(&stats[0], points);
 }
 
 }  // namespace tskv

@@ -1,6 +1,7 @@
 // tskv_gpu.cu — C-ABI entry points of include/tskv_gpu.h: context, page upload, decode-only and the
 // fused scan/aggregate launches. Host logic only; the device code is in scan_kernels.cuh.
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -13,7 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "host_util.h"
-#include "coop_kernels.cuh"
+#include "decode_kernels.cuh"
 
 using namespace tskv;
 
@@ -30,10 +31,9 @@ struct tskv_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // [0] fork, [N_BINS] join of the fused phase
   cudaStream_t bin_stream[N_BINS] = {nullptr};  // the per-bin fused kernels run concurrently
-  cudaEvent_t ev_bin_start[N_BINS] = {nullptr}, ev_bin_done[N_BINS] = {nullptr}, ev_gather[N_BINS] = {nullptr};
   int sm_count = 148;
+  int max_dyn_smem = 48 * 1024;
   std::mutex mu;
   std::string err;
   int64_t err_page = -1;
@@ -64,6 +64,7 @@ struct tskv_pages {
   uint32_t *d_item_cg = nullptr;
   uint32_t h_bin_start[N_BINS + 1]{};
   uint64_t h_bin_bytes[N_BINS]{};    // field-page bytes per bin (orders the PCIe gathers of host-resident scans)
+  uint64_t h_bin_rows[N_BINS]{};     // rows of the bin's field pages (serial cost of its chunks)
   uint32_t *d_bin_start = nullptr;
   // tombstones (tskvgpu_pages_set_tombstones); the epoch invalidates scans prepared before a change
   uint64_t *d_tomb_keys = nullptr;
@@ -114,6 +115,11 @@ struct tskv_scan {
   tskv_ctx *ctx = nullptr;
   uint32_t n_series_sel = 0;
   bool enqueued = false;
+  // timing / ordering events of THIS scan (several scans of one context may be in flight from different host threads)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // [0] fork, [N_BINS] join of the fused phase
+  cudaEvent_t ev_bin_start[N_BINS] = {nullptr}, ev_bin_done[N_BINS] = {nullptr}, ev_gather[N_BINS] = {nullptr};
+  tskv_counters counters{};  // of the last completed pass of this scan
 };
 
 namespace {
@@ -187,6 +193,13 @@ double bin_cost(int bin, bool coop) {
 size_t serial_smem_bytes(int serial_bin, uint32_t table_words) {
   return (size_t)((table_words + 1) & ~1u) * 8 + (size_t)scan_warp_bytes(serial_bin / N_VK) * (SCAN_THREADS / 32);
 }
+// Serial time of one row of one 32-page chunk, relative (measured on C4, round 2: 0.28 / 0.30 / 0.43 / 0.49 ms per
+// 1000-row chunk for RLE+simple8b, RLE+gorilla, simple8b+simple8b, simple8b+gorilla; generic codecs are rarer and slower).
+double chunk_cost(int bin) {
+  static const double tk[N_TK] = {0.0, 0.16, 0.35}, vk[N_VK] = {0.28, 0.31, 0.45};
+  const int sb = serial_bin_of(bin);
+  return tk[sb / N_VK] + vk[sb % N_VK];
+}
 size_t coop_smem_bytes(int bin, uint32_t table_words) {
   size_t per_warp = bin == BIN_COOP_S8B_S8B   ? sizeof(CoopSmem<true, false>)
                     : bin == BIN_COOP_RLE_S8B ? sizeof(CoopSmem<false, false>)
@@ -257,6 +270,15 @@ void free_scan(tskv_scan *s) {
                   s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1]};
   for (void *b : bufs)
     if (b) cudaFreeAsync(b, st);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  for (int b = 0; b <= N_BINS; b++)
+    if (s->ev_bin[b]) cudaEventDestroy(s->ev_bin[b]);
+  for (int b = 0; b < N_BINS; b++) {
+    if (s->ev_bin_start[b]) cudaEventDestroy(s->ev_bin_start[b]);
+    if (s->ev_bin_done[b]) cudaEventDestroy(s->ev_bin_done[b]);
+    if (s->ev_gather[b]) cudaEventDestroy(s->ev_gather[b]);
+  }
   delete s;
 }
 
@@ -299,12 +321,27 @@ tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
     return TSKV_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
-  for (int b = 0; b <= N_BINS; b++) cudaEventCreate(&ctx->ev_bin[b]);
-  for (int b = 0; b < N_BINS; b++) {
-    cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking);
-    cudaEventCreate(&ctx->ev_bin_start[b]);
-    cudaEventCreate(&ctx->ev_bin_done[b]);
-    cudaEventCreateWithFlags(&ctx->ev_gather[b], cudaEventDisableTiming);
+  for (int b = 0; b < N_BINS; b++) cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking);
+  // Dynamic shared memory ceiling of every scan kernel, set ONCE: the attribute belongs to the kernel, not to a launch,
+  // so per-scan values would race between host threads that prepare scans with different table sizes.
+  {
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
+    ctx->max_dyn_smem = optin;
+    auto raise = [&](const void *fn) {  // the opt-in limit covers static + dynamic shared memory
+      cudaFuncAttributes fa{};
+      if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess)
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    };
+    for (int b = 0; b < N_SERIAL_BINS; b++) {
+      raise((const void *)scan_kernel_for<false>(b));
+      raise((const void *)scan_kernel_for<true>(b));
+    }
+    for (int b = N_SERIAL_BINS; b < N_BINS; b++) {
+      raise(coop_kernel_for(b, false));
+      raise(coop_kernel_for(b, true));
+    }
+    cudaGetLastError();
   }
   // per-scan buffers come from the stream-ordered pool; keep freed memory cached in the pool
   cudaMemPool_t pool;
@@ -325,14 +362,8 @@ void tskvgpu_ctx_destroy(tskv_ctx *ctx) {
   }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  for (int b = 0; b <= N_BINS; b++)
-    if (ctx->ev_bin[b]) cudaEventDestroy(ctx->ev_bin[b]);
-  for (int b = 0; b < N_BINS; b++) {
+  for (int b = 0; b < N_BINS; b++)
     if (ctx->bin_stream[b]) cudaStreamDestroy(ctx->bin_stream[b]);
-    if (ctx->ev_bin_start[b]) cudaEventDestroy(ctx->ev_bin_start[b]);
-    if (ctx->ev_bin_done[b]) cudaEventDestroy(ctx->ev_bin_done[b]);
-    if (ctx->ev_gather[b]) cudaEventDestroy(ctx->ev_gather[b]);
-  }
   delete ctx;
 }
 
@@ -377,7 +408,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   auto work = [&](uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi && bad_status.load(std::memory_order_relaxed) == 0; i++) {
       tskv_page_desc &d = pg->h_descs[i];
-      if (d.offset & 15 || d.offset + d.size > arena_len || d.phys_type > TSKV_PT_F64 || d.reserved != 0) {
+      if (d.offset & 15 || d.size > arena_len || d.offset > arena_len - d.size || d.phys_type > TSKV_PT_F64 || d.reserved != 0) {
         fail(TSKV_ERR_INVALID_ARG, (int64_t)i);
         return;
       }
@@ -486,6 +517,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
       ic[k] = item_cg[src];
       counts[key[k] >> 48]++;
       pg->h_bin_bytes[key[k] >> 48] += pg->h_descs[item_page[src]].size;
+      pg->h_bin_rows[key[k] >> 48] += pg->h_descs[item_page[src]].num_values;
     }
     item_page.swap(ip);
     item_cg.swap(ic);
@@ -522,7 +554,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   if (e == cudaSuccess) e = up(&pg->d_item_page, item_page.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
-  if (e == cudaSuccess && (flags & TSKV_UPLOAD_VERIFY_CRC) && (flags & TSKV_UPLOAD_HOST_RESIDENT)) {
+  if (e == cudaSuccess && (((flags & TSKV_UPLOAD_VERIFY_CRC) && (flags & TSKV_UPLOAD_HOST_RESIDENT)) || (flags & TSKV_UPLOAD_VERIFY_ON_READ))) {
     pg->verify_on_read = true;  // like the reference: every read of a page re-checks its CRC (device side)
     e = up(&pg->d_crc_tables, crc32_tables(), 2048);
   }
@@ -618,7 +650,7 @@ tskv_status tskvgpu_pages_set_tombstones(tskv_ctx *ctx, tskv_pages *pg, const ts
 // ------------------------------------------------------------------------------------------------
 tskv_status tskvgpu_decode_pages(tskv_ctx *ctx, const tskv_pages *pages, uint64_t first_page,
                                  uint64_t n_pages, uint64_t *out_values, uint8_t *out_validity) {
-  if (!ctx || !pages || first_page + n_pages > pages->n_descs || (n_pages && (!out_values || !out_validity)))
+  if (!ctx || !pages || n_pages > pages->n_descs || first_page > pages->n_descs - n_pages || (n_pages && (!out_values || !out_validity)))
     return TSKV_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->set_error("");
@@ -658,9 +690,9 @@ tskv_status tskvgpu_decode_pages(tskv_ctx *ctx, const tskv_pages *pages, uint64_
   if (e == cudaSuccess) e = cudaMemsetAsync(d_vals, 0, std::max<uint64_t>(rows, 1) * 8, ctx->stream);
   if (e == cudaSuccess) {
     cudaEventRecord(ctx->ev0, ctx->stream);
-    uint32_t threads = 128;
-    uint32_t blocks = (uint32_t)((n_pages + threads - 1) / threads);
-    k_decode_pages<<<blocks, threads, 0, ctx->stream>>>(pages->d_arena, pages->d_descs, first_page, (uint32_t)n_pages,
+    uint32_t blocks = (uint32_t)((n_pages * 32 + DECODE_THREADS - 1) / DECODE_THREADS);  // one warp per page
+    // host-resident page sets: d_arena is only the scans' gather target, the pages are read through the mapped host range
+    k_decode_warp<<<blocks, DECODE_THREADS, 0, ctx->stream>>>(pages->h_mapped ? pages->h_mapped : pages->d_arena, pages->d_descs, first_page, (uint32_t)n_pages,
                                                         d_row_off, d_bm_off, d_vals, d_valid, d_status, d_aux, d_aux + 1);
     cudaEventRecord(ctx->ev1, ctx->stream);
     e = cudaGetLastError();
@@ -728,6 +760,14 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
         ctx->set_error("series_ids must be sorted ascending and unique");
         return TSKV_ERR_INVALID_ARG;
       }
+  if ((q->reserved & TSKV_QUERY_MULTI_RANK) && !q->series_ids) {
+    bool needs_slots = q->group_by_series != 0;
+    for (uint32_t c = 0; c < q->n_columns; c++) needs_slots |= (q->columns[c].agg_mask & (TSKV_AGG_FIRST | TSKV_AGG_LAST)) != 0;
+    if (needs_slots) {
+      ctx->set_error("multi-rank scan: GROUP BY series and first/last need the global series_ids list (slots are positions in it)");
+      return TSKV_ERR_INVALID_ARG;
+    }
+  }
   cudaSetDevice(ctx->device);
   tskv_scan *s = new tskv_scan();
   s->pages = pages;
@@ -748,10 +788,16 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     if (q->width > 0) {
       if (q->width < (int64_t)1 << 61) rel_bits = bits_for(2 * (uint64_t)q->width);
     } else {
-      // unbucketed: rel = t - (lower bound of every in-range timestamp); the arena's own time
-      // bounds tighten unbounded / loose query ranges
-      ensure_time_bounds(ctx, pages);
-      int64_t lo = pages->ts_min, hi = pages->ts_max;
+      // unbucketed: rel = t - (lower bound of every in-range timestamp). A single-rank scan tightens unbounded / loose
+      // query ranges with the arena's own time bounds; a scan whose partials are merged with other ranks'
+      // (TSKV_QUERY_MULTI_RANK) must build keys every rank agrees on, i.e. from the query alone.
+      const bool multi_rank = (q->reserved & TSKV_QUERY_MULTI_RANK) != 0;
+      int64_t lo = INT64_MIN, hi = INT64_MAX;
+      if (!multi_rank) {
+        ensure_time_bounds(ctx, pages);
+        lo = pages->ts_min;
+        hi = pages->ts_max;
+      }
       if (q->n_time_ranges > 0) {
         int64_t qlo = q->time_ranges[0].min_ts, qhi = q->time_ranges[0].max_ts;
         for (uint32_t k = 1; k < q->n_time_ranges; k++) {
@@ -900,10 +946,17 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   // ---- device allocations (stream-ordered) + query arguments H2D --------------------------------------
   const uint32_t n_items = pages->n_items;
   s->ctx = ctx;
+  cudaEventCreate(&s->ev0);
+  cudaEventCreate(&s->ev1);
+  for (int b = 0; b <= N_BINS; b++) cudaEventCreate(&s->ev_bin[b]);
+  for (int b = 0; b < N_BINS; b++) {
+    cudaEventCreate(&s->ev_bin_start[b]);
+    cudaEventCreate(&s->ev_bin_done[b]);
+    cudaEventCreateWithFlags(&s->ev_gather[b], cudaEventDisableTiming);
+  }
   s->n_series_sel = q->series_ids ? q->n_series : 0;
   s->n_blocks = (n_items + 1023) / 1024;
   cudaError_t e = cudaSuccess;
-  cudaEventRecord(ctx->ev0, ctx->stream);
   uint64_t h2d = 0;
   if (q->series_ids) {
     e = stream_alloc(ctx, &s->d_series, q->n_series);
@@ -942,7 +995,6 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   s->d_err_page = aux + 9;
   s->d_stats = aux + 10;
   s->d_counters = aux + 12;
-  cudaEventRecord(ctx->ev1, ctx->stream);
 
   // ---- kernel parameters ------------------------------------------------------------------------------
   ScanParams &P = s->params;
@@ -1012,9 +1064,12 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     const double sel_frac = plan_selected_fraction(pages->series.data(), pages->series.size(), q->series_ids, q->n_series);
     const double est_total = (double)pages->n_items * sel_frac;  // selected field pages, all bins
     for (int b = N_SERIAL_BINS; b < N_BINS; b++)
+      // Round 2: the lane-per-page kernels (staged streams, fused row loops) beat the round-1 cooperative kernels on
+      // every shard size measured (1/8 of C4 on one GPU: 0.49 ms vs 0.75 ms), so those run only on request.
       s->use_coop[b] = pages->n_tomb_ranges ? false  // tombstones are handled by the lane-per-page kernels
                        : mode             ? (mode[0] == '1')
-                                          : plan_use_cooperative(est_total, ctx->sm_count, SCAN_MIN_BLOCKS, SCAN_THREADS);
+                                          : false;
+    (void)est_total;
     // Grid sizes. Every kernel is persistent (warps pull tasks from their bin's counter). If the resident
     // capacity allows, each bin gets one warp per estimated task (a single round: the makespan of a bin is
     // quantised in units of one task = one page's serial decode); otherwise the blocks are split by cost.
@@ -1027,7 +1082,6 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
         if (is_gor_coop_bin(b) && s->use_coop[b]) est_gor += (pages->h_bin_start[b + 1] - pages->h_bin_start[b]) * sel_frac;
       int gocc = 0;  // resident CTAs per SM of the gorilla cooperative kernel (shared memory bound)
       const void *gfn = coop_kernel_for(BIN_COOP_RLE_GOR, s->has_sel);
-      cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(BIN_COOP_RLE_GOR, P.smem_words));
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&gocc, gfn, SCAN_THREADS, coop_smem_bytes(BIN_COOP_RLE_GOR, P.smem_words));
       const double resident_warps = (double)ctx->sm_count * std::max(1, gocc) * (SCAN_THREADS / 32);
       gor_group = plan_gorilla_group(est_gor, resident_warps);
@@ -1035,7 +1089,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       s->coop.gor_group = gor_group;
     }
     double w[N_BINS], wsum = 0, need_sum = 0, occ_weighted = 0;
-    int need[N_BINS] = {0};
+    int need[N_BINS] = {0}, occ_bin[N_BINS] = {0};
     for (int b = 0; b < N_BINS; b++) {
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       w[b] = n_bin * bin_cost(b, s->use_coop[b]);
@@ -1045,15 +1099,14 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       if (!s->use_coop[b]) {
         const int sb = serial_bin_of(b);
         const void *fn = (const void *)(s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb));
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)serial_smem_bytes(sb, P.smem_words));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->has_sel ? scan_kernel_for<true>(sb) : scan_kernel_for<false>(sb),
                                                       SCAN_THREADS, serial_smem_bytes(sb, P.smem_words));
       } else {
         const void *fn = coop_kernel_for(b, s->has_sel);
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes(b, P.smem_words));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, SCAN_THREADS, coop_smem_bytes(b, P.smem_words));
       }
       occ = std::max(1, occ);
+      occ_bin[b] = occ;
       const double est_items = n_bin * sel_frac * 1.02 + 32;
       const uint32_t per_task = !s->use_coop[b] ? 32u : is_gor_coop_bin(b) ? gor_group : 1u;  // pages per warp task
       const double tasks = est_items / per_task;
@@ -1069,10 +1122,16 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       for (int b = 0; b < N_BINS; b++)
         if (need[b]) s->grid[b] = std::max(1, need[b]);
     } else if (!any_coop) {
-      // lane-per-page kernels only (long tasks): plain cost shares, leaving the slack of the bins that need less than
-      // their share unused - an over-subscribed persistent grid would queue whole blocks behind ~1 ms tasks
-      for (int b = 0; b < N_BINS; b++)
-        if (need[b]) s->grid[b] = std::max(1, std::min(need[b], (int)(capacity * w[b] / wsum + 0.5)));
+      // lane-per-page kernels only: a chunk of 32 pages is one long serial task, so a bin's time is quantised in rounds
+      // of its chunk time - choose the grids that minimise the makespan (plan_serial_grids)
+      double chunks[N_BINS], t_chunk[N_BINS];
+      for (int b = 0; b < N_BINS; b++) {
+        const uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
+        chunks[b] = need[b] ? std::ceil((n_bin * sel_frac * 1.02 + 16) / 32.0) : 0;
+        t_chunk[b] = n_bin ? chunk_cost(b) * (double)pages->h_bin_rows[b] / n_bin : 1.0;
+      }
+      plan_serial_grids(N_BINS, chunks, t_chunk, occ_bin, ctx->sm_count, SCAN_THREADS / 32, s->grid);
+      for (int b = 0; b < N_BINS; b++) s->grid[b] = std::min(s->grid[b], std::max(need[b], 0));
     } else {
       // water-filling: bins that need less than their cost share keep their need, the rest split what is left
       bool fixed[N_BINS] = {false};
@@ -1129,7 +1188,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
     ctx->set_error("the page set's tombstones changed after this scan was prepared", -1);
     return TSKV_ERR_INVALID_ARG;
   }
-  cudaEventRecord(ctx->ev0, ctx->stream);
+  cudaEventRecord(s->ev0, ctx->stream);
   unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
   CU_TRY(ctx, cudaMemsetAsync(aux, 0, 32 * 8, ctx->stream));
   CU_TRY(ctx, cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream));
@@ -1155,7 +1214,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
   k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
   launches++;
-  cudaEventRecord(ctx->ev_bin[0], ctx->stream);  // fork
+  cudaEventRecord(s->ev_bin[0], ctx->stream);  // fork
   // Host-resident pages: one bin's gather already saturates PCIe, so the gathers are chained largest bin first
   // (an event per bin); each bin's CRC check and scan then overlap the next bins' transfers and only the smallest
   // bin's tail is exposed after the last byte has arrived.
@@ -1168,26 +1227,28 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   for (int oi = 0; oi < N_BINS; oi++) {
     const int b = order[oi];
     if (!s->grid[b]) continue;
-    cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_bin[0], 0);
+    cudaStreamWaitEvent(ctx->bin_stream[b], s->ev_bin[0], 0);
     int bin = b;
     if (pages->h_mapped) {
-      if (prev_gather >= 0 && !gather_concurrent) cudaStreamWaitEvent(ctx->bin_stream[b], ctx->ev_gather[prev_gather], 0);
+      if (prev_gather >= 0 && !gather_concurrent) cudaStreamWaitEvent(ctx->bin_stream[b], s->ev_gather[prev_gather], 0);
       uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
       uint32_t gblocks = std::max(1u, std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (n_bin + 7) / 8));
       k_gather_pages<<<gblocks, 256, 0, ctx->bin_stream[b]>>>(pages->h_mapped, pages->d_arena, pages->d_descs,
                                                               pages->d_time_page_of, s->d_work_page, s->d_work_qcol,
                                                               s->d_bin_cstart, bin);
       launches++;
-      cudaEventRecord(ctx->ev_gather[b], ctx->bin_stream[b]);
+      cudaEventRecord(s->ev_gather[b], ctx->bin_stream[b]);
       prev_gather = b;
-      if (pages->verify_on_read) {
-        k_verify_crc<<<gblocks, 256, 0, ctx->bin_stream[b]>>>(pages->d_arena, pages->d_descs, pages->d_time_page_of,
-                                                              s->d_work_page, s->d_work_qcol, s->d_bin_cstart, bin,
-                                                              pages->d_crc_tables, s->d_status, s->d_err_page);
-        launches++;
-      }
     }
-    cudaEventRecord(ctx->ev_bin_start[b], ctx->bin_stream[b]);
+    if (pages->verify_on_read) {  // Page::crc_validation on every read (tsm/reader.rs:259), also for pages resident in HBM
+      uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
+      uint32_t gblocks = std::max(1u, std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (n_bin + 7) / 8));
+      k_verify_crc<<<gblocks, 256, 0, ctx->bin_stream[b]>>>(pages->d_arena, pages->d_descs, pages->d_time_page_of,
+                                                            s->d_work_page, s->d_work_qcol, s->d_bin_cstart, bin,
+                                                            pages->d_crc_tables, s->d_status, s->d_err_page);
+      launches++;
+    }
+    cudaEventRecord(s->ev_bin_start[b], ctx->bin_stream[b]);
     if (!s->use_coop[b]) {
       const int sb = serial_bin_of(b);
       void *args[] = {(void *)&s->params, (void *)&bin};
@@ -1198,18 +1259,18 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
       CU_TRY(ctx, cudaLaunchKernel(coop_kernel_for(b, s->has_sel), dim3(s->grid[b]), dim3(SCAN_THREADS), args,
                                    coop_smem_bytes(b, s->params.smem_words), ctx->bin_stream[b]));
     }
-    cudaEventRecord(ctx->ev_bin_done[b], ctx->bin_stream[b]);
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_bin_done[b], 0);  // join
+    cudaEventRecord(s->ev_bin_done[b], ctx->bin_stream[b]);
+    cudaStreamWaitEvent(ctx->stream, s->ev_bin_done[b], 0);  // join
     launches++;
   }
-  cudaEventRecord(ctx->ev_bin[N_BINS], ctx->stream);
+  cudaEventRecord(s->ev_bin[N_BINS], ctx->stream);
   if (s->has_sel || s->n_means) {
     uint64_t work = std::max(std::max(s->sl.first_cells, s->sl.last_cells), s->n_means ? s->layout.n_cells : 0);
     uint32_t b = (uint32_t)std::min<uint64_t>((work + 255) / 256, 4096);
     k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl, s->d_means, s->n_means, s->layout.n_cells);
     launches++;
   }
-  cudaEventRecord(ctx->ev1, ctx->stream);
+  cudaEventRecord(s->ev1, ctx->stream);
   CU_TRY(ctx, cudaGetLastError());
   ctx->counters.kernel_launches = launches;
   s->enqueued = true;
@@ -1226,14 +1287,14 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
   unsigned long long aux[4 + N_BINS + 1] = {0};  // stats[2], pages, bytes, per-bin bytes[N_BINS]
   CU_TRY(ctx, cudaMemcpy(aux, s->d_stats, (4 + N_BINS) * 8, cudaMemcpyDeviceToHost));
   float ms = 0;
-  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  cudaEventElapsedTime(&ms, s->ev0, s->ev1);
   ctx->counters.elapsed_scan_ms = ms;
   ctx->counters.points_decoded = aux[0];
   ctx->counters.rows_in_range = aux[1];
   ctx->counters.page_read_count = aux[2];
   ctx->counters.page_read_bytes = aux[3];
   float fused = 0;
-  cudaEventElapsedTime(&fused, ctx->ev_bin[0], ctx->ev_bin[N_BINS]);
+  cudaEventElapsedTime(&fused, s->ev_bin[0], s->ev_bin[N_BINS]);
   ctx->counters.elapsed_fused_ms = fused;
   ctx->counters.dominant_kernel_ms = 0;
   ctx->counters.dominant_kernel_bytes = 0;
@@ -1241,10 +1302,10 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
   for (int b = 0; b < N_BINS; b++) {
     if (!s->grid[b]) continue;
     float t = 0;
-    cudaEventElapsedTime(&t, ctx->ev_bin_start[b], ctx->ev_bin_done[b]);
+    cudaEventElapsedTime(&t, s->ev_bin_start[b], s->ev_bin_done[b]);
     if (getenv("TSKV_DEBUG_BINS")) {
       float t0 = 0;
-      cudaEventElapsedTime(&t0, ctx->ev_bin[0], ctx->ev_bin_start[b]);
+      cudaEventElapsedTime(&t0, s->ev_bin[0], s->ev_bin_start[b]);
       fprintf(stderr, "[tskv] bin %d%s grid %d: start +%.3f ms, run %.3f ms, %llu bytes\n", b, s->use_coop[b] ? " (coop)" : "",
               s->grid[b], t0, t, aux[4 + b]);
     }

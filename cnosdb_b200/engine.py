@@ -50,7 +50,7 @@ class QueryOption:
     """The pushed-down scan: series selection, closed time ranges, bucket expression, aggregates."""
 
     def __init__(self, columns, series_ids=None, time_ranges=(), origin=0, width=0,
-                 first_bucket_start=0, n_buckets=1, group_by_series=False):
+                 first_bucket_start=0, n_buckets=1, group_by_series=False, multi_rank=False):
         self.columns = list(columns)
         self.series_ids = None if series_ids is None else np.ascontiguousarray(series_ids, dtype=np.uint32)
         self.time_ranges = [(int(a), int(b)) for a, b in time_ranges]
@@ -59,6 +59,7 @@ class QueryOption:
         self.first_bucket_start = int(first_bucket_start)
         self.n_buckets = int(n_buckets)
         self.group_by_series = bool(group_by_series)
+        self.multi_rank = bool(multi_rank)  # TSKV_QUERY_MULTI_RANK: partials get merged with other ranks'
         self._keep = None
 
     def to_c(self):
@@ -74,6 +75,7 @@ class QueryOption:
         q.origin, q.width = self.origin, self.width
         q.first_bucket_start, q.n_buckets = self.first_bucket_start, self.n_buckets
         q.group_by_series = 1 if self.group_by_series else 0
+        q.reserved = cabi.TSKV_QUERY_MULTI_RANK if self.multi_rank else 0
         cols = (cabi.AggColumn * len(self.columns))()
         for i, c in enumerate(self.columns):
             cols[i].column_id, cols[i].phys_type, cols[i].agg_mask = c.column_id, c.phys_type, c.agg_mask
@@ -244,10 +246,11 @@ class Engine:
         self._check(self.lib.tskvgpu_get_counters(self.ctx, C.byref(c)))
         return {k: getattr(c, k) for k, _ in cabi.Counters._fields_ if k != "reserved"}
 
-    def upload_pages(self, arena, descs, verify_crc=True, host_resident=False):
+    def upload_pages(self, arena, descs, verify_crc=True, host_resident=False, verify_on_read=False):
         """arena: uint8 array (or (ptr, len)); descs: array of PAGE_DESC_DTYPE.
         host_resident=True keeps the page bytes in (page-locked) host memory: every scan then pulls the
-        selected pages over PCIe itself; the caller must keep `arena` alive until PageSet.close()."""
+        selected pages over PCIe itself; the caller must keep `arena` alive until PageSet.close().
+        verify_on_read=True re-checks the CRC32 of every page a scan reads on the device, every scan."""
         if isinstance(arena, tuple):
             aptr, alen = arena
         else:
@@ -255,7 +258,8 @@ class Engine:
             aptr, alen = arena.ctypes.data, arena.size
         descs = np.ascontiguousarray(descs, dtype=cabi.PAGE_DESC_DTYPE)
         h = C.c_void_p()
-        flags = (cabi.TSKV_UPLOAD_VERIFY_CRC if verify_crc else 0) | (cabi.TSKV_UPLOAD_HOST_RESIDENT if host_resident else 0)
+        flags = ((cabi.TSKV_UPLOAD_VERIFY_CRC if verify_crc else 0) | (cabi.TSKV_UPLOAD_HOST_RESIDENT if host_resident else 0) |
+                 (cabi.TSKV_UPLOAD_VERIFY_ON_READ if verify_on_read else 0))
         st = self.lib.tskvgpu_upload_pages(self.ctx, aptr, alen, descs.ctypes.data, len(descs), flags, C.byref(h))
         self._check(st)
         ps = PageSet(self, h, len(descs))

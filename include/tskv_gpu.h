@@ -133,8 +133,13 @@ typedef struct tskv_query {
   uint32_t group_by_series;   /* 0: GROUP BY bucket ; 1: GROUP BY series, bucket */
   const tskv_agg_column *columns;
   uint32_t n_columns;         /* 1..126 */
-  uint32_t reserved;
+  uint32_t reserved;          /* TSKV_QUERY_* flags (0 for a plain single-device scan) */
 } tskv_query;
+/* The partial state of this scan will be merged with other ranks' (tskvgpu_scan_partials / _exchange_view): every
+ * exchanged key is then derived from the query alone, never from this rank's own arena (its time bounds, its local
+ * series ranks), so that all ranks build comparable first/last tie-break keys. Requires series_ids != NULL when the
+ * query groups by series or asks for first/last; unbucketed first/last across series need bounded time ranges. */
+#define TSKV_QUERY_MULTI_RANK 1u
 
 /* Result layout. Outputs are dense: for output column j (query columns in order, and inside a
  * column the set agg bits in ascending bit order) and cell c = group * n_buckets + bucket:
@@ -195,7 +200,11 @@ enum {
    * metadata is cached in the reference too: tsfamily/version.rs:158-172). Combined with
    * TSKV_UPLOAD_VERIFY_CRC the CRC32 of every page a scan reads is re-checked on the device after the
    * transfer, i.e. on every read like Page::crc_validation (tsm/reader.rs:259,492). */
-  TSKV_UPLOAD_HOST_RESIDENT = 2u
+  TSKV_UPLOAD_HOST_RESIDENT = 2u,
+  /* Re-check the CRC32 of every page a scan reads on the device, on every scan, also for a device-resident arena
+   * (host-resident + VERIFY_CRC page sets always do): the reference validates a page's CRC on each read
+   * (tsm/reader.rs:259,492), not once per file. */
+  TSKV_UPLOAD_VERIFY_ON_READ = 4u
 };
 tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t arena_len,
                                  const tskv_page_desc *descs, uint64_t n_descs, uint32_t flags,

@@ -510,6 +510,74 @@ def test_host_resident_pages_verify_crc_on_every_read(engine):
     hp.close()
 
 
+def test_host_resident_series_with_fields_in_different_bins(engine):
+    """A series whose selected fields decode in different kind bins (i64 simple8b + f64 gorilla): every bin's gather has
+    to bring the column group's time page itself - the bins run on different streams (round-1 advisor finding). Also
+    decode-only on a host-resident page set, which must read the mapped host arena, not the scans' gather target."""
+    rng = np.random.default_rng(77)
+    arena, descs, _ = random_arena(rng, n_series=300, n_points=257, fields=((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64)),
+                                   jitter=200, null_frac=0.02)
+    t_lo, t_hi = 1_000_000 - 400, 1_000_000 + 300_000
+    fbs, nb = bucket_spec(t_lo, t_hi, 17_000, origin=3)
+    q = make_query(((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64)), aggs=("count", "sum", "min", "max", "mean"),
+                   series_ids=np.arange(0, 300, 3, dtype=np.uint32), origin=3, width=17_000, first_bucket_start=fbs,
+                   n_buckets=nb)
+    exp = orc.scan_aggregate(arena, descs, q)
+    for verify in (True, False):
+        for _ in range(3):  # fresh page sets: the gather target starts out uninitialised
+            hp = engine.upload_pages(arena, descs, verify_crc=verify, host_resident=True)
+            assert_results_equal(engine.scan_aggregate(hp, q), exp, what="host-resident, two bins per series")
+            hp.close()
+    hp = engine.upload_pages(arena, descs, verify_crc=True, host_resident=True)
+    got = engine.decode_pages(hp, descs, 0, 60)
+    exp_pages = orc.decode_pages(arena, descs, 0, 60)
+    for (gv, gm), (ev, em) in zip(got, exp_pages):
+        assert (gm == em).all() and (gv[em] == ev[em]).all()
+    hp.close()
+
+
+def test_two_shard_unbucketed_first_last_with_different_time_minima(engine):
+    """Unbucketed FIRST/LAST across series merged from two shards whose arenas start at different times: the tie-break
+    keys must be built from the query alone (TSKV_QUERY_MULTI_RANK), not from each rank's own time bounds
+    (round-1 advisor finding); and a multi-rank scan without the global series list is refused."""
+    import torch
+    from cnosdb_b200.parallel import device_tensor
+    rng = np.random.default_rng(5)
+    fields = ((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64))
+    parts = [random_arena(rng, n_series=20, n_points=200, fields=fields, ids=range(0, 20), t0=5_000_000),
+             random_arena(rng, n_series=20, n_points=200, fields=fields, ids=range(20, 40), t0=1_000_000)]
+    b = datagen.ArenaBuilder()
+    for _, _, truth in parts:
+        for sid, cgs in truth.items():
+            for ts, cols in cgs:
+                b.add_column_group(sid, ts, [(c, pt, cols[c][0], cols[c][1], None) for c, pt in fields])
+    arena, descs = b.finish()
+    sel = np.arange(1, 40, 2, dtype=np.uint32)
+    q = make_query(fields, series_ids=sel, time_ranges=[(900_000, 6_000_000)], multi_rank=True)
+    exp = orc.scan_aggregate(arena, descs, q)
+    dev = torch.device("cuda", engine.device)
+    scans, regions, keep = [], [], []
+    for a, d, _ in parts:
+        pages = engine.upload_pages(a, d)
+        s = engine.prepare(pages, q)
+        s.run()
+        ptr, words = s.exchange_view()
+        regions.append(device_tensor(ptr, words, torch.int64, dev).clone())
+        scans.append(s)
+        keep.append(pages)
+    gathered = torch.cat(regions)
+    torch.cuda.synchronize()
+    for s in scans:
+        s.merge_gathered(gathered.data_ptr(), 2)
+        assert_results_equal(s.finalize(), exp, what="2-shard unbucketed first/last")
+        s.close()
+    with pytest.raises(TskvError) as e:
+        engine.prepare(keep[0], make_query(fields, time_ranges=[(900_000, 6_000_000)], multi_rank=True))
+    assert e.value.status == cabi.TSKV_ERR_INVALID_ARG
+    for pages in keep:
+        pages.close()
+
+
 def random_tombstones(rng, descs, t_lo, t_hi, n=60):
     """Column masks, series-scoped row drops and a few page-set-wide row drops over random sub-ranges."""
     fields = descs[descs["phys_type"] != cabi.TSKV_PT_TIME]

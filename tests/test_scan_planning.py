@@ -40,9 +40,37 @@ def test_selected_fraction_counts_only_ids_inside_the_shard():
     assert frac(np.arange(100, 200), np.arange(0, 1000)) == 1.0
 
 
+def test_serial_grid_planner_minimises_the_quantised_makespan():
+    """plan_serial_grids: a chunk of 32 pages is one serial task, bins finish in whole rounds of their chunk time. For C4
+    on one GPU (1250 / 1250 / 313 / 313 chunks, measured chunk times) everything does not fit in one round: the long
+    simple8b-timestamp chunks get one round, the RLE bins two; a 1/8 shard fits in a single round."""
+    L = lib()
+    L.tskvplan_serial_grids.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+
+    def plan(chunks, t, occ, sm=148, wpb=4):
+        c = np.array(chunks, dtype=np.float64)
+        tt = np.array(t, dtype=np.float64)
+        o = np.array(occ, dtype=np.int32)
+        g = np.zeros(len(c), dtype=np.int32)
+        L.tskvplan_serial_grids(len(c), c.ctypes.data, tt.ctypes.data, o.ctypes.data, sm, wpb, g.ctypes.data)
+        return g
+
+    chunks, t, occ = [1250, 1250, 313, 313, 0], [0.28, 0.31, 0.44, 0.47, 1.0], [4, 4, 3, 3, 4]
+    g = plan(chunks, t, occ)
+    assert g[4] == 0
+    rounds = [int(np.ceil(c / (x * 4))) for c, x in zip(chunks[:4], g[:4])]
+    assert rounds == [2, 2, 1, 1], (g, rounds)
+    assert sum(x / o for x, o in zip(g[:4], occ)) <= 148
+    g8 = plan([157, 157, 40, 40], t[:4], occ[:4])
+    assert [int(np.ceil(c / (x * 4))) for c, x in zip([157, 157, 40, 40], g8)] == [1, 1, 1, 1]
+    # a machine too small even for the largest round count considered still gets a valid (over-subscribed) plan
+    g1 = plan([1000], [1.0], [1], sm=2, wpb=4)
+    assert g1[0] >= 1
+
+
 def test_kernel_family_and_group_size_for_the_c4_shards():
-    """148 SMs x 4 CTAs x 128 lanes: lane-per-page kernels down to 1/4 of C4 per GPU, cooperative kernels on the
-    8-GPU shards, where the gorilla pages go in groups of 4 (measured best)."""
+    """The round-1 crossover between the kernel families (the cooperative kernels are opt-in since round 2, TSKV_COOP=1;
+    the rule still sizes their gorilla page groups)."""
     L = lib()
     selected_pages = {1: 100_000, 2: 50_000, 4: 25_000, 8: 12_500}  # 10 % of 1 M series, one field page each
     family = {w: bool(L.tskvplan_use_cooperative(float(p), 148, 4, 128)) for w, p in selected_pages.items()}
