@@ -58,75 +58,77 @@ struct BeStream {
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory staging of a lane's byte stream (round 2). One lane owns one page, so a warp reads 32 different
-// pages: each lane stages ITS stream through a ring of RING_CHUNKS 16-byte chunks filled by 128-bit cp.async
-// (LDGSTS.128, L2 -> shared memory without a register round trip). Chunk c of lane l lives at
-//   ring + ((c mod RING_CHUNKS) * 32 + l) * 16        (lane-interleaved: a warp-wide LDS hits 32 different 16-byte slots)
+// pages: each lane stages ITS stream through a private ring of RING_CHUNKS 16-byte chunks filled by 128-bit cp.async
+// (LDGSTS.128, L2 -> shared memory without a register round trip). A lane's ring is contiguous (RING_BYTES bytes) and
+// the lanes' rings are RING_LANE_STRIDE = RING_BYTES + 16 bytes apart: word k of the stream lives at
+//   ring + lane * RING_LANE_STRIDE + (k mod 2 * RING_CHUNKS) * 8
+// (one AND + one scaled add per word; the 16 bytes of skew spread lanes that sit at the same ring offset over the banks).
 // A decoder calls step(c) once per element / word BEFORE reading, c = the chunk its read window starts in; a window
 // never spans more than chunks c and c + 1, and c advances by at most one per step (an element is <= 77 bits, a word
-// 64). step() issues at most one new chunk - branch-free, a predicated LDGSTS - commits exactly one group and waits
-// until at most RING_CHUNKS - 2 groups are pending: chunk c + 1 was issued when the window first reached chunk
-// c + 2 - RING_CHUNKS, i.e. at least RING_CHUNKS - 2 steps (= groups) ago, so it has landed; the RING_CHUNKS - 2
-// chunks behind it (96 bytes, ~12 full-mantissa gorilla values) stay in flight and hide the HBM / L2 latency.
+// 64). step() issues at most one new chunk - a predicated LDGSTS - commits exactly one group and waits until at most
+// RING_CHUNKS - 2 groups are pending: chunk c + 1 was issued when the window first reached chunk c + 2 - RING_CHUNKS,
+// i.e. at least RING_CHUNKS - 2 steps (= groups) ago, so it has landed; the RING_CHUNKS - 2 chunks behind it (96
+// bytes, ~12 full-mantissa gorilla values) stay in flight and hide the HBM / L2 latency.
 // The initial fill is one group the caller waits for once per page (ring_drain) before the first step.
-// A chunk may extend <= 15 bytes past its page (next page or arena slack); chunks past the page are never issued and a
-// decoder that runs into them reads stale shared memory, which its own end-of-stream accounting turns into an error.
+// A stream is read at most RING_BYTES + 15 bytes past its last byte (the initial fill of a short stream; otherwise up to
+// the end of its last 16-byte chunk): the following pages, or the ARENA_SLACK bytes after the last page of the arena -
+// never past the allocation. A decoder that consumes bytes past its block reads stale shared memory, and its own
+// end-of-stream accounting reports the overrun.
 #ifndef TSKV_RING_CHUNKS
 #define TSKV_RING_CHUNKS 8
 #endif
 constexpr int RING_CHUNKS = TSKV_RING_CHUNKS;
-constexpr uint32_t RING_BYTES_PER_WARP = RING_CHUNKS * 32 * 16;  // one stream of one warp
+constexpr uint32_t RING_BYTES = RING_CHUNKS * 16;            // one lane, one stream
+constexpr uint32_t RING_LANE_STRIDE = RING_BYTES + 16;
+constexpr uint32_t RING_BYTES_PER_WARP = 32 * RING_LANE_STRIDE;  // one stream of one warp
 static_assert((RING_CHUNKS & (RING_CHUNKS - 1)) == 0 && RING_CHUNKS >= 4, "ring size must be a power of two >= 4");
+static_assert(ARENA_SLACK >= RING_BYTES + 32, "the arena slack has to cover the rings' read-ahead");
 
 struct ChunkRing {
   const uint8_t *gnext;  // global address of the next chunk to issue (16-byte aligned)
-  uint32_t sbase;        // shared-space address of this lane's slot of ring position 0
-  uint32_t snext;        // ring offset (bytes) of the slot the next chunk goes to
-  uint32_t trig;         // the next chunk is issued once the read window reaches chunk `trig` (0xffffffff: page fully issued)
-  uint32_t left;         // chunks of the page not yet issued
+  uint32_t sbase;        // shared-space address of this lane's ring
+  uint32_t snext;        // ring offset (bytes) the next chunk goes to
+  uint32_t trig;         // the next chunk is issued once the read window reaches chunk `trig` (0xffffffff: none left)
+  uint32_t trig_last;    // value of `trig` at which the page's last chunk goes out
   __device__ __forceinline__ void issue_one() {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(sbase + snext), "l"(gnext) : "memory");
     gnext += 16;
-    snext = (snext + 512) & (RING_CHUNKS * 512 - 1);
-    left--;
+    snext = (snext + 16) & (RING_BYTES - 1);
   }
-  __device__ __forceinline__ void init(const uint8_t *start, const uint8_t *end, uint32_t lane_slot) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15;
+  __device__ __forceinline__ void init(const uint8_t *start, const uint8_t *end, uint32_t lane_ring) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15, e = reinterpret_cast<uintptr_t>(end);
     gnext = reinterpret_cast<const uint8_t *>(a);
-    const uintptr_t e = reinterpret_cast<uintptr_t>(end);
-    left = e > a ? (uint32_t)((e - a + 15) >> 4) : 0u;
-    sbase = lane_slot;
+    const uint32_t n_chunks = e > a ? (uint32_t)((e - a + 15) >> 4) : 0u;  // chunks that intersect the stream
+    sbase = lane_ring;
     snext = 0;
 #pragma unroll
-    for (int i = 0; i < RING_CHUNKS; i++)
-      if (left) issue_one();
-    trig = left ? 1u : 0xffffffffu;  // chunk RING_CHUNKS goes out when the window reaches chunk 1
+    for (int i = 0; i < RING_CHUNKS; i++) issue_one();  // (a short stream's fill reads < RING_BYTES past its end)
+    trig = n_chunks > RING_CHUNKS ? 1u : 0xffffffffu;   // chunk RING_CHUNKS goes out when the window reaches chunk 1
+    trig_last = n_chunks - RING_CHUNKS;
   }
-  // One decoder step whose read window starts in chunk c (see above).
+  // One decoder step whose read window starts in chunk c (see above). Nothing is issued past the stream's last chunk,
+  // however far a decoder that ran off a truncated block pushes its window.
   __device__ __forceinline__ void step(uint32_t c) {
     if (c >= trig) {
       issue_one();
-      trig = left ? trig + 1 : 0xffffffffu;
+      trig = trig == trig_last ? 0xffffffffu : trig + 1;
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group %0;\n" :: "n"(RING_CHUNKS - 2) : "memory");
   }
-  // An empty ring: steps issue nothing, reads return stale shared memory (lanes without a page / kinds without a stream).
-  __device__ __forceinline__ void reset(uint32_t lane_slot) { gnext = nullptr; sbase = lane_slot; snext = 0; trig = 0xffffffffu; left = 0; }
-  // shared-space address of the chunk holding 64-bit word k (8-byte units from the aligned start)
-  __device__ __forceinline__ uint32_t chunk_addr(uint32_t k) const { return sbase + ((k & (2 * RING_CHUNKS - 2)) << 8); }
+  // An idle ring: steps issue nothing (lanes without a page / kinds without a stream).
+  __device__ __forceinline__ void reset(uint32_t lane_ring) { gnext = nullptr; sbase = lane_ring; snext = 0; trig = 0xffffffffu; trig_last = 0; }
   static __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
   }
-  // 64-bit word k of the stream, as stored (little-endian load of stream bytes)
-  __device__ __forceinline__ uint2 word(uint32_t k) const { return lds64(chunk_addr(k) + ((k & 1) << 3)); }
-  // words k, k + 1, k + 2 (they span two chunks)
+  // 64-bit word k of the stream (8-byte units from the aligned start), as stored (little-endian load of stream bytes)
+  __device__ __forceinline__ uint2 word(uint32_t k) const { return lds64(sbase + ((k & (2 * RING_CHUNKS - 1)) << 3)); }
+  // words k, k + 1, k + 2
   __device__ __forceinline__ void words3(uint32_t k, uint2 &w0, uint2 &w1, uint2 &w2) const {
-    const uint32_t c0 = chunk_addr(k), c1 = chunk_addr(k + 2);
-    const bool odd = k & 1;
-    w0 = lds64(odd ? c0 + 8 : c0);
-    w1 = lds64(odd ? c1 : c0 + 8);
-    w2 = lds64(odd ? c1 + 8 : c1);
+    w0 = word(k);
+    w1 = word(k + 1);
+    w2 = word(k + 2);
   }
 };
 // Commits the initial fills of the lane's rings and waits for them (once per page, before the first step).
@@ -546,8 +548,10 @@ struct GorillaRing {
     const uint32_t len = c0 ? (c1 ? 13u : 2u) : 1u;
     const uint32_t sig = c0 ? meaningful : 0u;
     const uint64_t payload = ((uint64_t)__funnelshift_l(M, H, len) << 32) | __funnelshift_l(L, M, len);
-    const uint64_t delta = (payload >> ((64u - sig) & 63u)) << (trailing & 63u);
-    val ^= c0 ? delta : 0ull;
+    // shr.b64 / shl.b64 clamp the shift amount at 64: a repeat element (sig = 0) shifts everything out, delta = 0
+    uint64_t delta;
+    asm("{\n\t.reg .b64 t;\n\tshr.b64 t, %1, %2;\n\tshl.b64 %0, t, %3;\n\t}" : "=l"(delta) : "l"(payload), "r"(64u - sig), "r"(trailing & 63u));
+    val ^= delta;
     pos += cur_ok ? len + sig : 0u;  // frozen once the sentinel has been seen (the lane keeps re-reading it, harmlessly)
     // the sentinel ends the stream (float.rs:585-589); repeats are pushed without the test (float.rs:493-497)
     cur_ok = cur_ok && !(c0 && val == 0x7ff80000000000ffull);

@@ -865,10 +865,13 @@ struct ValueAcc {  // count / sum / min / max of one run; VK fixes the arithmeti
 // instructions per 6-row segment. Instead every lane parks its partial in a per-warp staging area
 //   stage[slot][quantity][lane]          (one conflict-free STS.64 per quantity)
 // and every FLUSH_SLOTS flushes the warp reduces the parked partials TRANSPOSED: lane j owns slot j % FLUSH_SLOTS and
-// sums the partials of source lanes 4 * (j / FLUSH_SLOTS) .. + 3 serially (every lane does useful work on every
-// instruction), three xor-shuffle steps combine the 8 lane groups, and FLUSH_SLOTS lanes update the CTA table.
+// sums the partials of FLUSH_SLOTS source lanes serially (every lane does useful work on every instruction),
+// xor-shuffle steps combine the 32 / FLUSH_SLOTS lane groups, and FLUSH_SLOTS lanes update the CTA table.
 // ------------------------------------------------------------------------------------------------
-constexpr int FLUSH_SLOTS = 4;
+#ifndef TSKV_FLUSH_SLOTS
+#define TSKV_FLUSH_SLOTS 4
+#endif
+constexpr int FLUSH_SLOTS = TSKV_FLUSH_SLOTS;  // 2: 2.6 KB per warp (5 CTAs of 4 warps per SM), 4: fewer reduce passes
 constexpr int FLUSH_Q = 5;  // count | sum | sum_hi | min key | max key
 constexpr uint32_t FLUSH_STAGE_WORDS = FLUSH_SLOTS * FLUSH_Q * 32 + FLUSH_SLOTS;  // + one meta word per slot
 constexpr uint32_t FLUSH_STAGE_BYTES = FLUSH_STAGE_WORDS * 8;
@@ -885,10 +888,10 @@ __device__ __forceinline__ void reduce_staged(const ScanParams &P, uint64_t *sta
   uint64_t cnt = 0, sum = 0;
   int64_t hi = 0, kmin = INT64_MAX, kmax = INT64_MIN;
   const uint64_t *base = stage + (size_t)s * FLUSH_Q * 32;
-  static_assert(FLUSH_SLOTS == 4, "reduce_staged: 8 lane groups x 4 source lanes");
+  static_assert(FLUSH_SLOTS == 2 || FLUSH_SLOTS == 4, "reduce_staged: lane j owns slot j % FLUSH_SLOTS");
 #pragma unroll
-  for (int i = 0; i < 4; i++) {  // 4 source lanes per group, rotated by the slot: conflict-free
-    const uint32_t src = g * 4 + ((i + s) & 3);
+  for (int i = 0; i < FLUSH_SLOTS; i++) {  // FLUSH_SLOTS source lanes per lane group, rotated by the slot: conflict-free
+    const uint32_t src = g * FLUSH_SLOTS + ((i + s) & (FLUSH_SLOTS - 1));
     const uint64_t c = base[src], v = base[32 + src];
     cnt += c;
     if (is_f64) {
@@ -970,8 +973,8 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
   // this lane's slots in the warp's staging rings: [time ring (simple8b timestamps only)] [value ring]
-  const uint32_t tslot = ring_base + lane * 16;
-  const uint32_t vslot = ring_base + (TK == TK_S8B ? RING_BYTES_PER_WARP : 0) + lane * 16;
+  const uint32_t tslot = ring_base + lane * RING_LANE_STRIDE;
+  const uint32_t vslot = ring_base + (TK == TK_S8B ? RING_BYTES_PER_WARP : 0) + lane * RING_LANE_STRIDE;
 
   uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
   uint8_t pt = VK == VK_GOR ? TSKV_PT_F64 : TSKV_PT_I64, mask = 0;
@@ -1321,8 +1324,8 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
 #ifndef SCAN_MIN_BLOCKS
 #define SCAN_MIN_BLOCKS 4
 #endif
-// 4 blocks of 4 warps per SM: the per-CTA shared memory (table + rings + flush staging) allows no more, and 128
-// registers keep every variant free of spills.
+// 4 blocks of 4 warps per SM: 128 registers keep every variant free of spills. (Measured, round 2: forcing the RLE
+// kernels to 5 blocks - 96 registers, ~100 bytes of spills in the row loop - made them 1.7x SLOWER.)
 __host__ __device__ constexpr int scan_min_blocks(int /*tk*/, bool /*sel*/) { return SCAN_MIN_BLOCKS; }
 // staging-ring bytes one warp of the fused kernel needs (generic time pages read from global memory)
 __host__ __device__ constexpr uint32_t scan_ring_bytes_per_warp(int tk) {

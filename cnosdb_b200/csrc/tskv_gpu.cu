@@ -321,7 +321,19 @@ tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
     return TSKV_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
-  for (int b = 0; b < N_BINS; b++) cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking);
+  {
+    // Bins whose chunks take longest get the highest stream priority: when the grids of a scan over-subscribe the
+    // machine, the block scheduler starts the long serial tasks first and back-fills with the short ones.
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    for (int b = 0; b < N_BINS; b++) {
+      int rank = 0;
+      for (int o = 0; o < N_BINS; o++) rank += chunk_cost(o) > chunk_cost(b) ? 1 : 0;
+      const int prio = std::min(least, greatest + rank / 2);
+      if (cudaStreamCreateWithPriority(&ctx->bin_stream[b], cudaStreamNonBlocking, prio) != cudaSuccess)
+        cudaStreamCreateWithFlags(&ctx->bin_stream[b], cudaStreamNonBlocking);
+    }
+  }
   // Dynamic shared memory ceiling of every scan kernel, set ONCE: the attribute belongs to the kernel, not to a launch,
   // so per-scan values would race between host threads that prepare scans with different table sizes.
   {
@@ -1132,6 +1144,10 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       }
       plan_serial_grids(N_BINS, chunks, t_chunk, occ_bin, ctx->sm_count, SCAN_THREADS / 32, s->grid);
       for (int b = 0; b < N_BINS; b++) s->grid[b] = std::min(s->grid[b], std::max(need[b], 0));
+      // TSKV_GRID_MODE=1: one warp per chunk for every bin; the block scheduler queues what does not fit
+      static const char *gm = getenv("TSKV_GRID_MODE");
+      if (gm && gm[0] == '1')
+        for (int b = 0; b < N_BINS; b++) s->grid[b] = need[b];
     } else {
       // water-filling: bins that need less than their cost share keep their need, the rest split what is left
       bool fixed[N_BINS] = {false};
@@ -1223,6 +1239,8 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   static const bool gather_concurrent = getenv("TSKV_GATHER_CONCURRENT") != nullptr;
   if (pages->h_mapped && !gather_concurrent)
     std::stable_sort(order, order + N_BINS, [&](int a, int b) { return pages->h_bin_bytes[a] > pages->h_bin_bytes[b]; });
+  else if (!pages->h_mapped)
+    std::stable_sort(order, order + N_BINS, [&](int a, int b) { return chunk_cost(a) > chunk_cost(b); });
   int prev_gather = -1;
   for (int oi = 0; oi < N_BINS; oi++) {
     const int b = order[oi];
