@@ -396,11 +396,16 @@ def main():
     g = wl.generate(lo, hi - lo)
     t_gen = time.perf_counter() - t_gen
     eng = Engine(local_rank)
+    # the exchange runs inside the library (NCCL through the C ABI); TSKV_BENCH_TORCH_EXCHANGE=1 keeps torch.distributed's
+    use_torch_x = os.environ.get("TSKV_BENCH_TORCH_EXCHANGE", "0") == "1"
+    if world > 1 and not use_torch_x:
+        from cnosdb_b200.parallel import init_engine_comm
+        use_torch_x = not init_engine_comm(eng, rank, world)
     stream = torch.cuda.ExternalStream(eng.stream(), device=device)
     pages = eng.upload_pages(g.arena, g.descs, verify_crc=True)
     q = wl.query(sel_all, multi_rank=world > 1)
     scan = eng.prepare(pages, q)
-    exchange = GatherExchange(scan, eng, world) if world > 1 else None
+    exchange = GatherExchange(scan, eng, world, use_torch=use_torch_x) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def barrier():
@@ -451,7 +456,7 @@ def main():
     # ---- the same with Page::crc_validation on every read: CRC32 of every selected page re-checked per step -----
     pages_crc = eng.upload_pages(g.arena, g.descs, verify_crc=False, verify_on_read=True)
     scan_crc = eng.prepare(pages_crc, q)
-    ex_crc = GatherExchange(scan_crc, eng, world) if world > 1 else None
+    ex_crc = GatherExchange(scan_crc, eng, world, use_torch=use_torch_x) if world > 1 else None
     timed_steps(scan_crc, ex_crc, 2)
     barrier()
     crc_ms = timed_steps(scan_crc, ex_crc, steps)
@@ -515,7 +520,7 @@ def main():
         s = eng.prepare(hp, q)
         s.enqueue()
         if world > 1:
-            GatherExchange(s, eng, world).run()
+            GatherExchange(s, eng, world, use_torch=use_torch_x).run()
         res = s.finalize()
         s.sync()
         cc = eng.counters()
@@ -565,7 +570,7 @@ def main():
         qs = wl.query(ids, multi_rank=True)
         s = eng.prepare(pages, qs)
         s.enqueue()
-        GatherExchange(s, eng, world).run()
+        GatherExchange(s, eng, world, use_torch=use_torch_x).run()
         got = s.finalize()
         s.sync()
         s.close()
@@ -591,6 +596,7 @@ def main():
                 "warmup": warmup, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "i64/f64", "data": "synthetic", "config": config,
                 "run": {"l2_flush_between_steps": True, "pages_resident": "HBM",
+                        "exchange": None if world == 1 else ("torch.distributed all_gather + merge kernel" if use_torch_x else "tskvgpu_scan_exchange (ncclAllGather inside the library) + merge kernel"),
                         "encoded_bytes_selected_per_rank": int(page_bytes), "generate_s": round(t_gen, 2)},
                 "value_crc_per_step": value_crc, "ms_per_step_crc_per_step": float(tc[0]) / steps,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * steps),

@@ -47,7 +47,7 @@ def build_gpu(force=False):
     deps = _glob_sources(CSRC) + [os.path.join(ROOT, "include", "tskv_gpu.h")]
     if force or _newer(target, deps):
         _run([nvcc] + NVCC_FLAGS + ["-o", target, os.path.join(CSRC, "tskv_gpu.cu"),
-                                    os.path.join(CSRC, "host_util.cc")])
+                                    os.path.join(CSRC, "host_util.cc"), "-ldl"])  # libnccl is dlopen-ed on first use
     return target
 
 

@@ -73,12 +73,21 @@ class AggColumn(C.Structure):
     _fields_ = [("column_id", C.c_uint16), ("phys_type", C.c_uint8), ("agg_mask", C.c_uint8)]
 
 
+class FieldPredicate(C.Structure):
+    _fields_ = [("column_id", C.c_uint16), ("phys_type", C.c_uint8), ("op", C.c_uint8), ("reserved", C.c_uint32),
+                ("value", C.c_uint64)]
+
+
+CMP_OPS = {"==": 0, "=": 0, "!=": 1, "<>": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
+
+
 class Query(C.Structure):
     _fields_ = [("series_ids", C.POINTER(C.c_uint32)), ("n_series", C.c_uint32),
                 ("n_time_ranges", C.c_uint32), ("time_ranges", C.POINTER(TimeRange)),
                 ("origin", C.c_int64), ("width", C.c_int64), ("first_bucket_start", C.c_int64),
                 ("n_buckets", C.c_uint32), ("group_by_series", C.c_uint32),
-                ("columns", C.POINTER(AggColumn)), ("n_columns", C.c_uint32), ("reserved", C.c_uint32)]
+                ("columns", C.POINTER(AggColumn)), ("n_columns", C.c_uint32), ("reserved", C.c_uint32),
+                ("predicates", C.POINTER(FieldPredicate)), ("n_predicates", C.c_uint32), ("reserved2", C.c_uint32)]
 
 
 class OutputLayout(C.Structure):
@@ -93,7 +102,7 @@ class Counters(C.Structure):
                 ("elapsed_scan_ms", C.c_double), ("elapsed_h2d_ms", C.c_double),
                 ("kernel_launches", C.c_uint64), ("elapsed_fused_ms", C.c_double),
                 ("dominant_kernel_ms", C.c_double), ("dominant_kernel_bytes", C.c_uint64),
-                ("dominant_kernel_bin", C.c_uint64), ("h2d_bytes", C.c_uint64)]
+                ("dominant_kernel_bin", C.c_uint64), ("h2d_bytes", C.c_uint64), ("pruned_page_count", C.c_uint64)]
 
 
 class PartialsView(C.Structure):
@@ -109,7 +118,8 @@ class PartialsView(C.Structure):
 GPU_SYMBOLS = [
     "tskvgpu_ctx_create", "tskvgpu_ctx_destroy", "tskvgpu_last_error", "tskvgpu_last_error_page",
     "tskvgpu_get_counters", "tskvgpu_ctx_stream", "tskvgpu_upload_pages", "tskvgpu_pages_destroy",
-    "tskvgpu_pages_series_count", "tskvgpu_pages_set_tombstones", "tskvgpu_decode_pages", "tskvgpu_query_output_layout",
+    "tskvgpu_pages_series_count", "tskvgpu_pages_set_time_bounds", "tskvgpu_pages_set_tombstones", "tskvgpu_decode_pages",
+    "tskvgpu_query_output_layout", "tskvgpu_comm_unique_id", "tskvgpu_comm_init", "tskvgpu_comm_destroy", "tskvgpu_scan_exchange",
     "tskvgpu_scan_aggregate", "tskvgpu_scan_prepare", "tskvgpu_scan_run", "tskvgpu_scan_enqueue",
     "tskvgpu_scan_sync", "tskvgpu_scan_partials", "tskvgpu_scan_exchange_view", "tskvgpu_scan_merge_gathered",
     "tskvgpu_scan_snapshot_keys", "tskvgpu_scan_mask_values", "tskvgpu_scan_finalize",
@@ -159,6 +169,12 @@ def load_gpu_library():
     lib.tskvgpu_pages_series_count.argtypes = [vp]
     lib.tskvgpu_pages_series_count.restype = C.c_uint64
     lib.tskvgpu_pages_set_tombstones.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.tskvgpu_pages_set_time_bounds.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.tskvgpu_comm_unique_id.argtypes = [vp]
+    lib.tskvgpu_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    lib.tskvgpu_comm_destroy.argtypes = [vp]
+    lib.tskvgpu_comm_destroy.restype = None
+    lib.tskvgpu_scan_exchange.argtypes = [vp, vp]
     lib.tskvgpu_decode_pages.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, vp]
     lib.tskvgpu_query_output_layout.argtypes = [vp, C.POINTER(Query), C.POINTER(OutputLayout)]
     lib.tskvgpu_scan_aggregate.argtypes = [vp, vp, C.POINTER(Query), vp, vp]

@@ -96,6 +96,10 @@ struct ScanParams {
   const tskv_time_range *tomb_ranges;
   uint32_t n_tomb_keys;
   uint32_t n_tomb_global;
+  // Row filter (tskv_field_predicate): one keep bit per row of every column group, written by k_row_filter before the
+  // fused kernels; words of a group start at row_keep + keep_off[index of the group's time page]. null: no predicates.
+  const uint32_t *row_keep;
+  const uint32_t *keep_off;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -132,11 +136,20 @@ __device__ __forceinline__ int find_qcol(const ColState *cols, uint32_t n_cols, 
 // "this item also brings its column group's time page"), per-block counts and the byte/page counters
 // of the reference's reader metrics (column_group/mod.rs:141-193), split per decode-kind bin.
 // counters: [0] pages, [1] bytes, [2 + bin] bytes read by bin's fused kernel.
+// Statistics pruning (filter_column_groups, tskv/src/reader/chunk.rs:12-50 with the column group's time_range(),
+// tsm/column_group.rs:9-17): a group whose [min_ts, max_ts] overlaps none of the query's time ranges is dropped here,
+// so its pages are neither gathered nor decoded. counters[2 + N_BINS] counts the pruned groups' field pages.
+struct PruneRanges {
+  tskv_time_range r[MAX_RANGES];
+  uint32_t n;
+  uint32_t pad;
+};
 __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_page,
                              const uint32_t *item_cg, const uint32_t *cg_time_page, uint32_t n_items,
                              const int32_t *cg_slot, const ColState *cols, uint32_t n_cols,
                              const uint32_t *bin_start, uint8_t *item_flag, uint32_t *block_count,
-                             unsigned long long *counters, int32_t *status) {
+                             unsigned long long *counters, int32_t *status, const tskv_time_range *cg_bounds,
+                             const PruneRanges prune) {
   __shared__ uint32_t s_cnt;
   __shared__ unsigned long long s_pages, s_bytes[N_BINS];
   if (threadIdx.x == 0) { s_cnt = 0; s_pages = 0; }
@@ -150,7 +163,14 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_p
     uint32_t cg = item_cg[i];
     int qc = find_qcol(cols, n_cols, d.column_id);
     bool first_sel = false;
-    if (qc >= 0 && cg_slot[cg] >= 0) {
+    bool in_time = true;
+    if (cg_bounds && prune.n) {  // TimeRange::overlaps against the group's statistics
+      const tskv_time_range b = cg_bounds[cg];
+      in_time = false;
+      for (uint32_t k = 0; k < prune.n; k++) in_time = in_time || (b.min_ts <= prune.r[k].max_ts && b.max_ts >= prune.r[k].min_ts);
+      if (!in_time && qc >= 0 && cg_slot[cg] >= 0) atomicAdd(&counters[2 + N_BINS], 1ull);
+    }
+    if (qc >= 0 && cg_slot[cg] >= 0 && in_time) {
       if (cols[qc].phys_type != d.phys_type) {
         atomicCAS(status, 0, TSKV_ERR_INVALID_ARG);
       } else {
@@ -340,6 +360,88 @@ k_verify_crc(const uint8_t *arena, const tskv_page_desc *descs, const uint32_t *
         if (atomicCAS(status, 0, (int)TSKV_ERR_CRC_MISMATCH) == 0) *err_page = pg;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row filter of the pushed field predicates (DataFilter, tskv/src/reader/filter.rs:23-142; `column <op> constant`
+// joined by AND). One lane per selected column group decodes the group's predicate columns and writes one keep bit per
+// row: 1 = every comparison is TRUE. A NULL value, or a group without a page of the column (null-filled by the
+// reference, schema_alignmenter.rs:24-44), keeps no row. The fused kernels read the bits next to the validity bitmaps;
+// only a bit per row leaves this kernel, never a decoded value.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cmp_true(uint8_t pt, uint8_t op, uint64_t v, uint64_t c) {
+  int r;  // -1 / 0 / +1, or 2 for unordered (NaN)
+  if (pt == TSKV_PT_I64) r = (int64_t)v < (int64_t)c ? -1 : ((int64_t)v > (int64_t)c ? 1 : 0);
+  else if (pt == TSKV_PT_U64) r = v < c ? -1 : (v > c ? 1 : 0);
+  else {
+    const double a = __longlong_as_double((long long)v), b = __longlong_as_double((long long)c);
+    r = (a != a || b != b) ? 2 : (a < b ? -1 : (a > b ? 1 : 0));
+  }
+  switch (op) {
+    case TSKV_CMP_EQ: return r == 0;
+    case TSKV_CMP_NE: return r == -1 || r == 1;
+    case TSKV_CMP_LT: return r == -1;
+    case TSKV_CMP_LE: return r == -1 || r == 0;
+    case TSKV_CMP_GT: return r == 1;
+    case TSKV_CMP_GE: return r == 1 || r == 0;
+    default: return false;
+  }
+}
+
+struct PredicateSet {
+  tskv_field_predicate p[TSKV_MAX_PREDICATES];
+  uint32_t n;
+  uint32_t pad;
+};
+
+__global__ void k_row_filter(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs, const uint32_t *cg_time_page,
+                             uint32_t n_cg, const int32_t *cg_slot, const PredicateSet preds, const uint32_t *keep_off,
+                             uint32_t *row_keep, int32_t *status, unsigned long long *err_page) {
+  const uint32_t cg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cg >= n_cg || cg_slot[cg] < 0) return;
+  const uint32_t tp = cg_time_page[cg];
+  const uint32_t n_rows = descs[tp].num_values;
+  const uint32_t n_words = (n_rows + 31) >> 5;
+  uint32_t *keep = row_keep + keep_off[tp];
+  for (uint32_t w = 0; w < n_words; w++) keep[w] = 0xffffffffu;
+  for (uint32_t k = 0; k < preds.n; k++) {
+    const tskv_field_predicate fp = preds.p[k];
+    uint64_t pg = 0;
+    bool found = false;
+    for (uint64_t j = tp + 1; j < n_descs && descs[j].phys_type != TSKV_PT_TIME; j++)
+      if (descs[j].column_id == fp.column_id) { pg = j; found = true; break; }
+    if (!found) {  // the column is NULL for every row of this group
+      for (uint32_t w = 0; w < n_words; w++) keep[w] = 0;
+      continue;
+    }
+    const tskv_page_desc d = descs[pg];
+    tskv_status st = d.phys_type != fp.phys_type ? TSKV_ERR_INVALID_ARG : kind_status(d.reserved);
+    if (st == TSKV_OK) {
+      PageView pv;
+      pv.open(arena, d);
+      BitCursor bits;
+      bits.init(pv.bitset);
+      AnyCursor<> cur;
+      st = cur.open(pv, d.reserved);
+      const bool allnull = d.reserved == DK_ALLNULL;
+      uint32_t word = 0;
+      for (uint32_t r = 0; r < n_rows && st == TSKV_OK; r++) {
+        const bool valid = bits.next(r) && !allnull;
+        bool pass = false;
+        if (valid) {
+          const uint64_t v = cur.next();
+          if (cur.failed()) { st = cur.stream_error() ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH; break; }
+          pass = cmp_true(fp.phys_type, fp.op, v, fp.value);
+        } else if (r == 0 && !cur.is_gorilla) {
+          cur.d.skip_first_if_s8b_sc();
+        }
+        word |= (pass ? 1u : 0u) << (r & 31);
+        if ((r & 31) == 31 || r == n_rows - 1) { keep[r >> 5] &= word; word = 0; }
+      }
+      if (st == TSKV_OK && cur.is_gorilla && cur.g.consumed_any() && !cur.g.drain()) st = TSKV_ERR_SHORT_BLOCK;
+    }
+    if (st != TSKV_OK && atomicCAS(status, 0, (int)st) == 0) *err_page = pg;
   }
 }
 
@@ -680,6 +782,8 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
   DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, BeStream> vcur_d;
   GorillaCursor<BeStream> vcur_g;
   bool allnull = false;
+  const uint32_t *keepw = nullptr;  // row-filter keep bits of the column group (k_row_filter), or null
+  uint32_t kword = 0xffffffffu;
 
   if (have_item) {
     page = P.work_page[item];
@@ -688,6 +792,7 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
     const tskv_page_desc vd = P.descs[page];
     const uint32_t tpage = P.time_page_of[page];
     const tskv_page_desc td = P.descs[tpage];
+    if (P.row_keep) keepw = P.row_keep + P.keep_off[tpage];
     pt = P.cols[qcol].phys_type;
     mask = P.cols[qcol].agg_mask;
     if (P.has_tomb) s_tomb[threadIdx.x] = tomb_lookup(P, vd.series_id, vd.column_id);
@@ -746,8 +851,10 @@ __device__ __forceinline__ void scan_chunk_rows(const ScanParams &P, uint32_t it
           n_points++;
         }
       }
+      if (keepw && (row & 31) == 0) kword = __ldg(keepw + (row >> 5));
+      const bool kept = (kword >> (row & 31)) & 1;  // the row filter (DataFilter) drops the row like the time ranges do
       row++;
-      if (ok && tv) {
+      if (ok && tv && kept) {
         inr = P.n_ranges == 0;
 #pragma unroll 1
         for (uint32_t k = 0; k < P.n_ranges && !inr; k++) inr = t >= P.ranges[k].min_ts && t <= P.ranges[k].max_ts;
@@ -985,6 +1092,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, SeqStream> vcur_d;
   GorillaRing vcur_g;
   const uint32_t *vbm = nullptr;  // value validity bitmap, 32 rows per word
+  const uint32_t *keepw = nullptr;  // row-filter keep bits of the column group (k_row_filter), or null
   bool allnull = false;
   int64_t pend_t = 0;  // timestamp of row `row`
   __shared__ uint4 s_tomb[SCAN_THREADS];  // per lane tombstone lists (only touched when the page set has any)
@@ -1010,6 +1118,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
       vpv.open(P.arena, vd);
       n_rows = vd.num_values;
       vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
+      if (P.row_keep) keepw = P.row_keep + P.keep_off[tpage];
       if (TK == TK_RLE) {  // timestamp.rs:226-259
         DeltaCursor<DK_RLE_SC, BeStream> rc;
         st = rc.open(tpv, td.reserved);
@@ -1045,6 +1154,8 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   uint32_t row = 0;
   uint32_t n_points = 0, n_inrange = 0;
   uint32_t vword = 0, vahead = vbm ? __ldg(vbm) : 0;  // bitmap word of `row`, and the next one (prefetched)
+  uint32_t kword = 0xffffffffu;                        // row-filter bits of the same 32 rows (all ones without predicates)
+  bool first_pending = false;                          // FIRST/LAST: the run has not seen a kept row yet
   const uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull : 0ull;
   const uint64_t group_base = P.group_by_series ? (uint64_t)slot * P.n_buckets : 0;
   uint32_t staged = 0;  // staged flush slots in use (warp-uniform)
@@ -1063,17 +1174,19 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   };
   // One row's value: validity bit, decode (every valid row is decoded - rows outside the time ranges too, the streams
   // are sequential), accumulate when the segment is selected. Returns the value; `vv` = the row holds one.
-  auto row_value = [&](bool accumulate, bool &vv) -> uint64_t {
+  auto row_value = [&](bool accumulate, bool &vv, bool &kept) -> uint64_t {
     if ((row & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
       vword = vahead;
       vahead = __ldg(vbm + (row >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
+      if (keepw) kword = __ldg(keepw + (row >> 5));
     }
     vv = ((vword >> (row & 31)) & 1) && !allnull;
+    kept = (kword >> (row & 31)) & 1;
     uint64_t v = 0;
     if (vv) {
       v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
       n_points++;
-      if (accumulate) { va.count++; va.add(v, pt, flip); }
+      if (accumulate && kept) { va.count++; va.add(v, pt, flip); }
     }
     return v;
   };
@@ -1220,6 +1333,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
       have_run = true;
       run_idx = seg_b;
       va.reset();
+      if (SEL) { acc.first_ok = acc.last_ok = false; first_pending = true; }
     }
     // ---- 3. the segment's rows --------------------------------------------------------------------------
     if (go) {
@@ -1227,44 +1341,42 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
       const bool accumulate = seg_in && !seg_masked;
       if (TK == TK_RLE) {
         // the row count is known: values one bitmap word at a time (no per-row timestamp, no per-row bitmap fetch)
-        const uint32_t rend = row + seg_n, row0 = row;
-        if (seg_in) n_inrange += seg_n;
+        const uint32_t rend = row + seg_n;
         uint32_t r = row;
         while (r < rend) {
           if ((r & 31) == 0) {  // entering a new bitmap word: take the prefetched one, prefetch the next
             vword = vahead;
             vahead = __ldg(vbm + (r >> 5) + 1);  // reads at most 8 bytes past the bitmap (inside the page)
+            if (keepw) kword = __ldg(keepw + (r >> 5));
           }
           const uint32_t off = r & 31;
           const uint32_t span = min(32u - off, rend - r);
-          const uint32_t m = allnull ? 0u : ((vword >> off) & (0xffffffffu >> (32 - span)));
+          const uint32_t smask = 0xffffffffu >> (32 - span);
+          const uint32_t m = allnull ? 0u : ((vword >> off) & smask);  // rows holding a value
+          const uint32_t kb = (kword >> off) & smask;                   // rows the row filter keeps
           n_points += __popc(m);
+          if (seg_in) n_inrange += __popc(kb);
           if (!SEL) {  // one loop for dense and sparse bitmaps: a warp holds pages of both kinds
-            if (accumulate) va.count += __popc(m);
+            if (accumulate) va.count += __popc(m & kb);
 #pragma unroll 1
             for (uint32_t j = 0; j < span; j++) {
               if ((m >> j) & 1) {
                 const uint64_t v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
-                if (accumulate) va.add(v, pt, flip);
+                if (accumulate && ((kb >> j) & 1)) va.add(v, pt, flip);
               }
             }
-          } else {  // FIRST / LAST wanted: the run's end rows keep (ts, value, valid)
+          } else {  // FIRST / LAST wanted: the run's first and last KEPT rows keep (ts, value, valid)
             for (uint32_t j = 0; j < span; j++) {
               bool vv = (m >> j) & 1;
               uint64_t v = 0;
               if (vv) v = VK == VK_GOR ? vcur_g.next() : vcur_d.next();
               vv = vv && !seg_masked;
-              if (seg_in) {
-                if (r + j == row0 && newrun) {
-                  acc.first_ts = (int64_t)(rle_t0 + (uint64_t)row0 * rle_delta);
-                  acc.first_val = vv ? v : 0;
-                  acc.first_ok = vv;
-                }
-                if (r + j == rend - 1) {
-                  acc.last_ts = (int64_t)(rle_t0 + (uint64_t)(rend - 1) * rle_delta);
-                  acc.last_val = vv ? v : 0;
-                  acc.last_ok = vv;
-                }
+              if (seg_in && ((kb >> j) & 1)) {
+                const int64_t t = (int64_t)(rle_t0 + (uint64_t)(r + j) * rle_delta);
+                if (first_pending) { acc.first_ts = t; acc.first_val = vv ? v : 0; acc.first_ok = vv; first_pending = false; }
+                acc.last_ts = t;
+                acc.last_val = vv ? v : 0;
+                acc.last_ok = vv;
                 if (vv) { va.count++; va.add(v, pt, flip); }
               }
             }
@@ -1277,21 +1389,20 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
         // simple8b timestamps: ONE loop decodes the row's value and the NEXT row's timestamp - two independent dependent
         // chains in flight per lane - and stops at the first timestamp outside the segment's interval
         int64_t t = pend_t;
-        bool first_row = newrun;
         const uint64_t span = (uint64_t)lim_hi - (uint64_t)lim_lo;
         bool more;
 #pragma unroll 1
         do {
-          bool vv;
-          const uint64_t v = row_value(accumulate, vv);
-          if (SEL && seg_in) {
+          bool vv, kept;
+          const uint64_t v = row_value(accumulate, vv, kept);
+          if (SEL && seg_in && kept) {
             const bool ok = vv && !seg_masked;
-            if (first_row) { acc.first_ts = t; acc.first_val = ok ? v : 0; acc.first_ok = ok; first_row = false; }
+            if (first_pending) { acc.first_ts = t; acc.first_val = ok ? v : 0; acc.first_ok = ok; first_pending = false; }
             acc.last_ts = t;
             acc.last_val = ok ? v : 0;
             acc.last_ok = ok;
           }
-          if (seg_in) n_inrange++;
+          if (seg_in && kept) n_inrange++;
           row++;
           t = (int64_t)tcur.next();  // (past the last row this runs one value too far - harmless)
           more = row < n_rows && (uint64_t)t - (uint64_t)lim_lo <= span;
@@ -1567,7 +1678,8 @@ __global__ void k_finalize(const uint64_t *state, const OutCol *outs, uint32_t n
 // upload-time statistics: min / max timestamp of the arena (the reference keeps them per page in
 // PageMeta.statistics, written at flush time: tsm/page.rs:212-231). One lane per time page.
 __global__ void k_time_bounds(const uint8_t *arena, const tskv_page_desc *descs, const uint32_t *cg_time_page,
-                              uint32_t n_cg, long long *bounds /* [0]=min [1]=max */) {
+                              uint32_t n_cg, long long *bounds /* [0]=min [1]=max */,
+                              tskv_time_range *cg_bounds /* per column group (min > max: no timestamps), may be null */) {
   uint32_t cg = blockIdx.x * blockDim.x + threadIdx.x;
   long long lo = INT64_MAX, hi = INT64_MIN;
   if (cg < n_cg) {
@@ -1589,6 +1701,7 @@ __global__ void k_time_bounds(const uint8_t *arena, const tskv_page_desc *descs,
       }
     }
   }
+  if (cg_bounds && cg < n_cg) cg_bounds[cg] = tskv_time_range{lo, hi};
   for (int o = 16; o; o >>= 1) {
     long long l2 = (long long)shfl_xor_u64((uint64_t)lo, o), h2 = (long long)shfl_xor_u64((uint64_t)hi, o);
     lo = l2 < lo ? l2 : lo;

@@ -12,6 +12,8 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the library is loaded with dlopen on first use
 
 #include "host_util.h"
 #include "decode_kernels.cuh"
@@ -34,6 +36,8 @@ struct tskv_ctx {
   cudaStream_t bin_stream[N_BINS] = {nullptr};  // the per-bin fused kernels run concurrently
   int sm_count = 148;
   int max_dyn_smem = 48 * 1024;
+  ncclComm_t comm = nullptr;  // tskvgpu_comm_init
+  int n_ranks = 1, rank = 0;
   std::mutex mu;
   std::string err;
   int64_t err_page = -1;
@@ -77,6 +81,12 @@ struct tskv_pages {
   // PageMeta.statistics); only unbucketed first/last across series needs them
   mutable bool bounds_known = false;
   mutable int64_t ts_min = INT64_MIN, ts_max = INT64_MAX;
+  // per-column-group [min_ts, max_ts] (ColumnGroup::time_range()): handed in by the caller
+  // (tskvgpu_pages_set_time_bounds) or computed together with the arena-wide bounds; drives statistics pruning
+  mutable tskv_time_range *d_cg_bounds = nullptr;
+  // row-filter masks: 32-bit words per column group, offset stored at the index of the group's time page
+  uint32_t *d_keep_off = nullptr;
+  uint64_t keep_words = 0;
 };
 
 struct tskv_scan {
@@ -120,6 +130,17 @@ struct tskv_scan {
   cudaEvent_t ev_bin[N_BINS + 1] = {nullptr};  // [0] fork, [N_BINS] join of the fused phase
   cudaEvent_t ev_bin_start[N_BINS] = {nullptr}, ev_bin_done[N_BINS] = {nullptr}, ev_gather[N_BINS] = {nullptr};
   tskv_counters counters{};  // of the last completed pass of this scan
+  // A scan that is enqueued repeatedly replays its whole pass (2 memsets, ~7 small kernels, the fused kernels forked
+  // over the bin streams, export) as ONE CUDA graph launch: captured on the second enqueue, so one-shot scans never pay
+  // for a capture.
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaEvent_t ev_cfork = nullptr, ev_cjoin[N_BINS] = {nullptr};  // dependency-only events of the captured pass
+  uint32_t n_enqueued = 0;
+  bool graph_failed = false;
+  PruneRanges prune{};
+  uint64_t *d_gathered = nullptr;  // all ranks' exchange regions (tskvgpu_scan_exchange)
+  PredicateSet preds{};            // pushed field predicates (row filter)
+  uint32_t *d_row_keep = nullptr;  // one keep bit per row of every column group (k_row_filter)
 };
 
 namespace {
@@ -233,8 +254,10 @@ void ensure_time_bounds(tskv_ctx *ctx, const tskv_pages *pg) {
   if (cudaMalloc(reinterpret_cast<void **>(&d_bounds), 16) != cudaSuccess) return;
   long long b[2] = {INT64_MAX, INT64_MIN};
   cudaMemcpyAsync(d_bounds, b, sizeof(b), cudaMemcpyHostToDevice, ctx->stream);
+  if (!pg->d_cg_bounds && cudaMalloc(reinterpret_cast<void **>(&pg->d_cg_bounds), (size_t)pg->n_cg * sizeof(tskv_time_range)) != cudaSuccess)
+    pg->d_cg_bounds = nullptr;
   k_time_bounds<<<(pg->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pg->h_mapped ? pg->h_mapped : pg->d_arena, pg->d_descs,
-                                                                pg->d_cg_time_page, pg->n_cg, d_bounds);
+                                                                pg->d_cg_time_page, pg->n_cg, d_bounds, pg->d_cg_bounds);
   if (cudaMemcpyAsync(b, d_bounds, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
       cudaStreamSynchronize(ctx->stream) == cudaSuccess && b[0] <= b[1]) {
     pg->ts_min = b[0];
@@ -267,9 +290,13 @@ void free_scan(tskv_scan *s) {
   cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
   void *bufs[] = {s->d_series, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
                   s->d_work_qcol, s->d_bin_cstart, s->d_cols, s->d_outs, s->d_means, s->d_state,
-                  s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1]};
+                  s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1], s->d_gathered, s->d_row_keep};
   for (void *b : bufs)
     if (b) cudaFreeAsync(b, st);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->ev_cfork) cudaEventDestroy(s->ev_cfork);
+  for (int b = 0; b < N_BINS; b++)
+    if (s->ev_cjoin[b]) cudaEventDestroy(s->ev_cjoin[b]);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   for (int b = 0; b <= N_BINS; b++)
@@ -301,9 +328,84 @@ tskv_status fetch_status(tskv_ctx *ctx, int32_t *d_status, unsigned long long *d
   return st;
 }
 
+// NCCL entry points, resolved from libnccl.so.2 on first use.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+const NcclApi &nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+  });
+  return api;
+}
+
 }  // namespace
 
 extern "C" {
+
+static_assert(sizeof(ncclUniqueId) == TSKV_NCCL_UNIQUE_ID_BYTES, "tskv_gpu.h: NCCL unique id size");
+
+tskv_status tskvgpu_comm_unique_id(uint8_t *out_id) {
+  const NcclApi &N = nccl_api();
+  if (!out_id) return TSKV_ERR_INVALID_ARG;
+  if (!N.ok) return TSKV_ERR_NCCL;
+  ncclUniqueId id;
+  if (N.GetUniqueId(&id) != ncclSuccess) return TSKV_ERR_NCCL;
+  memcpy(out_id, &id, sizeof(id));
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_comm_init(tskv_ctx *ctx, const uint8_t *id_bytes, int32_t rank, int32_t n_ranks) {
+  if (!ctx || !id_bytes || n_ranks < 1 || rank < 0 || rank >= n_ranks) return TSKV_ERR_INVALID_ARG;
+  const NcclApi &N = nccl_api();
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_error("");
+  if (!N.ok) {
+    ctx->set_error("libnccl.so.2 could not be loaded");
+    return TSKV_ERR_NCCL;
+  }
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->comm) {
+    N.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  const ncclResult_t r = N.CommInitRank(&ctx->comm, n_ranks, id, rank);
+  if (r != ncclSuccess) {
+    ctx->set_error(std::string("ncclCommInitRank: ") + N.GetErrorString(r));
+    ctx->comm = nullptr;
+    return TSKV_ERR_NCCL;
+  }
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return TSKV_OK;
+}
+
+void tskvgpu_comm_destroy(tskv_ctx *ctx) {
+  if (!ctx || !ctx->comm) return;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  nccl_api().CommDestroy(ctx->comm);
+  ctx->comm = nullptr;
+  ctx->n_ranks = 1;
+}
 
 const char *tskvgpu_version(void) { return "tskv-b200 0.1.0 sm_100a"; }
 
@@ -368,6 +470,7 @@ tskv_status tskvgpu_ctx_create(int32_t device_id, tskv_ctx **out_ctx) {
 void tskvgpu_ctx_destroy(tskv_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->comm) tskvgpu_comm_destroy(ctx);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
@@ -493,6 +596,16 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   }
   pg->n_cg = (uint32_t)cg_time_page.size();
   pg->n_items = (uint32_t)item_page.size();
+  std::vector<uint32_t> keep_off(n_descs, 0);
+  for (uint32_t tp : cg_time_page) {
+    keep_off[tp] = (uint32_t)pg->keep_words;
+    pg->keep_words += ((uint64_t)pg->h_descs[tp].num_values + 31) / 32;
+  }
+  if (pg->keep_words >= (1ull << 32)) {
+    ctx->set_error("too many rows for one arena (2^37)");
+    delete pg;
+    return TSKV_ERR_INVALID_ARG;
+  }
   // series ranks
   pg->series.reserve(pg->n_cg);
   for (uint32_t cg = 0; cg < pg->n_cg; cg++) pg->series.push_back(pg->h_descs[cg_time_page[cg]].series_id);
@@ -566,6 +679,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   if (e == cudaSuccess) e = up(&pg->d_item_page, item_page.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
+  if (e == cudaSuccess) e = up(&pg->d_keep_off, keep_off.data(), n_descs);
   if (e == cudaSuccess && (((flags & TSKV_UPLOAD_VERIFY_CRC) && (flags & TSKV_UPLOAD_HOST_RESIDENT)) || (flags & TSKV_UPLOAD_VERIFY_ON_READ))) {
     pg->verify_on_read = true;  // like the reference: every read of a page re-checks its CRC (device side)
     e = up(&pg->d_crc_tables, crc32_tables(), 2048);
@@ -602,10 +716,33 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_tomb_keys);
   cudaFree(pg->d_tomb_off);
   cudaFree(pg->d_tomb_ranges);
+  cudaFree(pg->d_cg_bounds);
+  cudaFree(pg->d_keep_off);
   delete pg;
 }
 
 uint64_t tskvgpu_pages_series_count(const tskv_pages *pages) { return pages ? pages->series.size() : 0; }
+
+tskv_status tskvgpu_pages_set_time_bounds(tskv_ctx *ctx, tskv_pages *pg, const tskv_time_range *bounds, uint64_t n) {
+  if (!ctx || !pg || !bounds || n != pg->n_cg) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_error("");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!pg->d_cg_bounds) CU_TRY(ctx, cudaMalloc(reinterpret_cast<void **>(&pg->d_cg_bounds), std::max<size_t>(n, 1) * sizeof(tskv_time_range)));
+  CU_TRY(ctx, cudaMemcpy(pg->d_cg_bounds, bounds, n * sizeof(tskv_time_range), cudaMemcpyHostToDevice));
+  int64_t lo = INT64_MAX, hi = INT64_MIN;
+  for (uint64_t i = 0; i < n; i++)
+    if (bounds[i].min_ts <= bounds[i].max_ts) {
+      lo = std::min(lo, bounds[i].min_ts);
+      hi = std::max(hi, bounds[i].max_ts);
+    }
+  if (lo <= hi) {
+    pg->ts_min = lo;
+    pg->ts_max = hi;
+  }
+  pg->bounds_known = true;
+  return TSKV_OK;
+}
 
 // TsmTombstone cache -> device tables: the all-series ranges first, then one CSR row per (series, column) key.
 tskv_status tskvgpu_pages_set_tombstones(tskv_ctx *ctx, tskv_pages *pg, const tskv_tombstone *tombs, uint64_t n_tombs) {
@@ -754,6 +891,15 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     ctx->set_error("invalid query: at most 126 columns and 8 time ranges");
     return TSKV_ERR_INVALID_ARG;
   }
+  if (q->n_predicates > TSKV_MAX_PREDICATES || (q->n_predicates && !q->predicates)) {
+    ctx->set_error("invalid query: at most 8 field predicates");
+    return TSKV_ERR_INVALID_ARG;
+  }
+  for (uint32_t k = 0; k < q->n_predicates; k++)
+    if (q->predicates[k].phys_type < TSKV_PT_I64 || q->predicates[k].phys_type > TSKV_PT_F64 || q->predicates[k].op > TSKV_CMP_GE) {
+      ctx->set_error("invalid field predicate (type or operator)");
+      return TSKV_ERR_INVALID_ARG;
+    }
   for (uint32_t c = 0; c < q->n_columns; c++) {
     const tskv_agg_column &qc = q->columns[c];
     if (qc.phys_type < TSKV_PT_I64 || qc.phys_type > TSKV_PT_F64 || (qc.agg_mask & ~TSKV_AGG_ALL) || qc.agg_mask == 0) {
@@ -990,6 +1136,9 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   if (e == cudaSuccess && !means.empty())
     e = cudaMemcpyAsync(s->d_means, means.data(), means.size() * sizeof(MeanExport), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_state, sl.total);
+  s->preds.n = q->n_predicates;
+  for (uint32_t k = 0; k < q->n_predicates; k++) s->preds.p[k] = q->predicates[k];
+  if (e == cudaSuccess && q->n_predicates) e = stream_alloc(ctx, &s->d_row_keep, (size_t)pages->keep_words);
   // aux block (8-byte units): [0..7] task counters (N_BINS x u32) | 8 status | 9 err_page | 10,11 stats
   //                           | 12 pages 13 bytes 14..22 per-bin bytes
   if (e == cudaSuccess) e = stream_alloc(ctx, reinterpret_cast<unsigned long long **>(&s->d_task_counter), 32);
@@ -1025,6 +1174,11 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   P.stats = s->d_stats;
   P.n_ranges = q->n_time_ranges;
   for (uint32_t k = 0; k < q->n_time_ranges; k++) P.ranges[k] = q->time_ranges[k];
+  if (q->n_time_ranges) {  // statistics pruning needs the groups' time bounds (one pass over the time pages, once per page set)
+    ensure_time_bounds(ctx, pages);
+    s->prune.n = q->n_time_ranges;
+    for (uint32_t k = 0; k < q->n_time_ranges; k++) s->prune.r[k] = q->time_ranges[k];
+  }
   P.width = q->width;
   P.origin_mod = q->width > 0 ? q->origin % q->width : 0;
   P.first_bucket_start = q->first_bucket_start;
@@ -1054,6 +1208,8 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     P.use_smem = (!q->group_by_series && (uint64_t)words * 8 <= limit) ? 1u : 0u;
     P.smem_words = P.use_smem ? words : 0;
     P.n_cols = q->n_columns;
+    P.row_keep = s->d_row_keep;
+    P.keep_off = pages->d_keep_off;
     P.has_tomb = pages->n_tomb_ranges ? 1u : 0u;
     P.tomb_keys = pages->d_tomb_keys;
     P.tomb_off = pages->d_tomb_off;
@@ -1078,7 +1234,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     for (int b = N_SERIAL_BINS; b < N_BINS; b++)
       // Round 2: the lane-per-page kernels (staged streams, fused row loops) beat the round-1 cooperative kernels on
       // every shard size measured (1/8 of C4 on one GPU: 0.49 ms vs 0.75 ms), so those run only on request.
-      s->use_coop[b] = pages->n_tomb_ranges ? false  // tombstones are handled by the lane-per-page kernels
+      s->use_coop[b] = (pages->n_tomb_ranges || q->n_predicates) ? false  // tombstones / row filters: lane-per-page kernels only
                        : mode             ? (mode[0] == '1')
                                           : false;
     (void)est_total;
@@ -1197,14 +1353,16 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
 // Enqueues one full pass on the context stream, no host synchronisation:
 //   selection -> compacted work list -> (host-resident arenas: PCIe gather of the selected pages)
 //   -> state init -> one fused decode/filter/reduce kernel per decode-kind bin -> export.
-static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
+// `capturing`: the calls are being recorded into a CUDA graph - timing events are left out (only the fork / join / gather
+// dependencies are recorded, on events created without timing).
+static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = false) {
   const tskv_pages *pages = s->pages;
   const uint32_t n_items = pages->n_items;
   if (s->tomb_epoch != pages->tomb_epoch) {
     ctx->set_error("the page set's tombstones changed after this scan was prepared", -1);
     return TSKV_ERR_INVALID_ARG;
   }
-  cudaEventRecord(s->ev0, ctx->stream);
+  if (!capturing) cudaEventRecord(s->ev0, ctx->stream);
   unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
   CU_TRY(ctx, cudaMemsetAsync(aux, 0, 32 * 8, ctx->stream));
   CU_TRY(ctx, cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream));
@@ -1215,11 +1373,18 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
                                                                      pages->d_cg_series_rank, s->d_cg_slot);
     launches++;
   }
+  if (s->preds.n && pages->n_cg) {  // row filter: keep bits of every selected column group (host-resident pages: read in place)
+    k_row_filter<<<(pages->n_cg + 127) / 128, 128, 0, ctx->stream>>>(pages->h_mapped ? pages->h_mapped : pages->d_arena, pages->d_descs,
+                                                                     pages->n_descs, pages->d_cg_time_page, pages->n_cg, s->d_cg_slot,
+                                                                     s->preds, pages->d_keep_off, s->d_row_keep, s->d_status, s->d_err_page);
+    launches++;
+  }
   if (n_items) {
     k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_page, pages->d_item_cg,
                                                         pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
                                                         s->n_cols, pages->d_bin_start, s->d_item_flag,
-                                                        s->d_block_count, s->d_counters, s->d_status);
+                                                        s->d_block_count, s->d_counters, s->d_status,
+                                                        s->prune.n ? pages->d_cg_bounds : nullptr, s->prune);
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(s->d_block_count, s->n_blocks, s->d_bin_cstart + N_BINS + 1);
     k_scatter_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_item_page, pages->d_item_cg, n_items, s->d_item_flag,
                                                            s->d_block_count, s->d_cg_slot, pages->d_bin_start,
@@ -1230,7 +1395,8 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
   k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
   launches++;
-  cudaEventRecord(s->ev_bin[0], ctx->stream);  // fork
+  cudaEvent_t ev_fork = capturing ? s->ev_cfork : s->ev_bin[0];
+  cudaEventRecord(ev_fork, ctx->stream);  // fork
   // Host-resident pages: one bin's gather already saturates PCIe, so the gathers are chained largest bin first
   // (an event per bin); each bin's CRC check and scan then overlap the next bins' transfers and only the smallest
   // bin's tail is exposed after the last byte has arrived.
@@ -1245,7 +1411,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
   for (int oi = 0; oi < N_BINS; oi++) {
     const int b = order[oi];
     if (!s->grid[b]) continue;
-    cudaStreamWaitEvent(ctx->bin_stream[b], s->ev_bin[0], 0);
+    cudaStreamWaitEvent(ctx->bin_stream[b], ev_fork, 0);
     int bin = b;
     if (pages->h_mapped) {
       if (prev_gather >= 0 && !gather_concurrent) cudaStreamWaitEvent(ctx->bin_stream[b], s->ev_gather[prev_gather], 0);
@@ -1266,7 +1432,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
                                                             pages->d_crc_tables, s->d_status, s->d_err_page);
       launches++;
     }
-    cudaEventRecord(s->ev_bin_start[b], ctx->bin_stream[b]);
+    if (!capturing) cudaEventRecord(s->ev_bin_start[b], ctx->bin_stream[b]);
     if (!s->use_coop[b]) {
       const int sb = serial_bin_of(b);
       void *args[] = {(void *)&s->params, (void *)&bin};
@@ -1277,18 +1443,19 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s) {
       CU_TRY(ctx, cudaLaunchKernel(coop_kernel_for(b, s->has_sel), dim3(s->grid[b]), dim3(SCAN_THREADS), args,
                                    coop_smem_bytes(b, s->params.smem_words), ctx->bin_stream[b]));
     }
-    cudaEventRecord(s->ev_bin_done[b], ctx->bin_stream[b]);
-    cudaStreamWaitEvent(ctx->stream, s->ev_bin_done[b], 0);  // join
+    cudaEvent_t ev_done = capturing ? s->ev_cjoin[b] : s->ev_bin_done[b];
+    cudaEventRecord(ev_done, ctx->bin_stream[b]);
+    cudaStreamWaitEvent(ctx->stream, ev_done, 0);  // join
     launches++;
   }
-  cudaEventRecord(s->ev_bin[N_BINS], ctx->stream);
+  if (!capturing) cudaEventRecord(s->ev_bin[N_BINS], ctx->stream);
   if (s->has_sel || s->n_means) {
     uint64_t work = std::max(std::max(s->sl.first_cells, s->sl.last_cells), s->n_means ? s->layout.n_cells : 0);
     uint32_t b = (uint32_t)std::min<uint64_t>((work + 255) / 256, 4096);
     k_export_pairs<<<std::max(1u, b), 256, 0, ctx->stream>>>(s->d_state, s->sl, s->d_means, s->n_means, s->layout.n_cells);
     launches++;
   }
-  cudaEventRecord(s->ev1, ctx->stream);
+  if (!capturing) cudaEventRecord(s->ev1, ctx->stream);
   CU_TRY(ctx, cudaGetLastError());
   ctx->counters.kernel_launches = launches;
   s->enqueued = true;
@@ -1302,8 +1469,9 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
     if (st == TSKV_ERR_INVALID_ARG) ctx->set_error("page type does not match the query column type", ctx->err_page);
     return st;
   }
-  unsigned long long aux[4 + N_BINS + 1] = {0};  // stats[2], pages, bytes, per-bin bytes[N_BINS]
-  CU_TRY(ctx, cudaMemcpy(aux, s->d_stats, (4 + N_BINS) * 8, cudaMemcpyDeviceToHost));
+  unsigned long long aux[5 + N_BINS] = {0};  // stats[2], pages, bytes, per-bin bytes[N_BINS], pruned pages
+  CU_TRY(ctx, cudaMemcpy(aux, s->d_stats, (5 + N_BINS) * 8, cudaMemcpyDeviceToHost));
+  ctx->counters.pruned_page_count = aux[4 + N_BINS];
   float ms = 0;
   cudaEventElapsedTime(&ms, s->ev0, s->ev1);
   ctx->counters.elapsed_scan_ms = ms;
@@ -1340,7 +1508,33 @@ tskv_status tskvgpu_scan_enqueue(tskv_ctx *ctx, tskv_scan *s) {
   if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
   cudaSetDevice(ctx->device);
-  return enqueue_scan(ctx, s);
+  static const bool no_graph = getenv("TSKV_NO_GRAPH") != nullptr;
+  s->n_enqueued++;
+  if (no_graph || s->graph_failed || s->n_enqueued < 2) return enqueue_scan(ctx, s);
+  if (!s->graph_exec) {
+    cudaGraph_t graph = nullptr;
+    if (!s->ev_cfork) {
+      cudaEventCreateWithFlags(&s->ev_cfork, cudaEventDisableTiming);
+      for (int b = 0; b < N_BINS; b++) cudaEventCreateWithFlags(&s->ev_cjoin[b], cudaEventDisableTiming);
+    }
+    bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const tskv_status st = enqueue_scan(ctx, s, true);  // the bin streams join the capture through the fork event
+      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      ok = st == TSKV_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&s->graph_exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (!ok) {  // anything the capture did not like: replay the pass call by call, as before
+      if (getenv("TSKV_DEBUG_BINS")) fprintf(stderr, "[tskv] graph capture failed (%s): direct launches\n", cudaGetErrorString(cudaGetLastError()));
+      cudaGetLastError();
+      s->graph_exec = nullptr;
+      s->graph_failed = true;
+      return enqueue_scan(ctx, s);
+    }
+  }
+  CU_TRY(ctx, cudaGraphLaunch(s->graph_exec, ctx->stream));
+  s->enqueued = true;
+  return TSKV_OK;
 }
 
 tskv_status tskvgpu_scan_sync(tskv_ctx *ctx, tskv_scan *s) {
@@ -1393,6 +1587,28 @@ tskv_status tskvgpu_scan_merge_gathered(tskv_ctx *ctx, tskv_scan *s, uint64_t ga
   uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, 2048);
   k_merge_gathered<<<std::max(1u, blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl, reinterpret_cast<const uint64_t *>((uintptr_t)gathered_dptr),
                                                                    n_ranks, words);
+  CU_TRY(ctx, cudaGetLastError());
+  return TSKV_OK;
+}
+
+tskv_status tskvgpu_scan_exchange(tskv_ctx *ctx, tskv_scan *s) {
+  if (!ctx || !s) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  if (!ctx->comm) {
+    ctx->set_error("tskvgpu_scan_exchange: no communicator (tskvgpu_comm_init)");
+    return TSKV_ERR_NCCL;
+  }
+  const NcclApi &N = nccl_api();
+  const uint64_t words = s->sl.selval_off + s->sl.selval_len;  // sum_i64 | sum_f64 | min+first keys | max+last keys | values
+  if (!s->d_gathered) CU_TRY(ctx, stream_alloc(ctx, &s->d_gathered, (size_t)ctx->n_ranks * words));
+  const ncclResult_t r = N.AllGather(s->d_state, s->d_gathered, words, ncclUint64, ctx->comm, ctx->stream);
+  if (r != ncclSuccess) {
+    ctx->set_error(std::string("ncclAllGather: ") + N.GetErrorString(r));
+    return TSKV_ERR_NCCL;
+  }
+  uint32_t blocks = (uint32_t)std::min<uint64_t>((words + 255) / 256, 2048);
+  k_merge_gathered<<<std::max(1u, blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl, s->d_gathered, (uint32_t)ctx->n_ranks, words);
   CU_TRY(ctx, cudaGetLastError());
   return TSKV_OK;
 }

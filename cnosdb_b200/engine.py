@@ -50,7 +50,7 @@ class QueryOption:
     """The pushed-down scan: series selection, closed time ranges, bucket expression, aggregates."""
 
     def __init__(self, columns, series_ids=None, time_ranges=(), origin=0, width=0,
-                 first_bucket_start=0, n_buckets=1, group_by_series=False, multi_rank=False):
+                 first_bucket_start=0, n_buckets=1, group_by_series=False, multi_rank=False, predicates=()):
         self.columns = list(columns)
         self.series_ids = None if series_ids is None else np.ascontiguousarray(series_ids, dtype=np.uint32)
         self.time_ranges = [(int(a), int(b)) for a, b in time_ranges]
@@ -59,6 +59,8 @@ class QueryOption:
         self.first_bucket_start = int(first_bucket_start)
         self.n_buckets = int(n_buckets)
         self.group_by_series = bool(group_by_series)
+        # field comparisons AND-ed into the row filter: (column_id, phys_type, op, constant), op in == != < <= > >=
+        self.predicates = [(int(c), int(pt), op if isinstance(op, int) else cabi.CMP_OPS[op], v) for c, pt, op, v in predicates]
         self.multi_rank = bool(multi_rank)  # TSKV_QUERY_MULTI_RANK: partials get merged with other ranks'
         self._keep = None
 
@@ -81,7 +83,17 @@ class QueryOption:
             cols[i].column_id, cols[i].phys_type, cols[i].agg_mask = c.column_id, c.phys_type, c.agg_mask
         q.columns = cols
         q.n_columns = len(self.columns)
-        self._keep = (tr, cols)  # keep the ctypes arrays alive as long as the query
+        preds = (cabi.FieldPredicate * max(1, len(self.predicates)))()
+        for i, (c, pt, op, v) in enumerate(self.predicates):
+            preds[i].column_id, preds[i].phys_type, preds[i].op = c, pt, op
+            if pt == TSKV_PT_F64:
+                preds[i].value = int(np.float64(v).view(np.uint64))
+            else:
+                preds[i].value = int(v) & 0xFFFFFFFFFFFFFFFF
+        if self.predicates:
+            q.predicates = preds
+            q.n_predicates = len(self.predicates)
+        self._keep = (tr, cols, preds)  # keep the ctypes arrays alive as long as the query
         return q
 
     def output_names(self):
@@ -135,10 +147,16 @@ class PageSet:
         self.engine._check(self.engine.lib.tskvgpu_pages_set_tombstones(
             self.engine.ctx, self.handle, tombs.ctypes.data if len(tombs) else None, len(tombs)))
 
+    def set_time_bounds(self, bounds):
+        """Per-column-group (min_ts, max_ts), ColumnGroup::time_range() order = descriptor order: lets scans with time
+        ranges skip whole column groups (statistics pruning). bounds: [(lo, hi), ...] or an int64 array of shape [n, 2]."""
+        b = np.ascontiguousarray(bounds, dtype=np.int64).reshape(-1, 2)
+        self.engine._check(self.engine.lib.tskvgpu_pages_set_time_bounds(self.engine.ctx, self.handle, b.ctypes.data, len(b)))
+
     def close(self):
-        if self.handle:
+        if self.handle and self.engine.ctx:
             self.engine.lib.tskvgpu_pages_destroy(self.engine.ctx, self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -172,6 +190,11 @@ class PreparedScan:
         self.engine._check(self.engine.lib.tskvgpu_scan_exchange_view(self.engine.ctx, self.handle, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def exchange(self):
+        """The multi-GPU exchange inside the library: one ncclAllGather of the exchange region + the local merge
+        (Engine.comm_init first)."""
+        self.engine._check(self.engine.lib.tskvgpu_scan_exchange(self.engine.ctx, self.handle))
+
     def merge_gathered(self, gathered_ptr, n_ranks):
         self.engine._check(self.engine.lib.tskvgpu_scan_merge_gathered(self.engine.ctx, self.handle, gathered_ptr, n_ranks))
 
@@ -196,9 +219,9 @@ class PreparedScan:
         return a.value, b.value
 
     def close(self):
-        if self.handle:
+        if self.handle and self.engine.ctx:  # (an engine closed first has already released the device)
             self.engine.lib.tskvgpu_scan_destroy(self.engine.ctx, self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -237,6 +260,19 @@ class Engine:
 
     def version(self):
         return self.lib.tskvgpu_version().decode()
+
+    def comm_unique_id(self):
+        """rank 0: the 128-byte NCCL unique id the other ranks need for comm_init."""
+        buf = (C.c_uint8 * 128)()
+        st = self.lib.tskvgpu_comm_unique_id(buf)
+        if st != cabi.TSKV_OK:
+            raise TskvError(st, "tskvgpu_comm_unique_id: NCCL unavailable")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        """ncclCommInitRank on this engine's device (collective: every rank calls it)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.tskvgpu_comm_init(self.ctx, buf, int(rank), int(n_ranks)))
 
     def stream(self):
         return int(self.lib.tskvgpu_ctx_stream(self.ctx))

@@ -106,19 +106,40 @@ def allreduce_scan(scan, engine, sections=None, group=None):
     return sections
 
 
-class GatherExchange:
-    """The one collective of a multi-GPU scan: all-gather every rank's exchange region, merge locally
-    (tskvgpu_scan_merge_gathered). Buffers are allocated once per PreparedScan."""
+def init_engine_comm(engine, rank, world_size, group=None):
+    """Creates the library's NCCL communicator for this rank's engine: rank 0 draws the unique id, torch.distributed
+    (any backend) only carries those 128 bytes to the other ranks. Returns False if the library cannot load NCCL."""
+    try:
+        ident = [engine.comm_unique_id() if rank == 0 else None]
+    except Exception:
+        ident = [None]
+    dist.broadcast_object_list(ident, src=0, group=group)
+    if ident[0] is None:
+        return False
+    engine.comm_init(ident[0], rank, world_size)
+    return True
 
-    def __init__(self, scan, engine, world_size, group=None):
+
+class GatherExchange:
+    """The one collective of a multi-GPU scan: all-gather every rank's exchange region, merge locally. Default: inside
+    the library (tskvgpu_scan_exchange: ncclAllGather + merge kernel on the engine stream; the engine needs
+    init_engine_comm first). use_torch=True keeps the round-1 path - torch.distributed's all_gather into a torch buffer +
+    tskvgpu_scan_merge_gathered - for hosts that drive their own collectives."""
+
+    def __init__(self, scan, engine, world_size, group=None, use_torch=False):
         self.scan, self.engine, self.world, self.group = scan, engine, world_size, group
-        self.device = torch.device("cuda", engine.device)
-        ptr, words = scan.exchange_view()
-        self.local = device_tensor(ptr, words, torch.int64, self.device)
-        self.gathered = torch.empty(world_size * words, dtype=torch.int64, device=self.device)
-        self.stream = torch.cuda.ExternalStream(engine.stream(), device=self.device)
+        self.use_torch = use_torch
+        if use_torch:
+            self.device = torch.device("cuda", engine.device)
+            ptr, words = scan.exchange_view()
+            self.local = device_tensor(ptr, words, torch.int64, self.device)
+            self.gathered = torch.empty(world_size * words, dtype=torch.int64, device=self.device)
+            self.stream = torch.cuda.ExternalStream(engine.stream(), device=self.device)
 
     def run(self):
+        if not self.use_torch:
+            self.scan.exchange()
+            return
         with torch.cuda.stream(self.stream):
             dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
         self.scan.merge_gathered(self.gathered.data_ptr(), self.world)

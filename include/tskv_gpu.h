@@ -44,7 +44,7 @@ enum {
                                    not fit 63 bits */
   TSKV_ERR_BUCKET_RANGE = 7,    /* an in-range row fell outside [first_bucket_start, +n*width) */
   TSKV_ERR_CUDA = 8,
-  TSKV_ERR_NCCL = 9,            /* reserved (collectives are driven by the host runtime) */
+  TSKV_ERR_NCCL = 9,            /* an NCCL call failed, or libnccl could not be loaded (tskvgpu_comm_*) */
   TSKV_ERR_OOM = 10,
   TSKV_ERR_BAD_LENGTH = 11,     /* "invalid uncompressed block length" (timestamp.rs:203) */
   TSKV_ERR_PAGE_FORMAT = 12     /* page shorter than its own header / bitset (page.rs:78-94) */
@@ -113,6 +113,23 @@ typedef struct tskv_agg_column {
   uint8_t agg_mask;  /* TSKV_AGG_* bits */
 } tskv_agg_column;
 
+/* A field-value comparison pushed into the scan (the row filter of DataFilter, tskv/src/reader/filter.rs:23-142, for
+ * predicates of the form `column <op> constant` joined by AND): a row is kept only if EVERY predicate is TRUE for it.
+ * A NULL value - or a column group that holds no page of the column, which the reference null-fills
+ * (reader/schema_alignmenter.rs:24-44) - makes the comparison NULL, and filter_record_batch drops the row like a FALSE.
+ * Dropped rows count for no projected column (count, sum, first/last ...), exactly like rows outside the time ranges.
+ * Integers compare as their type, f64 numerically (NaN: never TRUE; the reference's arrow kernels are not pinned for
+ * NaN / signed zeros inside /root/reference). `value` holds the constant's bit pattern. */
+enum { TSKV_CMP_EQ = 0, TSKV_CMP_NE = 1, TSKV_CMP_LT = 2, TSKV_CMP_LE = 3, TSKV_CMP_GT = 4, TSKV_CMP_GE = 5 };
+#define TSKV_MAX_PREDICATES 8
+typedef struct tskv_field_predicate {
+  uint16_t column_id;
+  uint8_t phys_type; /* TSKV_PT_I64 / U64 / F64 */
+  uint8_t op;        /* TSKV_CMP_* */
+  uint32_t reserved;
+  uint64_t value;
+} tskv_field_predicate;
+
 /* The pushed-down scan. Mirrors the fields of `QueryOption` the hot path consumes
  * (tskv/src/reader/iterator.rs:713-741): split.time_ranges(), the series ids produced by
  * `get_series_id_by_filter` (tskv/src/kvcore.rs:249-279), the aggregate list; plus the bucket
@@ -134,6 +151,9 @@ typedef struct tskv_query {
   const tskv_agg_column *columns;
   uint32_t n_columns;         /* 1..126 */
   uint32_t reserved;          /* TSKV_QUERY_* flags (0 for a plain single-device scan) */
+  const tskv_field_predicate *predicates; /* AND-ed field comparisons, or NULL */
+  uint32_t n_predicates;      /* 0..TSKV_MAX_PREDICATES */
+  uint32_t reserved2;
 } tskv_query;
 /* The partial state of this scan will be merged with other ranks' (tskvgpu_scan_partials / _exchange_view): every
  * exchanged key is then derived from the query alone, never from this rank's own arena (its time bounds, its local
@@ -170,6 +190,8 @@ typedef struct tskv_counters {
   uint64_t dominant_kernel_bytes; /* encoded page bytes that kernel read (its algorithmic bytes) */
   uint64_t dominant_kernel_bin; /* time-codec class * 3 + value-codec class */
   uint64_t h2d_bytes;           /* query arguments copied host->device by the last prepare */
+  uint64_t pruned_page_count;   /* selected field pages the last scan skipped because their column group's time bounds
+                                   miss every query range (filter_column_groups, reader/chunk.rs:12-50) */
 } tskv_counters;
 
 typedef struct tskv_ctx tskv_ctx;       /* one CUDA device + stream */
@@ -212,6 +234,11 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
 void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pages);
 /* Number of distinct series in the arena. */
 uint64_t tskvgpu_pages_series_count(const tskv_pages *pages);
+/* Per-column-group time bounds, `ColumnGroup::time_range()` (tskv/src/tsm/column_group.rs:9-17), in descriptor order
+ * (one entry per TIME page; n must equal the number of column groups). Optional: scans with time ranges use them to
+ * skip whole column groups (statistics pruning, reader/chunk.rs:12-50 + column_group/statistics.rs:11-80); a page set
+ * without them gets its bounds from one device pass over the time pages on the first scan that needs them. */
+tskv_status tskvgpu_pages_set_time_bounds(tskv_ctx *ctx, tskv_pages *pages, const tskv_time_range *bounds, uint64_t n);
 
 /* ---- tombstones ------------------------------------------------------------------------------
  * Replaces the tombstone half of decode_pages (tskv/src/tsm/reader.rs:507-551,634-656) with the
@@ -286,6 +313,21 @@ tskv_status tskvgpu_scan_partials(tskv_ctx *ctx, tskv_scan *scan, tskv_partials_
  * 8-byte words) of every rank into `gathered` (rank-major, n_ranks * words) and merge locally. */
 tskv_status tskvgpu_scan_exchange_view(tskv_ctx *ctx, tskv_scan *scan, uint64_t *out_dptr, uint64_t *out_words);
 tskv_status tskvgpu_scan_merge_gathered(tskv_ctx *ctx, tskv_scan *scan, uint64_t gathered_dptr, uint32_t n_ranks);
+
+/* ---- multi-GPU inside the library: series sharded over ranks (one context = one GPU = one rank), NCCL for the one
+ * exchange step. The reference shards series the same way (hash(SeriesKey) % n_shards, common/models/src/meta_data.rs:81-85)
+ * and merges per-partition partial aggregates in DataFusion's final AggregateExec.
+ *   tskvgpu_comm_unique_id  rank 0: ncclGetUniqueId; the host runtime hands the 128 bytes to the other ranks
+ *   tskvgpu_comm_init       every rank: ncclCommInitRank on the context's device (collective: all ranks call it)
+ *   tskvgpu_scan_exchange   after tskvgpu_scan_enqueue, every rank: ONE ncclAllGather of the scan's exchange region on
+ *                           the context stream + the local merge (== exchange_view + merge_gathered). Queries of a
+ *                           multi-rank scan carry TSKV_QUERY_MULTI_RANK and the global series_ids list.
+ * libnccl.so.2 is loaded on first use (dlopen), so single-GPU users need no NCCL. */
+#define TSKV_NCCL_UNIQUE_ID_BYTES 128
+tskv_status tskvgpu_comm_unique_id(uint8_t out_id[TSKV_NCCL_UNIQUE_ID_BYTES]);
+tskv_status tskvgpu_comm_init(tskv_ctx *ctx, const uint8_t id[TSKV_NCCL_UNIQUE_ID_BYTES], int32_t rank, int32_t n_ranks);
+void tskvgpu_comm_destroy(tskv_ctx *ctx);
+tskv_status tskvgpu_scan_exchange(tskv_ctx *ctx, tskv_scan *scan);
 /* Snapshot the local first/last keys before they are all-reduced in place (multi-GPU only). */
 tskv_status tskvgpu_scan_snapshot_keys(tskv_ctx *ctx, tskv_scan *scan);
 /* Zero every first/last value whose local key (snapshot) lost the key all-reduce. */

@@ -39,6 +39,29 @@ inline bool less_typed(uint8_t pt, uint64_t a, uint64_t b) {
   return f64_okey(a) < f64_okey(b);
 }
 
+// One `column <op> constant` of the pushed row filter (reader/filter.rs:130-142: the predicate is evaluated on the
+// schema-aligned batch and applied with filter_record_batch, which keeps a row only where the predicate is TRUE).
+inline bool cmp_true(uint8_t pt, uint8_t op, uint64_t v, uint64_t c) {
+  int r;  // -1 / 0 / +1, or 2 for unordered (NaN)
+  if (pt == TSKV_PT_I64) r = (int64_t)v < (int64_t)c ? -1 : ((int64_t)v > (int64_t)c ? 1 : 0);
+  else if (pt == TSKV_PT_U64) r = v < c ? -1 : (v > c ? 1 : 0);
+  else {
+    double a, b;
+    memcpy(&a, &v, 8);
+    memcpy(&b, &c, 8);
+    r = (a != a || b != b) ? 2 : (a < b ? -1 : (a > b ? 1 : 0));
+  }
+  switch (op) {
+    case TSKV_CMP_EQ: return r == 0;
+    case TSKV_CMP_NE: return r == -1 || r == 1;
+    case TSKV_CMP_LT: return r == -1;
+    case TSKV_CMP_LE: return r == -1 || r == 0;
+    case TSKV_CMP_GT: return r == 1;
+    case TSKV_CMP_GE: return r == 1 || r == 0;
+    default: return false;
+  }
+}
+
 struct Cell {
   uint64_t count = 0;
   uint64_t sum_bits = 0;  // i64/u64 wrapping sum
@@ -151,8 +174,8 @@ void clear_bits_by_time_range(const std::vector<uint64_t> &ts, uint64_t n_rows, 
 tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, bool shared_table,
                        uint64_t *points) {
   const tskv_query &q = *S.q;
-  std::vector<uint64_t> ts, vals;
-  std::vector<uint8_t> tvalid, vvalid, keep;
+  std::vector<uint64_t> ts, vals, pvals;
+  std::vector<uint8_t> tvalid, vvalid, keep, pred_keep, pvalid;
   bool have_keep = false;
   int64_t page_min = 0, page_max = 0;
   for (uint64_t slot = s0; slot < s1; slot++) {
@@ -166,8 +189,8 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
       uint64_t n_rows = td.num_values;
       ts.assign(n_rows ? n_rows : 1, 0);
       tvalid.assign(n_rows ? n_rows : 1, 0);
-      bool time_decoded = false;
-      for (uint32_t c = 0; c < q.n_columns; c++) {
+      bool time_decoded = false, pruned = false;
+      for (uint32_t c = 0; c < q.n_columns && !pruned; c++) {
         const tskv_agg_column &qc = q.columns[c];
         const tskv_page_desc *fd = nullptr;
         for (uint64_t k = 1; k < cg.n_descs; k++)
@@ -188,6 +211,46 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
           if (st != TSKV_OK) return st;
           if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
           time_decoded = true;
+          // Statistics pruning (filter_column_groups, tskv/src/reader/chunk.rs:12-50): a column group whose time range
+          // (ColumnGroup::time_range(), here: min / max of its time values) overlaps none of the query's ranges is never
+          // read - its field pages are neither decoded nor counted.
+          if (q.n_time_ranges && n_rows) {
+            int64_t gmin = INT64_MAX, gmax = INT64_MIN;
+            for (uint64_t r = 0; r < n_rows; r++)
+              if (tvalid[r]) { gmin = std::min(gmin, (int64_t)ts[r]); gmax = std::max(gmax, (int64_t)ts[r]); }
+            bool overlaps = false;
+            for (uint32_t k = 0; k < q.n_time_ranges; k++)
+              overlaps = overlaps || (gmin <= q.time_ranges[k].max_ts && gmax >= q.time_ranges[k].min_ts);
+            if (!overlaps) { pruned = true; break; }
+          }
+          // the row filter: every predicate column of this column group decoded, rows kept where all comparisons are TRUE;
+          // a column the group does not hold is null-filled by SchemaAlignmenter (schema_alignmenter.rs:24-44) => no row passes
+          pred_keep.assign(n_rows ? n_rows : 1, 1);
+          for (uint32_t k = 0; k < q.n_predicates; k++) {
+            const tskv_field_predicate &fp = q.predicates[k];
+            const tskv_page_desc *pd = nullptr;
+            for (uint64_t j = 1; j < cg.n_descs; j++)
+              if (S.descs[cg.first_desc + j].column_id == fp.column_id) {
+                pd = &S.descs[cg.first_desc + j];
+                break;
+              }
+            if (!pd) {
+              std::fill(pred_keep.begin(), pred_keep.end(), (uint8_t)0);
+              continue;
+            }
+            if (pd->phys_type != fp.phys_type) {
+              g_err = "page type does not match the predicate column type";
+              return TSKV_ERR_INVALID_ARG;
+            }
+            pvals.assign(n_rows ? n_rows : 1, 0);
+            pvalid.assign(n_rows ? n_rows : 1, 0);
+            uint64_t pr = 0;
+            tskv_status pst = orc_page_decode(pd->phys_type, S.arena + pd->offset, pd->size, S.verify_crc, pvals.data(),
+                                              pvalid.data(), n_rows, &pr);
+            if (pst != TSKV_OK) return pst;
+            for (uint64_t r = 0; r < n_rows; r++)
+              if (!(pvalid[r] && cmp_true(fp.phys_type, fp.op, pvals[r], fp.value))) pred_keep[r] = 0;
+          }
           // decode_pages with a tombstone (reader.rs:507-524): the all-fields excluded ranges that overlap the
           // page's time range clear bits of the TIME page's null bitset; the result filters the rows.
           keep.assign(n_rows ? n_rows : 1, 1);
@@ -253,6 +316,7 @@ tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, boo
         for (uint64_t r = 0; r < n_rows; r++) {
           if (vvalid[r] && points) (*points)++;
           if (have_keep && !keep[r]) continue;  // filter_record_batch(&record_batch, time_null_bits) (reader.rs:546-550)
+          if (q.n_predicates && !pred_keep[r]) continue;  // DataFilter (reader/filter.rs:130-142)
           if (!tvalid[r]) continue;  // is_not_null(time) (transform_time_window.rs:313)
           int64_t t = (int64_t)ts[r];
           bool in = q.n_time_ranges == 0;

@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert C.sizeof(cabi.PageDesc) == 24 and cabi.PAGE_DESC_DTYPE.itemsize == 24
     assert C.sizeof(cabi.TimeRange) == 16 and C.sizeof(cabi.AggColumn) == 4
-    assert C.sizeof(cabi.Query) == 72 and C.sizeof(cabi.OutputLayout) == 48
-    assert C.sizeof(cabi.Counters) == 96 and C.sizeof(cabi.PartialsView) == 96
+    assert C.sizeof(cabi.Query) == 88 and C.sizeof(cabi.FieldPredicate) == 16 and C.sizeof(cabi.OutputLayout) == 48
+    assert C.sizeof(cabi.Counters) == 104 and C.sizeof(cabi.PartialsView) == 96
 
 
 def test_header_compiles_as_c(tmp_path):

@@ -578,6 +578,85 @@ def test_two_shard_unbucketed_first_last_with_different_time_minima(engine):
         pages.close()
 
 
+def test_statistics_pruning_skips_column_groups_outside_the_time_ranges(engine):
+    """filter_column_groups on the device (reader/chunk.rs:12-50): a page set uploaded once and scanned with a narrow time
+    range reads only the column groups whose time bounds overlap it - same results, fewer pages (page_read_count /
+    page_read_bytes / pruned_page_count) - with bounds computed by the library or handed in like ColumnGroup::time_range()."""
+    rng = np.random.default_rng(21)
+    fields = ((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64))
+    arena, descs, truth = random_arena(rng, n_series=120, n_points=200, fields=fields, multi_cg=True, null_frac=0.05)
+    groups = [(sid, ts) for sid, cgs in truth.items() for ts, _ in cgs]   # descriptor order: series by series, group by group
+    lo, hi = 1_000_000 + 150_000, 1_000_000 + 180_000
+    ranges = [(lo, hi), (1_000_000 - 50, 1_000_000 + 10)]
+    q = make_query(fields, aggs=("count", "sum", "min", "max", "mean"), time_ranges=ranges, group_by_series=True)
+    exp = orc.scan_aggregate(arena, descs, q)
+    overlapping = sum(1 for _, ts in groups if any(ts.min() <= b and ts.max() >= a for a, b in ranges))
+    assert 0 < overlapping < len(groups)
+    for given in (False, True):
+        pages = engine.upload_pages(arena, descs)
+        if given:
+            pages.set_time_bounds([(int(ts.min()), int(ts.max())) for _, ts in groups])
+        assert_results_equal(engine.scan_aggregate(pages, q), exp, what="pruned scan (bounds given: %s)" % given)
+        c = engine.counters()
+        assert c["page_read_count"] == 3 * overlapping, (c["page_read_count"], overlapping)
+        assert c["pruned_page_count"] == 2 * (len(groups) - overlapping)
+        all_time = make_query(fields, aggs=("count",), group_by_series=True)   # no ranges: nothing is pruned
+        engine.scan_aggregate(pages, all_time)
+        c = engine.counters()
+        assert c["page_read_count"] == 3 * len(groups) and c["pruned_page_count"] == 0
+        pages.close()
+    with pytest.raises(TskvError):
+        p2 = engine.upload_pages(arena, descs)
+        try:
+            p2.set_time_bounds([(0, 1)])   # wrong number of column groups
+        finally:
+            p2.close()
+
+
+@pytest.mark.parametrize("variant", ["plain", "nulls", "jitter", "multi_cg"])
+def test_field_predicates_filter_rows_like_the_reference_data_filter(engine, variant):
+    """`column <op> constant` row filters pushed into the scan (DataFilter, reader/filter.rs:23-142): a row survives only
+    if every comparison is TRUE (NULL drops it), for all projected columns, counts and first()/last() included."""
+    rng = np.random.default_rng(300 + len(variant))
+    fields = ((1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64), (3, cabi.TSKV_PT_U64))
+    kw = dict(n_series=90, n_points=300, fields=fields)
+    if variant == "nulls":
+        kw["null_frac"] = 0.15
+    if variant == "jitter":
+        kw.update(jitter=300, null_frac=0.03)
+    if variant == "multi_cg":
+        kw.update(multi_cg=True, null_frac=0.05)
+    arena, descs, _ = random_arena(rng, **kw)
+    pages = engine.upload_pages(arena, descs)
+    t_lo, t_hi = 1_000_000 - 400, 1_000_000 + 700_000
+    fbs, nb = bucket_spec(t_lo, t_hi, 17_000, origin=3)
+    proj = fields[:2]
+    cases = [
+        [(1, cabi.TSKV_PT_I64, ">", 0)],
+        [(2, cabi.TSKV_PT_F64, "<=", 1.5), (1, cabi.TSKV_PT_I64, "!=", 7)],
+        [(3, cabi.TSKV_PT_U64, ">=", 2**63 + 40)],                          # a column that is not projected
+        [(9, cabi.TSKV_PT_I64, "==", 1)],                                   # a column no group holds: no row survives
+        [(1, cabi.TSKV_PT_I64, "<", -10**9)],                               # nothing passes
+    ]
+    for preds in cases:
+        for group_by_series in (False, True):
+            for ranges in ([], [(t_lo + 30_000, t_lo + 250_000)]):
+                q = make_query(proj, time_ranges=ranges, origin=3, width=17_000, first_bucket_start=fbs, n_buckets=nb,
+                               group_by_series=group_by_series, predicates=preds)
+                got = engine.scan_aggregate(pages, q)
+                exp = orc.scan_aggregate(arena, descs, q)
+                assert_results_equal(got, exp, what="predicates %s gbs=%s %s %s" % (preds, group_by_series, ranges, variant))
+        q = make_query(proj, aggs=("count", "sum", "min", "max", "mean"), predicates=preds)   # unbucketed, staged flush
+        assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q), what="predicates unbucketed")
+    hp = engine.upload_pages(arena, descs, verify_crc=True, host_resident=True)
+    q = make_query(proj, width=17_000, origin=3, first_bucket_start=fbs, n_buckets=nb, predicates=cases[1])
+    assert_results_equal(engine.scan_aggregate(hp, q), orc.scan_aggregate(arena, descs, q), what="predicates, host-resident pages")
+    with pytest.raises(TskvError):
+        engine.scan_aggregate(pages, make_query(proj, predicates=[(1, cabi.TSKV_PT_F64, ">", 0.0)]))  # wrong column type
+    hp.close()
+    pages.close()
+
+
 def random_tombstones(rng, descs, t_lo, t_hi, n=60):
     """Column masks, series-scoped row drops and a few page-set-wide row drops over random sub-ranges."""
     fields = descs[descs["phys_type"] != cabi.TSKV_PT_TIME]
