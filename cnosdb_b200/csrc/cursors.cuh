@@ -387,6 +387,66 @@ struct DeltaCursor {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Lean simple8b delta cursor of the fused scan: DK_S8B_SC (ZZ = false: timestamps, deltas * 10^k, timestamp.rs:261-299)
+// or DK_S8B_ZZ (ZZ = true: zig-zag deltas, integer.rs:216-248) through a staged SeqStream. Same values as
+// DeltaCursor, less bookkeeping per word - the timestamp stream of an irregular series holds ONE 60-bit value per
+// word, so per-word work is per-row work there:
+//   * selector 15 (1 x 60 bits) takes a branch of its own (warp-uniform on such pages) instead of the table lookup;
+//   * running out of words is not tracked per refill: the stream position says how many words were consumed, and
+//     exhausted() compares it with the block's word count when the caller checks (after a segment). A cursor that ran
+//     past its block decodes stale bytes in the meantime, which the caller discards with the error.
+// ------------------------------------------------------------------------------------------------
+template <bool ZZ>
+struct S8bCursor {
+  SeqStream bs;
+  uint64_t v;        // running value (raw bits)
+  uint64_t scaler;   // !ZZ
+  uint64_t w;        // current word, consumed from the low bits
+  uint64_t mask;     // low `bits` bits
+  uint32_t in_word;  // values left in `w`
+  uint32_t bits;
+  uint32_t ones;     // 1 for the run-of-ones selectors (payload ignored)
+  uint32_t k_end;    // stream word index of the block's last word
+
+  __device__ __forceinline__ tskv_status open(const PageView &pv, uint8_t /*kind*/, uint32_t lane_ring) {
+    const uint8_t *d = pv.data;
+    scaler = ZZ ? 1 : pow10_u64(__ldg(d + 1) & 0xf);
+    const uint64_t first = load_be64(d + 2);  // header fields straight from global memory; the stream covers the packed words
+    v = ZZ ? (uint64_t)zigzag_dec(first) : first;
+    bs.init(d + 10, lane_ring, d + pv.data_len);
+    k_end = bs.k + ((pv.data_len - 10) >> 3);
+    w = 0; mask = 0; bits = 0; ones = 0;
+    in_word = 1;  // a fake zero delta in front of the packed ones: the first next() yields the first value
+    return TSKV_OK;
+  }
+  __device__ __forceinline__ void reset(uint32_t lane_ring) {
+    bs.reset(lane_ring);
+    v = 0; scaler = 1; w = 0; mask = 0; in_word = 0; bits = 0; ones = 0; k_end = 0;
+  }
+  // more words were consumed than the block holds ("Mismatch between bit set and decoded values")
+  __device__ __forceinline__ bool exhausted() const { return bs.k > k_end; }
+
+  __device__ __forceinline__ uint64_t next() {
+    if (in_word == 0) {
+      w = bs.next();
+      const uint32_t sel = (uint32_t)(w >> 60);
+      if (sel == 15) {  // 1 x 60 bits
+        in_word = 1; bits = 60; ones = 0; mask = 0x0fffffffffffffffull;
+      } else {
+        s8b_lut(sel, in_word, bits);
+        ones = sel < 2 ? 1u : 0u;
+        mask = bits ? (~0ull >> (64 - bits)) : 0ull;
+      }
+    }
+    in_word--;
+    const uint64_t u = (w & mask) | ones;
+    w >>= bits;  // bits <= 60
+    v += ZZ ? (uint64_t)zigzag_dec(u) : u * scaler;
+    return v;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Gorilla cursor (float.rs:418-606): MSB-first bit stream after id | 0x10 | first(8).
 // Terminates on the sentinel 0x7ff8_0000_0000_00ff (float.rs:16). Like DeltaCursor, the first next()
 // needs no special case: a fake "repeat" control bit is queued in front of the stream.

@@ -8,6 +8,8 @@
 //   k_export_pairs / k_mask_values / k_finalize : partial state -> dense Arrow-style result
 //   (decode-only, Page::to_arrow_array: decode_kernels.cuh)
 #pragma once
+#include <type_traits>
+
 #include "cursors.cuh"
 
 namespace tskv {
@@ -1062,6 +1064,15 @@ __device__ __forceinline__ void flush_runs(const ScanParams &P, uint64_t *stab, 
   }
 }
 
+template <int K, typename S>
+__device__ __forceinline__ bool cursor_exhausted(const DeltaCursor<K, S> &c) { return c.exhausted; }
+template <bool ZZ>
+__device__ __forceinline__ bool cursor_exhausted(const S8bCursor<ZZ> &c) { return c.exhausted(); }
+template <int K, typename S>
+__device__ __forceinline__ void cursor_reset(DeltaCursor<K, S> &c, uint32_t lane_ring) { c.bs.reset(lane_ring); }
+template <bool ZZ>
+__device__ __forceinline__ void cursor_reset(S8bCursor<ZZ> &c, uint32_t lane_ring) { c.reset(lane_ring); }
+
 // Rows of an RLE time page that stay inside [t, t + d] when stepping by delta > 0 from t: min(left, floor(d / delta) + 1),
 // with the quotient estimated in double precision (inv = 1.0 / delta, one division per page) and corrected exactly.
 __device__ __forceinline__ uint32_t rle_rows_within(uint64_t d, uint64_t delta, double inv, uint32_t left) {
@@ -1086,10 +1097,10 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   uint32_t page = 0, slot = 0, qcol = 0, n_rows = 0;
   uint8_t pt = VK == VK_GOR ? TSKV_PT_F64 : TSKV_PT_I64, mask = 0;
   PageView tpv, vpv;
-  DeltaCursor<DK_S8B_SC, SeqStream> tcur;     // TK_S8B: timestamps staged through the time ring
+  S8bCursor<false> tcur;                       // TK_S8B: timestamps staged through the time ring
   uint64_t rle_t0 = 0, rle_delta = 0;          // TK_RLE: t(row) = rle_t0 + row * rle_delta (wrapping), closed form
   double rle_inv = 0.0;
-  DeltaCursor<VK == VK_S8B ? DK_S8B_ZZ : -1, SeqStream> vcur_d;
+  typename std::conditional<VK == VK_S8B, S8bCursor<true>, DeltaCursor<-1, SeqStream>>::type vcur_d;
   GorillaRing vcur_g;
   const uint32_t *vbm = nullptr;  // value validity bitmap, 32 rows per word
   const uint32_t *keepw = nullptr;  // row-filter keep bits of the column group (k_row_filter), or null
@@ -1097,9 +1108,9 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   int64_t pend_t = 0;  // timestamp of row `row`
   __shared__ uint4 s_tomb[SCAN_THREADS];  // per lane tombstone lists (only touched when the page set has any)
 
-  if (TK == TK_S8B) tcur.bs.reset(tslot);
+  if (TK == TK_S8B) tcur.reset(tslot);
   if (VK == VK_GOR) vcur_g.reset(vslot);
-  else vcur_d.bs.reset(vslot);
+  else cursor_reset(vcur_d, vslot);
   if (have_item) {
     page = P.work_page[item];
     slot = P.work_slot[item];
@@ -1136,7 +1147,6 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
         if (TK == TK_RLE) pend_t = (int64_t)rle_t0;
         else {
           pend_t = (int64_t)tcur.next();  // the first value: no ring access (cursors.cuh)
-          if (tcur.exhausted) st = TSKV_ERR_BITSET_MISMATCH;
         }
       }
       if (st != TSKV_OK) { report_error(P, st, st == TSKV_ERR_BITSET_MISMATCH ? tpage : page); n_rows = 0; }
@@ -1191,7 +1201,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     return v;
   };
   auto check_values = [&]() {
-    const bool bad = VK == VK_GOR ? vcur_g.failed() : vcur_d.exhausted;
+    const bool bad = VK == VK_GOR ? vcur_g.failed() : cursor_exhausted(vcur_d);
     if (bad) {
       report_error(P, (VK == VK_GOR && vcur_g.overran()) ? TSKV_ERR_SHORT_BLOCK : TSKV_ERR_BITSET_MISMATCH, page);
       n_rows = 0;
@@ -1408,7 +1418,7 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
           more = row < n_rows && (uint64_t)t - (uint64_t)lim_lo <= span;
         } while (more);
         pend_t = t;
-        if (tcur.exhausted && row < n_rows) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row; }
+        if (tcur.exhausted() && row < n_rows) { report_error(P, TSKV_ERR_BITSET_MISMATCH, P.time_page_of[page]); n_rows = row; }
       }
       check_values();
     }
