@@ -57,8 +57,8 @@ def build_hostgen(force=False):
     deps = _glob_sources(host) + [os.path.join(CSRC, "host_util.cc"), os.path.join(CSRC, "host_util.h")]
     if force or _newer(target, deps):
         _run(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-o", target,
-              os.path.join(host, "tsm_writer.cc"), os.path.join(host, "datagen.cc"),
-              os.path.join(CSRC, "host_util.cc")])
+              os.path.join(host, "tsm_writer.cc"), os.path.join(host, "datagen.cc"), os.path.join(host, "tsm_file.cc"),
+              os.path.join(CSRC, "host_util.cc"), "-lz"])
     return target
 
 

@@ -58,3 +58,17 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in txt and "tskv_oracle" not in txt and "orc_" not in txt, os.path.join(dp, f)
+
+
+def test_rust_shim_declares_exactly_the_header_symbols():
+    """rust/tskv-gpu-shim/src/sys.rs (source only: no Rust toolchain in this image) binds every entry point of the header
+    and nothing else, and asserts the struct sizes ctypes sees."""
+    txt = open(os.path.join(ROOT, "rust", "tskv-gpu-shim", "src", "sys.rs")).read()
+    assert sorted(set(re.findall(r"pub fn (tskvgpu_\w+)\s*\(", txt))) == header_symbols()
+    sizes = dict(re.findall(r"size_of::<(\w+)>\(\) == (\d+)", txt))
+    expected = {"tskv_page_desc": C.sizeof(cabi.PageDesc), "tskv_time_range": C.sizeof(cabi.TimeRange),
+                "tskv_agg_column": C.sizeof(cabi.AggColumn), "tskv_field_predicate": C.sizeof(cabi.FieldPredicate),
+                "tskv_query": C.sizeof(cabi.Query), "tskv_output_layout": C.sizeof(cabi.OutputLayout),
+                "tskv_counters": C.sizeof(cabi.Counters), "tskv_partials_view": C.sizeof(cabi.PartialsView),
+                "tskv_tombstone": cabi.TOMBSTONE_DTYPE.itemsize}
+    assert {k: int(v) for k, v in sizes.items()} == expected

@@ -5,7 +5,7 @@
 TOOL=${1:-memcheck}
 mkdir -p gpurun_out
 compute-sanitizer --tool "$TOOL" --error-exitcode 1 --print-limit 20 \
-  python -m pytest tests -m gpu -x -q -k "gorilla or tombstone or small or errors or crc or empty or maximum" \
+  python -m pytest tests -m gpu -x -q -k "gorilla or tombstone or small or errors or crc or empty or maximum or predicates or pruning or concurrent or host_resident or decode" \
   > gpurun_out/sanitize_${TOOL}.log 2>&1
 echo "exit $?"
 grep -E "ERROR SUMMARY|passed|failed|Invalid|Race" gpurun_out/sanitize_${TOOL}.log | tail -20

@@ -7,7 +7,7 @@ import json
 import shutil
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 src, dst = "gpurun_out/%s_" % tag, "profiles/%s_" % tag
 VARIANT = {"0, 0": "ts=RLE,val=simple8b", "0, 1": "ts=RLE,val=gorilla", "1, 0": "ts=simple8b,val=simple8b",
            "1, 1": "ts=simple8b,val=gorilla"}
@@ -40,7 +40,14 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warps_active.avg.per_cycle_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__occupancy_limit_registers",
-        "launch__occupancy_limit_shared_mem"]
+        "launch__occupancy_limit_shared_mem", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
 units = dict(zip(h, raw[1]))
 kernels = []
 for r in raw[2:]:
