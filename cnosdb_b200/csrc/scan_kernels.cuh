@@ -1044,7 +1044,10 @@ __device__ __forceinline__ void flush_runs(const ScanParams &P, uint64_t *stab, 
   const uint64_t gcell = ((uint64_t)qcol << 32) | (uint32_t)cell;
   const int leader = __ffs(m) - 1;
   const uint64_t lcell = shfl_u64(gcell, leader);
-  const bool same = P.use_smem && __all_sync(FULL, !active || gcell == lcell);
+  // (GROUP BY bucket only: cells of a per-series grouping can exceed 32 bits, and its lanes never share one.) The staged
+  // path also serves tables too large for shared memory - the reduced partial then goes to the global state with one
+  // atomic per quantity instead of 32 contended ones.
+  const bool same = !P.group_by_series && __all_sync(FULL, !active || gcell == lcell);
   if (same) {
     uint64_t *q = stage + (size_t)seq * FLUSH_Q * 32 + lane;
     const bool live = active && va.count;
