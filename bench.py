@@ -234,12 +234,31 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
-def host_threads():
-    """Threads the CPU arm may use: the affinity / cgroup view, not the machine's core count."""
+def cgroup_cpu_quota():
+    """CPUs the container may use according to its cgroup (cpu.max / cfs quota), or None when unlimited."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(p)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / p
+    except (OSError, ValueError):
+        return None
+
+
+def host_threads():
+    """Threads the CPU arm may use: the affinity mask capped by the cgroup CPU quota, not the machine's core count."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = cgroup_cpu_quota()
+    if quota:
+        n = max(1, min(n, int(quota + 0.999)))
+    return n
 
 
 def cpu_arm(arena, descs, query, steps, warmup, max_s=150.0):
@@ -265,6 +284,8 @@ def cpu_arm(arena, descs, query, steps, warmup, max_s=150.0):
     med = float(np.median(times))
     n_sel = len(query.series_ids) if query.series_ids is not None else None
     info = {"value": pts / med, "unit": "points/s", "cores": cores, "kind": "port",
+            "host": {"affinity_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+                     "cgroup_cpu_quota": cgroup_cpu_quota(), "os_cpu_count": os.cpu_count()},
             "sample": "the whole workload (%s selected series, %d points) every step, %d of %d steps timed, %d threads "
                       "(persistent pool, series index built once), CRC32 verified per page per step" % (
                           "all" if n_sel is None else str(n_sel), pts, len(times), steps, cores),
