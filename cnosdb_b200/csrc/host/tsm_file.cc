@@ -44,7 +44,7 @@
 
 #include <zlib.h>
 
-#include "../../../include/tskv_gpu.h"
+#include "../../../include/tskv_tsm.h"
 
 namespace {
 
@@ -268,18 +268,6 @@ thread_local std::string g_err;
 
 extern "C" {
 
-struct tskvtsm_result {
-  uint8_t *arena;            // repacked pages, 16-byte aligned each (malloc; tskvtsm_free)
-  uint64_t arena_len;
-  tskv_page_desc *descs;     // column group by column group, TIME page first
-  uint64_t n_descs;
-  tskv_time_range *cg_bounds;  // ColumnGroup::time_range() per column group, descriptor order
-  uint64_t n_column_groups;
-  uint64_t n_skipped_pages;  // pages of column types outside this engine's path (tag / bool / string / geometry)
-  int64_t min_ts, max_ts;    // Footer.time_range
-  uint32_t version;          // 1 | 2
-  uint32_t reserved;
-};
 
 const char *tskvtsm_last_error(void) { return g_err.c_str(); }
 

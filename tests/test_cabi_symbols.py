@@ -25,6 +25,19 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in cabi.load_gpu_library().tskvgpu_version()
 
 
+def test_tsm_loader_header_and_library_agree():
+    """include/tskv_tsm.h (row f2) is implemented by libtskv_hostgen.so."""
+    txt = open(os.path.join(ROOT, "include", "tskv_tsm.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(tskvtsm_\w+)\s*\(", txt)))
+    assert names == ["tskvtsm_free", "tskvtsm_last_error", "tskvtsm_load", "tskvtsm_write"]
+    lib = cabi.load_hostgen_library()
+    for name in names:
+        assert hasattr(lib, name), name
+    from cnosdb_b200 import tsmfile
+    assert C.sizeof(tsmfile._Result) == 80
+
+
 def test_struct_sizes_match_header():
     assert C.sizeof(cabi.PageDesc) == 24 and cabi.PAGE_DESC_DTYPE.itemsize == 24
     assert C.sizeof(cabi.TimeRange) == 16 and C.sizeof(cabi.AggColumn) == 4
@@ -35,7 +48,7 @@ def test_struct_sizes_match_header():
 def test_header_compiles_as_c(tmp_path):
     import subprocess
     src = tmp_path / "t.c"
-    src.write_text('#include "tskv_gpu.h"\nint main(void){tskv_query q; (void)q; return sizeof(tskv_page_desc)==24?0:1;}\n')
+    src.write_text('#include "tskv_gpu.h"\n#include "tskv_tsm.h"\nint main(void){tskv_query q; (void)q; return sizeof(tskv_page_desc)==24 && sizeof(tskvtsm_result)==80?0:1;}\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t")])
     subprocess.check_call([str(tmp_path / "t")])
 
