@@ -106,6 +106,20 @@ struct ChunkRing {
     trig = n_chunks > RING_CHUNKS ? 1u : 0xffffffffu;   // chunk RING_CHUNKS goes out when the window reaches chunk 1
     trig_last = n_chunks - RING_CHUNKS;
   }
+  // The same ring entered in the middle of the stream (restart points, SkipEntry below): the first chunk staged is
+  // chunk c0 (counted from the stream's aligned start, like every chunk / word index of the decoders) and it lands at
+  // ring offset (c0 mod RING_CHUNKS) * 16, so word k of the stream stays at (k mod 2 * RING_CHUNKS) * 8.
+  __device__ __forceinline__ void init_at(const uint8_t *start, const uint8_t *end, uint32_t lane_ring, uint32_t c0) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15, e = reinterpret_cast<uintptr_t>(end);
+    const uint32_t n_chunks = e > a ? (uint32_t)((e - a + 15) >> 4) : 0u;
+    gnext = reinterpret_cast<const uint8_t *>(a) + (size_t)c0 * 16;
+    sbase = lane_ring;
+    snext = (c0 & (RING_CHUNKS - 1)) * 16;
+#pragma unroll
+    for (int i = 0; i < RING_CHUNKS; i++) issue_one();  // (near the end of the stream: < RING_BYTES past its end)
+    trig = n_chunks > c0 + RING_CHUNKS ? c0 + 1 : 0xffffffffu;
+    trig_last = n_chunks - RING_CHUNKS;
+  }
   // One decoder step whose read window starts in chunk c (see above). Nothing is issued past the stream's last chunk,
   // however far a decoder that ran off a truncated block pushes its window.
   __device__ __forceinline__ void step(uint32_t c) {
@@ -134,6 +148,34 @@ struct ChunkRing {
 // Commits the initial fills of the lane's rings and waits for them (once per page, before the first step).
 __device__ __forceinline__ void ring_drain() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;\n" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------
+// Restart points (round 2, "skip index"). A page is one serial stream: the value of row r depends on every element
+// before it, so one page is one dependent chain of ~1000 elements however many SMs are idle. TSM pages are immutable,
+// so the page set carries - built ONCE, on the device, when the pages are uploaded (k_build_skip) - the decoder state
+// at every SKIP_ROWS-th row of every simple8b / gorilla page: 16 bytes per restart point. A scan then cuts a page into
+// parts of m * SKIP_ROWS rows, each decoded by its own lane from the restart point (RLE pages need none: closed form).
+// The entry is the cursor's own state (save() / restore() below), so a restarted cursor continues bit-identically:
+//   simple8b (S8bCursor):  v = running value, a = aligned-word index of the stream position (relative to the
+//                          stream's first word), b = values left in the current packed word
+//   gorilla (GorillaRing): v = the value the next call returns, a = bit position of the following element (relative
+//                          to the stream's first bit), b = meaningful | trailing << 8 | cur_ok << 16 | any << 17
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t SKIP_ROWS = 128;
+constexpr uint32_t SKIP_NONE = 0xffffffffu;
+struct SkipEntry {
+  uint64_t v;
+  uint32_t a, b;
+};
+static_assert(sizeof(SkipEntry) == 16, "restart points are 16-byte records");
+__device__ __forceinline__ SkipEntry load_skip(const SkipEntry *p) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+  SkipEntry e;
+  e.v = ((uint64_t)r.y << 32) | r.x;
+  e.a = r.z;
+  e.b = r.w;
+  return e;
+}
+
 // Sequential big-endian u64 words of an arbitrarily aligned byte range through a ChunkRing (simple8b / raw pages).
 // Same interface as BeStream.
 struct SeqStream {
@@ -152,6 +194,19 @@ struct SeqStream {
     const uint64_t w = __ldg(reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7));  // the first word straight from global memory
     cur = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
   }
+  // Enters the stream at aligned word k0 + rel (k0 = the index init() starts at): the next next() composes the packed
+  // word that starts in aligned word k0 + rel.
+  __device__ __forceinline__ void init_at(const uint8_t *p, uint32_t lane_slot, const uint8_t *end, uint32_t rel) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t o = (uint32_t)(a & 7), q = o & 3;
+    high = o >= 4;
+    psel = (q + 3) | ((q + 2) << 4) | ((q + 1) << 8) | (q << 12);
+    k = ((uint32_t)(a & 15) >> 3) + rel;
+    ring.init_at(p, end, lane_slot, k >> 1);
+    const uint64_t w = __ldg(reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)15) + k);
+    cur = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+  }
+  __device__ __forceinline__ uint32_t first_word_index(const uint8_t *p) const { return (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15) >> 3; }
   __device__ __forceinline__ uint64_t next() {
     k++;
     ring.step(k >> 1);
@@ -425,6 +480,32 @@ struct S8bCursor {
   }
   // more words were consumed than the block holds ("Mismatch between bit set and decoded values")
   __device__ __forceinline__ bool exhausted() const { return bs.k > k_end; }
+  // Restart points (SkipEntry): the state after some number of next() calls, and a cursor re-entered there.
+  __device__ __forceinline__ SkipEntry save(const PageView &pv) const {
+    SkipEntry e;
+    e.v = v;
+    e.a = bs.k - bs.first_word_index(pv.data + 10);
+    e.b = in_word;
+    return e;
+  }
+  __device__ __forceinline__ void restore(const PageView &pv, uint32_t lane_ring, const SkipEntry &e) {
+    const uint8_t *d = pv.data;
+    scaler = ZZ ? 1 : pow10_u64(__ldg(d + 1) & 0xf);
+    v = e.v;
+    bs.init_at(d + 10, lane_ring, d + pv.data_len, e.a);
+    k_end = bs.first_word_index(d + 10) + ((pv.data_len - 10) >> 3);
+    w = 0; mask = 0; bits = 0; ones = 0;
+    in_word = e.b;
+    if (e.a) {  // inside packed word e.a - 1: re-read it and drop the values already consumed
+      const uint64_t full = load_be64(d + 10 + (size_t)(e.a - 1) * 8);
+      const uint32_t sel = (uint32_t)(full >> 60);
+      uint32_t count;
+      s8b_lut(sel, count, bits);
+      ones = sel < 2 ? 1u : 0u;
+      mask = bits ? (~0ull >> (64 - bits)) : 0ull;
+      w = full >> (bits * (count - in_word));  // <= 60
+    }
+  }
 
   __device__ __forceinline__ uint64_t next() {
     if (in_word == 0) {
@@ -581,6 +662,27 @@ struct GorillaRing {
     cur_ok = false; done = any = false;
   }
   __device__ __forceinline__ bool consumed_any() const { return any; }
+  // Restart points (SkipEntry): the state before some next() call, and a cursor re-entered there.
+  __device__ __forceinline__ SkipEntry save(const PageView &pv) const {
+    SkipEntry e;
+    e.v = val;
+    e.a = pos - (uint32_t)(reinterpret_cast<uintptr_t>(pv.data + 10) & 15) * 8;
+    e.b = meaningful | (trailing << 8) | ((cur_ok ? 1u : 0u) << 16) | ((any ? 1u : 0u) << 17);
+    return e;
+  }
+  __device__ __forceinline__ void restore(const PageView &pv, uint32_t lane_slot, const SkipEntry &e) {
+    const uint8_t *d = pv.data;
+    val = e.v;
+    const uint32_t pos0 = (uint32_t)(reinterpret_cast<uintptr_t>(d + 10) & 15) * 8;
+    pos = pos0 + e.a;
+    end_pos = pos0 + (pv.data_len - 10) * 8;
+    ring.init_at(d + 10, d + pv.data_len, lane_slot, pos >> 7);
+    meaningful = e.b & 0xff;
+    trailing = (e.b >> 8) & 0xff;
+    cur_ok = (e.b >> 16) & 1;
+    any = (e.b >> 17) & 1;
+    done = false;
+  }
   // "unexpected end of block" (float.rs:462): an element ran past the block. `pos` only grows and stops growing at the
   // sentinel, so this one comparison, made when the caller checks, stands for the serial cursor's per-element test: an
   // overrun BEFORE the sentinel leaves pos > end_pos, a sentinel inside the block freezes pos <= end_pos.

@@ -102,6 +102,14 @@ struct ScanParams {
   // fused kernels; words of a group start at row_keep + keep_off[index of the group's time page]. null: no predicates.
   const uint32_t *row_keep;
   const uint32_t *keep_off;
+  // Restart points of the page set (cursors.cuh, SkipEntry; null: none). skip_off[page] = index of the page's first
+  // entry in `skip` (entry j - 1 = the state at row j * SKIP_ROWS) or SKIP_NONE. A bin whose pages are cut into
+  // bin_parts[bin] > 1 parts of bin_part_rows[bin] rows (a multiple of SKIP_ROWS) runs parts x as many chunks; all
+  // lanes of a chunk decode the SAME part of 32 different pages.
+  const uint32_t *skip_off;
+  const SkipEntry *skip;
+  uint32_t bin_parts[N_BINS];
+  uint32_t bin_part_rows[N_BINS];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1089,7 +1097,8 @@ __device__ __forceinline__ uint32_t rle_rows_within(uint64_t d, uint64_t delta, 
 
 template <int TK, int VK, bool SEL>
 __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t item_begin, uint32_t item_end,
-                                               uint32_t ring_base, uint64_t *stab, uint64_t *stage) {
+                                               uint32_t ring_base, uint64_t *stab, uint64_t *stage,
+                                               uint32_t part, uint32_t n_parts, uint32_t part_rows) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t item = item_begin + lane;
   const bool have_item = item < item_end;
@@ -1114,6 +1123,10 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   if (TK == TK_S8B) tcur.reset(tslot);
   if (VK == VK_GOR) vcur_g.reset(vslot);
   else cursor_reset(vcur_d, vslot);
+  // This lane decodes rows [r0, n_rows) of its page: the whole page, or - the bin's pages are cut at restart points
+  // (n_parts > 1, never with FIRST / LAST) - part `part` of it. A page without restart points (short, or its streams did
+  // not decode cleanly when the index was built) is decoded whole by the lane of part 0, errors and all.
+  uint32_t r0 = 0, page_rows = 0;
   if (have_item) {
     page = P.work_page[item];
     slot = P.work_slot[item];
@@ -1124,37 +1137,58 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     const tskv_page_desc td = P.descs[tpage];
     if (VK != VK_GOR) pt = P.cols[qcol].phys_type;
     mask = P.cols[qcol].agg_mask;
+    page_rows = vd.num_values;
+    uint32_t sk_v = SKIP_NONE, sk_t = SKIP_NONE;  // the page's restart points (value stream, time stream)
+    bool split = false;
+    if (n_parts > 1 && page_rows > part_rows) {
+      sk_v = __ldg(P.skip_off + page);
+      sk_t = TK == TK_S8B ? __ldg(P.skip_off + tpage) : 0u;
+      split = sk_v != SKIP_NONE && sk_t != SKIP_NONE;
+    }
+    r0 = part * part_rows;
     tskv_status st = kind_status(vd.reserved);  // the time page is RLE / simple8b here: always decodable
-    if (st != TSKV_OK) {
+    if (part != 0 && (!split || r0 >= page_rows)) {
+      // nothing for this lane: the page ends before this part, or part 0's lane decodes all of it
+    } else if (st != TSKV_OK) {
       report_error(P, st, page);
     } else {
       tpv.open(P.arena, td);
       vpv.open(P.arena, vd);
-      n_rows = vd.num_values;
+      n_rows = split ? min(page_rows, r0 + part_rows) : page_rows;
       vbm = reinterpret_cast<const uint32_t *>(vpv.bitset);
       if (P.row_keep) keepw = P.row_keep + P.keep_off[tpage];
+      const uint32_t ent = r0 / SKIP_ROWS - 1;  // restart point of row r0 (part != 0)
       if (TK == TK_RLE) {  // timestamp.rs:226-259
         DeltaCursor<DK_RLE_SC, BeStream> rc;
         st = rc.open(tpv, td.reserved);
         rle_delta = rc.delta;
         rle_t0 = rc.v + rc.delta;
         if ((int64_t)rle_delta > 0) rle_inv = 1.0 / (double)rle_delta;
-      } else {
+      } else if (part == 0) {
         st = tcur.open(tpv, td.reserved, tslot);
+      } else {
+        tcur.restore(tpv, tslot, load_skip(P.skip + sk_t + ent));  // the state after row r0's timestamp
       }
       if (st == TSKV_OK) {
-        if (VK == VK_GOR) vcur_g.open(vpv, vslot);
-        else { st = vcur_d.open(vpv, vd.reserved, vslot); allnull = vd.reserved == DK_ALLNULL; }
+        if (part == 0) {
+          if (VK == VK_GOR) vcur_g.open(vpv, vslot);
+          else { st = vcur_d.open(vpv, vd.reserved, vslot); allnull = vd.reserved == DK_ALLNULL; }
+        } else {
+          const SkipEntry e = load_skip(P.skip + sk_v + ent);  // the state before the first value of row >= r0
+          if constexpr (VK == VK_GOR) vcur_g.restore(vpv, vslot, e);
+          else if constexpr (VK == VK_S8B) vcur_d.restore(vpv, vslot, e);
+          // (generic value codecs are never cut: n_parts == 1)
+        }
       }
       if (st == TSKV_OK && n_rows) {
-        if (TK == TK_RLE) pend_t = (int64_t)rle_t0;
-        else {
-          pend_t = (int64_t)tcur.next();  // the first value: no ring access (cursors.cuh)
-        }
+        if (TK == TK_RLE) pend_t = (int64_t)(rle_t0 + (uint64_t)r0 * rle_delta);
+        else if (part == 0) pend_t = (int64_t)tcur.next();  // the first value: no ring access (cursors.cuh)
+        else pend_t = (int64_t)tcur.v;
       }
       if (st != TSKV_OK) { report_error(P, st, st == TSKV_ERR_BITSET_MISMATCH ? tpage : page); n_rows = 0; }
     }
   }
+  const bool to_page_end = n_rows == page_rows;  // this lane reaches the end of the page's streams
   ring_drain();  // the rings' initial fills have landed before the first step (once per page)
 
   ValueAcc<VK> va;
@@ -1164,9 +1198,10 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   BucketState bk; bk.valid = false; bk.floor_regime = false; bk.lo = 0; bk.hi = 0; bk.idx = 0;
   bool have_run = false;
   uint32_t run_idx = 0;
-  uint32_t row = 0;
+  uint32_t row = r0;  // (a multiple of 32)
+  if (n_rows == 0) row = 0;
   uint32_t n_points = 0, n_inrange = 0;
-  uint32_t vword = 0, vahead = vbm ? __ldg(vbm) : 0;  // bitmap word of `row`, and the next one (prefetched)
+  uint32_t vword = 0, vahead = vbm ? __ldg(vbm + (row >> 5)) : 0;  // bitmap word of `row`, and the next one (prefetched)
   uint32_t kword = 0xffffffffu;                        // row-filter bits of the same 32 rows (all ones without predicates)
   bool first_pending = false;                          // FIRST/LAST: the run has not seen a kept row yet
   const uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull : 0ull;
@@ -1223,18 +1258,21 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
   if (TK == TK_RLE) {
     bool elig = P.n_ranges <= 1 && !P.has_tomb;
     if (elig && n_rows) {
-      const uint64_t span_t = (uint64_t)(n_rows - 1) * rle_delta;
-      elig = (int64_t)rle_delta > 0 && __umul64hi((uint64_t)(n_rows - 1), rle_delta) == 0 && span_t < (1ull << 62) &&
+      // (the parts of a page may take different paths: both give the same result)
+      const uint64_t span_t = (uint64_t)(page_rows - 1) * rle_delta;
+      elig = (int64_t)rle_delta > 0 && __umul64hi((uint64_t)(page_rows - 1), rle_delta) == 0 && span_t < (1ull << 62) &&
              rle_t0 + (1ull << 62) < (1ull << 63) && P.width < ((int64_t)1 << 61);
       if (elig) {
         const int64_t t0 = (int64_t)rle_t0;
         ra = 0;
-        rb1 = n_rows;
+        rb1 = page_rows;
         if (P.n_ranges == 1) {  // rows with t < a, rows with t <= b
           const int64_t a = P.ranges[0].min_ts, b = P.ranges[0].max_ts;
-          ra = a <= t0 ? 0u : rle_rows_within((uint64_t)(a - 1) - rle_t0, rle_delta, rle_inv, n_rows);
-          rb1 = b < t0 ? 0u : rle_rows_within((uint64_t)b - rle_t0, rle_delta, rle_inv, n_rows);
+          ra = a <= t0 ? 0u : rle_rows_within((uint64_t)(a - 1) - rle_t0, rle_delta, rle_inv, page_rows);
+          rb1 = b < t0 ? 0u : rle_rows_within((uint64_t)b - rle_t0, rle_delta, rle_inv, page_rows);
         }
+        ra = min(max(ra, row), n_rows);  // this lane's rows: [row, n_rows)
+        rb1 = min(max(rb1, row), n_rows);
         if (P.width > 0 && ra < rb1) {
           const int64_t tr = (int64_t)(rle_t0 + (uint64_t)ra * rle_delta);
           if ((int64_t)((uint64_t)tr - (uint64_t)P.origin_mod + (uint64_t)P.width) < 0) {
@@ -1430,7 +1468,8 @@ __device__ __forceinline__ void scan_chunk_seg(const ScanParams &P, uint32_t ite
     reduce_staged<VK>(P, stab, stage, staged);
     staged = 0;
   }
-  if (VK == VK_GOR && have_item && n_rows != 0 && vcur_g.consumed_any() && !vcur_g.drain())  // float.rs:480-591
+  // (only the lane that decodes the page's last rows walks on to the sentinel)
+  if (VK == VK_GOR && have_item && n_rows != 0 && to_page_end && vcur_g.consumed_any() && !vcur_g.drain())  // float.rs:480-591
     report_error(P, TSKV_ERR_SHORT_BLOCK, page);
   ring_drain();  // nothing in flight when the next chunk reuses the rings
   n_points = __reduce_add_sync(FULL, n_points);
@@ -1481,16 +1520,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, scan_min_blocks(TK, SEL)) k_scan
   const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(warp_area);
   uint64_t *stage = warp_area + scan_ring_bytes_per_warp(TK) / 8;
   const uint32_t begin0 = __ldg(P.bin_cstart + bin), end0 = __ldg(P.bin_cstart + bin + 1);
-  const uint32_t n_chunks = (end0 - begin0 + 31) >> 5;
+  // pages cut at restart points: n_parts chunks per group of 32 pages (consecutive chunk numbers = the parts of one group)
+  const uint32_t n_parts = (TK == TK_GEN || VK == VK_GEN || SEL) ? 1u : P.bin_parts[bin];
+  const uint32_t part_rows = P.bin_part_rows[bin];
+  const uint32_t n_chunks = ((end0 - begin0 + 31) >> 5) * n_parts;
   for (;;) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(P.task_counter + bin, 1u);
     c = __shfl_sync(FULL, c, 0);
     if (c >= n_chunks) break;
-    const uint32_t begin = begin0 + (c << 5);
+    const uint32_t group = n_parts > 1 ? c / n_parts : c;
+    const uint32_t part = c - group * n_parts;
+    const uint32_t begin = begin0 + (group << 5);
     const uint32_t end = min(begin + 32, end0);
-    if (TK == TK_GEN) scan_chunk_rows<TK, VK, SEL>(P, begin, end, ring_base, s_tab);
-    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base, s_tab, stage);
+    if constexpr (TK == TK_GEN) scan_chunk_rows<TK, VK, SEL>(P, begin, end, ring_base, s_tab);
+    else scan_chunk_seg<TK, VK, SEL>(P, begin, end, ring_base, s_tab, stage, part, n_parts, part_rows);
   }
   if (P.use_smem) {  // merge this CTA's table into the global state, once
     __syncthreads();

@@ -17,6 +17,7 @@
 
 #include "host_util.h"
 #include "decode_kernels.cuh"
+#include "skip_kernels.cuh"
 
 using namespace tskv;
 
@@ -87,6 +88,11 @@ struct tskv_pages {
   // row-filter masks: 32-bit words per column group, offset stored at the index of the group's time page
   uint32_t *d_keep_off = nullptr;
   uint64_t keep_words = 0;
+  // restart points (skip_kernels.cuh): per page the index of its first entry (or SKIP_NONE), built once at upload
+  uint32_t *d_skip_off = nullptr;
+  SkipEntry *d_skip = nullptr;
+  uint64_t n_skip = 0;
+  uint32_t h_bin_maxrows[N_BINS]{};  // longest field page of each bin (parts per page when a scan cuts the bin's pages)
 };
 
 struct tskv_scan {
@@ -643,6 +649,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
       counts[key[k] >> 48]++;
       pg->h_bin_bytes[key[k] >> 48] += pg->h_descs[item_page[src]].size;
       pg->h_bin_rows[key[k] >> 48] += pg->h_descs[item_page[src]].num_values;
+      pg->h_bin_maxrows[key[k] >> 48] = std::max(pg->h_bin_maxrows[key[k] >> 48], pg->h_descs[item_page[src]].num_values);
     }
     item_page.swap(ip);
     item_cg.swap(ic);
@@ -684,6 +691,50 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
     pg->verify_on_read = true;  // like the reference: every read of a page re-checks its CRC (device side)
     e = up(&pg->d_crc_tables, crc32_tables(), 2048);
   }
+  // ---- restart points of the simple8b / gorilla pages (pages resident in HBM only) -----------------------
+  const bool no_skip = getenv("TSKV_NO_SKIP") != nullptr;
+  if (e == cudaSuccess && !no_skip && !(flags & TSKV_UPLOAD_HOST_RESIDENT) && n_descs) {
+    std::vector<uint32_t> skip_off(n_descs, SKIP_NONE), list[3];
+    uint64_t n_skip = 0;
+    for (uint64_t i = 0; i < n_descs; i++) {
+      const tskv_page_desc &d = pg->h_descs[i];
+      int kind = -1;
+      if (d.phys_type == TSKV_PT_TIME) kind = (d.reserved == DK_S8B_SC && !time_has_nulls[i]) ? SKIP_KIND_TIME_S8B : -1;
+      else if (d.reserved == DK_S8B_ZZ) kind = SKIP_KIND_VALUE_S8B;
+      else if (d.reserved == DK_GORILLA) kind = SKIP_KIND_VALUE_GORILLA;
+      if (kind < 0 || d.num_values <= SKIP_ROWS || n_skip + d.num_values / SKIP_ROWS >= SKIP_NONE) continue;
+      skip_off[i] = (uint32_t)n_skip;
+      n_skip += (d.num_values - 1) / SKIP_ROWS;
+      list[kind].push_back((uint32_t)i);
+    }
+    if (n_skip) {
+      pg->n_skip = n_skip;
+      e = up(&pg->d_skip_off, skip_off.data(), n_descs);
+      if (e == cudaSuccess) e = dev_alloc(&pg->d_skip, n_skip);
+      uint32_t *d_list = nullptr;
+      const size_t n_list = list[0].size() + list[1].size() + list[2].size();
+      if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&d_list), n_list * 4, ctx->stream);
+      size_t lo = 0;
+      for (int k = 0; k < 3 && e == cudaSuccess; k++) {
+        const uint32_t n = (uint32_t)list[k].size();
+        if (!n) continue;
+        e = cudaMemcpyAsync(d_list + lo, list[k].data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) break;
+        const uint32_t blocks = (n + SKIP_THREADS - 1) / SKIP_THREADS;
+        if (k == SKIP_KIND_TIME_S8B)
+          k_build_skip<SKIP_KIND_TIME_S8B><<<blocks, SKIP_THREADS, SKIP_SMEM_BYTES, ctx->stream>>>(pg->d_arena, pg->d_descs, d_list + lo, n, pg->d_skip_off, pg->d_skip);
+        else if (k == SKIP_KIND_VALUE_S8B)
+          k_build_skip<SKIP_KIND_VALUE_S8B><<<blocks, SKIP_THREADS, SKIP_SMEM_BYTES, ctx->stream>>>(pg->d_arena, pg->d_descs, d_list + lo, n, pg->d_skip_off, pg->d_skip);
+        else
+          k_build_skip<SKIP_KIND_VALUE_GORILLA><<<blocks, SKIP_THREADS, SKIP_SMEM_BYTES, ctx->stream>>>(pg->d_arena, pg->d_descs, d_list + lo, n, pg->d_skip_off, pg->d_skip);
+        lo += n;
+      }
+      if (e == cudaSuccess) e = cudaGetLastError();
+      // the page lists are read by kernels still in flight: host vectors stay alive until the sync below
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (d_list) cudaFreeAsync(d_list, ctx->stream);
+    }
+  }
   cudaEventRecord(ctx->ev1, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
@@ -705,6 +756,8 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   if (pg->ctx && pg->ctx->stream) cudaStreamSynchronize(pg->ctx->stream);
   if (pg->h_registered) cudaHostUnregister(pg->h_registered);
   cudaFree(pg->d_arena);
+  cudaFree(pg->d_skip_off);
+  cudaFree(pg->d_skip);
   cudaFree(pg->d_descs);
   cudaFree(pg->d_time_page_of);
   cudaFree(pg->d_cg_time_page);
@@ -1210,6 +1263,9 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     P.n_cols = q->n_columns;
     P.row_keep = s->d_row_keep;
     P.keep_off = pages->d_keep_off;
+    P.skip_off = pages->d_skip_off;
+    P.skip = pages->d_skip;
+    for (int b = 0; b < N_BINS; b++) { P.bin_parts[b] = 1; P.bin_part_rows[b] = 0; }
     P.has_tomb = pages->n_tomb_ranges ? 1u : 0u;
     P.tomb_keys = pages->d_tomb_keys;
     P.tomb_off = pages->d_tomb_off;
@@ -1256,6 +1312,32 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       if (const char *g = getenv("TSKV_GOR_GROUP")) gor_group = (uint32_t)std::min(32, std::max(1, atoi(g)));
       s->coop.gor_group = gor_group;
     }
+    // Pages cut at restart points (skip_kernels.cuh): a chunk of 32 whole pages is one serial task of ~1000 rows; with
+    // few selected pages that chain is the scan's makespan, and with many the makespan is still quantised in chunk
+    // times. Cut the pages of the simple8b / gorilla bins into parts so that the scan has about PARTS_TARGET chunks
+    // per resident warp (more parts = shorter chains, but one more page open + two more run flushes per part).
+    uint32_t parts[N_BINS];
+    for (int b = 0; b < N_BINS; b++) parts[b] = 1;
+    if (pages->d_skip && !s->has_sel) {
+      double est_chunks = 0;
+      for (int b = 0; b < N_BINS; b++) est_chunks += std::ceil((pages->h_bin_start[b + 1] - pages->h_bin_start[b]) * sel_frac / 32.0);
+      const double resident_warps = (double)ctx->sm_count * SCAN_MIN_BLOCKS * (SCAN_THREADS / 32);
+      const char *pt_env = getenv("TSKV_PARTS_TARGET");
+      const double target = (pt_env ? atof(pt_env) : 4.0) * resident_warps;
+      uint32_t want = est_chunks > 0 ? (uint32_t)std::min(4096.0, std::ceil(target / est_chunks)) : 1u;
+      const char *parts_env = getenv("TSKV_PARTS");  // fixed number of parts (1 = never cut)
+      if (parts_env) want = (uint32_t)std::max(1, atoi(parts_env));
+      for (int b = 0; b < N_BINS; b++) {
+        const int sb = serial_bin_of(b);
+        const uint32_t maxrows = pages->h_bin_maxrows[b];
+        if (s->use_coop[b] || sb / N_VK == TK_GEN || sb % N_VK == VK_GEN || maxrows <= SKIP_ROWS || want <= 1) continue;
+        const uint32_t units = (maxrows + SKIP_ROWS - 1) / SKIP_ROWS;           // restart intervals of the longest page
+        const uint32_t m = (units + std::min(want, units) - 1) / std::min(want, units);  // intervals per part
+        parts[b] = (units + m - 1) / m;
+        P.bin_parts[b] = parts[b];
+        P.bin_part_rows[b] = m * SKIP_ROWS;
+      }
+    }
     double w[N_BINS], wsum = 0, need_sum = 0, occ_weighted = 0;
     int need[N_BINS] = {0}, occ_bin[N_BINS] = {0};
     for (int b = 0; b < N_BINS; b++) {
@@ -1277,9 +1359,9 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       occ_bin[b] = occ;
       const double est_items = n_bin * sel_frac * 1.02 + 32;
       const uint32_t per_task = !s->use_coop[b] ? 32u : is_gor_coop_bin(b) ? gor_group : 1u;  // pages per warp task
-      const double tasks = est_items / per_task;
+      const double tasks = est_items / per_task * parts[b];
       need[b] = (int)(tasks / (SCAN_THREADS / 32)) + 1;
-      need[b] = std::min(need[b], (int)((n_bin + per_task - 1) / per_task + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32));
+      need[b] = std::min(need[b], (int)(((uint64_t)(n_bin + per_task - 1) / per_task * parts[b] + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32)));
       need_sum += need[b];
       occ_weighted += (double)need[b] * occ;
     }
@@ -1295,13 +1377,21 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       double chunks[N_BINS], t_chunk[N_BINS];
       for (int b = 0; b < N_BINS; b++) {
         const uint32_t n_bin = pages->h_bin_start[b + 1] - pages->h_bin_start[b];
-        chunks[b] = need[b] ? std::ceil((n_bin * sel_frac * 1.02 + 16) / 32.0) : 0;
-        t_chunk[b] = n_bin ? chunk_cost(b) * (double)pages->h_bin_rows[b] / n_bin : 1.0;
+        chunks[b] = need[b] ? std::ceil((n_bin * sel_frac * 1.02 + 16) / 32.0) * parts[b] : 0;
+        // (+ 12 rows' worth per chunk for opening its pages)
+        t_chunk[b] = n_bin ? chunk_cost(b) * ((double)pages->h_bin_rows[b] / n_bin / parts[b] + 12.0) : 1.0;
       }
       plan_serial_grids(N_BINS, chunks, t_chunk, occ_bin, ctx->sm_count, SCAN_THREADS / 32, s->grid);
       for (int b = 0; b < N_BINS; b++) s->grid[b] = std::min(s->grid[b], std::max(need[b], 0));
+      // TSKV_GRID_OVERSUB=f: f x the planned blocks per bin; the blocks that are not resident at first start as the
+      // bins that finish early retire theirs and pick up what is left of the slower bins' chunks
+      if (const char *ov = getenv("TSKV_GRID_OVERSUB")) {
+        const double f = atof(ov);
+        if (f > 1.0)
+          for (int b = 0; b < N_BINS; b++) s->grid[b] = std::min(std::max(need[b], 0), (int)std::ceil(s->grid[b] * f));
+      }
       // TSKV_GRID_MODE=1: one warp per chunk for every bin; the block scheduler queues what does not fit
-      static const char *gm = getenv("TSKV_GRID_MODE");
+      const char *gm = getenv("TSKV_GRID_MODE");
       if (gm && gm[0] == '1')
         for (int b = 0; b < N_BINS; b++) s->grid[b] = need[b];
     } else {

@@ -55,6 +55,8 @@ def lib():
         L.orc_open.restype = C.c_int32
         L.orc_scan.argtypes = [vp, C.POINTER(cabi.Query), vp, C.c_uint64, C.c_int, vp, vp, C.POINTER(C.c_uint64)]
         L.orc_scan.restype = C.c_int32
+        L.orc_set_chunk_files.argtypes = [vp, vp, C.c_uint64]
+        L.orc_set_chunk_files.restype = C.c_int32
         L.orc_close.argtypes = [vp]
         L.orc_close.restype = None
         L.orc_last_error.restype = C.c_char_p
@@ -155,9 +157,18 @@ def decode_pages(arena, descs, first_page=0, n_pages=None, verify_crc=True):
     return out
 
 
-def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_points=False, tombstones=None):
+def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_points=False, tombstones=None,
+                   chunk_files=None):
     """Same inputs / ScanResult as cnosdb_b200.engine.Engine.scan_aggregate, computed on the CPU.
-    tombstones: cabi.TOMBSTONE_DTYPE array, what PageSet.set_tombstones takes."""
+    tombstones: cabi.TOMBSTONE_DTYPE array, what PageSet.set_tombstones takes.
+    chunk_files: file id of every column group (what PageSet.set_chunk_files takes): overlapping chunks are merged."""
+    if chunk_files is not None:
+        op = OpenPages(arena, descs, n_threads=n_threads)
+        try:
+            op.set_chunk_files(chunk_files)
+            return op.scan(query, verify_crc=verify_crc, return_points=return_points, tombstones=tombstones)
+        finally:
+            op.close()
     if isinstance(arena, tuple):
         aptr, alen = arena
     else:
@@ -197,6 +208,12 @@ class OpenPages:
         if st != 0:
             raise OracleError(st, lib().orc_last_error().decode())
         self.h = h
+
+    def set_chunk_files(self, cg_file_ids):
+        ids = np.ascontiguousarray(cg_file_ids, dtype=np.uint64)
+        st = lib().orc_set_chunk_files(self.h, ids.ctypes.data if len(ids) else None, len(ids))
+        if st != 0:
+            raise OracleError(st, lib().orc_last_error().decode())
 
     def scan(self, query, verify_crc=True, return_points=False, tombstones=None):
         q = query.to_c()

@@ -75,6 +75,8 @@ struct Cell {
 struct ColumnGroup {
   uint64_t first_desc;  // the TIME page
   uint64_t n_descs;     // incl. the time page
+  uint64_t orig;        // index of the column group in descriptor-table order
+  int64_t min_ts;       // first time value (orders the column groups of a chunk; filled by orc_set_chunk_files)
 };
 
 struct SeriesGroups {
@@ -113,7 +115,7 @@ tskv_status build_index(const tskv_page_desc *descs, uint64_t n, Index &ix) {
       }
       j++;
     }
-    ix.cgs.push_back(ColumnGroup{i, j - i});
+    ix.cgs.push_back(ColumnGroup{i, j - i, (uint64_t)ix.cgs.size(), 0});
     i = j;
   }
   // group by series keeping the arena order inside a series (compacted files are already sorted)
@@ -145,6 +147,7 @@ struct Scan {
   uint64_t n_cells;
   const tskv_tombstone *tombs = nullptr;
   uint64_t n_tombs = 0;
+  const uint64_t *cg_file = nullptr;  // file id of every column group (descriptor-table order), or null: one file
 };
 
 // update_nullbits_by_time_range (tsm/reader.rs:634-656): binary search over the page's time VALUES (the raw
@@ -170,198 +173,416 @@ void clear_bits_by_time_range(const std::vector<uint64_t> &ts, uint64_t n_rows, 
   for (uint64_t i = start; i < end && i < n_rows; i++) bits[i] = 0;
 }
 
-// One worker: slots [s0, s1) into `cells` (n_columns * n_cells). Returns status.
-tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, bool shared_table,
-                       uint64_t *points) {
-  const tskv_query &q = *S.q;
+// ---- overlapping chunks (reader/iterator.rs:463-560, reader/utils.rs:77-107, reader/sort_merge.rs, reader/batch_builder.rs)
+// A chunk = the column groups of one series in one file (tsm/chunk.rs); the caller tags every column group with the id
+// of the file it came from (orc_set_chunk_files). Per series the reference sorts the chunks by time range, groups the
+// ones whose ranges overlap (group_overlapping_segments), orders each group by file id and - for a group of more than
+// one chunk - k-way merges the chunks' row streams on `time` (DataMerger -> sort_merge): ties go to the lower stream
+// index, rows with equal time collapse into one whose every column takes the LAST non-null value in arrival order
+// (BatchMergeBuilder::take_last_and_merge), the first row's null otherwise.
+struct ChunkRef {
+  uint64_t file_id;
+  int64_t min_ts, max_ts;
+  std::vector<const ColumnGroup *> cgs;
+};
+
+struct Worker {
+  const Scan &S;
+  Cell *cells;
+  uint64_t *points;
   std::vector<uint64_t> ts, vals, pvals;
   std::vector<uint8_t> tvalid, vvalid, keep, pred_keep, pvalid;
   bool have_keep = false;
   int64_t page_min = 0, page_max = 0;
+  Worker(const Scan &s, Cell *c, uint64_t *p) : S(s), cells(c), points(p) {}
+
+  // Decodes the time page of a column group and evaluates what filters its ROWS: statistics pruning, the pushed
+  // predicates, the all-fields tombstones. `pruned` = the group is never read.
+  tskv_status prepare_cg(const ColumnGroup &cg, bool *pruned) {
+    const tskv_query &q = *S.q;
+    const tskv_page_desc &td = S.descs[cg.first_desc];
+    const uint64_t n_rows = td.num_values;
+    *pruned = false;
+    ts.assign(n_rows ? n_rows : 1, 0);
+    tvalid.assign(n_rows ? n_rows : 1, 0);
+    uint64_t nr = 0;
+    if (td.offset + td.size > S.arena_len) return TSKV_ERR_INVALID_ARG;
+    tskv_status st = orc_page_decode(TSKV_PT_TIME, S.arena + td.offset, td.size, S.verify_crc,
+                                     ts.data(), tvalid.data(), n_rows, &nr);
+    if (st != TSKV_OK) return st;
+    if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
+    // Statistics pruning (filter_column_groups, tskv/src/reader/chunk.rs:12-50): a column group whose time range
+    // (ColumnGroup::time_range(), here: min / max of its time values) overlaps none of the query's ranges is never
+    // read - its field pages are neither decoded nor counted.
+    if (q.n_time_ranges && n_rows) {
+      int64_t gmin = INT64_MAX, gmax = INT64_MIN;
+      for (uint64_t r = 0; r < n_rows; r++)
+        if (tvalid[r]) { gmin = std::min(gmin, (int64_t)ts[r]); gmax = std::max(gmax, (int64_t)ts[r]); }
+      bool overlaps = false;
+      for (uint32_t k = 0; k < q.n_time_ranges; k++)
+        overlaps = overlaps || (gmin <= q.time_ranges[k].max_ts && gmax >= q.time_ranges[k].min_ts);
+      if (!overlaps) { *pruned = true; return TSKV_OK; }
+    }
+    // the row filter: every predicate column of this column group decoded, rows kept where all comparisons are TRUE;
+    // a column the group does not hold is null-filled by SchemaAlignmenter (schema_alignmenter.rs:24-44) => no row passes
+    pred_keep.assign(n_rows ? n_rows : 1, 1);
+    for (uint32_t k = 0; k < q.n_predicates; k++) {
+      const tskv_field_predicate &fp = q.predicates[k];
+      const tskv_page_desc *pd = nullptr;
+      for (uint64_t j = 1; j < cg.n_descs; j++)
+        if (S.descs[cg.first_desc + j].column_id == fp.column_id) {
+          pd = &S.descs[cg.first_desc + j];
+          break;
+        }
+      if (!pd) {
+        std::fill(pred_keep.begin(), pred_keep.end(), (uint8_t)0);
+        continue;
+      }
+      if (pd->phys_type != fp.phys_type) {
+        g_err = "page type does not match the predicate column type";
+        return TSKV_ERR_INVALID_ARG;
+      }
+      pvals.assign(n_rows ? n_rows : 1, 0);
+      pvalid.assign(n_rows ? n_rows : 1, 0);
+      uint64_t pr = 0;
+      tskv_status pst = orc_page_decode(pd->phys_type, S.arena + pd->offset, pd->size, S.verify_crc, pvals.data(),
+                                        pvalid.data(), n_rows, &pr);
+      if (pst != TSKV_OK) return pst;
+      for (uint64_t r = 0; r < n_rows; r++)
+        if (!(pvalid[r] && cmp_true(fp.phys_type, fp.op, pvals[r], fp.value))) pred_keep[r] = 0;
+    }
+    // decode_pages with a tombstone (reader.rs:507-524): the all-fields excluded ranges that overlap the
+    // page's time range clear bits of the TIME page's null bitset; the result filters the rows.
+    keep.assign(n_rows ? n_rows : 1, 1);
+    have_keep = false;
+    if (S.n_tombs && n_rows) {
+      int64_t pmin = INT64_MAX, pmax = INT64_MIN;  // PageStatistics min/max of the time column
+      for (uint64_t r = 0; r < n_rows; r++)
+        if (tvalid[r]) { pmin = std::min(pmin, (int64_t)ts[r]); pmax = std::max(pmax, (int64_t)ts[r]); }
+      page_min = pmin; page_max = pmax;
+      for (uint64_t k = 0; k < S.n_tombs; k++) {
+        const tskv_tombstone &tb = S.tombs[k];
+        if (tb.column_id != TSKV_TOMB_ALL) continue;
+        if (tb.series_id != TSKV_TOMB_ALL && tb.series_id != td.series_id) continue;
+        if (!(tb.min_ts <= pmax && tb.max_ts >= pmin)) continue;  // TimeRange::overlaps
+        if (!have_keep) { keep = tvalid; have_keep = true; }
+        clear_bits_by_time_range(ts, n_rows, tb.min_ts, tb.max_ts, keep);
+      }
+    }
+    return TSKV_OK;
+  }
+
+  // Decodes one field page of the prepared column group into vals / vvalid (per-column tombstones applied).
+  tskv_status load_field(const tskv_page_desc *fd, uint64_t n_rows) {
+    vals.assign(n_rows ? n_rows : 1, 0);
+    vvalid.assign(n_rows ? n_rows : 1, 0);
+    uint64_t nr = 0;
+    if (fd->offset + fd->size > S.arena_len) return TSKV_ERR_INVALID_ARG;
+    tskv_status st = orc_page_decode(fd->phys_type, S.arena + fd->offset, fd->size, S.verify_crc,
+                                     vals.data(), vvalid.data(), n_rows, &nr);
+    if (st != TSKV_OK) return st;
+    if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
+    // per-column tombstones (reader.rs:531-542): clear the value validity of the excluded rows
+    for (uint64_t k = 0; k < S.n_tombs && n_rows; k++) {
+      const tskv_tombstone &tb = S.tombs[k];
+      if (tb.column_id == TSKV_TOMB_ALL || tb.series_id != fd->series_id || tb.column_id != fd->column_id) continue;
+      if (!(tb.min_ts <= page_max && tb.max_ts >= page_min)) continue;
+      clear_bits_by_time_range(ts, n_rows, tb.min_ts, tb.max_ts, vvalid);
+    }
+    return TSKV_OK;
+  }
+
+  const tskv_page_desc *find_field(const ColumnGroup &cg, const tskv_agg_column &qc, tskv_status *st) {
+    *st = TSKV_OK;
+    for (uint64_t k = 1; k < cg.n_descs; k++)
+      if (S.descs[cg.first_desc + k].column_id == qc.column_id) {
+        const tskv_page_desc *fd = &S.descs[cg.first_desc + k];
+        if (fd->phys_type != qc.phys_type) {
+          g_err = "page type does not match the query column type";
+          *st = TSKV_ERR_INVALID_ARG;
+        }
+        return fd;
+      }
+    return nullptr;  // column absent from this column group (null-filled by SchemaAlignmenter)
+  }
+
+  // The rows of one record batch into the cells of query column c: row keep flags (null: all kept), closed time
+  // ranges, bucket key, aggregates.
+  tskv_status aggregate_rows(uint32_t c, uint64_t group, uint64_t n_rows, const uint64_t *bts, const uint8_t *btvalid,
+                             const uint64_t *bvals, const uint8_t *bvvalid, const uint8_t *row_keep,
+                             const uint8_t *row_pred) {
+    const tskv_query &q = *S.q;
+    const tskv_agg_column &qc = q.columns[c];
+    const uint8_t pt = qc.phys_type;
+    Cell *ccells = cells + (uint64_t)c * S.n_cells + group * q.n_buckets;
+    // Run state for first/last: the rows of one (page, bucket) form one DataFusion group slice;
+    // FirstAccumulator::update_batch picks its min-time row and drops it when the VALUE is null
+    // (first.rs:139-148 + :91-94). Pages are time-sorted (mem_cache/series_data.rs:218-262), so a
+    // (page, bucket) group is one contiguous run of rows.
+    int64_t run_bucket = -1;
+    uint64_t run_first = 0, run_last = 0;
+    auto close_run = [&]() {
+      if (run_bucket < 0) return;
+      Cell &cell = ccells[run_bucket];
+      if ((qc.agg_mask & TSKV_AGG_FIRST) && bvvalid[run_first]) {
+        int64_t t = (int64_t)bts[run_first];
+        if (!cell.has_first || t < cell.first_ts) {  // strictly less: ties keep the earlier-seen
+          cell.has_first = true;
+          cell.first_ts = t;
+          cell.first_val = bvals[run_first];
+        }
+      }
+      if ((qc.agg_mask & TSKV_AGG_LAST) && bvvalid[run_last]) {
+        int64_t t = (int64_t)bts[run_last];
+        if (!cell.has_last || t > cell.last_ts) {
+          cell.has_last = true;
+          cell.last_ts = t;
+          cell.last_val = bvals[run_last];
+        }
+      }
+    };
+    for (uint64_t r = 0; r < n_rows; r++) {
+      if (row_keep && !row_keep[r]) continue;  // filter_record_batch(&record_batch, time_null_bits) (reader.rs:546-550)
+      if (row_pred && !row_pred[r]) continue;  // DataFilter (reader/filter.rs:130-142)
+      if (!btvalid[r]) continue;  // is_not_null(time) (transform_time_window.rs:313)
+      int64_t t = (int64_t)bts[r];
+      bool in = q.n_time_ranges == 0;
+      for (uint32_t k = 0; k < q.n_time_ranges && !in; k++)
+        in = t >= q.time_ranges[k].min_ts && t <= q.time_ranges[k].max_ts;  // TimeRange::contains
+      if (!in) continue;
+      int64_t b = 0;
+      if (q.width > 0) {
+        int64_t ws, we;
+        sliding_window(t, q.width, q.width, q.origin, 0, &ws, &we);
+        int64_t diff = (int64_t)((uint64_t)ws - (uint64_t)q.first_bucket_start);
+        if (diff < 0 || diff % q.width != 0 || diff / q.width >= (int64_t)q.n_buckets) {
+          g_err = "row outside the requested bucket range";
+          return TSKV_ERR_BUCKET_RANGE;
+        }
+        b = diff / q.width;
+      }
+      if (b != run_bucket) {
+        close_run();
+        run_bucket = b;
+        run_first = run_last = r;
+      } else {
+        if ((int64_t)bts[r] < (int64_t)bts[run_first]) run_first = r;
+        if ((int64_t)bts[r] > (int64_t)bts[run_last]) run_last = r;
+      }
+      if (!bvvalid[r]) continue;
+      Cell &cell = ccells[b];
+      uint64_t v = bvals[r];
+      if (cell.count == 0) {
+        cell.minv = cell.maxv = v;
+      } else {
+        if (less_typed(pt, v, cell.minv)) cell.minv = v;
+        if (less_typed(pt, cell.maxv, v)) cell.maxv = v;
+      }
+      cell.count++;
+      if (pt == TSKV_PT_F64) {
+        double d;
+        memcpy(&d, &v, 8);
+        cell.sum_d += d;
+      } else {
+        cell.sum_bits += v;
+        cell.sum_d += pt == TSKV_PT_I64 ? (double)(int64_t)v : (double)v;
+      }
+    }
+    close_run();
+    return TSKV_OK;
+  }
+
+  // One column group read on its own (no overlapping chunk): ColumnGroupReader -> DataFilter -> aggregate.
+  tskv_status scan_cg(const ColumnGroup &cg, uint64_t group) {
+    const tskv_query &q = *S.q;
+    const uint64_t n_rows = S.descs[cg.first_desc].num_values;
+    bool prepared = false, pruned = false;
+    for (uint32_t c = 0; c < q.n_columns && !pruned; c++) {
+      tskv_status st;
+      const tskv_page_desc *fd = find_field(cg, q.columns[c], &st);
+      if (st != TSKV_OK) return st;
+      if (!fd) continue;
+      if (!prepared) {
+        st = prepare_cg(cg, &pruned);
+        if (st != TSKV_OK) return st;
+        prepared = true;
+        if (pruned) break;
+      }
+      st = load_field(fd, n_rows);
+      if (st != TSKV_OK) return st;
+      if (points)
+        for (uint64_t r = 0; r < n_rows; r++)
+          if (vvalid[r]) (*points)++;
+      st = aggregate_rows(c, group, n_rows, ts.data(), tvalid.data(), vals.data(), vvalid.data(),
+                          have_keep ? keep.data() : nullptr, q.n_predicates ? pred_keep.data() : nullptr);
+      if (st != TSKV_OK) return st;
+    }
+    return TSKV_OK;
+  }
+
+  // A group of overlapping chunks, ordered by file id: every chunk is one sorted row stream (its column groups in time
+  // order, each filtered like scan_cg would), schema-aligned to time + the query's columns; the streams are merged
+  // and de-duplicated as described above, and the merged rows form ONE record batch (the reference cuts batches of
+  // `batch_size` rows; the cut only matters to first / last when the first / last row of a batch holds a NULL).
+  tskv_status scan_merged(const std::vector<const ChunkRef *> &streams, uint64_t group) {
+    const tskv_query &q = *S.q;
+    struct Row { int64_t t; uint32_t stream; };
+    const uint32_t nc = q.n_columns;
+    std::vector<int64_t> rt;                 // row time
+    std::vector<uint32_t> rs;                // row stream
+    std::vector<std::vector<uint64_t>> rv(nc);
+    std::vector<std::vector<uint8_t>> rok(nc);
+    for (uint32_t si = 0; si < streams.size(); si++) {
+      for (const ColumnGroup *cgp : streams[si]->cgs) {
+        const ColumnGroup &cg = *cgp;
+        const uint64_t n_rows = S.descs[cg.first_desc].num_values;
+        bool any = false;
+        std::vector<const tskv_page_desc *> fds(nc, nullptr);
+        for (uint32_t c = 0; c < nc; c++) {
+          tskv_status st;
+          fds[c] = find_field(cg, q.columns[c], &st);
+          if (st != TSKV_OK) return st;
+          any = any || fds[c];
+        }
+        if (!any) continue;  // (a column group without any projected column yields no batch: column_group/mod.rs:43-52)
+        bool pruned = false;
+        tskv_status st = prepare_cg(cg, &pruned);
+        if (st != TSKV_OK) return st;
+        if (pruned) continue;
+        const size_t base = rt.size();
+        std::vector<uint64_t> sel;  // rows of this column group that reach the merge
+        for (uint64_t r = 0; r < n_rows; r++) {
+          if (have_keep && !keep[r]) continue;
+          if (q.n_predicates && !pred_keep[r]) continue;
+          if (!tvalid[r]) continue;
+          sel.push_back(r);
+          rt.push_back((int64_t)ts[r]);
+          rs.push_back(si);
+        }
+        for (uint32_t c = 0; c < nc; c++) {
+          rv[c].resize(base + sel.size(), 0);
+          rok[c].resize(base + sel.size(), 0);
+          if (!fds[c]) continue;
+          st = load_field(fds[c], n_rows);
+          if (st != TSKV_OK) return st;
+          if (points)
+            for (uint64_t r = 0; r < n_rows; r++)
+              if (vvalid[r]) (*points)++;
+          for (size_t k = 0; k < sel.size(); k++) {
+            rv[c][base + k] = vvalid[sel[k]] ? vals[sel[k]] : 0;
+            rok[c][base + k] = vvalid[sel[k]];
+          }
+        }
+      }
+    }
+    // k-way merge on time, ties to the lower stream index then the earlier row (sort_merge.rs:300-306): the rows were
+    // appended stream by stream in row order, so a STABLE sort by time is that order
+    std::vector<uint32_t> order(rt.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    for (size_t i = 1; i < rt.size(); i++)
+      if (rs[i] == rs[i - 1] && rt[i] < rt[i - 1]) {
+        g_err = "data in stream is not sorted";  // batch_builder.rs:121-126
+        return TSKV_ERR_INVALID_ARG;
+      }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return rt[a] < rt[b]; });
+    std::vector<uint64_t> mts;
+    std::vector<uint8_t> mtvalid;
+    std::vector<std::vector<uint64_t>> mv(nc);
+    std::vector<std::vector<uint8_t>> mok(nc);
+    for (size_t i = 0; i < order.size();) {
+      size_t j = i;
+      while (j < order.size() && rt[order[j]] == rt[order[i]]) j++;
+      mts.push_back((uint64_t)rt[order[i]]);
+      mtvalid.push_back(1);
+      for (uint32_t c = 0; c < nc; c++) {  // take_last_and_merge (batch_builder.rs:133-155)
+        uint64_t v = 0;
+        uint8_t ok = 0;
+        for (size_t k = j; k-- > i;)
+          if (rok[c][order[k]]) { v = rv[c][order[k]]; ok = 1; break; }
+        mv[c].push_back(v);
+        mok[c].push_back(ok);
+      }
+      i = j;
+    }
+    for (uint32_t c = 0; c < nc; c++) {
+      tskv_status st = aggregate_rows(c, group, mts.size(), mts.data(), mtvalid.data(), mv[c].data(), mok[c].data(), nullptr, nullptr);
+      if (st != TSKV_OK) return st;
+    }
+    return TSKV_OK;
+  }
+};
+
+// group_overlapping_segments (reader/utils.rs:77-107) over chunks sorted by time range.
+std::vector<std::vector<const ChunkRef *>> group_overlapping(const std::vector<ChunkRef> &sorted) {
+  std::vector<std::vector<const ChunkRef *>> out;
+  int64_t global_max = INT64_MIN;  // (named global_min_ts in the reference)
+  for (const ChunkRef &ch : sorted) {
+    if (!out.empty() && ch.min_ts <= global_max) out.back().push_back(&ch);
+    else out.push_back({&ch});
+    global_max = std::max(ch.max_ts, global_max);
+  }
+  return out;
+}
+
+// One worker: slots [s0, s1) into `cells` (n_columns * n_cells). Returns status.
+tskv_status scan_slots(const Scan &S, uint64_t s0, uint64_t s1, Cell *cells, bool shared_table,
+                       uint64_t *points) {
+  const tskv_query &q = *S.q;
+  (void)shared_table;
+  Worker W(S, cells, points);
   for (uint64_t slot = s0; slot < s1; slot++) {
     auto range = S.ix->find(S.slots[slot]);
     if (range.first == nullptr) continue;  // selected id absent from this arena
-    uint64_t group = q.group_by_series ? slot : 0;
-    (void)shared_table;
-    for (const ColumnGroup *cgp = range.first; cgp != range.second; cgp++) {
-      const ColumnGroup &cg = *cgp;
-      const tskv_page_desc &td = S.descs[cg.first_desc];
-      uint64_t n_rows = td.num_values;
-      ts.assign(n_rows ? n_rows : 1, 0);
-      tvalid.assign(n_rows ? n_rows : 1, 0);
-      bool time_decoded = false, pruned = false;
-      for (uint32_t c = 0; c < q.n_columns && !pruned; c++) {
-        const tskv_agg_column &qc = q.columns[c];
-        const tskv_page_desc *fd = nullptr;
-        for (uint64_t k = 1; k < cg.n_descs; k++)
-          if (S.descs[cg.first_desc + k].column_id == qc.column_id) {
-            fd = &S.descs[cg.first_desc + k];
-            break;
-          }
-        if (!fd) continue;  // column absent from this column group (null-filled by SchemaAlignmenter)
-        if (fd->phys_type != qc.phys_type) {
-          g_err = "page type does not match the query column type";
-          return TSKV_ERR_INVALID_ARG;
-        }
-        if (!time_decoded) {
-          uint64_t nr = 0;
-          if (td.offset + td.size > S.arena_len) return TSKV_ERR_INVALID_ARG;
-          tskv_status st = orc_page_decode(TSKV_PT_TIME, S.arena + td.offset, td.size, S.verify_crc,
-                                           ts.data(), tvalid.data(), n_rows, &nr);
-          if (st != TSKV_OK) return st;
-          if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
-          time_decoded = true;
-          // Statistics pruning (filter_column_groups, tskv/src/reader/chunk.rs:12-50): a column group whose time range
-          // (ColumnGroup::time_range(), here: min / max of its time values) overlaps none of the query's ranges is never
-          // read - its field pages are neither decoded nor counted.
-          if (q.n_time_ranges && n_rows) {
-            int64_t gmin = INT64_MAX, gmax = INT64_MIN;
-            for (uint64_t r = 0; r < n_rows; r++)
-              if (tvalid[r]) { gmin = std::min(gmin, (int64_t)ts[r]); gmax = std::max(gmax, (int64_t)ts[r]); }
-            bool overlaps = false;
-            for (uint32_t k = 0; k < q.n_time_ranges; k++)
-              overlaps = overlaps || (gmin <= q.time_ranges[k].max_ts && gmax >= q.time_ranges[k].min_ts);
-            if (!overlaps) { pruned = true; break; }
-          }
-          // the row filter: every predicate column of this column group decoded, rows kept where all comparisons are TRUE;
-          // a column the group does not hold is null-filled by SchemaAlignmenter (schema_alignmenter.rs:24-44) => no row passes
-          pred_keep.assign(n_rows ? n_rows : 1, 1);
-          for (uint32_t k = 0; k < q.n_predicates; k++) {
-            const tskv_field_predicate &fp = q.predicates[k];
-            const tskv_page_desc *pd = nullptr;
-            for (uint64_t j = 1; j < cg.n_descs; j++)
-              if (S.descs[cg.first_desc + j].column_id == fp.column_id) {
-                pd = &S.descs[cg.first_desc + j];
-                break;
-              }
-            if (!pd) {
-              std::fill(pred_keep.begin(), pred_keep.end(), (uint8_t)0);
-              continue;
-            }
-            if (pd->phys_type != fp.phys_type) {
-              g_err = "page type does not match the predicate column type";
-              return TSKV_ERR_INVALID_ARG;
-            }
-            pvals.assign(n_rows ? n_rows : 1, 0);
-            pvalid.assign(n_rows ? n_rows : 1, 0);
-            uint64_t pr = 0;
-            tskv_status pst = orc_page_decode(pd->phys_type, S.arena + pd->offset, pd->size, S.verify_crc, pvals.data(),
-                                              pvalid.data(), n_rows, &pr);
-            if (pst != TSKV_OK) return pst;
-            for (uint64_t r = 0; r < n_rows; r++)
-              if (!(pvalid[r] && cmp_true(fp.phys_type, fp.op, pvals[r], fp.value))) pred_keep[r] = 0;
-          }
-          // decode_pages with a tombstone (reader.rs:507-524): the all-fields excluded ranges that overlap the
-          // page's time range clear bits of the TIME page's null bitset; the result filters the rows.
-          keep.assign(n_rows ? n_rows : 1, 1);
-          have_keep = false;
-          if (S.n_tombs && n_rows) {
-            int64_t pmin = INT64_MAX, pmax = INT64_MIN;  // PageStatistics min/max of the time column
-            for (uint64_t r = 0; r < n_rows; r++)
-              if (tvalid[r]) { pmin = std::min(pmin, (int64_t)ts[r]); pmax = std::max(pmax, (int64_t)ts[r]); }
-            page_min = pmin; page_max = pmax;
-            for (uint64_t k = 0; k < S.n_tombs; k++) {
-              const tskv_tombstone &tb = S.tombs[k];
-              if (tb.column_id != TSKV_TOMB_ALL) continue;
-              if (tb.series_id != TSKV_TOMB_ALL && tb.series_id != td.series_id) continue;
-              if (!(tb.min_ts <= pmax && tb.max_ts >= pmin)) continue;  // TimeRange::overlaps
-              if (!have_keep) { keep = tvalid; have_keep = true; }
-              clear_bits_by_time_range(ts, n_rows, tb.min_ts, tb.max_ts, keep);
-            }
-          }
-        }
-        vals.assign(n_rows ? n_rows : 1, 0);
-        vvalid.assign(n_rows ? n_rows : 1, 0);
-        uint64_t nr = 0;
-        if (fd->offset + fd->size > S.arena_len) return TSKV_ERR_INVALID_ARG;
-        tskv_status st = orc_page_decode(fd->phys_type, S.arena + fd->offset, fd->size, S.verify_crc,
-                                         vals.data(), vvalid.data(), n_rows, &nr);
+    const uint64_t group = q.group_by_series ? slot : 0;
+    if (!S.cg_file) {  // one file: its column groups in arena order
+      for (const ColumnGroup *cgp = range.first; cgp != range.second; cgp++) {
+        tskv_status st = W.scan_cg(*cgp, group);
         if (st != TSKV_OK) return st;
-        if (nr != n_rows) return TSKV_ERR_PAGE_FORMAT;
-        // per-column tombstones (reader.rs:531-542): clear the value validity of the excluded rows
-        for (uint64_t k = 0; k < S.n_tombs && n_rows; k++) {
-          const tskv_tombstone &tb = S.tombs[k];
-          if (tb.column_id == TSKV_TOMB_ALL || tb.series_id != fd->series_id || tb.column_id != fd->column_id) continue;
-          if (!(tb.min_ts <= page_max && tb.max_ts >= page_min)) continue;
-          clear_bits_by_time_range(ts, n_rows, tb.min_ts, tb.max_ts, vvalid);
+      }
+      continue;
+    }
+    // several files (build_series_reader, reader/iterator.rs:463-560): chunks = column groups by file id
+    std::vector<ChunkRef> chunks;
+    for (const ColumnGroup *cgp = range.first; cgp != range.second; cgp++) {
+      const uint64_t fid = S.cg_file[cgp->orig];
+      ChunkRef *ch = nullptr;
+      for (ChunkRef &c : chunks)
+        if (c.file_id == fid) ch = &c;
+      if (!ch) {
+        chunks.push_back(ChunkRef{fid, INT64_MAX, INT64_MIN, {}});
+        ch = &chunks.back();
+      }
+      // ColumnGroup::time_range(): min / max of the time values
+      const tskv_page_desc &td = S.descs[cgp->first_desc];
+      std::vector<uint64_t> t(td.num_values ? td.num_values : 1);
+      std::vector<uint8_t> tv(td.num_values ? td.num_values : 1);
+      uint64_t nr = 0;
+      tskv_status st = orc_page_decode(TSKV_PT_TIME, S.arena + td.offset, td.size, 0, t.data(), tv.data(), td.num_values, &nr);
+      if (st != TSKV_OK) return st;
+      for (uint64_t r = 0; r < nr; r++)
+        if (tv[r]) { ch->min_ts = std::min(ch->min_ts, (int64_t)t[r]); ch->max_ts = std::max(ch->max_ts, (int64_t)t[r]); }
+      ch->cgs.push_back(cgp);
+    }
+    for (ChunkRef &ch : chunks)  // a chunk's column groups in time order (Chunk::push keeps them so, tsm/chunk.rs:100-110)
+      std::stable_sort(ch.cgs.begin(), ch.cgs.end(), [&](const ColumnGroup *a, const ColumnGroup *b) { return a->min_ts < b->min_ts; });
+    // chunks.sort_unstable_by_key(|e| e.time_range()): (min_ts, max_ts); equal ranges: by file id, for determinism
+    std::sort(chunks.begin(), chunks.end(), [](const ChunkRef &a, const ChunkRef &b) {
+      if (a.min_ts != b.min_ts) return a.min_ts < b.min_ts;
+      if (a.max_ts != b.max_ts) return a.max_ts < b.max_ts;
+      return a.file_id < b.file_id;
+    });
+    auto groups = group_overlapping(chunks);
+    for (auto &g : groups) {
+      std::stable_sort(g.begin(), g.end(), [](const ChunkRef *a, const ChunkRef *b) { return a->file_id < b->file_id; });  // g.sort()
+      tskv_status st = TSKV_OK;
+      if (g.size() == 1) {
+        for (const ColumnGroup *cgp : g[0]->cgs) {
+          st = W.scan_cg(*cgp, group);
+          if (st != TSKV_OK) return st;
         }
-        const uint8_t pt = qc.phys_type;
-        Cell *ccells = cells + (uint64_t)c * S.n_cells + group * q.n_buckets;
-        // Run state for first/last: the rows of one (page, bucket) form one DataFusion group slice;
-        // FirstAccumulator::update_batch picks its min-time row and drops it when the VALUE is null
-        // (first.rs:139-148 + :91-94). Pages are time-sorted (mem_cache/series_data.rs:218-262), so a
-        // (page, bucket) group is one contiguous run of rows.
-        int64_t run_bucket = -1;
-        uint64_t run_first = 0, run_last = 0;
-        auto close_run = [&]() {
-          if (run_bucket < 0) return;
-          Cell &cell = ccells[run_bucket];
-          if ((qc.agg_mask & TSKV_AGG_FIRST) && vvalid[run_first]) {
-            int64_t t = (int64_t)ts[run_first];
-            if (!cell.has_first || t < cell.first_ts) {  // strictly less: ties keep the earlier-seen
-              cell.has_first = true;
-              cell.first_ts = t;
-              cell.first_val = vals[run_first];
-            }
-          }
-          if ((qc.agg_mask & TSKV_AGG_LAST) && vvalid[run_last]) {
-            int64_t t = (int64_t)ts[run_last];
-            if (!cell.has_last || t > cell.last_ts) {
-              cell.has_last = true;
-              cell.last_ts = t;
-              cell.last_val = vals[run_last];
-            }
-          }
-        };
-        for (uint64_t r = 0; r < n_rows; r++) {
-          if (vvalid[r] && points) (*points)++;
-          if (have_keep && !keep[r]) continue;  // filter_record_batch(&record_batch, time_null_bits) (reader.rs:546-550)
-          if (q.n_predicates && !pred_keep[r]) continue;  // DataFilter (reader/filter.rs:130-142)
-          if (!tvalid[r]) continue;  // is_not_null(time) (transform_time_window.rs:313)
-          int64_t t = (int64_t)ts[r];
-          bool in = q.n_time_ranges == 0;
-          for (uint32_t k = 0; k < q.n_time_ranges && !in; k++)
-            in = t >= q.time_ranges[k].min_ts && t <= q.time_ranges[k].max_ts;  // TimeRange::contains
-          if (!in) continue;
-          int64_t b = 0;
-          if (q.width > 0) {
-            int64_t ws, we;
-            sliding_window(t, q.width, q.width, q.origin, 0, &ws, &we);
-            int64_t diff = (int64_t)((uint64_t)ws - (uint64_t)q.first_bucket_start);
-            if (diff < 0 || diff % q.width != 0 || diff / q.width >= (int64_t)q.n_buckets) {
-              g_err = "row outside the requested bucket range";
-              return TSKV_ERR_BUCKET_RANGE;
-            }
-            b = diff / q.width;
-          }
-          if (b != run_bucket) {
-            close_run();
-            run_bucket = b;
-            run_first = run_last = r;
-          } else {
-            if ((int64_t)ts[r] < (int64_t)ts[run_first]) run_first = r;
-            if ((int64_t)ts[r] > (int64_t)ts[run_last]) run_last = r;
-          }
-          if (!vvalid[r]) continue;
-          Cell &cell = ccells[b];
-          uint64_t v = vals[r];
-          if (cell.count == 0) {
-            cell.minv = cell.maxv = v;
-          } else {
-            if (less_typed(pt, v, cell.minv)) cell.minv = v;
-            if (less_typed(pt, cell.maxv, v)) cell.maxv = v;
-          }
-          cell.count++;
-          if (pt == TSKV_PT_F64) {
-            double d;
-            memcpy(&d, &v, 8);
-            cell.sum_d += d;
-          } else {
-            cell.sum_bits += v;
-            cell.sum_d += pt == TSKV_PT_I64 ? (double)(int64_t)v : (double)v;
-          }
-        }
-        close_run();
+      } else {
+        st = W.scan_merged(g, group);
+        if (st != TSKV_OK) return st;
       }
     }
   }
@@ -545,6 +766,7 @@ struct orc_handle {
   int n_threads;
   Pool *pool;
   std::vector<std::vector<Cell>> priv;  // per-chunk partial tables, kept between scans
+  std::vector<uint64_t> cg_file;         // orc_set_chunk_files
 };
 
 namespace {
@@ -560,7 +782,7 @@ tskv_status orc_open(const uint8_t *arena, uint64_t arena_len, const tskv_page_d
                      int n_threads, orc_handle **out) {
   g_err.clear();
   if (!out) return TSKV_ERR_INVALID_ARG;
-  orc_handle *H = new orc_handle{arena, arena_len, descs, n_descs, Index{}, n_threads, nullptr, {}};
+  orc_handle *H = new orc_handle{arena, arena_len, descs, n_descs, Index{}, n_threads, nullptr, {}, {}};
   tskv_status st = build_index(descs, n_descs, H->ix);
   if (st != TSKV_OK) {
     delete H;
@@ -568,6 +790,35 @@ tskv_status orc_open(const uint8_t *arena, uint64_t arena_len, const tskv_page_d
   }
   if (n_threads > 1) H->pool = new Pool((unsigned)n_threads);
   *out = H;
+  return TSKV_OK;
+}
+
+// Tags every column group (descriptor-table order) with the id of the file its chunk belongs to: scans then group a
+// series' chunks by time-range overlap and merge overlapping ones (reader/iterator.rs:463-560). n_cg == 0 clears.
+tskv_status orc_set_chunk_files(orc_handle *H, const uint64_t *cg_file_id, uint64_t n_cg) {
+  if (!H || (n_cg && !cg_file_id)) return TSKV_ERR_INVALID_ARG;
+  if (n_cg == 0) {
+    H->cg_file.clear();
+    return TSKV_OK;
+  }
+  if (n_cg != H->ix.cgs.size()) {
+    g_err = "one file id per column group expected";
+    return TSKV_ERR_INVALID_ARG;
+  }
+  H->cg_file.assign(cg_file_id, cg_file_id + n_cg);
+  std::vector<uint64_t> t;
+  std::vector<uint8_t> tv;
+  for (ColumnGroup &cg : H->ix.cgs) {
+    const tskv_page_desc &td = H->descs[cg.first_desc];
+    t.assign(td.num_values ? td.num_values : 1, 0);
+    tv.assign(td.num_values ? td.num_values : 1, 0);
+    uint64_t nr = 0;
+    tskv_status st = orc_page_decode(TSKV_PT_TIME, H->arena + td.offset, td.size, 0, t.data(), tv.data(), td.num_values, &nr);
+    if (st != TSKV_OK) return st;
+    cg.min_ts = INT64_MAX;
+    for (uint64_t r = 0; r < nr; r++)
+      if (tv[r]) cg.min_ts = std::min(cg.min_ts, (int64_t)t[r]);
+  }
   return TSKV_OK;
 }
 
@@ -613,6 +864,7 @@ tskv_status scan_with(orc_handle *H, const tskv_query *q, const tskv_tombstone *
   Scan S{H->arena, H->arena_len, descs, q, verify_crc, &ix, {}, L.n_cells};
   S.tombs = tombs;
   S.n_tombs = n_tombs;
+  S.cg_file = H->cg_file.empty() ? nullptr : H->cg_file.data();
   if (q->series_ids) {
     for (uint32_t i = 0; i < q->n_series; i++) {
       if (i && q->series_ids[i] <= q->series_ids[i - 1]) {

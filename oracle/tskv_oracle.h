@@ -89,6 +89,9 @@ tskv_status orc_open(const uint8_t *arena, uint64_t arena_len, const tskv_page_d
                      int n_threads, orc_handle **out);
 tskv_status orc_scan(orc_handle *h, const tskv_query *q, const tskv_tombstone *tombs, uint64_t n_tombs,
                      int verify_crc, uint64_t *out_values, uint8_t *out_validity, uint64_t *out_points);
+/* Overlapping chunks (reader/iterator.rs:463-560, reader/sort_merge.rs, reader/batch_builder.rs): file id of every
+ * column group in descriptor-table order; later scans merge + de-duplicate the overlapping chunks of a series. */
+tskv_status orc_set_chunk_files(orc_handle *h, const uint64_t *cg_file_id, uint64_t n_cg);
 void orc_close(orc_handle *h);
 const char *orc_last_error(void);
 

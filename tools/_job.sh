@@ -1,8 +1,21 @@
-timeout 400 python -m pytest tests -m gpu -q -x > gpurun_out/t_all.log 2>&1; tail -3 gpurun_out/t_all.log
-timeout 400 python bench.py --workload C3 --steps 10 --warmup 3 > gpurun_out/r02_bench_C3.json 2> gpurun_out/r02_bench_C3.err; tail -c 300 gpurun_out/r02_bench_C3.err
-python - <<'PY'
+mkdir -p gpurun_out
+run() {
+  echo "== $*"
+  env "$@" TSKV_DEBUG_BINS=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/b.err | tail -1 > gpurun_out/b.json
+  python - <<PY
 import json
-for w in ("C3",):
-    d=json.loads([l for l in open("gpurun_out/r02_bench_%s.json"%w).read().splitlines() if l.startswith("{")][-1])
-    print(w, "value %.3g ms %.3f e2e %.3g frac %.3f cpu %.3g parity %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["cpu_baseline"]["value"], d["parity_sample"]))
+d=json.loads(open("gpurun_out/b.json").read())
+print('value %.3g pts/s, %.3f ms/step, fused %.3f ms' % (d['value'], d['ms_per_step'], d['roofline']['ms_per_launch']))
 PY
+  grep "\[tskv\] bin" gpurun_out/b.err | tail -4 | awk '{printf "%s %s g%s run %s | ", $2,$3,$5,$10} END {print ""}'
+}
+run TSKV_PARTS=1
+run TSKV_PARTS=4
+run TSKV_PARTS=4 TSKV_GRID_OVERSUB=1.5
+run TSKV_PARTS=4 TSKV_GRID_OVERSUB=2
+run TSKV_PARTS=4 TSKV_GRID_OVERSUB=4
+run TSKV_PARTS=4 TSKV_GRID_MODE=1
+run TSKV_PARTS=8 TSKV_GRID_OVERSUB=2
+run TSKV_PARTS=8 TSKV_GRID_MODE=1
+run TSKV_PARTS=2 TSKV_GRID_OVERSUB=2
+run TSKV_PARTS=2 TSKV_GRID_MODE=1
