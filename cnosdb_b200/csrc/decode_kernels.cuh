@@ -105,13 +105,13 @@ __device__ __forceinline__ uint64_t decode_s8b_to_global(const uint8_t *words, u
 constexpr int DECODE_THREADS = 128;
 
 __global__ void __launch_bounds__(DECODE_THREADS)
-k_decode_warp(const uint8_t *arena, const tskv_page_desc *descs, uint64_t first_page, uint32_t n_pages,
+k_decode_warp(const uint8_t *arena, const tskv_page_desc *descs, uint64_t first_page, const uint32_t *page_list, uint32_t n_pages,
               const uint64_t *row_off, const uint64_t *bm_off, uint64_t *out_values, uint8_t *out_validity,
               int32_t *status, unsigned long long *err_page, unsigned long long *stats) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n_pages) return;
-  const uint32_t page = (uint32_t)first_page + i;
+  const uint32_t page = page_list ? page_list[i] : (uint32_t)first_page + i;  // a page range, or a list of pages
   const tskv_page_desc d = descs[page];
   uint64_t *ov = out_values + row_off[i];
   uint32_t *ob = reinterpret_cast<uint32_t *>(out_validity + bm_off[i]);

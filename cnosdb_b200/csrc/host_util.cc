@@ -95,6 +95,83 @@ void plan_serial_grids(int n_bins, const double *chunks, const double *t_chunk, 
     if (chunks[b] > 0) grid_out[b] = std::max(1, (int)std::max(1.0, blocks_for(b, best)));
 }
 
+void plan_overlap_groups(uint64_t n_cg, const uint32_t *cg_series, const uint32_t *cg_rows, const tskv_time_range *cg_bounds,
+                         const uint64_t *cg_file, OverlapPlan *out) {
+  *out = OverlapPlan{};
+  out->cg_merge.assign(n_cg, 0);
+  out->mcg_row0.push_back(0);
+  out->stream_first_mcg.push_back(0);
+  out->group_first_stream.push_back(0);
+  std::vector<uint32_t> order(n_cg);
+  for (uint64_t i = 0; i < n_cg; i++) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cg_series[a] < cg_series[b]; });
+  struct Chunk {
+    uint64_t file;
+    int64_t lo, hi;
+    std::vector<uint32_t> cgs;
+  };
+  for (uint64_t i = 0; i < n_cg;) {
+    uint64_t j = i;
+    while (j < n_cg && cg_series[order[j]] == cg_series[order[i]]) j++;
+    std::vector<Chunk> chunks;  // of this series
+    for (uint64_t k = i; k < j; k++) {
+      const uint32_t cg = order[k];
+      Chunk *ch = nullptr;
+      for (Chunk &c : chunks)
+        if (c.file == cg_file[cg]) ch = &c;
+      if (!ch) {
+        chunks.push_back(Chunk{cg_file[cg], INT64_MAX, INT64_MIN, {}});
+        ch = &chunks.back();
+      }
+      ch->lo = std::min(ch->lo, cg_bounds[cg].min_ts);
+      ch->hi = std::max(ch->hi, cg_bounds[cg].max_ts);
+      ch->cgs.push_back(cg);
+    }
+    i = j;
+    if (chunks.size() == 1) {
+      out->n_groups_total++;
+      continue;
+    }
+    for (Chunk &c : chunks)  // a chunk's column groups in time order (tsm/chunk.rs:100-110 keeps them so)
+      std::stable_sort(c.cgs.begin(), c.cgs.end(), [&](uint32_t a, uint32_t b) { return cg_bounds[a].min_ts < cg_bounds[b].min_ts; });
+    std::sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &b) {  // by time range, then file id
+      if (a.lo != b.lo) return a.lo < b.lo;
+      if (a.hi != b.hi) return a.hi < b.hi;
+      return a.file < b.file;
+    });
+    size_t g0 = 0;
+    int64_t run_max = INT64_MIN;
+    auto close_group = [&](size_t a, size_t b) {  // chunks [a, b)
+      out->n_groups_total++;
+      if (b - a < 2) return;
+      std::vector<const Chunk *> g;
+      for (size_t k = a; k < b; k++) g.push_back(&chunks[k]);
+      std::stable_sort(g.begin(), g.end(), [](const Chunk *x, const Chunk *y) { return x->file < y->file; });
+      const uint32_t gi = (uint32_t)out->group_first_stream.size() - 1;
+      for (const Chunk *c : g) {
+        const uint32_t si = (uint32_t)out->stream_group.size();
+        out->stream_group.push_back(gi);
+        for (uint32_t cg : c->cgs) {
+          out->cg_merge[cg] = 1;
+          out->mcg_cg.push_back(cg);
+          out->mcg_stream.push_back(si);
+          out->mcg_row0.push_back(out->mcg_row0.back() + cg_rows[cg]);
+        }
+        out->stream_first_mcg.push_back((uint32_t)out->mcg_cg.size());
+      }
+      out->group_first_stream.push_back((uint32_t)out->stream_group.size());
+    };
+    for (size_t k = 0; k < chunks.size(); k++) {
+      if (k > g0 && !(chunks[k].lo <= run_max)) {
+        close_group(g0, k);
+        g0 = k;
+      }
+      run_max = std::max(run_max, chunks[k].hi);
+    }
+    close_group(g0, chunks.size());
+  }
+}
+
 bool parse_page(const uint8_t *page, uint64_t size, PageHeader *h) {
   if (size < 16) return false;
   h->bitset_len = rd32be(page);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 #include "../../include/tskv_gpu.h"
 #include "kinds.h"
@@ -51,5 +52,24 @@ void plan_serial_grids(int n_bins, const double *chunks, const double *t_chunk, 
                        int warps_per_block, int *grid_out);
 
 uint8_t classify_page(const PageHeader &h, uint8_t phys_type);
+
+// ---- overlapping chunks (reader/iterator.rs:463-560, reader/utils.rs:77-107) --------------------------------------
+// A chunk = the column groups of one series that come from one file. Per series: chunks sorted by time range, grouped
+// while a chunk starts at or before the running maximum end (group_overlapping_segments), each group ordered by file
+// id. Groups of more than one chunk are MERGE GROUPS: their column groups leave the normal work list and go through
+// the merge pass (merge_kernels.cuh). The plan lays the merge groups' rows out stream by stream (stream = one chunk,
+// its column groups in time order), so every stream is one time-sorted run of consecutive merge rows.
+struct OverlapPlan {
+  std::vector<uint8_t> cg_merge;          // [n_cg] 1: the column group belongs to a merge group
+  std::vector<uint32_t> mcg_cg;           // merge column groups in merge-row order -> column group index
+  std::vector<uint32_t> mcg_stream;       // -> stream index
+  std::vector<uint64_t> mcg_row0;         // [n_mcg + 1] first merge row of each merge column group
+  std::vector<uint32_t> stream_group;     // [n_streams] -> merge group
+  std::vector<uint32_t> stream_first_mcg; // [n_streams + 1]
+  std::vector<uint32_t> group_first_stream;  // [n_groups + 1]
+  uint64_t n_groups_total = 0;            // overlap groups of all series, merge groups or not (the reference's metric)
+};
+void plan_overlap_groups(uint64_t n_cg, const uint32_t *cg_series, const uint32_t *cg_rows, const tskv_time_range *cg_bounds,
+                         const uint64_t *cg_file, OverlapPlan *out);
 
 }  // namespace tskv

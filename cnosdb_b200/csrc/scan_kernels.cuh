@@ -159,7 +159,7 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_p
                              const int32_t *cg_slot, const ColState *cols, uint32_t n_cols,
                              const uint32_t *bin_start, uint8_t *item_flag, uint32_t *block_count,
                              unsigned long long *counters, int32_t *status, const tskv_time_range *cg_bounds,
-                             const PruneRanges prune) {
+                             const PruneRanges prune, const uint8_t *cg_merge) {
   __shared__ uint32_t s_cnt;
   __shared__ unsigned long long s_pages, s_bytes[N_BINS];
   if (threadIdx.x == 0) { s_cnt = 0; s_pages = 0; }
@@ -178,9 +178,10 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint32_t *item_p
       const tskv_time_range b = cg_bounds[cg];
       in_time = false;
       for (uint32_t k = 0; k < prune.n; k++) in_time = in_time || (b.min_ts <= prune.r[k].max_ts && b.max_ts >= prune.r[k].min_ts);
-      if (!in_time && qc >= 0 && cg_slot[cg] >= 0) atomicAdd(&counters[2 + N_BINS], 1ull);
+      if (!in_time && qc >= 0 && cg_slot[cg] >= 0 && !(cg_merge && cg_merge[cg])) atomicAdd(&counters[2 + N_BINS], 1ull);
     }
-    if (qc >= 0 && cg_slot[cg] >= 0 && in_time) {
+    // (column groups of overlapping chunks go through the merge pass instead, merge_kernels.cuh)
+    if (qc >= 0 && cg_slot[cg] >= 0 && in_time && !(cg_merge && cg_merge[cg])) {
       if (cols[qc].phys_type != d.phys_type) {
         atomicCAS(status, 0, TSKV_ERR_INVALID_ARG);
       } else {

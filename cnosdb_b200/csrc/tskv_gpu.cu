@@ -18,6 +18,7 @@
 #include "host_util.h"
 #include "decode_kernels.cuh"
 #include "skip_kernels.cuh"
+#include "merge_kernels.cuh"
 
 using namespace tskv;
 
@@ -93,6 +94,20 @@ struct tskv_pages {
   SkipEntry *d_skip = nullptr;
   uint64_t n_skip = 0;
   uint32_t h_bin_maxrows[N_BINS]{};  // longest field page of each bin (parts per page when a scan cuts the bin's pages)
+  // overlapping chunks (tskvgpu_pages_set_chunk_files, merge_kernels.cuh): the plan, its device copies and the merge
+  // rows' timestamps (decoded once); the epoch invalidates scans prepared before a change
+  std::vector<uint32_t> h_cg_time_page, h_cg_series;
+  std::vector<uint8_t> h_time_has_nulls;
+  OverlapPlan overlap;
+  std::vector<tskv_time_range> h_cg_bounds;
+  uint8_t *d_cg_merge = nullptr;
+  int64_t *d_merge_ts = nullptr;
+  uint64_t *d_mcg_row0 = nullptr, *d_mcg_bm0 = nullptr;
+  uint32_t *d_mcg_cg = nullptr, *d_mcg_stream = nullptr, *d_stream_group = nullptr, *d_stream_first_mcg = nullptr,
+           *d_group_first_stream = nullptr;
+  std::vector<uint64_t> h_mcg_bm0;
+  uint64_t merge_rows = 0, merge_bm_words = 0;
+  uint64_t chunk_epoch = 0;
 };
 
 struct tskv_scan {
@@ -147,6 +162,16 @@ struct tskv_scan {
   uint64_t *d_gathered = nullptr;  // all ranks' exchange regions (tskvgpu_scan_exchange)
   PredicateSet preds{};            // pushed field predicates (row filter)
   uint32_t *d_row_keep = nullptr;  // one keep bit per row of every column group (k_row_filter)
+  // merge pass over the overlapping chunks this scan reads (merge_kernels.cuh)
+  uint64_t chunk_epoch = 0;
+  MergeParams merge{};
+  uint32_t n_merge_pages = 0;      // field pages decoded per pass
+  uint64_t merge_page_bytes = 0, merge_read_pages = 0;
+  uint8_t *d_mcg_active = nullptr;
+  uint64_t *d_mvals = nullptr;
+  uint32_t *d_mvalid = nullptr;
+  uint32_t *d_mpage = nullptr;
+  uint64_t *d_mrow_off = nullptr, *d_mbm_off = nullptr;
 };
 
 namespace {
@@ -296,7 +321,8 @@ void free_scan(tskv_scan *s) {
   cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
   void *bufs[] = {s->d_series, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
                   s->d_work_qcol, s->d_bin_cstart, s->d_cols, s->d_outs, s->d_means, s->d_state,
-                  s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1], s->d_gathered, s->d_row_keep};
+                  s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1], s->d_gathered, s->d_row_keep,
+                  s->d_mcg_active, s->d_mvals, s->d_mvalid, s->d_mpage, s->d_mrow_off, s->d_mbm_off};
   for (void *b : bufs)
     if (b) cudaFreeAsync(b, st);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -313,6 +339,17 @@ void free_scan(tskv_scan *s) {
     if (s->ev_gather[b]) cudaEventDestroy(s->ev_gather[b]);
   }
   delete s;
+}
+
+void free_overlap(tskv_pages *pg) {
+  void *bufs[] = {pg->d_cg_merge, pg->d_merge_ts, pg->d_mcg_row0, pg->d_mcg_bm0, pg->d_mcg_cg, pg->d_mcg_stream,
+                  pg->d_stream_group, pg->d_stream_first_mcg, pg->d_group_first_stream};
+  for (void *b : bufs) cudaFree(b);
+  pg->d_cg_merge = nullptr; pg->d_merge_ts = nullptr; pg->d_mcg_row0 = nullptr; pg->d_mcg_bm0 = nullptr; pg->d_mcg_cg = nullptr;
+  pg->d_mcg_stream = nullptr; pg->d_stream_group = nullptr; pg->d_stream_first_mcg = nullptr; pg->d_group_first_stream = nullptr;
+  pg->overlap = OverlapPlan{};
+  pg->merge_rows = pg->merge_bm_words = 0;
+  pg->h_mcg_bm0.clear();
 }
 
 template <typename T>
@@ -602,6 +639,8 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   }
   pg->n_cg = (uint32_t)cg_time_page.size();
   pg->n_items = (uint32_t)item_page.size();
+  pg->h_cg_time_page = cg_time_page;
+  pg->h_time_has_nulls = time_has_nulls;
   std::vector<uint32_t> keep_off(n_descs, 0);
   for (uint32_t tp : cg_time_page) {
     keep_off[tp] = (uint32_t)pg->keep_words;
@@ -758,6 +797,7 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_arena);
   cudaFree(pg->d_skip_off);
   cudaFree(pg->d_skip);
+  free_overlap(pg);
   cudaFree(pg->d_descs);
   cudaFree(pg->d_time_page_of);
   cudaFree(pg->d_cg_time_page);
@@ -794,6 +834,99 @@ tskv_status tskvgpu_pages_set_time_bounds(tskv_ctx *ctx, tskv_pages *pg, const t
     pg->ts_max = hi;
   }
   pg->bounds_known = true;
+  return TSKV_OK;
+}
+
+// Overlapping chunks: file id of every column group -> merge groups (host_util.h, plan_overlap_groups) + the merge rows'
+// timestamps, decoded once.
+tskv_status tskvgpu_pages_set_chunk_files(tskv_ctx *ctx, tskv_pages *pg, const uint64_t *cg_file_id, uint64_t n_cg) {
+  if (!ctx || !pg || (n_cg && !cg_file_id) || (n_cg && n_cg != pg->n_cg)) return TSKV_ERR_INVALID_ARG;
+  {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->set_error("");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    free_overlap(pg);
+    pg->chunk_epoch++;
+    if (n_cg == 0) return TSKV_OK;
+    ensure_time_bounds(ctx, pg);  // ColumnGroup::time_range() of every group (the caller's, or one pass over the time pages)
+    if (!pg->d_cg_bounds) {
+      ctx->set_error("set_chunk_files: the column groups' time bounds are not available");
+      return TSKV_ERR_CUDA;
+    }
+    pg->h_cg_bounds.resize(pg->n_cg);
+    CU_TRY(ctx, cudaMemcpy(pg->h_cg_bounds.data(), pg->d_cg_bounds, (size_t)pg->n_cg * sizeof(tskv_time_range), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> cg_series(pg->n_cg), cg_rows(pg->n_cg);
+    for (uint32_t cg = 0; cg < pg->n_cg; cg++) {
+      cg_series[cg] = pg->h_descs[pg->h_cg_time_page[cg]].series_id;
+      cg_rows[cg] = pg->h_descs[pg->h_cg_time_page[cg]].num_values;
+    }
+    plan_overlap_groups(pg->n_cg, cg_series.data(), cg_rows.data(), pg->h_cg_bounds.data(), cg_file_id, &pg->overlap);
+    const OverlapPlan &op = pg->overlap;
+    const size_t n_mcg = op.mcg_cg.size();
+    if (n_mcg == 0) return TSKV_OK;  // no two chunks of a series overlap: nothing to merge
+    for (uint32_t cg : op.mcg_cg)
+      if (pg->h_time_has_nulls[pg->h_cg_time_page[cg]] || pg->h_descs[pg->h_cg_time_page[cg]].reserved >= DK_BAD_ENCODING) {
+        ctx->set_error("set_chunk_files: a time page of an overlapping chunk holds NULLs or does not decode", pg->h_cg_time_page[cg]);
+        free_overlap(pg);
+        return TSKV_ERR_UNSUPPORTED;
+      }
+    pg->merge_rows = op.mcg_row0.back();
+    pg->h_mcg_bm0.assign(n_mcg, 0);
+    uint64_t w = 0;
+    for (size_t k = 0; k < n_mcg; k++) {
+      pg->h_mcg_bm0[k] = w;
+      w += ((op.mcg_row0[k + 1] - op.mcg_row0[k] + 63) / 64) * 2;  // 8-byte padded bitmaps, in 32-bit words
+    }
+    pg->merge_bm_words = w;
+    auto up = [&](auto **dptr, const auto &vec) -> cudaError_t {
+      cudaError_t e = dev_alloc(dptr, vec.size());
+      if (e == cudaSuccess && !vec.empty()) e = cudaMemcpy(*dptr, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+      return e;
+    };
+    cudaError_t e = up(&pg->d_cg_merge, op.cg_merge);
+    if (e == cudaSuccess) e = up(&pg->d_mcg_row0, op.mcg_row0);
+    if (e == cudaSuccess) e = up(&pg->d_mcg_bm0, pg->h_mcg_bm0);
+    if (e == cudaSuccess) e = up(&pg->d_mcg_cg, op.mcg_cg);
+    if (e == cudaSuccess) e = up(&pg->d_mcg_stream, op.mcg_stream);
+    if (e == cudaSuccess) e = up(&pg->d_stream_group, op.stream_group);
+    if (e == cudaSuccess) e = up(&pg->d_stream_first_mcg, op.stream_first_mcg);
+    if (e == cudaSuccess) e = up(&pg->d_group_first_stream, op.group_first_stream);
+    if (e == cudaSuccess) e = dev_alloc(&pg->d_merge_ts, (size_t)pg->merge_rows);
+    // the merge rows' timestamps: the time pages of the merge column groups, decoded in merge-row order
+    std::vector<uint32_t> tpages(n_mcg);
+    std::vector<uint64_t> row_off(n_mcg), bm_off(n_mcg);
+    for (size_t k = 0; k < n_mcg; k++) {
+      tpages[k] = pg->h_cg_time_page[op.mcg_cg[k]];
+      row_off[k] = op.mcg_row0[k];
+      bm_off[k] = pg->h_mcg_bm0[k] * 4;
+    }
+    uint32_t *d_list = nullptr;
+    uint64_t *d_ro = nullptr, *d_bo = nullptr;
+    uint8_t *d_bm = nullptr;
+    int32_t *d_st = nullptr;
+    if (e == cudaSuccess) e = up(&d_list, tpages);
+    if (e == cudaSuccess) e = up(&d_ro, row_off);
+    if (e == cudaSuccess) e = up(&d_bo, bm_off);
+    if (e == cudaSuccess) e = dev_alloc(&d_bm, (size_t)pg->merge_bm_words * 4);
+    if (e == cudaSuccess) e = dev_alloc(&d_st, 8);  // status | err page (2 x 8 bytes) | points
+    tskv_status ret = TSKV_OK;
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_st, 0, 32, ctx->stream);
+    if (e == cudaSuccess) {
+      unsigned long long *aux = reinterpret_cast<unsigned long long *>(d_st);
+      const uint32_t blocks = (uint32_t)((n_mcg * 32 + DECODE_THREADS - 1) / DECODE_THREADS);
+      k_decode_warp<<<blocks, DECODE_THREADS, 0, ctx->stream>>>(pg->h_mapped ? pg->h_mapped : pg->d_arena, pg->d_descs, 0, d_list, (uint32_t)n_mcg,
+                                                               d_ro, d_bo, reinterpret_cast<uint64_t *>(pg->d_merge_ts), d_bm, d_st, aux + 1, aux + 2);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) ret = fetch_status(ctx, d_st, aux + 1);
+    }
+    cudaFree(d_list); cudaFree(d_ro); cudaFree(d_bo); cudaFree(d_bm); cudaFree(d_st);
+    if (e != cudaSuccess || ret != TSKV_OK) {
+      if (e != cudaSuccess) ctx->set_error(std::string("set_chunk_files: ") + cudaGetErrorString(e));
+      free_overlap(pg);
+      return e == cudaErrorMemoryAllocation ? TSKV_ERR_OOM : (e != cudaSuccess ? TSKV_ERR_CUDA : ret);
+    }
+  }
   return TSKV_OK;
 }
 
@@ -894,7 +1027,7 @@ tskv_status tskvgpu_decode_pages(tskv_ctx *ctx, const tskv_pages *pages, uint64_
     cudaEventRecord(ctx->ev0, ctx->stream);
     uint32_t blocks = (uint32_t)((n_pages * 32 + DECODE_THREADS - 1) / DECODE_THREADS);  // one warp per page
     // host-resident page sets: d_arena is only the scans' gather target, the pages are read through the mapped host range
-    k_decode_warp<<<blocks, DECODE_THREADS, 0, ctx->stream>>>(pages->h_mapped ? pages->h_mapped : pages->d_arena, pages->d_descs, first_page, (uint32_t)n_pages,
+    k_decode_warp<<<blocks, DECODE_THREADS, 0, ctx->stream>>>(pages->h_mapped ? pages->h_mapped : pages->d_arena, pages->d_descs, first_page, nullptr, (uint32_t)n_pages,
                                                         d_row_off, d_bm_off, d_vals, d_valid, d_status, d_aux, d_aux + 1);
     cudaEventRecord(ctx->ev1, ctx->stream);
     e = cudaGetLastError();
@@ -1385,8 +1518,14 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       for (int b = 0; b < N_BINS; b++) s->grid[b] = std::min(s->grid[b], std::max(need[b], 0));
       // TSKV_GRID_OVERSUB=f: f x the planned blocks per bin; the blocks that are not resident at first start as the
       // bins that finish early retire theirs and pick up what is left of the slower bins' chunks
-      if (const char *ov = getenv("TSKV_GRID_OVERSUB")) {
-        const double f = atof(ov);
+      // Measured on C4 at N = 1 (round 2, parts = 4): planned grids 1.11 ms, 2 x 0.98 ms, 4 x 0.88 ms = one warp per
+      // chunk 0.885 ms (uncut pages: 1.05 ms). Uncut pages keep the planned grids (a late block would start a whole
+      // page's serial decode: 1.08 vs 1.03 ms).
+      {
+        bool cut = false;
+        for (int b = 0; b < N_BINS; b++) cut = cut || parts[b] > 1;
+        const char *ov = getenv("TSKV_GRID_OVERSUB");
+        const double f = ov ? atof(ov) : (cut ? 4.0 : 1.0);
         if (f > 1.0)
           for (int b = 0; b < N_BINS; b++) s->grid[b] = std::min(std::max(need[b], 0), (int)std::ceil(s->grid[b] * f));
       }
@@ -1435,6 +1574,85 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       s->coop.q0 = s->coop.grid_ok ? d0 / q->width : 0;
     }
   }
+  // ---- merge pass over the overlapping chunks (merge_kernels.cuh): which merge column groups this scan reads
+  // (series selected, not pruned by its time bounds), and the field pages of the query's columns to decode for them
+  s->chunk_epoch = pages->chunk_epoch;
+  if (pages->merge_rows) {
+    const OverlapPlan &op = pages->overlap;
+    const size_t n_mcg = op.mcg_cg.size();
+    std::vector<uint8_t> active(n_mcg, 0);
+    std::vector<uint32_t> mpage;
+    std::vector<uint64_t> mrow_off, mbm_off;
+    for (size_t k = 0; k < n_mcg; k++) {
+      const uint32_t cg = op.mcg_cg[k], tp = pages->h_cg_time_page[cg];
+      const tskv_page_desc &td = pages->h_descs[tp];
+      if (q->series_ids && !std::binary_search(q->series_ids, q->series_ids + q->n_series, td.series_id)) continue;
+      if (q->n_time_ranges) {  // filter_column_groups (reader/chunk.rs:12-50)
+        bool overlaps = false;
+        for (uint32_t r = 0; r < q->n_time_ranges; r++)
+          overlaps = overlaps || (pages->h_cg_bounds[cg].min_ts <= q->time_ranges[r].max_ts && pages->h_cg_bounds[cg].max_ts >= q->time_ranges[r].min_ts);
+        if (!overlaps) continue;
+      }
+      bool any = false;
+      for (uint64_t p = (uint64_t)tp + 1; p < pages->n_descs && pages->h_descs[p].phys_type != TSKV_PT_TIME; p++)
+        for (uint32_t c = 0; c < q->n_columns; c++)
+          if (pages->h_descs[p].column_id == q->columns[c].column_id) {
+            if (pages->h_descs[p].phys_type != q->columns[c].phys_type) {
+              ctx->set_error("page type does not match the query column type", (int64_t)p);
+              free_scan(s);
+              return TSKV_ERR_INVALID_ARG;
+            }
+            any = true;
+            mpage.push_back((uint32_t)p);
+            mrow_off.push_back((uint64_t)c * pages->merge_rows + op.mcg_row0[k]);
+            mbm_off.push_back(((uint64_t)c * pages->merge_bm_words + pages->h_mcg_bm0[k]) * 4);
+            s->merge_page_bytes += pages->h_descs[p].size;
+          }
+      if (!any) continue;  // a column group without any projected column yields no batch (column_group/mod.rs:43-52)
+      active[k] = 1;
+      s->merge_page_bytes += td.size;
+      s->merge_read_pages++;
+    }
+    s->n_merge_pages = (uint32_t)mpage.size();
+    s->merge_read_pages += mpage.size();
+    cudaError_t me = stream_alloc(ctx, &s->d_mcg_active, n_mcg);
+    if (me == cudaSuccess) me = cudaMemcpyAsync(s->d_mcg_active, active.data(), n_mcg, cudaMemcpyHostToDevice, ctx->stream);
+    if (me == cudaSuccess) me = stream_alloc(ctx, &s->d_mvals, (size_t)q->n_columns * pages->merge_rows);
+    if (me == cudaSuccess) me = stream_alloc(ctx, &s->d_mvalid, (size_t)q->n_columns * pages->merge_bm_words);
+    if (me == cudaSuccess) me = stream_alloc(ctx, &s->d_mpage, mpage.size());
+    if (me == cudaSuccess) me = stream_alloc(ctx, &s->d_mrow_off, mpage.size());
+    if (me == cudaSuccess) me = stream_alloc(ctx, &s->d_mbm_off, mpage.size());
+    if (me == cudaSuccess && !mpage.empty()) {
+      me = cudaMemcpyAsync(s->d_mpage, mpage.data(), mpage.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+      if (me == cudaSuccess) me = cudaMemcpyAsync(s->d_mrow_off, mrow_off.data(), mpage.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+      if (me == cudaSuccess) me = cudaMemcpyAsync(s->d_mbm_off, mbm_off.data(), mpage.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (me == cudaSuccess) me = cudaStreamSynchronize(ctx->stream);  // the host vectors go out of scope
+    if (me != cudaSuccess) {
+      ctx->set_error(std::string("scan_prepare (merge pass): ") + cudaGetErrorString(me));
+      free_scan(s);
+      return me == cudaErrorMemoryAllocation ? TSKV_ERR_OOM : TSKV_ERR_CUDA;
+    }
+    h2d += n_mcg + mpage.size() * 20;
+    MergeParams &M = s->merge;
+    M.ts = pages->d_merge_ts;
+    M.mcg_row0 = pages->d_mcg_row0;
+    M.mcg_cg = pages->d_mcg_cg;
+    M.mcg_stream = pages->d_mcg_stream;
+    M.stream_group = pages->d_stream_group;
+    M.stream_first_mcg = pages->d_stream_first_mcg;
+    M.group_first_stream = pages->d_group_first_stream;
+    M.mcg_active = s->d_mcg_active;
+    M.vals = s->d_mvals;
+    M.valid = s->d_mvalid;
+    M.mcg_bm0 = pages->d_mcg_bm0;
+    M.cg_time_page = pages->d_cg_time_page;
+    M.cg_slot = s->d_cg_slot;
+    M.n_rows = pages->merge_rows;
+    M.bm_words = pages->merge_bm_words;
+    M.n_mcg = (uint32_t)n_mcg;
+    M.sel = s->has_sel ? 1u : 0u;
+  }
   ctx->counters.h2d_bytes = h2d;
   *out_scan = s;
   return TSKV_OK;
@@ -1450,6 +1668,10 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
   const uint32_t n_items = pages->n_items;
   if (s->tomb_epoch != pages->tomb_epoch) {
     ctx->set_error("the page set's tombstones changed after this scan was prepared", -1);
+    return TSKV_ERR_INVALID_ARG;
+  }
+  if (s->chunk_epoch != pages->chunk_epoch) {
+    ctx->set_error("the page set's chunk files changed after this scan was prepared", -1);
     return TSKV_ERR_INVALID_ARG;
   }
   if (!capturing) cudaEventRecord(s->ev0, ctx->stream);
@@ -1474,7 +1696,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
                                                         pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
                                                         s->n_cols, pages->d_bin_start, s->d_item_flag,
                                                         s->d_block_count, s->d_counters, s->d_status,
-                                                        s->prune.n ? pages->d_cg_bounds : nullptr, s->prune);
+                                                        s->prune.n ? pages->d_cg_bounds : nullptr, s->prune, pages->d_cg_merge);
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(s->d_block_count, s->n_blocks, s->d_bin_cstart + N_BINS + 1);
     k_scatter_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_item_page, pages->d_item_cg, n_items, s->d_item_flag,
                                                            s->d_block_count, s->d_cg_slot, pages->d_bin_start,
@@ -1485,6 +1707,16 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
   uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
   k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
   launches++;
+  if (s->merge.n_rows && s->n_merge_pages) {  // overlapping chunks: decode the query's columns, merge + aggregate per row
+    CU_TRY(ctx, cudaMemsetAsync(s->d_mvalid, 0, (size_t)s->n_cols * s->merge.bm_words * 4, ctx->stream));
+    const uint32_t dblocks = (uint32_t)(((uint64_t)s->n_merge_pages * 32 + DECODE_THREADS - 1) / DECODE_THREADS);
+    k_decode_warp<<<dblocks, DECODE_THREADS, 0, ctx->stream>>>(pages->h_mapped ? pages->h_mapped : pages->d_arena, pages->d_descs, 0, s->d_mpage,
+                                                              s->n_merge_pages, s->d_mrow_off, s->d_mbm_off, s->d_mvals,
+                                                              reinterpret_cast<uint8_t *>(s->d_mvalid), s->d_status, s->d_err_page, s->d_stats);
+    const uint32_t mblocks = (uint32_t)((s->merge.n_rows + 127) / 128);
+    k_merge_chunks<<<mblocks, 128, 0, ctx->stream>>>(s->params, s->merge);
+    launches += 2;
+  }
   cudaEvent_t ev_fork = capturing ? s->ev_cfork : s->ev_bin[0];
   cudaEventRecord(ev_fork, ctx->stream);  // fork
   // Host-resident pages: one bin's gather already saturates PCIe, so the gathers are chained largest bin first
@@ -1567,8 +1799,8 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
   ctx->counters.elapsed_scan_ms = ms;
   ctx->counters.points_decoded = aux[0];
   ctx->counters.rows_in_range = aux[1];
-  ctx->counters.page_read_count = aux[2];
-  ctx->counters.page_read_bytes = aux[3];
+  ctx->counters.page_read_count = aux[2] + s->merge_read_pages;
+  ctx->counters.page_read_bytes = aux[3] + s->merge_page_bytes;
   float fused = 0;
   cudaEventElapsedTime(&fused, s->ev_bin[0], s->ev_bin[N_BINS]);
   ctx->counters.elapsed_fused_ms = fused;

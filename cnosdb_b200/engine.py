@@ -147,6 +147,14 @@ class PageSet:
         self.engine._check(self.engine.lib.tskvgpu_pages_set_tombstones(
             self.engine.ctx, self.handle, tombs.ctypes.data if len(tombs) else None, len(tombs)))
 
+    def set_chunk_files(self, cg_file_ids):
+        """File id of every column group (descriptor order): later scans merge + de-duplicate the chunks of a series
+        whose time ranges overlap (DataMerger semantics: rows with equal time collapse, the newest file's non-null value
+        wins per column). An empty list clears."""
+        ids = np.ascontiguousarray(cg_file_ids, dtype=np.uint64)
+        self.engine._check(self.engine.lib.tskvgpu_pages_set_chunk_files(
+            self.engine.ctx, self.handle, ids.ctypes.data if len(ids) else None, len(ids)))
+
     def set_time_bounds(self, bounds):
         """Per-column-group (min_ts, max_ts), ColumnGroup::time_range() order = descriptor order: lets scans with time
         ranges skip whole column groups (statistics pruning). bounds: [(lo, hi), ...] or an int64 array of shape [n, 2]."""

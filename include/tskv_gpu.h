@@ -262,6 +262,22 @@ typedef struct tskv_tombstone {
 tskv_status tskvgpu_pages_set_tombstones(tskv_ctx *ctx, tskv_pages *pages, const tskv_tombstone *tombs,
                                          uint64_t n_tombs);
 
+/* Overlapping chunks. A page set may hold the column groups of SEVERAL files (TSM files, delta files) and of the
+ * memcache (its row groups handed in as raw-encoded pages): cg_file_id[k] is the id of the file column group k (in
+ * descriptor-table order) came from - ColumnFile::file_id() / the cache's file id. Replaces, for later scans,
+ *   build_series_reader: chunks sorted by time range, group_overlapping_segments, groups sorted by file id
+ *                        (tskv/src/reader/iterator.rs:463-560, tskv/src/reader/utils.rs:77-107)
+ *   DataMerger / sort_merge / BatchMergeBuilder: k-way merge on `time`, ties to the lower stream; rows with equal
+ *                        time collapse, every column taking the last non-null value (tskv/src/reader/merge.rs,
+ *                        sort_merge.rs:153-400, batch_builder.rs:74-155)
+ *   MemCacheReader       (tskv/src/reader/memcache_reader.rs:33-165): the cache is one more chunk.
+ * Chunks of a series whose time ranges do not overlap are scanned as before. The column groups' time bounds are
+ * taken from tskvgpu_pages_set_time_bounds when it was called, else computed from the time pages. n_cg = 0 clears;
+ * any change invalidates scans prepared earlier (TSKV_ERR_INVALID_ARG when run). Time pages of overlapping chunks
+ * must not hold NULLs (TSKV_ERR_UNSUPPORTED; the reference's writer never produces them). The merged rows of one
+ * overlap group count as ONE record batch for first / last (the reference cuts batches of QueryOption.batch_size). */
+tskv_status tskvgpu_pages_set_chunk_files(tskv_ctx *ctx, tskv_pages *pages, const uint64_t *cg_file_id, uint64_t n_cg);
+
 /* ---- decode only ---------------------------------------------------------------------------
  * Replaces Page::to_arrow_array / data_buf_to_arrow_array (tskv/src/tsm/reader.rs:658-731) for
  * pages [first_page, first_page + n_pages): row r of page p lands at out_values[row_offsets[p]+r]

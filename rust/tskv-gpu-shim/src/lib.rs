@@ -182,6 +182,13 @@ impl PageSet<'_> {
         let st = unsafe { sys::tskvgpu_pages_set_tombstones(self.engine.ctx, self.pages, tombs.as_ptr(), tombs.len() as u64) };
         self.engine.check(st)
     }
+    /// `ColumnFile::file_id()` (or the memcache's file id) of every column group, in descriptor order: scans merge
+    /// the chunks of a series whose time ranges overlap, the newest file's non-null value winning per column
+    /// (`DataMerger`, `reader/merge.rs`; `build_series_reader`, `reader/iterator.rs:463-560`).
+    pub fn set_chunk_files(&mut self, cg_file_ids: &[u64]) -> GpuResult<()> {
+        let st = unsafe { sys::tskvgpu_pages_set_chunk_files(self.engine.ctx, self.pages, cg_file_ids.as_ptr(), cg_file_ids.len() as u64) };
+        self.engine.check(st)
+    }
     pub fn series_count(&self) -> u64 {
         unsafe { sys::tskvgpu_pages_series_count(self.pages) }
     }

@@ -214,6 +214,13 @@ extern "C" {
         tombs: *const tskv_tombstone,
         n_tombs: u64,
     ) -> tskv_status;
+    /// File id of every column group: overlapping chunks of a series are merged (DataMerger, reader/merge.rs).
+    pub fn tskvgpu_pages_set_chunk_files(
+        ctx: *mut tskv_ctx,
+        pages: *mut tskv_pages,
+        cg_file_id: *const u64,
+        n_cg: u64,
+    ) -> tskv_status;
 
     pub fn tskvgpu_decode_pages(
         ctx: *mut tskv_ctx,

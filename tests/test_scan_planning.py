@@ -79,3 +79,37 @@ def test_kernel_family_and_group_size_for_the_c4_shards():
     assert L.tskvplan_gorilla_group(6250.0, float(resident_warps)) == 4
     assert L.tskvplan_gorilla_group(100.0, float(resident_warps)) == 1
     assert L.tskvplan_gorilla_group(1e9, float(resident_warps)) == 32
+
+
+def test_overlap_groups_follow_the_reference_grouping():
+    """plan_overlap_groups = build_series_reader's chunk grouping (reader/iterator.rs:463-560): the table of
+    reader/utils.rs:330-353 (groups of 4, 2 and 1 chunks), streams ordered by file id, column groups of a chunk in time order."""
+    L = lib()
+    L.tskvplan_overlap_groups.argtypes = [C.c_uint64] + [C.c_void_p] * 9
+    L.tskvplan_overlap_groups.restype = None
+
+    def plan(series, rows, bounds, files):
+        n = len(series)
+        a = [np.ascontiguousarray(series, dtype=np.uint32), np.ascontiguousarray(rows, dtype=np.uint32),
+             np.ascontiguousarray(bounds, dtype=np.int64).reshape(-1, 2), np.ascontiguousarray(files, dtype=np.uint64)]
+        merge = np.zeros(n, dtype=np.uint8)
+        counts = np.zeros(5, dtype=np.uint64)
+        mcg, mst, sgrp = (np.zeros(n, dtype=np.uint32) for _ in range(3))
+        L.tskvplan_overlap_groups(n, *[x.ctypes.data for x in a], merge.ctypes.data, counts.ctypes.data, mcg.ctypes.data,
+                                  mst.ctypes.data, sgrp.ctypes.data)
+        c = [int(x) for x in counts]
+        return merge, c, mcg[:c[2]], mst[:c[2]], sgrp[:c[1]]
+
+    trs = [(0, 10), (1, 3), (4, 7), (6, 10), (11, 14), (12, 15), (16, 18)]
+    # file ids descending in time order: inside a group the streams must come out ascending by file id
+    merge, c, mcg, mst, sgrp = plan([5] * 7, [10] * 7, trs, [70, 60, 50, 40, 30, 20, 10])
+    assert merge.tolist() == [1, 1, 1, 1, 1, 1, 0]
+    assert c == [2, 6, 6, 60, 3]          # 2 merge groups, 6 streams, 6 merge column groups, 60 rows, 3 overlap groups
+    assert mcg.tolist() == [3, 2, 1, 0, 5, 4] and sgrp.tolist() == [0, 0, 0, 0, 1, 1]
+    # one file with two column groups (one chunk): never merged with itself; another series' chunks do not interact
+    merge, c, mcg, mst, _ = plan([1, 1, 2, 2, 2], [5, 5, 5, 5, 7], [(0, 9), (10, 19), (0, 9), (20, 29), (5, 25)], [1, 1, 1, 1, 2])
+    assert merge.tolist() == [0, 0, 1, 1, 1] and c[0] == 1 and c[1] == 2 and c[4] == 2
+    assert mcg.tolist() == [2, 3, 4] and mst.tolist() == [0, 0, 1]    # chunk of file 1 = column groups 2, 3 in time order
+    # touching ranges overlap (min_ts <= running max), disjoint ones do not
+    assert plan([1, 1], [3, 3], [(0, 5), (5, 9)], [1, 2])[0].tolist() == [1, 1]
+    assert plan([1, 1], [3, 3], [(0, 5), (6, 9)], [1, 2])[0].tolist() == [0, 0]

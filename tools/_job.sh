@@ -1,21 +1,12 @@
 mkdir -p gpurun_out
-run() {
-  echo "== $*"
-  env "$@" TSKV_DEBUG_BINS=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/b.err | tail -1 > gpurun_out/b.json
-  python - <<PY
+timeout 600 python -m pytest tests/test_gpu_overlap_merge.py -m gpu -q -x > gpurun_out/t_merge.log 2>&1; tail -25 gpurun_out/t_merge.log
+timeout 900 python -m pytest tests -m gpu -q --deselect tests/test_gpu_overlap_merge.py > gpurun_out/t_all.log 2>&1; tail -8 gpurun_out/t_all.log
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/r02b_bench.json 2> gpurun_out/r02b_bench.err; tail -c 400 gpurun_out/r02b_bench.err
+python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/b.json").read())
-print('value %.3g pts/s, %.3f ms/step, fused %.3f ms' % (d['value'], d['ms_per_step'], d['roofline']['ms_per_launch']))
+d=json.loads([l for l in open("gpurun_out/r02b_bench.json").read().splitlines() if l.startswith("{")][-1])
+print("value %.3g ms %.3f crc %.3g e2e %.3g frac %.3f cpu %.3g parity %s launches %s" % (d["value"], d["ms_per_step"], d.get("value_crc_per_step",0), d["e2e"]["value"], d["roofline"]["frac"], d["cpu_baseline"]["value"], d["parity_sample"], d["gpu_launches"]))
+print(d["roofline"])
 PY
-  grep "\[tskv\] bin" gpurun_out/b.err | tail -4 | awk '{printf "%s %s g%s run %s | ", $2,$3,$5,$10} END {print ""}'
-}
-run TSKV_PARTS=1
-run TSKV_PARTS=4
-run TSKV_PARTS=4 TSKV_GRID_OVERSUB=1.5
-run TSKV_PARTS=4 TSKV_GRID_OVERSUB=2
-run TSKV_PARTS=4 TSKV_GRID_OVERSUB=4
-run TSKV_PARTS=4 TSKV_GRID_MODE=1
-run TSKV_PARTS=8 TSKV_GRID_OVERSUB=2
-run TSKV_PARTS=8 TSKV_GRID_MODE=1
-run TSKV_PARTS=2 TSKV_GRID_OVERSUB=2
-run TSKV_PARTS=2 TSKV_GRID_MODE=1
+echo "== 1/8 shard"
+TSKV_DEBUG_BINS=1 timeout 200 python tools/profile_scan.py --series 125000 --steps 6 2>&1 | tail -5
