@@ -26,9 +26,9 @@ TSKV_ERR_BAD_LENGTH = 11
 TSKV_ERR_PAGE_FORMAT = 12
 STATUS_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("TSKV_ERR_") or k == "TSKV_OK"}
 
-TSKV_PT_TIME, TSKV_PT_I64, TSKV_PT_U64, TSKV_PT_F64 = 0, 1, 2, 3
+TSKV_PT_TIME, TSKV_PT_I64, TSKV_PT_U64, TSKV_PT_F64, TSKV_PT_BOOL = 0, 1, 2, 3, 4
 TSKV_ENC_DEFAULT, TSKV_ENC_NULL, TSKV_ENC_DELTA, TSKV_ENC_QUANTILE = 0, 1, 2, 3
-TSKV_ENC_GORILLA, TSKV_ENC_DELTA_TS = 6, 11
+TSKV_ENC_GORILLA, TSKV_ENC_BITPACK, TSKV_ENC_DELTA_TS = 6, 10, 11
 
 TSKV_AGG_COUNT, TSKV_AGG_SUM, TSKV_AGG_MIN, TSKV_AGG_MAX = 1, 2, 4, 8
 TSKV_AGG_MEAN, TSKV_AGG_FIRST, TSKV_AGG_LAST, TSKV_AGG_ALL = 16, 32, 64, 0x7F

@@ -384,10 +384,45 @@ struct DeltaCursor {
         bs.init(d + 1, smem_slot, d + pv.data_len);
         words_left = (pv.data_len - 1) >> 3;
         break;
+      case DK_BOOL_PACK: {  // boolean.rs:79-111: id | 0x10 | varint count | bits, MSB first
+        uint64_t count = 0;
+        uint32_t vl = 0, shift = 0;
+        for (;; vl++) {  // (the host checked that the varint ends inside the block)
+          const uint8_t b = __ldg(d + 2 + vl);
+          if (shift < 64) count |= (uint64_t)(b & 0x7f) << shift;
+          shift += 7;
+          if (!(b & 0x80)) break;
+        }
+        vl++;
+        const uint64_t have = (uint64_t)(pv.data_len - 2 - vl) * 8;  // bits the block really holds (src[bit_index / 8])
+        words_left = (uint32_t)min(min(count, have), (uint64_t)0xffffffffu);   // VALUES left
+        bs.init(d + 2 + vl, smem_slot, d + pv.data_len);
+        break;
+      }
+      case DK_BOOL_RAW:  // boolean.rs:112-140: id | one byte per value
+        words_left = pv.data_len - 1;  // VALUES left
+        bs.init(d + 1, smem_slot, d + pv.data_len);
+        break;
       default:
         break;
     }
     return TSKV_OK;
+  }
+  // Next boolean: `w` holds the unread part of the current 64-bit chunk of the stream, MSB first.
+  __device__ __forceinline__ uint64_t next_bool(uint32_t width) {
+    if (words_left == 0) {  // "Insufficient data for decoding" / the block ends before the bitset is served
+      exhausted = true;
+      return 0;
+    }
+    words_left--;
+    if (in_word == 0) {
+      w = bs.next();
+      in_word = 64 / width;
+    }
+    in_word--;
+    const uint64_t v = w >> (64 - width);
+    w <<= width;
+    return width == 1 ? v : (v == 1 ? 1ull : 0ull);
   }
 
   __device__ __forceinline__ void refill() {
@@ -431,6 +466,8 @@ struct DeltaCursor {
       case DK_RAW_SC: v += next_word(); return v;
       case DK_RAW_ZZ: v += (uint64_t)zigzag_dec(next_word()); return v;
       case DK_RAWBE: return next_word();
+      case DK_BOOL_PACK: return next_bool(1);
+      case DK_BOOL_RAW: return next_bool(8);
       default: exhausted = true; return 0;  // DK_ALLNULL never reaches here with a valid bit
     }
   }

@@ -108,8 +108,9 @@ int phys_type_of(const ColType &c) {
     if (c.sub == 1) return TSKV_PT_F64;
     if (c.sub == 2) return TSKV_PT_I64;
     if (c.sub == 3) return TSKV_PT_U64;
+    if (c.sub == 4) return TSKV_PT_BOOL;
   }
-  return -1;  // tags, bool, string, geometry: not on this engine's path (yet)
+  return -1;  // tags, string, geometry: not on this engine's path
 }
 struct Column {
   uint32_t id = 0;
@@ -450,7 +451,7 @@ uint64_t tskvtsm_write(const uint8_t *arena, const tskv_page_desc *descs, uint64
     w.u32(d.column_id);
     w.str(d.phys_type == TSKV_PT_TIME ? "time" : "c" + std::to_string(d.column_id));
     if (d.phys_type == TSKV_PT_TIME) { w.u32(1); w.u32(3); }  // Time(Nanosecond)
-    else { w.u32(2); w.u32(d.phys_type == TSKV_PT_F64 ? 1 : d.phys_type == TSKV_PT_I64 ? 2 : 3); }
+    else { w.u32(2); w.u32(d.phys_type == TSKV_PT_F64 ? 1 : d.phys_type == TSKV_PT_I64 ? 2 : d.phys_type == TSKV_PT_BOOL ? 4 : 3); }
     w.u32(0);  // Encoding::Default
   };
   // chunks (one per series, series ascending like the BTreeMap), then the chunk group, then the chunk group meta
@@ -487,7 +488,7 @@ uint64_t tskvtsm_write(const uint8_t *arena, const tskv_page_desc *descs, uint64
         c.u64(cg.off[p]); c.u64(d.size);
         c.u32(d.num_values);
         column(c, d);
-        c.u32(d.phys_type == TSKV_PT_F64 ? 1 : d.phys_type == TSKV_PT_U64 ? 3 : 2);  // PageStatistics variant (time: I64)
+        c.u32(d.phys_type == TSKV_PT_F64 ? 1 : d.phys_type == TSKV_PT_U64 ? 3 : d.phys_type == TSKV_PT_BOOL ? 0 : 2);  // PageStatistics variant (time: I64)
         c.u8(0); c.u8(0); c.u8(0); c.u64(0);  // min None, max None, distinct None, null_count
       }
       id++;

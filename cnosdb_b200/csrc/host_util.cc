@@ -189,6 +189,18 @@ uint8_t classify_page(const PageHeader &h, uint8_t phys_type) {
   if (h.data_len == 0) return DK_ALLNULL;  // every codec: empty buffer => all-null array
   const uint8_t *d = h.data;
   unsigned enc = d[0];
+  if (phys_type == TSKV_PT_BOOL) {  // get_bool_codec (instance.rs:415-421): Null => bytes, everything else => bit-pack
+    if (enc == TSKV_ENC_NULL) return DK_BOOL_RAW;
+    if (h.data_len < 3) return DK_SHORT;
+    if (d[1] != 0x10) return DK_BAD_ENCODING;  // assert_eq!(src[0], BOOLEAN_COMPRESSED_BIT_PACKED << 4) (boolean.rs:84)
+    uint64_t shift = 0;
+    for (uint64_t i = 2; i < h.data_len; i++) {  // "boolean decoder: invalid count": the varint must end inside the block
+      if ((d[i] & 0x80) == 0) return DK_BOOL_PACK;
+      shift += 7;
+      if (shift > 63) break;
+    }
+    return DK_SHORT;
+  }
   if (enc == TSKV_ENC_QUANTILE) return DK_UNSUPPORTED;
   if (enc == TSKV_ENC_NULL) return ((h.data_len - 1) & 7) ? DK_BAD_LENGTH : DK_RAWBE;
   bool ts_family;

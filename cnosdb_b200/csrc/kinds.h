@@ -20,7 +20,10 @@ enum : uint8_t {
   DK_UNSUPPORTED = 10,   // Quantile (pco)
   DK_SHORT = 11,         // data too short for its header ("not enough data to decode ...")
   DK_BAD_LENGTH = 12,    // "invalid uncompressed block length"
-  DK_BAD_PAGE = 13       // page shorter than header + bitset
+  DK_BAD_PAGE = 13,      // page shorter than header + bitset
+  DK_BOOL_PACK = 14,     // boolean bit-pack (boolean.rs:79-111): 0x10 | varint count | bits, MSB first
+  DK_BOOL_RAW = 15       // boolean under Encoding::Null (boolean.rs:112-140): one byte per value, 1 = true
 };
+inline bool dk_is_error(uint8_t k) { return k >= DK_BAD_ENCODING && k <= DK_BAD_PAGE; }
 
 }  // namespace tskv

@@ -566,7 +566,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   auto work = [&](uint64_t lo, uint64_t hi) {
     for (uint64_t i = lo; i < hi && bad_status.load(std::memory_order_relaxed) == 0; i++) {
       tskv_page_desc &d = pg->h_descs[i];
-      if (d.offset & 15 || d.size > arena_len || d.offset > arena_len - d.size || d.phys_type > TSKV_PT_F64 || d.reserved != 0) {
+      if (d.offset & 15 || d.size > arena_len || d.offset > arena_len - d.size || d.phys_type > TSKV_PT_BOOL || d.reserved != 0) {
         fail(TSKV_ERR_INVALID_ARG, (int64_t)i);
         return;
       }
@@ -866,7 +866,7 @@ tskv_status tskvgpu_pages_set_chunk_files(tskv_ctx *ctx, tskv_pages *pg, const u
     const size_t n_mcg = op.mcg_cg.size();
     if (n_mcg == 0) return TSKV_OK;  // no two chunks of a series overlap: nothing to merge
     for (uint32_t cg : op.mcg_cg)
-      if (pg->h_time_has_nulls[pg->h_cg_time_page[cg]] || pg->h_descs[pg->h_cg_time_page[cg]].reserved >= DK_BAD_ENCODING) {
+      if (pg->h_time_has_nulls[pg->h_cg_time_page[cg]] || dk_is_error(pg->h_descs[pg->h_cg_time_page[cg]].reserved)) {
         ctx->set_error("set_chunk_files: a time page of an overlapping chunk holds NULLs or does not decode", pg->h_cg_time_page[cg]);
         free_overlap(pg);
         return TSKV_ERR_UNSUPPORTED;
@@ -1088,8 +1088,12 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     }
   for (uint32_t c = 0; c < q->n_columns; c++) {
     const tskv_agg_column &qc = q->columns[c];
-    if (qc.phys_type < TSKV_PT_I64 || qc.phys_type > TSKV_PT_F64 || (qc.agg_mask & ~TSKV_AGG_ALL) || qc.agg_mask == 0) {
+    if (qc.phys_type < TSKV_PT_I64 || qc.phys_type > TSKV_PT_BOOL || (qc.agg_mask & ~TSKV_AGG_ALL) || qc.agg_mask == 0) {
       ctx->set_error("invalid query column (type or aggregate mask)");
+      return TSKV_ERR_INVALID_ARG;
+    }
+    if (qc.phys_type == TSKV_PT_BOOL && (qc.agg_mask & (TSKV_AGG_SUM | TSKV_AGG_MEAN))) {
+      ctx->set_error("sum / mean of a boolean column");
       return TSKV_ERR_INVALID_ARG;
     }
     for (uint32_t c2 = 0; c2 < c; c2++)

@@ -79,6 +79,25 @@ def encode_raw(v):
     return _encode("tskvw_encode_raw", np.asarray(v).view(np.uint64) if np.asarray(v).dtype.itemsize == 8 else v, np.uint64)
 
 
+def encode_bools(v):
+    """Boolean bit-pack (tskv/src/tsm/codec/boolean.rs:24-64): BitPack id | 0x10 | LEB128 count | 1 bit per value, MSB first.
+    (numpy only: independent of the CPU checker's restatement.)"""
+    v = np.asarray(v, dtype=bool)
+    if v.size == 0:
+        return np.zeros(0, dtype=np.uint8)
+    n, var = int(v.size), []
+    while n >= 0x80:
+        var.append((n & 0x7F) | 0x80)
+        n >>= 7
+    var.append(n)
+    return np.concatenate([np.array([cabi.TSKV_ENC_BITPACK, 0x10] + var, dtype=np.uint8), np.packbits(v, bitorder="big")])
+
+
+def encode_bools_raw(v):
+    """Boolean column under Encoding::Null (boolean.rs:66-76): one byte per value."""
+    return np.concatenate([np.array([cabi.TSKV_ENC_NULL], dtype=np.uint8), np.asarray(v, dtype=bool).astype(np.uint8)])
+
+
 def simple8b_pack(v):
     return _encode("tskvw_simple8b_pack", v, np.uint64)
 
@@ -127,7 +146,7 @@ class ArenaBuilder:
             vv = None if valid is None else np.asarray(valid, dtype=bool)
             kept = vals if vv is None else vals[vv]
             if enc is None:
-                enc = encode_floats if pt == cabi.TSKV_PT_F64 else encode_integers
+                enc = encode_floats if pt == cabi.TSKV_PT_F64 else encode_bools if pt == cabi.TSKV_PT_BOOL else encode_integers
             if pt == cabi.TSKV_PT_U64 and enc is encode_integers:
                 kept = np.asarray(kept, dtype=np.uint64).view(np.int64)
             self.add_page(build_page(enc(kept), n, vv), series_id, column_id, pt, n)

@@ -50,13 +50,16 @@ enum {
   TSKV_ERR_PAGE_FORMAT = 12     /* page shorter than its own header / bitset (page.rs:78-94) */
 };
 
-/* Physical column type of a page: PhysicalCType::Time / PhysicalDType::{Integer,Unsigned,Float}
- * (dispatch in tskv/src/tsm/reader.rs:658-731). */
+/* Physical column type of a page: PhysicalCType::Time / PhysicalDType::{Integer,Unsigned,Float,Boolean}
+ * (dispatch in tskv/src/tsm/reader.rs:658-731). Boolean pages (tskv/src/tsm/codec/boolean.rs:79-140: bit-packed, or one
+ * byte per value under Encoding::Null) decode to 0 / 1 in the 8-byte cells; aggregates on them: count, min, max, first,
+ * last (SUM / MEAN of a boolean column are rejected like DataFusion's type check does). String pages are not handled. */
 enum {
   TSKV_PT_TIME = 0,
   TSKV_PT_I64 = 1,
   TSKV_PT_U64 = 2,
-  TSKV_PT_F64 = 3
+  TSKV_PT_F64 = 3,
+  TSKV_PT_BOOL = 4
 };
 
 /* Encoding ids stored in data[0] of a page (common/models/src/codec.rs:37-54). */
@@ -66,6 +69,7 @@ enum {
   TSKV_ENC_DELTA = 2,
   TSKV_ENC_QUANTILE = 3,
   TSKV_ENC_GORILLA = 6,
+  TSKV_ENC_BITPACK = 10,
   TSKV_ENC_DELTA_TS = 11
 };
 
@@ -109,7 +113,7 @@ enum {
  * has Count(col). */
 typedef struct tskv_agg_column {
   uint16_t column_id;
-  uint8_t phys_type; /* TSKV_PT_I64 / U64 / F64: pages of another type under this id are an error */
+  uint8_t phys_type; /* TSKV_PT_I64 / U64 / F64 / BOOL: pages of another type under this id are an error */
   uint8_t agg_mask;  /* TSKV_AGG_* bits */
 } tskv_agg_column;
 

@@ -655,9 +655,92 @@ tskv_status raw_decode(const uint8_t *src, size_t len, const uint8_t *bitset, ui
   return scatter_valid(vals, bitset, n_rows, out_vals, out_valid);
 }
 
+// bool_bitpack_decode (boolean.rs:79-111), `src` = data after the Encoding id byte
+tskv_status bool_bitpack_decode(const uint8_t *src, size_t len, const uint8_t *bitset, uint64_t n_rows,
+                                uint64_t *out_vals, uint8_t *out_valid) {
+  if (len < 1) return TSKV_ERR_SHORT_BLOCK;          // src[0] on an empty slice panics
+  if (src[0] != (1u << 4)) return TSKV_ERR_BAD_ENCODING;  // assert_eq!(src[0], BOOLEAN_COMPRESSED_BIT_PACKED << 4)
+  src += 1;
+  len -= 1;
+  uint64_t count = 0;
+  if (!decode_var(src, len, &count)) return TSKV_ERR_SHORT_BLOCK;  // "boolean decoder: invalid count"
+  size_t nread = 0;
+  while (src[nread] & 0x80) nread++;
+  nread++;
+  src += nread;
+  len -= nread;
+  uint64_t bit_index = 0;
+  for (uint64_t r = 0; r < n_rows; r++) {
+    if (bit_is_set(bitset, r)) {
+      if (bit_index >= count) return TSKV_ERR_BITSET_MISMATCH;   // "Insufficient data for decoding"
+      if (bit_index / 8 >= len) return TSKV_ERR_BITSET_MISMATCH;  // src[bit_index / 8] out of bounds: panic in the reference
+      out_vals[r] = (src[bit_index / 8] >> (7 - (bit_index % 8))) & 1;
+      out_valid[r] = 1;
+      bit_index++;
+    } else {
+      out_vals[r] = 0;
+      out_valid[r] = 0;
+    }
+  }
+  return TSKV_OK;
+}
+// bool_without_compress_decode (boolean.rs:112-140), `src` = data after the Encoding id byte
+tskv_status bool_raw_decode(const uint8_t *src, size_t len, const uint8_t *bitset, uint64_t n_rows, uint64_t *out_vals,
+                            uint8_t *out_valid) {
+  size_t k = 0;
+  for (uint64_t r = 0; r < n_rows; r++) {
+    if (bit_is_set(bitset, r)) {
+      // `if let Some(v) = iter.next()`: a valid row past the data appends NOTHING - the array comes out shorter than
+      // the bitset and the RecordBatch build fails; reported as the bitset / data mismatch it is
+      if (k >= len) return TSKV_ERR_BITSET_MISMATCH;
+      out_vals[r] = src[k++] == 1 ? 1 : 0;
+      out_valid[r] = 1;
+    } else {
+      out_vals[r] = 0;
+      out_valid[r] = 0;
+    }
+  }
+  return TSKV_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+static int64_t emit_bytes(const Bytes &b, uint8_t *dst, uint64_t cap) {
+  if (b.v.size() > cap) return -TSKV_ERR_OOM;
+  if (!b.v.empty()) memcpy(dst, b.v.data(), b.v.size());
+  return (int64_t)b.v.size();
+}
+// bool_bitpack_encode (boolean.rs:24-64): id | 0x10 | varint n | 1 bit per value, MSB first
+int64_t orc_bool_encode(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap) {
+  Bytes b;
+  if (n) {
+    b.push(TSKV_ENC_BITPACK);
+    const size_t size = 1 + 8 + (n + 7) / 8;  // header + count + data
+    b.v.resize(size + 1, 0);
+    b.v[1] = 1u << 4;
+    uint64_t nbit = 8;
+    nbit += 8 * encode_var(n, &b.v[2]);
+    for (uint64_t i = 0; i < n; i++) {
+      const size_t index = (size_t)(nbit >> 3);
+      if (src[i]) b.v[index + 1] |= (uint8_t)(128 >> (nbit & 7));
+      else b.v[index + 1] &= (uint8_t)~(128 >> (nbit & 7));
+      nbit++;
+    }
+    uint64_t length = nbit >> 3;
+    if (nbit & 7) length++;
+    b.v.resize(length + 1);
+  }
+  return emit_bytes(b, dst, cap);
+}
+// bool_without_compress_encode (boolean.rs:66-76)
+int64_t orc_bool_raw_encode(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap) {
+  Bytes b;
+  b.push(TSKV_ENC_NULL);
+  for (uint64_t i = 0; i < n; i++) b.push(src[i] ? 1 : 0);
+  return emit_bytes(b, dst, cap);
+}
 
 uint64_t orc_zigzag_encode(int64_t v) { return zz_enc(v); }
 int64_t orc_zigzag_decode(uint64_t v) { return zz_dec(v); }
@@ -720,6 +803,10 @@ tskv_status orc_decode_column(uint32_t phys_type, const uint8_t *data, uint64_t 
   if (enc > 11) enc = 15;  // Encoding::Unknown (codec.rs:119-137)
   const uint8_t *src = data + 1;
   size_t len = (size_t)data_len - 1;
+  if (phys_type == TSKV_PT_BOOL) {  // get_bool_codec (instance.rs:415-421): Null => bytes, everything else => bit-pack
+    if (enc == TSKV_ENC_NULL) return bool_raw_decode(src, len, bitset, n_rows, out_vals, out_valid);
+    return bool_bitpack_decode(src, len, bitset, n_rows, out_vals, out_valid);
+  }
   if (enc == TSKV_ENC_QUANTILE) return TSKV_ERR_UNSUPPORTED;  // pco: out of scope
   if (enc == TSKV_ENC_NULL) return raw_decode(src, len, bitset, n_rows, out_vals, out_valid);
   switch (phys_type) {

@@ -21,7 +21,7 @@ def lib():
         L = C.CDLL(path)
         vp = C.c_void_p
         for name in ("orc_simple8b_encode", "orc_simple8b_decode", "orc_ts_encode", "orc_i64_encode",
-                     "orc_f64_encode", "orc_raw_encode"):
+                     "orc_f64_encode", "orc_raw_encode", "orc_bool_encode", "orc_bool_raw_encode"):
             getattr(L, name).argtypes = [vp, C.c_uint64, vp, C.c_uint64]
             getattr(L, name).restype = C.c_int64
         L.orc_zigzag_encode.argtypes = [C.c_int64]
@@ -105,6 +105,14 @@ def f64_encode(v):
 
 def raw_encode(v):
     return _enc("orc_raw_encode", v, np.uint64)
+
+
+def bool_encode(v):
+    return _enc("orc_bool_encode", np.asarray(v, dtype=bool).astype(np.uint8), np.uint8)
+
+
+def bool_raw_encode(v):
+    return _enc("orc_bool_raw_encode", np.asarray(v, dtype=bool).astype(np.uint8), np.uint8)
 
 
 def decode_column(phys_type, data, n_rows, validity=None):

@@ -35,7 +35,7 @@ inline int64_t f64_okey(uint64_t b) { return (int64_t)(b ^ (((int64_t)b >> 63) &
 
 inline bool less_typed(uint8_t pt, uint64_t a, uint64_t b) {
   if (pt == TSKV_PT_I64) return (int64_t)a < (int64_t)b;
-  if (pt == TSKV_PT_U64) return a < b;
+  if (pt == TSKV_PT_U64 || pt == TSKV_PT_BOOL) return a < b;
   return f64_okey(a) < f64_okey(b);
 }
 

@@ -36,6 +36,8 @@ int64_t orc_ts_encode(const int64_t *src, uint64_t n, uint8_t *dst, uint64_t cap
 int64_t orc_i64_encode(const int64_t *src, uint64_t n, uint8_t *dst, uint64_t cap);  /* Delta=2 */
 int64_t orc_f64_encode(const double *src, uint64_t n, uint8_t *dst, uint64_t cap);   /* Gorilla=6 */
 int64_t orc_raw_encode(const uint64_t *src, uint64_t n, uint8_t *dst, uint64_t cap); /* Null=1 */
+int64_t orc_bool_encode(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap);     /* BitPack=10 (boolean.rs:24-64) */
+int64_t orc_bool_raw_encode(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap); /* Null=1 (boolean.rs:66-76) */
 /* Column decode with codec dispatch (tsm/reader.rs:658-731 + codec/instance.rs:358-401).
  * out_vals: n_rows 8-byte cells (0 for null rows); out_valid: n_rows bytes (0/1). */
 tskv_status orc_decode_column(uint32_t phys_type, const uint8_t *data, uint64_t data_len,
