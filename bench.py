@@ -515,7 +515,7 @@ def main():
     traffic = None
     if world == 1 and args.workload == "C4" and n_series == wl.default_series:
         try:  # DRAM bytes of the same launches from the committed `ncu --set full` capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_scan_ncu_summary.json")))["step_dram_traffic_bytes"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02b_scan_ncu_summary.json")))["step_dram_traffic_bytes"]
         except (OSError, ValueError, KeyError):
             pass
     roofline = {"bound": "hbm", "kernel": "k_scan_aggregate<TK,VK,SEL> (fused decode+filter+bucket-reduce), one launch "
@@ -529,7 +529,7 @@ def main():
                                 "ms": float(np.mean(dom_ms)), "page_bytes": int(dom_bytes),
                                 "gbs": dom_bytes / max(float(np.mean(dom_ms)), 1e-9) / 1e6},
                 "step_ms": float(np.mean(scan_ms)),
-                "bound_note": "issue-bound lane-per-page decode (see DESIGN.md section 5 and profiles/)"}
+                "bound_note": "integer-pipe-bound lane-per-page-part decode (see DESIGN.md section 5 and profiles/)"}
 
     # ---- end to end: pages in host memory, PCIe gather inside the timed region ---------------------
     # Page CRC32s are re-checked on the device after every transfer (what the reference does on every page read, and

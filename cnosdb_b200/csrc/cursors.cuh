@@ -160,7 +160,11 @@ __device__ __forceinline__ void ring_drain() { asm volatile("cp.async.commit_gro
 //   gorilla (GorillaRing): v = the value the next call returns, a = bit position of the following element (relative
 //                          to the stream's first bit), b = meaningful | trailing << 8 | cur_ok << 16 | any << 17
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t SKIP_ROWS = 128;
+#ifndef TSKV_SKIP_ROWS
+#define TSKV_SKIP_ROWS 128
+#endif
+constexpr uint32_t SKIP_ROWS = TSKV_SKIP_ROWS;  // a multiple of 32 (bitmap words)
+static_assert(SKIP_ROWS % 32 == 0 && SKIP_ROWS >= 32, "restart points sit on bitmap-word boundaries");
 constexpr uint32_t SKIP_NONE = 0xffffffffu;
 struct SkipEntry {
   uint64_t v;

@@ -65,6 +65,8 @@ struct tskv_pages {
   uint32_t n_cg = 0;
   uint32_t *d_cg_time_page = nullptr;
   uint32_t *d_cg_series_rank = nullptr;
+  uint32_t *d_series_sorted = nullptr;  // the page set's distinct series ids, ascending (rank -> id)
+  uint4 *d_item_info = nullptr;         // per item: page, column group, size, column id | type | kind
   uint32_t n_items = 0;
   uint32_t *d_item_page = nullptr;
   uint32_t *d_item_cg = nullptr;
@@ -120,6 +122,7 @@ struct tskv_scan {
   bool has_sel = false;  // any FIRST/LAST
   // device buffers
   uint32_t *d_series = nullptr;
+  int32_t *d_rank_slot = nullptr;  // rank of a series in the page set -> position in the selection list (or -1)
   int32_t *d_cg_slot = nullptr;
   uint8_t *d_item_flag = nullptr;
   uint32_t *d_block_count = nullptr;
@@ -319,7 +322,7 @@ tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_ou
 void free_scan(tskv_scan *s) {
   if (!s) return;
   cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
-  void *bufs[] = {s->d_series, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
+  void *bufs[] = {s->d_series, s->d_rank_slot, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
                   s->d_work_qcol, s->d_bin_cstart, s->d_cols, s->d_outs, s->d_means, s->d_state,
                   s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1], s->d_gathered, s->d_row_keep,
                   s->d_mcg_active, s->d_mvals, s->d_mvalid, s->d_mpage, s->d_mrow_off, s->d_mbm_off};
@@ -722,6 +725,13 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   if (e == cudaSuccess) e = up(&pg->d_time_page_of, time_page_of.data(), n_descs);
   if (e == cudaSuccess) e = up(&pg->d_cg_time_page, cg_time_page.data(), pg->n_cg);
   if (e == cudaSuccess) e = up(&pg->d_cg_series_rank, cg_rank.data(), pg->n_cg);
+  if (e == cudaSuccess) e = up(&pg->d_series_sorted, pg->series.data(), pg->series.size());
+  std::vector<uint4> item_info(pg->n_items);
+  for (uint32_t k = 0; k < pg->n_items; k++) {
+    const tskv_page_desc &d = pg->h_descs[item_page[k]];
+    item_info[k] = make_uint4(item_page[k], item_cg[k], d.size, (uint32_t)d.column_id | ((uint32_t)d.phys_type << 16) | ((uint32_t)d.reserved << 24));
+  }
+  if (e == cudaSuccess) e = up(&pg->d_item_info, item_info.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_item_page, item_page.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
@@ -802,6 +812,8 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_time_page_of);
   cudaFree(pg->d_cg_time_page);
   cudaFree(pg->d_cg_series_rank);
+  cudaFree(pg->d_series_sorted);
+  cudaFree(pg->d_item_info);
   cudaFree(pg->d_item_page);
   cudaFree(pg->d_item_cg);
   cudaFree(pg->d_bin_start);
@@ -1312,6 +1324,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       e = cudaMemcpyAsync(s->d_series, q->series_ids, (size_t)q->n_series * 4, cudaMemcpyHostToDevice, ctx->stream);
     h2d += (uint64_t)q->n_series * 4;
   }
+  if (e == cudaSuccess && q->series_ids) e = stream_alloc(ctx, &s->d_rank_slot, pages->series.size());
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_cg_slot, pages->n_cg);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_item_flag, n_items);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_block_count, s->n_blocks);
@@ -1684,9 +1697,15 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
   CU_TRY(ctx, cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream));
   uint64_t launches = 0;
   if (pages->n_cg) {
-    k_select_cg<<<(pages->n_cg + 255) / 256, 256, 0, ctx->stream>>>(pages->d_descs, pages->d_cg_time_page, pages->n_cg,
-                                                                     s->d_series, s->n_series_sel,
-                                                                     pages->d_cg_series_rank, s->d_cg_slot);
+    if (s->d_rank_slot) {
+      CU_TRY(ctx, cudaMemsetAsync(s->d_rank_slot, 0xff, pages->series.size() * 4, ctx->stream));
+      if (s->n_series_sel) {
+        k_select_ids<<<(s->n_series_sel + 255) / 256, 256, 0, ctx->stream>>>(pages->d_series_sorted, (uint32_t)pages->series.size(), s->d_series,
+                                                                         s->n_series_sel, s->d_rank_slot);
+        launches++;
+      }
+    }
+    k_select_cg<<<(pages->n_cg + 255) / 256, 256, 0, ctx->stream>>>(pages->n_cg, s->d_rank_slot, pages->d_cg_series_rank, s->d_cg_slot);
     launches++;
   }
   if (s->preds.n && pages->n_cg) {  // row filter: keep bits of every selected column group (host-resident pages: read in place)
@@ -1696,7 +1715,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
     launches++;
   }
   if (n_items) {
-    k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_page, pages->d_item_cg,
+    k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_info,
                                                         pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
                                                         s->n_cols, pages->d_bin_start, s->d_item_flag,
                                                         s->d_block_count, s->d_counters, s->d_status,
