@@ -1830,6 +1830,13 @@ static tskv_status sync_scan(tskv_ctx *ctx, tskv_scan *s) {
   ctx->counters.dominant_kernel_ms = 0;
   ctx->counters.dominant_kernel_bytes = 0;
   ctx->counters.dominant_kernel_bin = 0;
+  if (getenv("TSKV_DEBUG_BINS")) {  // (events of the un-captured pass: meaningful with TSKV_NO_GRAPH=1)
+    float pro = 0, epi = 0;
+    cudaEventElapsedTime(&pro, s->ev0, s->ev_bin[0]);
+    cudaEventElapsedTime(&epi, s->ev_bin[N_BINS], s->ev1);
+    fprintf(stderr, "[tskv] prologue (select, work list, init%s) %.3f ms, fused %.3f ms, epilogue %.3f ms\n",
+            s->merge.n_rows ? ", merge pass" : "", pro, fused, epi);
+  }
   for (int b = 0; b < N_BINS; b++) {
     if (!s->grid[b]) continue;
     float t = 0;
