@@ -228,6 +228,191 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint4 *item_info
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Work list driven by the SELECTION (round 2): one thread per selected series walks that series' column groups and
+// their field pages, so the cost follows the selection (C4: 10 % of the series) instead of the page set. Two passes
+// over the same walk - count per (decode-kind bin, query column) bucket, then place - with a block-local histogram in
+// shared memory so that the global atomics are one per (block, bucket). Inside a bucket the order is arbitrary (the
+// fused kernels only need warps that are homogeneous in codec and, for GROUP BY bucket, in column).
+// Same outputs as k_flag_items / k_scan_blocks / k_scatter_items: work_page / work_slot / work_qcol (bit 7 = "brings
+// the column group's time page": the first selected field page of each value class of a group), bin_cstart, the
+// reader counters, statistics pruning.
+// ------------------------------------------------------------------------------------------------
+constexpr int WL_THREADS = 256;
+constexpr int WL_MAX_BUCKETS = N_BINS * 128;
+struct WorkListArgs {
+  const tskv_page_desc *descs;
+  uint64_t n_descs;
+  const uint32_t *cg_time_page;  // [n_cg]
+  uint32_t n_cg;
+  const uint32_t *rank_cg_start; // [n_set_series + 1] CSR: column groups of the series with this rank
+  const uint32_t *rank_cg;
+  const uint8_t *page_bin;       // [n_descs] decode-kind bin of a field page
+  const uint32_t *set_series;    // the page set's distinct series ids, ascending
+  uint32_t n_set_series;
+  const uint32_t *series_ids;    // the selection (null: every series, slot = rank)
+  uint32_t n_sel;                // threads: selected ids, or n_set_series
+  const ColState *cols;
+  uint32_t n_cols;
+  const tskv_time_range *cg_bounds;  // statistics pruning (null: none)
+  PruneRanges prune;
+  const uint8_t *cg_merge;       // column groups of overlapping chunks go through the merge pass
+  uint32_t *bucket_count;        // [N_BINS * n_cols] totals (pass 1), then running cursors (pass 2)
+  uint32_t *bucket_off;          // [N_BINS * n_cols + 1] exclusive offsets (k_worklist_offsets)
+  uint32_t *work_page, *work_slot;
+  uint8_t *work_qcol;
+  unsigned long long *counters;  // [0] pages [1] bytes [2 + bin] bytes per bin [2 + N_BINS] pruned pages
+  int32_t *status;
+};
+
+// Walks the items of selected series i; F(page, bin, qcol, with_time, desc).
+template <typename F>
+__device__ __forceinline__ void worklist_walk(const WorkListArgs &A, uint32_t i, bool count_stats, F &&emit) {
+  uint32_t rank = i;
+  if (A.series_ids) {
+    const uint32_t id = __ldg(A.series_ids + i);
+    uint32_t lo = 0, hi = A.n_set_series;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(A.set_series + mid) < id) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= A.n_set_series || __ldg(A.set_series + lo) != id) return;  // a selected id this page set does not hold
+    rank = lo;
+  }
+  const uint32_t c0 = __ldg(A.rank_cg_start + rank), c1 = __ldg(A.rank_cg_start + rank + 1);
+  for (uint32_t k = c0; k < c1; k++) {
+    const uint32_t cg = __ldg(A.rank_cg + k);
+    if (A.cg_merge && A.cg_merge[cg]) continue;
+    bool in_time = true;
+    if (A.cg_bounds && A.prune.n) {  // TimeRange::overlaps against the group's statistics
+      const tskv_time_range b = A.cg_bounds[cg];
+      in_time = false;
+      for (uint32_t r = 0; r < A.prune.n; r++) in_time = in_time || (b.min_ts <= A.prune.r[r].max_ts && b.max_ts >= A.prune.r[r].min_ts);
+    }
+    const uint32_t tp = __ldg(A.cg_time_page + cg);
+    const uint64_t end = cg + 1 < A.n_cg ? (uint64_t)__ldg(A.cg_time_page + cg + 1) : A.n_descs;
+    uint32_t seen_classes = 0;  // value classes that already brought the time page
+    bool any = false;
+    for (uint64_t p = (uint64_t)tp + 1; p < end; p++) {
+      const tskv_page_desc d = A.descs[p];
+      const int qc = find_qcol(A.cols, A.n_cols, d.column_id);
+      if (qc < 0) continue;
+      if (!in_time) {
+        if (count_stats) atomicAdd(&A.counters[2 + N_BINS], 1ull);
+        continue;
+      }
+      if (A.cols[qc].phys_type != d.phys_type) {
+        atomicCAS(A.status, 0, TSKV_ERR_INVALID_ARG);
+        continue;
+      }
+      const uint32_t vclass = (uint32_t)value_class(d.reserved);
+      const bool with_time = !((seen_classes >> vclass) & 1);
+      seen_classes |= 1u << vclass;
+      emit((uint32_t)p, (uint32_t)A.page_bin[p], (uint32_t)qc, with_time, d, !any, tp);
+      any = true;
+    }
+  }
+}
+
+// Pass 1: bucket totals + the reader counters.
+__global__ void __launch_bounds__(WL_THREADS) k_worklist_count(const WorkListArgs A) {
+  extern __shared__ uint32_t s_hist[];  // [N_BINS * n_cols]
+  __shared__ unsigned long long s_pages, s_bytes[N_BINS];
+  const uint32_t n_buckets = N_BINS * A.n_cols;
+  for (uint32_t k = threadIdx.x; k < n_buckets; k += WL_THREADS) s_hist[k] = 0;
+  if (threadIdx.x == 0) s_pages = 0;
+  if (threadIdx.x < N_BINS) s_bytes[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * WL_THREADS + threadIdx.x;
+  if (i < A.n_sel)
+    worklist_walk(A, i, true, [&](uint32_t, uint32_t bin, uint32_t qc, bool, const tskv_page_desc &d, bool first_in_group, uint32_t tp) {
+      atomicAdd(&s_hist[bin * A.n_cols + qc], 1u);
+      // the reader metrics (page_read_count / page_read_bytes) count the time page once per column group
+      unsigned long long bytes = d.size, pages = 1;
+      if (first_in_group) { bytes += A.descs[tp].size; pages += 1; }
+      atomicAdd(&s_bytes[bin], bytes);
+      atomicAdd(&s_pages, pages);
+    });
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_buckets; k += WL_THREADS)
+    if (s_hist[k]) atomicAdd(&A.bucket_count[k], s_hist[k]);
+  if (threadIdx.x == 0 && s_pages) atomicAdd(&A.counters[0], s_pages);
+  if (threadIdx.x < N_BINS && s_bytes[threadIdx.x]) {
+    atomicAdd(&A.counters[1], s_bytes[threadIdx.x]);
+    atomicAdd(&A.counters[2 + threadIdx.x], s_bytes[threadIdx.x]);
+  }
+}
+
+// Exclusive offsets of the buckets (bin-major), bin_cstart, and the cursors reset for pass 2. One block.
+__global__ void k_worklist_offsets(uint32_t *bucket_count, uint32_t *bucket_off, uint32_t n_cols, uint32_t *bin_cstart) {
+  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_warp[32];
+  const uint32_t n_buckets = N_BINS * n_cols;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_buckets; base += blockDim.x) {
+    const uint32_t k = base + threadIdx.x;
+    const uint32_t v = k < n_buckets ? bucket_count[k] : 0;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, x, o);
+      if ((threadIdx.x & 31) >= (uint32_t)o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t w = threadIdx.x < (blockDim.x >> 5) ? s_warp[threadIdx.x] : 0;
+      uint32_t xs = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, xs, o);
+        if (threadIdx.x >= (uint32_t)o) xs += y;
+      }
+      s_warp[threadIdx.x] = xs - w;
+    }
+    __syncthreads();
+    const uint32_t excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
+    if (k < n_buckets) {
+      bucket_off[k] = excl;
+      bucket_count[k] = 0;  // pass 2's cursor
+      if (k % n_cols == 0) bin_cstart[k / n_cols] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    bucket_off[n_buckets] = s_carry;
+    bin_cstart[N_BINS] = s_carry;
+    bin_cstart[N_BINS + 1] = s_carry;  // total
+  }
+}
+
+// Pass 2: the same walk; a block reserves its share of every bucket with one atomic and places its items inside it.
+__global__ void __launch_bounds__(WL_THREADS) k_worklist_emit(const WorkListArgs A) {
+  extern __shared__ uint32_t s_hist[];  // [2][N_BINS * n_cols]: block counts -> block bases, and the running cursors
+  const uint32_t n_buckets = N_BINS * A.n_cols;
+  uint32_t *s_base = s_hist, *s_cur = s_hist + n_buckets;
+  for (uint32_t k = threadIdx.x; k < 2 * n_buckets; k += WL_THREADS) s_hist[k] = 0;
+  __syncthreads();
+  const uint32_t i = blockIdx.x * WL_THREADS + threadIdx.x;
+  if (i < A.n_sel)
+    worklist_walk(A, i, false, [&](uint32_t, uint32_t bin, uint32_t qc, bool, const tskv_page_desc &, bool, uint32_t) {
+      atomicAdd(&s_base[bin * A.n_cols + qc], 1u);
+    });
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_buckets; k += WL_THREADS)
+    if (s_base[k]) s_base[k] = A.bucket_off[k] + atomicAdd(&A.bucket_count[k], s_base[k]);
+  __syncthreads();
+  if (i < A.n_sel)
+    worklist_walk(A, i, false, [&](uint32_t page, uint32_t bin, uint32_t qc, bool with_time, const tskv_page_desc &, bool, uint32_t) {
+      const uint32_t key = bin * A.n_cols + qc;
+      const uint32_t pos = s_base[key] + atomicAdd(&s_cur[key], 1u);
+      A.work_page[pos] = page;
+      A.work_slot[pos] = i;
+      A.work_qcol[pos] = (uint8_t)(qc | (with_time ? 0x80 : 0));
+    });
+}
+
 // Host-resident arenas: pull the selected pages over PCIe into the device arena (same offsets).
 // One warp per work item, 16-byte coalesced loads from the mapped host range. Replaces the per-series
 // file reads of TsmReader::read_adjacent_pages (tsm/reader.rs:236-264).
@@ -1579,9 +1764,15 @@ struct StateLayout {
   uint64_t total;
 };
 
-__global__ void k_init_state(uint64_t *state, StateLayout L) {
+// Identities of the partial state; the same launch zeroes the scan's small per-pass scratch (task counters / status /
+// counters, bin starts, work-list buckets) so that a pass starts with ONE node instead of three memsets + a kernel.
+__global__ void k_init_state(uint64_t *state, StateLayout L, unsigned long long *aux, uint32_t aux_words, uint32_t *zero32,
+                             uint32_t n_zero32, uint32_t *zero32b, uint32_t n_zero32b) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = i; k < aux_words; k += stride) aux[k] = 0;
+  for (uint64_t k = i; k < n_zero32; k += stride) zero32[k] = 0;
+  for (uint64_t k = i; k < n_zero32b; k += stride) zero32b[k] = 0;
   for (uint64_t k = i; k < L.total; k += stride) {
     uint64_t v = 0;
     if (k >= L.min_off && k < L.min_off + L.min_len) v = 0x7fffffffffffffffull;

@@ -67,6 +67,8 @@ struct tskv_pages {
   uint32_t *d_cg_series_rank = nullptr;
   uint32_t *d_series_sorted = nullptr;  // the page set's distinct series ids, ascending (rank -> id)
   uint4 *d_item_info = nullptr;         // per item: page, column group, size, column id | type | kind
+  uint32_t *d_rank_cg_start = nullptr, *d_rank_cg = nullptr;  // CSR: series rank -> its column groups (arena order)
+  uint8_t *d_page_bin = nullptr;        // decode-kind bin of every field page
   uint32_t n_items = 0;
   uint32_t *d_item_page = nullptr;
   uint32_t *d_item_cg = nullptr;
@@ -123,6 +125,8 @@ struct tskv_scan {
   // device buffers
   uint32_t *d_series = nullptr;
   int32_t *d_rank_slot = nullptr;  // rank of a series in the page set -> position in the selection list (or -1)
+  uint32_t *d_bucket = nullptr;    // selection-driven work list: [N_BINS * n_cols] counts / cursors | [.. + 1] offsets
+  bool worklist_by_items = false;  // TSKV_WORKLIST=items: the round-1 pass over every field page of the page set
   int32_t *d_cg_slot = nullptr;
   uint8_t *d_item_flag = nullptr;
   uint32_t *d_block_count = nullptr;
@@ -322,7 +326,7 @@ tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_ou
 void free_scan(tskv_scan *s) {
   if (!s) return;
   cudaStream_t st = s->ctx ? s->ctx->stream : nullptr;
-  void *bufs[] = {s->d_series, s->d_rank_slot, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
+  void *bufs[] = {s->d_series, s->d_rank_slot, s->d_bucket, s->d_cg_slot, s->d_item_flag, s->d_block_count, s->d_work_page, s->d_work_slot,
                   s->d_work_qcol, s->d_bin_cstart, s->d_cols, s->d_outs, s->d_means, s->d_state,
                   s->d_task_counter, s->d_values, s->d_validity, s->d_gor_scratch[0], s->d_gor_scratch[1], s->d_gathered, s->d_row_keep,
                   s->d_mcg_active, s->d_mvals, s->d_mvalid, s->d_mpage, s->d_mrow_off, s->d_mbm_off};
@@ -662,6 +666,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
   std::vector<uint32_t> cg_rank(pg->n_cg);
   for (uint32_t cg = 0; cg < pg->n_cg; cg++)
     cg_rank[cg] = (uint32_t)(std::lower_bound(pg->series.begin(), pg->series.end(), pg->h_descs[cg_time_page[cg]].series_id) - pg->series.begin());
+  std::vector<uint8_t> page_bin(n_descs, 0);
   // sort items by (bin, column id, arena order): warps are homogeneous in codec and, for GROUP BY
   // bucket, lanes of a warp flush the same (column, bucket) cell in lock step.
   {
@@ -680,6 +685,7 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
         bin = tclass == TK_RLE ? BIN_COOP_RLE_GOR : BIN_COOP_S8B_GOR;
       key[k] = (bin << 48) | ((uint64_t)vd.column_id << 32) | k;
       order[k] = k;
+      page_bin[item_page[k]] = (uint8_t)bin;
     }
     std::sort(key.begin(), key.end());
     std::vector<uint32_t> ip(pg->n_items), ic(pg->n_items);
@@ -732,6 +738,16 @@ tskv_status tskvgpu_upload_pages(tskv_ctx *ctx, const uint8_t *arena, uint64_t a
     item_info[k] = make_uint4(item_page[k], item_cg[k], d.size, (uint32_t)d.column_id | ((uint32_t)d.phys_type << 16) | ((uint32_t)d.reserved << 24));
   }
   if (e == cudaSuccess) e = up(&pg->d_item_info, item_info.data(), pg->n_items);
+  {  // series rank -> its column groups (the selection-driven work list walks a selected series' groups)
+    std::vector<uint32_t> start(pg->series.size() + 1, 0), list(pg->n_cg);
+    for (uint32_t cg = 0; cg < pg->n_cg; cg++) start[cg_rank[cg] + 1]++;
+    for (size_t r = 0; r < pg->series.size(); r++) start[r + 1] += start[r];
+    std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+    for (uint32_t cg = 0; cg < pg->n_cg; cg++) list[cur[cg_rank[cg]]++] = cg;
+    if (e == cudaSuccess) e = up(&pg->d_rank_cg_start, start.data(), start.size());
+    if (e == cudaSuccess) e = up(&pg->d_rank_cg, list.data(), list.size());
+    if (e == cudaSuccess) e = up(&pg->d_page_bin, page_bin.data(), n_descs);
+  }
   if (e == cudaSuccess) e = up(&pg->d_item_page, item_page.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_item_cg, item_cg.data(), pg->n_items);
   if (e == cudaSuccess) e = up(&pg->d_bin_start, pg->h_bin_start, N_BINS + 1);
@@ -814,6 +830,9 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_cg_series_rank);
   cudaFree(pg->d_series_sorted);
   cudaFree(pg->d_item_info);
+  cudaFree(pg->d_rank_cg_start);
+  cudaFree(pg->d_rank_cg);
+  cudaFree(pg->d_page_bin);
   cudaFree(pg->d_item_page);
   cudaFree(pg->d_item_cg);
   cudaFree(pg->d_bin_start);
@@ -1325,6 +1344,11 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
     h2d += (uint64_t)q->n_series * 4;
   }
   if (e == cudaSuccess && q->series_ids) e = stream_alloc(ctx, &s->d_rank_slot, pages->series.size());
+  if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_bucket, (size_t)2 * N_BINS * q->n_columns + 1);
+  {
+    const char *wl = getenv("TSKV_WORKLIST");
+    s->worklist_by_items = wl && wl[0] == 'i';
+  }
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_cg_slot, pages->n_cg);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_item_flag, n_items);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_block_count, s->n_blocks);
@@ -1693,10 +1717,17 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
   }
   if (!capturing) cudaEventRecord(s->ev0, ctx->stream);
   unsigned long long *aux = reinterpret_cast<unsigned long long *>(s->d_task_counter);
-  CU_TRY(ctx, cudaMemsetAsync(aux, 0, 32 * 8, ctx->stream));
-  CU_TRY(ctx, cudaMemsetAsync(s->d_bin_cstart, 0, (N_BINS + 2) * 4, ctx->stream));
   uint64_t launches = 0;
-  if (pages->n_cg) {
+  {  // state identities + the pass's scratch (task counters / status / counters, bin starts, work-list buckets): one launch
+    const uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
+    k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl, aux, 32, s->d_bin_cstart, N_BINS + 2, s->d_bucket,
+                                                                   N_BINS * s->n_cols);
+    launches++;
+  }
+  // slot of every column group: the row filter, the merge pass and the item-driven work list need it per GROUP; the
+  // selection-driven work list finds a selected series' groups itself
+  const bool need_cg_slot = s->worklist_by_items || s->preds.n || (s->merge.n_rows && s->n_merge_pages);
+  if (pages->n_cg && need_cg_slot) {
     if (s->d_rank_slot) {
       CU_TRY(ctx, cudaMemsetAsync(s->d_rank_slot, 0xff, pages->series.size() * 4, ctx->stream));
       if (s->n_series_sel) {
@@ -1714,7 +1745,7 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
                                                                      s->preds, pages->d_keep_off, s->d_row_keep, s->d_status, s->d_err_page);
     launches++;
   }
-  if (n_items) {
+  if (n_items && s->worklist_by_items) {
     k_flag_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_descs, pages->d_item_info,
                                                         pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
                                                         s->n_cols, pages->d_bin_start, s->d_item_flag,
@@ -1726,10 +1757,38 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
                                                            s->d_work_page, s->d_work_slot, s->d_work_qcol,
                                                            s->d_bin_cstart, s->d_bin_cstart + N_BINS + 1);
     launches += 3;
+  } else if (n_items) {
+    WorkListArgs A{};
+    A.descs = pages->d_descs;
+    A.n_descs = pages->n_descs;
+    A.cg_time_page = pages->d_cg_time_page;
+    A.n_cg = pages->n_cg;
+    A.rank_cg_start = pages->d_rank_cg_start;
+    A.rank_cg = pages->d_rank_cg;
+    A.page_bin = pages->d_page_bin;
+    A.set_series = pages->d_series_sorted;
+    A.n_set_series = (uint32_t)pages->series.size();
+    A.series_ids = s->d_series;
+    A.n_sel = s->d_series ? s->n_series_sel : (uint32_t)pages->series.size();
+    A.cols = s->d_cols;
+    A.n_cols = s->n_cols;
+    A.cg_bounds = s->prune.n ? pages->d_cg_bounds : nullptr;
+    A.prune = s->prune;
+    A.cg_merge = pages->d_cg_merge;
+    const uint32_t n_buckets = N_BINS * s->n_cols;
+    A.bucket_count = s->d_bucket;
+    A.bucket_off = s->d_bucket + n_buckets;
+    A.work_page = s->d_work_page;
+    A.work_slot = s->d_work_slot;
+    A.work_qcol = s->d_work_qcol;
+    A.counters = s->d_counters;
+    A.status = s->d_status;
+    const uint32_t wblocks = std::max(1u, (A.n_sel + WL_THREADS - 1) / WL_THREADS);
+    if (A.n_sel) k_worklist_count<<<wblocks, WL_THREADS, n_buckets * 4, ctx->stream>>>(A);
+    k_worklist_offsets<<<1, 256, 0, ctx->stream>>>(s->d_bucket, s->d_bucket + n_buckets, s->n_cols, s->d_bin_cstart);
+    if (A.n_sel) k_worklist_emit<<<wblocks, WL_THREADS, 2 * n_buckets * 4, ctx->stream>>>(A);
+    launches += 3;
   }
-  uint32_t init_blocks = (uint32_t)std::min<uint64_t>((s->sl.total + 255) / 256, 4096);
-  k_init_state<<<std::max(1u, init_blocks), 256, 0, ctx->stream>>>(s->d_state, s->sl);
-  launches++;
   if (s->merge.n_rows && s->n_merge_pages) {  // overlapping chunks: decode the query's columns, merge + aggregate per row
     CU_TRY(ctx, cudaMemsetAsync(s->d_mvalid, 0, (size_t)s->n_cols * s->merge.bm_words * 4, ctx->stream));
     const uint32_t dblocks = (uint32_t)(((uint64_t)s->n_merge_pages * 32 + DECODE_THREADS - 1) / DECODE_THREADS);
