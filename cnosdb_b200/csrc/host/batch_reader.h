@@ -37,7 +37,7 @@ struct TimeRange {  // closed interval
   }
 };
 
-enum class PhysicalDType : uint8_t { Time = TSKV_PT_TIME, Integer = TSKV_PT_I64, Unsigned = TSKV_PT_U64, Float = TSKV_PT_F64 };
+enum class PhysicalDType : uint8_t { Time = TSKV_PT_TIME, Integer = TSKV_PT_I64, Unsigned = TSKV_PT_U64, Float = TSKV_PT_F64, Boolean = TSKV_PT_BOOL };
 
 struct TableColumn {
   ColumnId id;

@@ -21,6 +21,7 @@ pub const TSKV_PT_TIME: u8 = 0;
 pub const TSKV_PT_I64: u8 = 1;
 pub const TSKV_PT_U64: u8 = 2;
 pub const TSKV_PT_F64: u8 = 3;
+pub const TSKV_PT_BOOL: u8 = 4;
 
 pub const TSKV_AGG_COUNT: u8 = 1 << 0;
 pub const TSKV_AGG_SUM: u8 = 1 << 1;

@@ -176,3 +176,29 @@ def test_cut_and_whole_scans_agree_bit_for_bit_on_integers(engine, monkeypatch):
             if r.names[j][1] != "mean":
                 assert (r.values[j] == ref.values[j]).all(), (parts, r.names[j])
     pages.close()
+
+
+def test_item_driven_work_list_still_agrees(engine, monkeypatch):
+    """TSKV_WORKLIST=items: the round-1 work list (every field page of the page set flagged, ordered compaction) must
+    give what the selection-driven one gives - with a selection list, without one, with pruning and a row filter."""
+    g = datagen.generate(4000, n_fields=2, n_points=700, value_kind=datagen.MIXED, seed=77, jitter_permille=300, jitter_max=999_999,
+                         null_page_permille=100, null_row_permille=80)
+    pages = engine.upload_pages(g.arena, g.descs)
+    w = 60_000_000_000
+    fbs, nb = bucket_spec(datagen.TSBS_T0 - 1_000_000, datagen.TSBS_T0 + 999 * datagen.TSBS_STEP + 1_000_000, w)
+    cols = [PushedAggregate(1, cabi.TSKV_PT_I64, AGGS + ("first", "last")), PushedAggregate(3, cabi.TSKV_PT_F64, AGGS)]
+    t0, st = datagen.TSBS_T0, datagen.TSBS_STEP
+    for sel in (np.arange(0, 4000, 7, dtype=np.uint32), None):
+        for kw in (dict(), dict(time_ranges=[(t0 + 100 * st, t0 + 300 * st)]), dict(predicates=[(1, cabi.TSKV_PT_I64, ">", 10)])):
+            q = QueryOption(cols, series_ids=sel, width=w, first_bucket_start=fbs, n_buckets=nb, **kw)
+            exp = orc.scan_aggregate(g.arena, g.descs, q, n_threads=8)
+            for mode in ("items", "series"):
+                monkeypatch.setenv("TSKV_WORKLIST", mode)
+                got = engine.scan_aggregate(pages, q)
+                assert_results_equal(got, exp, what="work list %s sel=%s %s" % (mode, sel is not None, kw))
+                c = engine.counters()
+                if mode == "items":
+                    ref_counts = (c["page_read_count"], c["page_read_bytes"], c["pruned_page_count"])
+                else:
+                    assert (c["page_read_count"], c["page_read_bytes"], c["pruned_page_count"]) == ref_counts
+    pages.close()
