@@ -515,7 +515,7 @@ def main():
     traffic = None
     if world == 1 and args.workload == "C4" and n_series == wl.default_series:
         try:  # DRAM bytes of the same launches from the committed `ncu --set full` capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02b_scan_ncu_summary.json")))["step_dram_traffic_bytes"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02c_scan_ncu_summary.json")))["step_dram_traffic_bytes"]
         except (OSError, ValueError, KeyError):
             pass
     roofline = {"bound": "hbm", "kernel": "k_scan_aggregate<TK,VK,SEL> (fused decode+filter+bucket-reduce), one launch "
