@@ -239,7 +239,6 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint4 *item_info
 // reader counters, statistics pruning.
 // ------------------------------------------------------------------------------------------------
 constexpr int WL_THREADS = 256;
-constexpr int WL_MAX_BUCKETS = N_BINS * 128;
 struct WorkListArgs {
   const tskv_page_desc *descs;
   uint64_t n_descs;

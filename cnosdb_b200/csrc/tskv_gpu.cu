@@ -1356,8 +1356,11 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   if (e == cudaSuccess && q->series_ids) e = stream_alloc(ctx, &s->d_rank_slot, pages->series.size());
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_bucket, (size_t)2 * N_BINS * q->n_columns + 1);
   {
+    // One thread walks ALL column groups of a selected series: right for many series with a few groups each (TSBS
+    // shapes), serial for a handful of series with thousands of groups (one host over a year) - those take the pass
+    // over every field page instead, which is parallel in the pages. TSKV_WORKLIST=items / series forces one.
     const char *wl = getenv("TSKV_WORKLIST");
-    s->worklist_by_items = wl && wl[0] == 'i';
+    s->worklist_by_items = wl ? wl[0] == 'i' : (uint64_t)pages->n_cg > 32ull * std::max<uint64_t>(1, pages->series.size());
   }
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_cg_slot, pages->n_cg);
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_item_flag, n_items);

@@ -202,3 +202,30 @@ def test_item_driven_work_list_still_agrees(engine, monkeypatch):
                 else:
                     assert (c["page_read_count"], c["page_read_bytes"], c["pruned_page_count"]) == ref_counts
     pages.close()
+
+
+def test_few_series_with_many_column_groups(engine):
+    """3 series x 90 column groups: the work list is built by the pass over the field pages (a thread per selected series
+    would walk 90 groups serially); same results as the oracle either way."""
+    rng = np.random.default_rng(8)
+    b = datagen.ArenaBuilder()
+    for sid in (4, 9, 11):
+        t = 1_000_000
+        for _ in range(90):
+            n = int(rng.integers(1, 400))
+            ts = t + np.arange(n, dtype=np.int64) * 1000
+            t = int(ts[-1]) + 1000
+            b.add_column_group(sid, ts, [(1, cabi.TSKV_PT_I64, np.cumsum(rng.integers(-9, 10, n)), rng.random(n) > 0.1),
+                                         (2, cabi.TSKV_PT_F64, np.cumsum(rng.integers(-3, 4, n)) + rng.random(n), None)])
+    arena, descs = b.finish()
+    pages = engine.upload_pages(arena, descs)
+    fbs, nb = bucket_spec(1_000_000, 1_000_000 + 90 * 400 * 1000, 500_000)
+    for sel in (None, np.array([4, 11], dtype=np.uint32)):
+        for ranges in ([], [(1_000_000 + 3_000_000, 1_000_000 + 9_000_000)]):
+            q = make_query(FIELDS[:2], aggs=AGGS + ("first", "last"), series_ids=sel, time_ranges=ranges, width=500_000, first_bucket_start=fbs,
+                           n_buckets=nb, group_by_series=True)
+            got = engine.scan_aggregate(pages, q)
+            exp, pts = orc.scan_aggregate(arena, descs, q, return_points=True)
+            assert_results_equal(got, exp, what="many groups sel=%s %s" % (sel is not None, ranges))
+            assert engine.counters()["points_decoded"] == pts
+    pages.close()
