@@ -9,7 +9,10 @@
  * (integer.rs:438-483), the zig-zag table (integer.rs:270-280), simple8b encoded lengths
  * (simple8b.rs:232-252), every round-trip corpus of timestamp.rs / integer.rs / simple8b.rs /
  * float.rs, the time_window known-answer tuples (time_window.rs:318-368) and the SQL goldens of
- * sqllogicaltests/cases/function/common/ .slt files.  The reference itself (Rust) cannot be compiled in
+ * sqllogicaltests/cases/function/common/ .slt files; the overlap merge against the three tables of
+ * reader/sort_merge.rs:449-539 and the grouping table of reader/utils.rs:330-353 (tests/test_oracle_merge.py); the
+ * boolean codec against the vectors of tsm/codec/boolean.rs:150-260 (tests/test_oracle_bool.py).
+ * The reference itself (Rust) cannot be compiled in
  * this image (no rustc/cargo), so there is no oracle/_ref build.
  *
  * All citations are relative to /root/reference.
