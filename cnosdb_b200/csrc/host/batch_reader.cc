@@ -2,6 +2,7 @@
 #include "batch_reader.h"
 
 #include <algorithm>
+#include <functional>
 #include <map>
 
 namespace tskv {
@@ -64,6 +65,7 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
   TskvResult<SendableTskvRecordBatchStream> out;
   // ---- descriptor table: column group by column group, time page first (column_group.rs:9-17) --------
   std::vector<tskv_page_desc> descs;
+  std::vector<uint64_t> cg_files;  // file id of every column group handed to the engine
   TimeRange data_range = TimeRange::none();
   pruned_column_groups_ = 0;
   for (const ColumnGroup &cg : column_groups_) {
@@ -75,6 +77,7 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
       continue;
     }
     data_range.merge(cg.time_range());
+    cg_files.push_back(cg.file_id());
     for (const PageWriteSpec &p : cg.pages()) {
       tskv_page_desc d{};
       d.offset = p.offset;
@@ -154,6 +157,15 @@ TskvResult<SendableTskvRecordBatchStream> GpuAggregateBatchReader::process() {
   }
   if (!tombstones_.empty()) {
     st = tskvgpu_pages_set_tombstones(ctx, pages, tombstones_.data(), tombstones_.size());
+    if (st != TSKV_OK) {
+      out.error = engine_->last_error(st);
+      tskvgpu_pages_destroy(ctx, pages);
+      return out;
+    }
+  }
+  // chunks of several files (build_series_reader, reader/iterator.rs:463-560): overlapping ones are merged on the device
+  if (std::adjacent_find(cg_files.begin(), cg_files.end(), std::not_equal_to<uint64_t>()) != cg_files.end()) {
+    st = tskvgpu_pages_set_chunk_files(ctx, pages, cg_files.data(), cg_files.size());
     if (st != TSKV_OK) {
       out.error = engine_->last_error(st);
       tskvgpu_pages_destroy(ctx, pages);

@@ -64,8 +64,13 @@ class ColumnGroup {
   const std::vector<PageWriteSpec> &pages() const { return pages_; }
   void push(PageWriteSpec page) { pages_.push_back(std::move(page)); }  // time page first, then fields by column id
   size_t row_len() const { return pages_.empty() ? 0 : pages_.front().meta.num_values; }
+  // ColumnFile::file_id() of the file (or memcache) this group's chunk lives in. Column groups of one series with
+  // different file ids are chunks of different files: overlapping ones are merged (DataMerger, reader/merge.rs).
+  uint64_t file_id() const { return file_id_; }
+  void set_file_id(uint64_t id) { file_id_ = id; }
 
  private:
+  uint64_t file_id_ = 0;
   uint64_t column_group_id_;
   SeriesId series_id_;
   TimeRange time_range_;

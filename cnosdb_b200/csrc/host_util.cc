@@ -95,6 +95,21 @@ void plan_serial_grids(int n_bins, const double *chunks, const double *t_chunk, 
     if (chunks[b] > 0) grid_out[b] = std::max(1, (int)std::max(1.0, blocks_for(b, best)));
 }
 
+uint32_t plan_parts_wanted(double est_chunks, double resident_warps, double target) {
+  if (est_chunks <= 0) return 1;
+  return (uint32_t)std::min(4096.0, std::max(1.0, std::ceil(target * resident_warps / est_chunks)));
+}
+
+uint32_t plan_bin_parts(uint32_t maxrows, uint32_t skip_rows, uint32_t want, uint32_t *part_rows) {
+  *part_rows = 0;
+  if (maxrows <= skip_rows || want <= 1) return 1;
+  const uint32_t units = (maxrows + skip_rows - 1) / skip_rows;       // restart intervals of the longest page
+  const uint32_t w = std::min(want, units);
+  const uint32_t m = (units + w - 1) / w;                              // intervals per part
+  *part_rows = m * skip_rows;
+  return (units + m - 1) / m;
+}
+
 void plan_overlap_groups(uint64_t n_cg, const uint32_t *cg_series, const uint32_t *cg_rows, const tskv_time_range *cg_bounds,
                          const uint64_t *cg_file, OverlapPlan *out) {
   *out = OverlapPlan{};

@@ -51,6 +51,13 @@ uint32_t plan_gorilla_group(double est_gorilla_pages, double resident_warps);
 void plan_serial_grids(int n_bins, const double *chunks, const double *t_chunk, const int *occ, int sm_count,
                        int warps_per_block, int *grid_out);
 
+// Pages cut at restart points: how many parts per page a scan wants so that it has about `target` chunks (32 pages x
+// 1 part) per resident warp - est_chunks = the scan's chunks with whole pages.
+uint32_t plan_parts_wanted(double est_chunks, double resident_warps, double target);
+// Parts of a bin whose longest page has `maxrows` rows when `want` parts are wanted: parts are whole multiples of the
+// restart interval (`skip_rows` rows), at most one part per interval. Returns the parts; *part_rows = rows per part.
+uint32_t plan_bin_parts(uint32_t maxrows, uint32_t skip_rows, uint32_t want, uint32_t *part_rows);
+
 uint8_t classify_page(const PageHeader &h, uint8_t phys_type);
 
 // ---- overlapping chunks (reader/iterator.rs:463-560, reader/utils.rs:77-107) --------------------------------------

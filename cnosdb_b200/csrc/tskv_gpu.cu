@@ -1514,25 +1514,22 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
       for (int b = 0; b < N_BINS; b++) est_chunks += std::ceil((pages->h_bin_start[b + 1] - pages->h_bin_start[b]) * sel_frac / 32.0);
       const double resident_warps = (double)ctx->sm_count * SCAN_MIN_BLOCKS * (SCAN_THREADS / 32);
       const char *pt_env = getenv("TSKV_PARTS_TARGET");
-      const double target = (pt_env ? atof(pt_env) : 4.0) * resident_warps;
-      uint32_t want = est_chunks > 0 ? (uint32_t)std::min(4096.0, std::ceil(target / est_chunks)) : 1u;
+      uint32_t want = plan_parts_wanted(est_chunks, resident_warps, pt_env ? atof(pt_env) : 4.0);
       const char *parts_env = getenv("TSKV_PARTS");  // fixed number of parts (1 = never cut)
       if (parts_env) want = (uint32_t)std::max(1, atoi(parts_env));
       for (int b = 0; b < N_BINS; b++) {
         const int sb = serial_bin_of(b);
-        const uint32_t maxrows = pages->h_bin_maxrows[b];
-        if (s->use_coop[b] || sb / N_VK == TK_GEN || sb % N_VK == VK_GEN || maxrows <= SKIP_ROWS || want <= 1) continue;
-        const uint32_t units = (maxrows + SKIP_ROWS - 1) / SKIP_ROWS;           // restart intervals of the longest page
+        if (s->use_coop[b] || sb / N_VK == TK_GEN || sb % N_VK == VK_GEN) continue;
         uint32_t want_b = want;
         if (sb / N_VK == TK_S8B) {  // TSKV_PARTS_TS: another number of parts for the simple8b-timestamp bins (their rows cost
           // ~1.6 x the rows of RLE-timestamp pages; measured on C4 and C4 / 2: twice the parts changes nothing, 0.793 vs 0.770 ms)
           const char *ts_env = getenv("TSKV_PARTS_TS");
           if (ts_env) want_b = (uint32_t)std::max(1, atoi(ts_env));
         }
-        const uint32_t m = (units + std::min(want_b, units) - 1) / std::min(want_b, units);  // intervals per part
-        parts[b] = (units + m - 1) / m;
+        uint32_t part_rows = 0;
+        parts[b] = plan_bin_parts(pages->h_bin_maxrows[b], SKIP_ROWS, want_b, &part_rows);
         P.bin_parts[b] = parts[b];
-        P.bin_part_rows[b] = m * SKIP_ROWS;
+        P.bin_part_rows[b] = part_rows;
       }
     }
     double w[N_BINS], wsum = 0, need_sum = 0, occ_weighted = 0;

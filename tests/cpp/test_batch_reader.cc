@@ -155,6 +155,79 @@ int main() {
     CHECK(none_reader.pruned_column_groups() == (uint64_t)n_series && none_reader.metrics().page_read_count == 0);
     CHECK(reader.pruned_column_groups() == 0);
   }
+  // ---- overlapping chunks (DataMerger, reader/merge.rs): a "delta file" (file id 2) rewrites rows 100..199 of the first
+  //      selected series and adds 50 rows after its end; the merged scan must equal the oracle's merge ------------------
+  {
+    tskv::Bytes arena2 = arena;
+    std::vector<ColumnGroup> cgs2 = cgs;
+    std::vector<tskv_page_desc> descs2 = descs;
+    std::vector<uint64_t> files(cgs.size(), 1);
+    const int m = 150;
+    std::vector<int64_t> ts(m), iv(m);
+    for (int i = 0; i < m; i++) {
+      ts[i] = t0 + (i < 100 ? 100 + i : 500 + (i - 100)) * step;  // rows 100..199 get series 100's exact (jittered) times below
+      iv[i] = 1000000 + i;
+    }
+    // series 100 is s = 0, which has jittered timestamps: take the exact timestamps of its rows 100..199 from the page we wrote
+    {
+      uint64_t sd = 7;
+      auto r2 = [&]() { sd = sd * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(sd >> 33); };
+      (void)r2();  // v
+      for (int i = 0; i < n; i++) {
+        const int64_t t = t0 + i * step + (int64_t)(r2() % 1000);
+        (void)r2(); (void)r2();
+        if (i >= 100 && i < 200) ts[i - 100] = t;
+      }
+    }
+    ColumnGroup cg((uint64_t)cgs.size(), (SeriesId)100);
+    cg.set_file_id(2);
+    cg.time_range_merge(TimeRange{ts.front(), ts.back()});
+    auto add2 = [&](const tskv::Bytes &data, ColumnId id, const char *name, PhysicalDType pt) {
+      while (arena2.size() & 15) arena2.push_back(0);
+      uint64_t off = arena2.size();
+      tskv::append_page(nullptr, m, data, arena2);
+      cg.push(PageWriteSpec{off, arena2.size() - off, PageMeta{(uint32_t)m, TableColumn{id, name, pt}}});
+      descs2.push_back(tskv_page_desc{off, (uint32_t)(arena2.size() - off), (uint32_t)m, 100u, id, (uint8_t)pt, 0});
+    };
+    tskv::Bytes d;
+    tskv::encode_timestamps(ts.data(), m, d); add2(d, 0, "time", PhysicalDType::Time);
+    d.clear(); tskv::encode_integers(iv.data(), m, d); add2(d, 1, "usage_user", PhysicalDType::Integer);
+    for (ColumnGroup &c : cgs2) c.set_file_id(1);
+    cgs2.push_back(cg);
+    files.push_back(2);
+    QueryOption mo = opt;
+    mo.time_ranges.clear();
+    mo.aggregates = {{AggregateKind::Count, 1}, {AggregateKind::Sum, 1}, {AggregateKind::Max, 1}, {AggregateKind::Count, 2}};
+    GpuAggregateBatchReader mreader(eng.value, arena2.data(), arena2.size(), cgs2, mo);
+    auto mres = mreader.process();
+    CHECK(mres.ok() && mres.value.size() == 1);
+    const RecordBatch &mb = mres.value[0];
+    tskv_agg_column mcols[2] = {{1, TSKV_PT_I64, (uint8_t)(TSKV_AGG_COUNT | TSKV_AGG_SUM | TSKV_AGG_MAX)}, {2, TSKV_PT_F64, (uint8_t)TSKV_AGG_COUNT}};
+    tskv_query mq{};
+    mq.series_ids = sel.data(); mq.n_series = (uint32_t)sel.size();
+    mq.origin = 0; mq.width = w;
+    mq.first_bucket_start = (int64_t)mb.columns[0].values[0];
+    mq.n_buckets = (uint32_t)mb.num_rows;
+    mq.columns = mcols; mq.n_columns = 2;
+    tskv_output_layout ML{};
+    CHECK(orc_query_output_layout(descs2.data(), descs2.size(), &mq, &ML) == TSKV_OK);
+    std::vector<uint64_t> mv(ML.n_out * ML.n_cells);
+    std::vector<uint8_t> mbm(ML.validity_bytes);
+    orc_handle *H = nullptr;
+    CHECK(orc_open(arena2.data(), arena2.size(), descs2.data(), descs2.size(), 1, &H) == TSKV_OK);
+    CHECK(orc_set_chunk_files(H, files.data(), files.size()) == TSKV_OK);
+    CHECK(orc_scan(H, &mq, nullptr, 0, 1, mv.data(), mbm.data(), nullptr) == TSKV_OK);
+    orc_close(H);
+    // oracle output order: col1 {count, sum, max}, col2 {count}; batch: time, count(1), sum(1), max(1), count(2)
+    uint64_t total_rows = 0;
+    for (int k = 0; k < 4; k++)
+      for (uint64_t i = 0; i < ML.n_cells; i++) {
+        CHECK(mb.columns[1 + k].is_valid(i) == (bool)((mbm[k * ML.bitmap_stride + (i >> 3)] >> (i & 7)) & 1));
+        if (mb.columns[1 + k].is_valid(i)) CHECK(mb.columns[1 + k].values[i] == mv[k * ML.n_cells + i]);
+        if (k == 0) total_rows += mb.columns[1].values[i];
+      }
+    CHECK(total_rows == (uint64_t)(n_series / 2) * n + 50);  // 100 rewritten rows collapse, 50 are new
+  }
   // ---- error behaviour: a corrupted page surfaces TsmPageFileHashCheckFailed, not a crash ----------------
   tskv::Bytes bad = arena;
   bad[cgs[0].pages()[1].offset + cgs[0].pages()[1].size - 1] ^= 0x10;

@@ -113,3 +113,33 @@ def test_overlap_groups_follow_the_reference_grouping():
     # touching ranges overlap (min_ts <= running max), disjoint ones do not
     assert plan([1, 1], [3, 3], [(0, 5), (5, 9)], [1, 2])[0].tolist() == [1, 1]
     assert plan([1, 1], [3, 3], [(0, 5), (6, 9)], [1, 2])[0].tolist() == [0, 0]
+
+
+def test_page_parts_follow_the_selection_size():
+    """Pages cut at restart points: about 4 chunks per resident warp. C4 on one GPU (3 125 chunks of whole pages on
+    2 368 warp slots) -> 4 parts of 256 rows; an eighth of it -> one part per 128-row restart interval; C3 (31 k chunks)
+    -> whole pages; parts are whole multiples of the interval and never more than the intervals of the longest page."""
+    L = lib()
+    L.tskvplan_parts_wanted.argtypes = [C.c_double, C.c_double, C.c_double]
+    L.tskvplan_parts_wanted.restype = C.c_uint32
+    L.tskvplan_bin_parts.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.tskvplan_bin_parts.restype = C.c_uint32
+
+    def bin_parts(maxrows, want, skip=128):
+        pr = C.c_uint32(0)
+        return L.tskvplan_bin_parts(maxrows, skip, want, C.byref(pr)), pr.value
+
+    warps = 148 * 4 * 4
+    assert L.tskvplan_parts_wanted(3125.0, float(warps), 4.0) == 4
+    assert L.tskvplan_parts_wanted(391.0, float(warps), 4.0) == 25
+    assert L.tskvplan_parts_wanted(31250.0, float(warps), 4.0) == 1
+    assert L.tskvplan_parts_wanted(0.0, float(warps), 4.0) == 1
+    assert bin_parts(1000, 4) == (4, 256)
+    assert bin_parts(1000, 25) == (8, 128)
+    assert bin_parts(1000, 3) == (3, 384)          # 8 intervals in parts of 3: 3 + 3 + 2
+    assert bin_parts(1000, 1) == (1, 0) and bin_parts(128, 8) == (1, 0) and bin_parts(129, 8) == (2, 128)
+    assert bin_parts(102_400, 64) == (62, 1664)    # 800 intervals, 13 per part
+    for maxrows in (129, 255, 1000, 1024, 1025, 50_000):
+        for want in (2, 3, 5, 8, 64, 4096):
+            parts, rows = bin_parts(maxrows, want)
+            assert rows % 128 == 0 and parts * rows >= maxrows and (parts - 1) * rows < maxrows and parts <= max(want, 1)
