@@ -216,4 +216,39 @@ k_decode_warp(const uint8_t *arena, const tskv_page_desc *descs, uint64_t first_
   }
 }
 
+// Value statistics of every field page (what the reference keeps in PageMeta.statistics, tsm/page.rs:599-613): min / max
+// of the non-null (f64: non-NaN) values as ordered keys (stats_key, scan_kernels.cuh), once per page set, for the
+// value-statistics pruning of scans with field predicates. One lane per page, the serial cursors.
+__global__ void k_page_stats(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs, int64_t *stats) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_descs) return;
+  const tskv_page_desc d = descs[p];
+  int64_t kmin = INT64_MAX, kmax = INT64_MIN;
+  bool ok = d.phys_type != TSKV_PT_TIME && kind_status(d.reserved) == TSKV_OK;
+  if (ok) {
+    PageView pv;
+    pv.open(arena, d);
+    BitCursor bits;
+    bits.init(pv.bitset);
+    AnyCursor<> cur;
+    ok = cur.open(pv, d.reserved) == TSKV_OK;
+    const bool allnull = d.reserved == DK_ALLNULL;
+    for (uint32_t r = 0; r < d.num_values && ok; r++) {
+      if (bits.next(r) && !allnull) {
+        const uint64_t v = cur.next();
+        if (cur.failed()) { ok = false; break; }
+        if (d.phys_type == TSKV_PT_F64 && (v & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) continue;  // NaN: never TRUE
+        const int64_t k = stats_key(v, d.phys_type);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
+      } else if (r == 0 && !cur.is_gorilla) {
+        cur.d.skip_first_if_s8b_sc();
+      }
+    }
+  }
+  if (!ok) { kmin = INT64_MIN; kmax = INT64_MAX; }  // unknown: nothing can be ruled out
+  stats[2 * p] = kmin;
+  stats[2 * p + 1] = kmax;
+}
+
 }  // namespace tskv

@@ -138,6 +138,59 @@ __global__ void k_select_cg(uint32_t n_cg, const int32_t *rank_slot, const uint3
   cg_slot[cg] = rank_slot ? rank_slot[rank] : (int32_t)rank;  // no selection list: every series, slot = rank
 }
 
+// The pushed field predicates of a query (row filter: k_row_filter; value-statistics pruning: below).
+struct PredicateSet {
+  tskv_field_predicate p[TSKV_MAX_PREDICATES];
+  uint32_t n;
+  uint32_t pad;
+};
+
+// ---- value-statistics pruning (filter_column_groups with PageMeta.statistics, tskv/src/reader/chunk.rs:12-50 +
+// reader/column_group/statistics.rs:11-80: PruningPredicate over the pages' min / max) ------------------------------
+// Per field page: {min key, max key} of its non-null (f64: non-NaN) values as ordered i64 keys (okey; -0.0 counted as
+// +0.0 so that key order = numeric order). No such value: {INT64_MAX, INT64_MIN}. A page that did not decode:
+// {INT64_MIN, INT64_MAX} = nothing can be ruled out (the scan reports its error). Built once per page set, on the first
+// scan that carries field predicates (k_page_stats); the reference keeps the same numbers in PageMeta.statistics.
+__host__ __device__ inline int64_t stats_key(uint64_t v, uint8_t pt) {
+  if (pt == TSKV_PT_F64 && v == 0x8000000000000000ull) v = 0;  // -0.0 == +0.0
+  uint64_t flip = pt == TSKV_PT_U64 ? 0x8000000000000000ull
+                  : pt == TSKV_PT_F64 ? (uint64_t)(((int64_t)v >> 63) & 0x7fffffffffffffffll)
+                                      : 0ull;
+  return (int64_t)(v ^ flip);
+}
+// Can NO value in [kmin, kmax] satisfy `value <op> constant`? (what PruningPredicate derives from min / max)
+__host__ __device__ inline bool stats_rule_out(uint8_t pt, uint8_t op, uint64_t constant, int64_t kmin, int64_t kmax) {
+  if (pt == TSKV_PT_F64) {
+    const uint64_t a = constant & 0x7fffffffffffffffull;
+    if (a > 0x7ff0000000000000ull) return true;  // NaN constant: the comparison is never TRUE
+  }
+  if (kmin > kmax) return true;                  // no value at all: every row is NULL, never TRUE
+  const int64_t kc = stats_key(constant, pt);
+  switch (op) {
+    case TSKV_CMP_EQ: return kc < kmin || kc > kmax;
+    case TSKV_CMP_NE: return kmin == kmax && kmin == kc;
+    case TSKV_CMP_LT: return kmin >= kc;
+    case TSKV_CMP_LE: return kmin > kc;
+    case TSKV_CMP_GT: return kmax <= kc;
+    case TSKV_CMP_GE: return kmax < kc;
+    default: return false;
+  }
+}
+// Is the column group whose pages are descriptors (tp, end) ruled out by some predicate's page statistics?
+// (a predicate column the group does not hold is not ruled out here: the row filter drops its rows)
+__device__ __forceinline__ bool cg_ruled_out_by_stats(const tskv_page_desc *descs, uint64_t tp, uint64_t end, const PredicateSet &preds,
+                                                      const int64_t *page_stats) {
+  for (uint32_t k = 0; k < preds.n; k++) {
+    const tskv_field_predicate fp = preds.p[k];
+    for (uint64_t p = tp + 1; p < end; p++)
+      if (descs[p].column_id == fp.column_id) {
+        if (descs[p].phys_type == fp.phys_type && stats_rule_out(fp.phys_type, fp.op, fp.value, page_stats[2 * p], page_stats[2 * p + 1])) return true;
+        break;
+      }
+  }
+  return false;
+}
+
 __device__ __forceinline__ int find_qcol(const ColState *cols, uint32_t n_cols, uint16_t column_id) {
   for (uint32_t c = 0; c < n_cols; c++)
     if (cols[c].column_id == column_id) return (int)c;
@@ -163,7 +216,8 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint4 *item_info
                              const int32_t *cg_slot, const ColState *cols, uint32_t n_cols,
                              const uint32_t *bin_start, uint8_t *item_flag, uint32_t *block_count,
                              unsigned long long *counters, int32_t *status, const tskv_time_range *cg_bounds,
-                             const PruneRanges prune, const uint8_t *cg_merge) {
+                             const PruneRanges prune, const uint8_t *cg_merge, const int64_t *page_stats,
+                             const PredicateSet preds, uint64_t n_descs, uint32_t n_cg) {
   __shared__ uint32_t s_cnt;
   __shared__ unsigned long long s_pages, s_bytes[N_BINS];
   if (threadIdx.x == 0) { s_cnt = 0; s_pages = 0; }
@@ -182,8 +236,13 @@ __global__ void k_flag_items(const tskv_page_desc *descs, const uint4 *item_info
       const tskv_time_range b = cg_bounds[cg];
       in_time = false;
       for (uint32_t k = 0; k < prune.n; k++) in_time = in_time || (b.min_ts <= prune.r[k].max_ts && b.max_ts >= prune.r[k].min_ts);
-      if (!in_time && qc >= 0 && cg_slot[cg] >= 0 && !(cg_merge && cg_merge[cg])) atomicAdd(&counters[2 + N_BINS], 1ull);
     }
+    if (in_time && page_stats && qc >= 0 && cg_slot[cg] >= 0) {  // value statistics against the pushed predicates
+      const uint32_t tp0 = cg_time_page[cg];
+      const uint64_t end = cg + 1 < n_cg ? (uint64_t)cg_time_page[cg + 1] : n_descs;
+      if (cg_ruled_out_by_stats(descs, tp0, end, preds, page_stats)) in_time = false;
+    }
+    if (!in_time && qc >= 0 && cg_slot[cg] >= 0 && !(cg_merge && cg_merge[cg])) atomicAdd(&counters[2 + N_BINS], 1ull);
     // (column groups of overlapping chunks go through the merge pass instead, merge_kernels.cuh)
     if (qc >= 0 && cg_slot[cg] >= 0 && in_time && !(cg_merge && cg_merge[cg])) {
       if (cols[qc].phys_type != d.phys_type) {
@@ -256,6 +315,8 @@ struct WorkListArgs {
   const tskv_time_range *cg_bounds;  // statistics pruning (null: none)
   PruneRanges prune;
   const uint8_t *cg_merge;       // column groups of overlapping chunks go through the merge pass
+  const int64_t *page_stats;     // value-statistics pruning against `preds` (null: none)
+  PredicateSet preds;
   uint32_t *bucket_count;        // [N_BINS * n_cols] totals (pass 1), then running cursors (pass 2)
   uint32_t *bucket_off;          // [N_BINS * n_cols + 1] exclusive offsets (k_worklist_offsets)
   uint32_t *work_page, *work_slot;
@@ -290,6 +351,7 @@ __device__ __forceinline__ void worklist_walk(const WorkListArgs &A, uint32_t i,
     }
     const uint32_t tp = __ldg(A.cg_time_page + cg);
     const uint64_t end = cg + 1 < A.n_cg ? (uint64_t)__ldg(A.cg_time_page + cg + 1) : A.n_descs;
+    if (in_time && A.page_stats && cg_ruled_out_by_stats(A.descs, tp, end, A.preds, A.page_stats)) in_time = false;
     uint32_t seen_classes = 0;  // value classes that already brought the time page
     bool any = false;
     for (uint64_t p = (uint64_t)tp + 1; p < end; p++) {
@@ -587,12 +649,6 @@ __device__ __forceinline__ bool cmp_true(uint8_t pt, uint8_t op, uint64_t v, uin
     default: return false;
   }
 }
-
-struct PredicateSet {
-  tskv_field_predicate p[TSKV_MAX_PREDICATES];
-  uint32_t n;
-  uint32_t pad;
-};
 
 __global__ void k_row_filter(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs, const uint32_t *cg_time_page,
                              uint32_t n_cg, const int32_t *cg_slot, const PredicateSet preds, const uint32_t *keep_off,

@@ -70,6 +70,7 @@ struct tskv_pages {
   uint4 *d_item_info = nullptr;         // per item: page, column group, size, column id | type | kind
   uint32_t *d_rank_cg_start = nullptr, *d_rank_cg = nullptr;  // CSR: series rank -> its column groups (arena order)
   uint8_t *d_page_bin = nullptr;        // decode-kind bin of every field page
+  mutable int64_t *d_page_stats = nullptr;  // {min key, max key} of every field page (k_page_stats), built on first use
   uint32_t n_items = 0;
   uint32_t *d_item_page = nullptr;
   uint32_t *d_item_cg = nullptr;
@@ -307,6 +308,24 @@ void ensure_time_bounds(tskv_ctx *ctx, const tskv_pages *pg) {
   }
   pg->bounds_known = true;
   cudaFree(d_bounds);
+}
+
+// Value statistics of the field pages, computed on the device the first time a scan with field predicates is prepared
+// (pages resident in HBM only; the reference reads them from PageMeta.statistics).
+void ensure_page_stats(tskv_ctx *ctx, const tskv_pages *pg) {
+  static const bool off = getenv("TSKV_NO_VALUE_STATS") != nullptr;
+  if (off || pg->d_page_stats || pg->h_mapped || pg->n_descs == 0) return;
+  int64_t *d = nullptr;
+  if (cudaMalloc(reinterpret_cast<void **>(&d), (size_t)pg->n_descs * 16) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  k_page_stats<<<(unsigned)((pg->n_descs + 127) / 128), 128, 0, ctx->stream>>>(pg->d_arena, pg->d_descs, pg->n_descs, d);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    cudaFree(d);
+    return;
+  }
+  pg->d_page_stats = d;
 }
 
 tskv_status compute_layout(const tskv_pages *pages, const tskv_query *q, tskv_output_layout *out) {
@@ -843,6 +862,7 @@ void tskvgpu_pages_destroy(tskv_ctx *ctx, tskv_pages *pg) {
   cudaFree(pg->d_rank_cg_start);
   cudaFree(pg->d_rank_cg);
   cudaFree(pg->d_page_bin);
+  cudaFree(pg->d_page_stats);
   cudaFree(pg->d_item_page);
   cudaFree(pg->d_item_cg);
   cudaFree(pg->d_bin_start);
@@ -1378,6 +1398,7 @@ tskv_status tskvgpu_scan_prepare(tskv_ctx *ctx, const tskv_pages *pages, const t
   if (e == cudaSuccess) e = stream_alloc(ctx, &s->d_state, sl.total);
   s->preds.n = q->n_predicates;
   for (uint32_t k = 0; k < q->n_predicates; k++) s->preds.p[k] = q->predicates[k];
+  if (q->n_predicates) ensure_page_stats(ctx, pages);  // value-statistics pruning (filter_column_groups, reader/chunk.rs:12-50)
   if (e == cudaSuccess && q->n_predicates) e = stream_alloc(ctx, &s->d_row_keep, (size_t)pages->keep_words);
   // aux block (8-byte units): [0..7] task counters (N_BINS x u32) | 8 status | 9 err_page | 10,11 stats
   //                           | 12 pages 13 bytes 14..22 per-bin bytes
@@ -1770,7 +1791,8 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
                                                         pages->d_cg_time_page, n_items, s->d_cg_slot, s->d_cols,
                                                         s->n_cols, pages->d_bin_start, s->d_item_flag,
                                                         s->d_block_count, s->d_counters, s->d_status,
-                                                        s->prune.n ? pages->d_cg_bounds : nullptr, s->prune, pages->d_cg_merge);
+                                                        s->prune.n ? pages->d_cg_bounds : nullptr, s->prune, pages->d_cg_merge,
+                                                        s->preds.n ? pages->d_page_stats : nullptr, s->preds, pages->n_descs, pages->n_cg);
     k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(s->d_block_count, s->n_blocks, s->d_bin_cstart + N_BINS + 1);
     k_scatter_items<<<s->n_blocks, 1024, 0, ctx->stream>>>(pages->d_item_page, pages->d_item_cg, n_items, s->d_item_flag,
                                                            s->d_block_count, s->d_cg_slot, pages->d_bin_start,
@@ -1795,6 +1817,8 @@ static tskv_status enqueue_scan(tskv_ctx *ctx, tskv_scan *s, bool capturing = fa
     A.cg_bounds = s->prune.n ? pages->d_cg_bounds : nullptr;
     A.prune = s->prune;
     A.cg_merge = pages->d_cg_merge;
+    A.page_stats = s->preds.n ? pages->d_page_stats : nullptr;
+    A.preds = s->preds;
     const uint32_t n_buckets = N_BINS * s->n_cols;
     A.bucket_count = s->d_bucket;
     A.bucket_off = s->d_bucket + n_buckets;

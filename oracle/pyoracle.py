@@ -60,6 +60,8 @@ def lib():
         L.orc_close.argtypes = [vp]
         L.orc_close.restype = None
         L.orc_last_error.restype = C.c_char_p
+        L.orc_set_value_stats_pruning.argtypes = [C.c_int]
+        L.orc_set_value_stats_pruning.restype = None
         _lib = L
     return _lib
 
@@ -200,6 +202,10 @@ def scan_aggregate(arena, descs, query, verify_crc=True, n_threads=1, return_poi
         raise OracleError(st, lib().orc_last_error().decode())
     res = ScanResult(query, L, values[: int(L.n_out * L.n_cells)], bitmaps[: int(L.validity_bytes)])
     return (res, int(pts.value)) if return_points else res
+
+
+def set_value_stats_pruning(on):
+    lib().orc_set_value_stats_pruning(1 if on else 0)
 
 
 class OpenPages:

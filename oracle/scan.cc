@@ -16,6 +16,7 @@
 namespace {
 
 thread_local std::string g_err;
+bool g_value_stats_pruning = true;  // orc_set_value_stats_pruning (tests compare pruned and unpruned scans)
 
 
 // `sliding_window` (query_server/query/src/extension/expr/window/time_window.rs:184-198); Rust `%`
@@ -148,6 +149,7 @@ struct Scan {
   const tskv_tombstone *tombs = nullptr;
   uint64_t n_tombs = 0;
   const uint64_t *cg_file = nullptr;  // file id of every column group (descriptor-table order), or null: one file
+  bool value_stats_pruning = true;
 };
 
 // update_nullbits_by_time_range (tsm/reader.rs:634-656): binary search over the page's time VALUES (the raw
@@ -248,6 +250,43 @@ struct Worker {
       tskv_status pst = orc_page_decode(pd->phys_type, S.arena + pd->offset, pd->size, S.verify_crc, pvals.data(),
                                         pvalid.data(), n_rows, &pr);
       if (pst != TSKV_OK) return pst;
+      // Value statistics (filter_column_groups -> PruningPredicate over PageMeta.statistics, reader/chunk.rs:12-50,
+      // reader/column_group/statistics.rs:11-80): when the page's min / max rule the comparison out for every row, the
+      // column group is never read. min / max over the non-null, non-NaN values; -0.0 counts as +0.0.
+      {
+        bool have = false;
+        uint64_t vmin = 0, vmax = 0;
+        for (uint64_t r = 0; r < n_rows; r++) {
+          if (!pvalid[r]) continue;
+          uint64_t v = pvals[r];
+          if (fp.phys_type == TSKV_PT_F64) {
+            if ((v & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) continue;
+            if (v == 0x8000000000000000ull) v = 0;
+          }
+          if (!have) { vmin = vmax = v; have = true; }
+          else {
+            if (less_typed(fp.phys_type, v, vmin)) vmin = v;
+            if (less_typed(fp.phys_type, vmax, v)) vmax = v;
+          }
+        }
+        uint64_t c = fp.value;
+        bool nan_const = fp.phys_type == TSKV_PT_F64 && (c & 0x7fffffffffffffffull) > 0x7ff0000000000000ull;
+        if (fp.phys_type == TSKV_PT_F64 && c == 0x8000000000000000ull) c = 0;
+        bool out = !have || nan_const;
+        if (!out) {
+          const bool c_lt_min = less_typed(fp.phys_type, c, vmin), c_gt_max = less_typed(fp.phys_type, vmax, c);
+          switch (fp.op) {
+            case TSKV_CMP_EQ: out = c_lt_min || c_gt_max; break;
+            case TSKV_CMP_NE: out = vmin == vmax && vmin == c; break;
+            case TSKV_CMP_LT: out = !less_typed(fp.phys_type, vmin, c); break;   // min >= c
+            case TSKV_CMP_LE: out = c_lt_min; break;                              // min > c
+            case TSKV_CMP_GT: out = !less_typed(fp.phys_type, c, vmax); break;   // max <= c
+            case TSKV_CMP_GE: out = c_gt_max; break;                              // max < c
+            default: break;
+          }
+        }
+        if (out && S.value_stats_pruning) { *pruned = true; return TSKV_OK; }
+      }
       for (uint64_t r = 0; r < n_rows; r++)
         if (!(pvalid[r] && cmp_true(fp.phys_type, fp.op, pvals[r], fp.value))) pred_keep[r] = 0;
     }
@@ -619,6 +658,7 @@ void merge_cell(Cell &a, const Cell &b, uint8_t pt) {
 extern "C" {
 
 const char *orc_last_error(void) { return g_err.c_str(); }
+void orc_set_value_stats_pruning(int on) { g_value_stats_pruning = on != 0; }
 
 void orc_sliding_window(int64_t t, int64_t window, int64_t slide, int64_t start_time, int64_t i,
                         int64_t *out_start, int64_t *out_end) {
@@ -865,6 +905,7 @@ tskv_status scan_with(orc_handle *H, const tskv_query *q, const tskv_tombstone *
   S.tombs = tombs;
   S.n_tombs = n_tombs;
   S.cg_file = H->cg_file.empty() ? nullptr : H->cg_file.data();
+  S.value_stats_pruning = g_value_stats_pruning;
   if (q->series_ids) {
     for (uint32_t i = 0; i < q->n_series; i++) {
       if (i && q->series_ids[i] <= q->series_ids[i - 1]) {

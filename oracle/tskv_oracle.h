@@ -99,6 +99,9 @@ tskv_status orc_scan(orc_handle *h, const tskv_query *q, const tskv_tombstone *t
 tskv_status orc_set_chunk_files(orc_handle *h, const uint64_t *cg_file_id, uint64_t n_cg);
 void orc_close(orc_handle *h);
 const char *orc_last_error(void);
+/* Tests only: scans with field predicates normally skip the column groups whose page min / max rule a predicate out
+ * (filter_column_groups, reader/chunk.rs:12-50); 0 turns that off so that both ways can be compared. */
+void orc_set_value_stats_pruning(int on);
 
 #ifdef __cplusplus
 }

@@ -277,3 +277,41 @@ def test_reference_reader_tables():
     r = orc.scan_aggregate(arena, descs, q)
     assert int(r.column(1, "count")[0][0, 0]) == 3 and int(r.column(1, "sum")[0][0, 0]) == 30
     assert float(r.column(2, "min")[0][0, 0]) == 4.0 and float(r.column(2, "max")[0][0, 0]) == 18.0
+
+
+def test_value_statistics_pruning_never_changes_the_result():
+    """filter_column_groups with the pages' min / max (reader/chunk.rs:12-50): skipping the column groups a predicate
+    rules out gives what evaluating the predicate on every row gives, and decodes fewer points."""
+    rng = np.random.default_rng(17)
+    b = datagen.ArenaBuilder()
+    for sid in range(60):
+        t = 1_000_000
+        for _ in range(int(rng.integers(1, 4))):
+            n = int(rng.integers(1, 300))
+            ts = t + np.arange(n, dtype=np.int64) * 1000
+            t = int(ts[-1]) + 1000
+            base = int(rng.integers(-4, 5)) * 1000
+            fv = (base + rng.integers(0, 900, n)).astype(np.float64) * 0.5
+            if sid % 9 == 0:
+                fv[rng.integers(0, n)] = np.nan
+            if sid % 10 == 0:
+                fv[:] = -0.0
+            b.add_column_group(sid, ts, [(1, cabi.TSKV_PT_I64, base + rng.integers(0, 900, n), rng.random(n) > 0.1),
+                                         (2, cabi.TSKV_PT_F64, fv, None)])
+    arena, descs = b.finish()
+    fbs, nb = bucket_spec(1_000_000, 1_000_000 + 1_000_000, 50_000)
+    fields = [(1, cabi.TSKV_PT_I64), (2, cabi.TSKV_PT_F64)]
+    try:
+        for preds in ([(1, cabi.TSKV_PT_I64, ">", 1500)], [(1, cabi.TSKV_PT_I64, "<=", -2000), (2, cabi.TSKV_PT_F64, "<", 0.0)],
+                      [(2, cabi.TSKV_PT_F64, ">=", 0.0)], [(2, cabi.TSKV_PT_F64, "!=", -0.0)], [(2, cabi.TSKV_PT_F64, "==", 250.5)],
+                      [(1, cabi.TSKV_PT_I64, "!=", 7)], [(2, cabi.TSKV_PT_F64, "<", float("nan"))], [(1, cabi.TSKV_PT_I64, ">=", 4899)]):
+            q = make_query(fields, width=50_000, first_bucket_start=fbs, n_buckets=nb, group_by_series=True, predicates=preds)
+            orc.set_value_stats_pruning(True)
+            a, pa = orc.scan_aggregate(arena, descs, q, return_points=True)
+            orc.set_value_stats_pruning(False)
+            b2, pb = orc.scan_aggregate(arena, descs, q, return_points=True)
+            assert a.names == b2.names and pa <= pb
+            for j in range(len(a.names)):
+                assert (a.validity[j] == b2.validity[j]).all() and (a.values[j] == b2.values[j]).all(), (preds, a.names[j])
+    finally:
+        orc.set_value_stats_pruning(True)
