@@ -123,7 +123,10 @@ typedef struct tskv_agg_column {
  * (reader/schema_alignmenter.rs:24-44) - makes the comparison NULL, and filter_record_batch drops the row like a FALSE.
  * Dropped rows count for no projected column (count, sum, first/last ...), exactly like rows outside the time ranges.
  * Integers compare as their type, f64 numerically (NaN: never TRUE; the reference's arrow kernels are not pinned for
- * NaN / signed zeros inside /root/reference). `value` holds the constant's bit pattern. */
+ * NaN / signed zeros inside /root/reference). `value` holds the constant's bit pattern.
+ * Column groups in which the min / max of a predicate column's page rule the comparison out for every row are not read at
+ * all (filter_column_groups with PageMeta.statistics, tskv/src/reader/chunk.rs:12-50; the statistics are computed on the
+ * device once per HBM-resident page set); tskv_counters.pruned_page_count counts their pages. */
 enum { TSKV_CMP_EQ = 0, TSKV_CMP_NE = 1, TSKV_CMP_LT = 2, TSKV_CMP_LE = 3, TSKV_CMP_GT = 4, TSKV_CMP_GE = 5 };
 #define TSKV_MAX_PREDICATES 8
 typedef struct tskv_field_predicate {
