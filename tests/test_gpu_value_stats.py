@@ -25,15 +25,17 @@ def banded_arena(rng, n_series=120, multi_cg=True):
             base = int(rng.integers(-5, 6)) * 1000
             iv = base + rng.integers(0, 900, n)
             fv = (base + rng.integers(0, 900, n)).astype(np.float64) * 0.5
+            qv = fv.copy()                               # column 4: only ever a predicate column (NaN is never aggregated)
             if sid % 11 == 0:
-                fv[rng.integers(0, n)] = np.nan          # NaN never satisfies a comparison and is not part of min / max
+                qv[rng.integers(0, n)] = np.nan          # NaN never satisfies a comparison and is not part of min / max
             if sid % 13 == 0:
-                fv[:] = -0.0                             # -0.0 == +0.0 for `>= 0.0`
+                qv[:] = -0.0                             # -0.0 == +0.0 for `>= 0.0`
             uv = (np.uint64(2**63) + np.uint64(base + 6000) + rng.integers(0, 900, n).astype(np.uint64))
             valid = rng.random(n) > 0.1 if sid % 5 == 0 else None
             fields = [(1, cabi.TSKV_PT_I64, iv, valid), (2, cabi.TSKV_PT_F64, fv, valid)]
             if sid % 7:
                 fields.append((3, cabi.TSKV_PT_U64, uv, None))   # some groups do not hold column 3
+            fields.append((4, cabi.TSKV_PT_F64, qv, None))
             if sid % 17 == 0:
                 fields[0] = (1, cabi.TSKV_PT_I64, iv, np.zeros(n, dtype=bool))   # an all-null predicate column
             b.add_column_group(sid, ts, fields)
@@ -48,12 +50,13 @@ def test_value_statistics_prune_column_groups(engine):
     cases = [
         [(1, cabi.TSKV_PT_I64, ">", 2500)],
         [(1, cabi.TSKV_PT_I64, "<=", -3000), (2, cabi.TSKV_PT_F64, "<", 0.0)],
-        [(2, cabi.TSKV_PT_F64, ">=", 0.0)],                      # keeps the -0.0 groups
-        [(2, cabi.TSKV_PT_F64, "==", 1250.5)],
-        [(2, cabi.TSKV_PT_F64, "!=", -0.0)],
+        [(4, cabi.TSKV_PT_F64, ">=", 0.0)],                      # keeps the -0.0 groups
+        [(4, cabi.TSKV_PT_F64, "==", 1250.5)],
+        [(4, cabi.TSKV_PT_F64, "!=", -0.0)],
+        [(4, cabi.TSKV_PT_F64, "<", -1000.25), (1, cabi.TSKV_PT_I64, "!=", 0)],
         [(3, cabi.TSKV_PT_U64, ">", 2**63 + 9000)],
         [(1, cabi.TSKV_PT_I64, "==", 10**12)],                    # rules everything out
-        [(2, cabi.TSKV_PT_F64, ">", float("nan"))],               # a NaN constant is never TRUE
+        [(4, cabi.TSKV_PT_F64, ">", float("nan"))],               # a NaN constant is never TRUE
     ]
     total_pruned = 0
     for preds in cases:
@@ -69,7 +72,7 @@ def test_value_statistics_prune_column_groups(engine):
                 total_pruned += c["pruned_page_count"]
     assert total_pruned > 0
     # the predicate that rules everything out reads nothing at all
-    q = make_query(FIELDS[:2], aggs=("count",), predicates=cases[6])
+    q = make_query(FIELDS[:2], aggs=("count",), predicates=[(1, cabi.TSKV_PT_I64, "==", 10**12)])
     engine.scan_aggregate(pages, q)
     assert engine.counters()["page_read_count"] == 0 and engine.counters()["points_decoded"] == 0
     pages.close()
