@@ -118,13 +118,17 @@ class PartialsView(C.Structure):
 GPU_SYMBOLS = [
     "tskvgpu_ctx_create", "tskvgpu_ctx_destroy", "tskvgpu_last_error", "tskvgpu_last_error_page",
     "tskvgpu_get_counters", "tskvgpu_ctx_stream", "tskvgpu_upload_pages", "tskvgpu_pages_destroy",
-    "tskvgpu_pages_series_count", "tskvgpu_pages_set_time_bounds", "tskvgpu_pages_set_tombstones", "tskvgpu_pages_set_chunk_files", "tskvgpu_decode_pages",
+    "tskvgpu_pages_series_count", "tskvgpu_pages_set_time_bounds", "tskvgpu_pages_set_tombstones", "tskvgpu_pages_set_chunk_files", "tskvgpu_pages_set_value_stats", "tskvgpu_decode_pages",
     "tskvgpu_query_output_layout", "tskvgpu_comm_unique_id", "tskvgpu_comm_init", "tskvgpu_comm_destroy", "tskvgpu_scan_exchange",
     "tskvgpu_scan_aggregate", "tskvgpu_scan_prepare", "tskvgpu_scan_run", "tskvgpu_scan_enqueue",
     "tskvgpu_scan_sync", "tskvgpu_scan_partials", "tskvgpu_scan_exchange_view", "tskvgpu_scan_merge_gathered",
     "tskvgpu_scan_snapshot_keys", "tskvgpu_scan_mask_values", "tskvgpu_scan_finalize",
     "tskvgpu_scan_finalize_device", "tskvgpu_scan_destroy", "tskvgpu_version",
 ]
+
+
+TSKV_STATS_MINMAX = 1
+VALUE_STATS_DTYPE = np.dtype([("min", "<u8"), ("max", "<u8"), ("flags", "<u4"), ("reserved", "<u4")])  # tskv_value_stats
 
 
 def gpu_library_path():
@@ -171,6 +175,7 @@ def load_gpu_library():
     lib.tskvgpu_pages_set_tombstones.argtypes = [vp, vp, vp, C.c_uint64]
     lib.tskvgpu_pages_set_time_bounds.argtypes = [vp, vp, vp, C.c_uint64]
     lib.tskvgpu_pages_set_chunk_files.argtypes = [vp, vp, vp, C.c_uint64]
+    lib.tskvgpu_pages_set_value_stats.argtypes = [vp, vp, vp, C.c_uint64]
     lib.tskvgpu_comm_unique_id.argtypes = [vp]
     lib.tskvgpu_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
     lib.tskvgpu_comm_destroy.argtypes = [vp]

@@ -126,20 +126,25 @@ Column read_table_column(Rd &r) {
   c.encoding = r.u32();
   return c;
 }
-void skip_value_statistics(Rd &r, uint32_t variant) {
-  auto opt = [&](auto skip_value) { if (r.u8()) skip_value(); };
-  auto val = [&]() {
+// PageStatistics{Bool|F64|I64|U64|Bytes}(ValueStatistics{min, max: Option<T>, distinct_count: Option<u64>, null_count})
+// (page.rs:607-613, statistics/mod.rs:4-9). min / max of the numeric / boolean variants -> tskv_value_stats.
+tskv_value_stats read_value_statistics(Rd &r, uint32_t variant) {
+  tskv_value_stats st{};
+  bool have[2] = {false, false};
+  uint64_t v[2] = {0, 0};
+  for (int k = 0; k < 2; k++) {
+    if (!r.u8()) continue;  // None
     switch (variant) {
-      case 0: r.u8(); break;             // bool
-      case 1: case 2: case 3: r.u64(); break;
-      case 4: r.skip_bytes_vec(); break; // Vec<u8>
+      case 0: v[k] = r.u8(); have[k] = true; break;             // bool
+      case 1: case 2: case 3: v[k] = r.u64(); have[k] = true; break;  // f64 bits / i64 / u64
+      case 4: r.skip_bytes_vec(); break;                         // Vec<u8> (strings): not on this engine's path
       default: r.ok = false;
     }
-  };
-  opt(val);
-  opt(val);
-  opt([&]() { r.u64(); });  // distinct_count
-  r.u64();                   // null_count
+  }
+  if (r.u8()) r.u64();  // distinct_count
+  r.u64();              // null_count
+  if (have[0] && have[1]) { st.min = v[0]; st.max = v[1]; st.flags = TSKV_STATS_MINMAX; }
+  return st;
 }
 void skip_table_schema(Rd &r) {
   r.str(); r.str(); r.str();  // tenant, db, name
@@ -277,6 +282,7 @@ void tskvtsm_free(tskvtsm_result *r) {
   free(r->arena);
   free(r->descs);
   free(r->cg_bounds);
+  free(r->value_stats);
   memset(r, 0, sizeof(*r));
 }
 
@@ -336,6 +342,7 @@ tskv_status tskvtsm_load(const uint8_t *file, uint64_t len, const char *table, t
     if (!r.ok) { g_err = "chunk group meta does not parse"; return TSKV_ERR_PAGE_FORMAT; }
   }
   std::vector<tskv_page_desc> descs;
+  std::vector<tskv_value_stats> vstats;  // per descriptor
   std::vector<tskv_time_range> bounds;
   std::vector<uint8_t> arena;
   uint64_t skipped = 0;
@@ -368,6 +375,7 @@ tskv_status tskvtsm_load(const uint8_t *file, uint64_t len, const char *table, t
         const uint64_t n_pages = r.u64();
         // the engine's descriptor order: TIME page first, then the field pages by ascending column id
         std::vector<tskv_page_desc> field;
+        std::vector<tskv_value_stats> field_stats;
         tskv_page_desc time_desc{};
         bool have_time = false;
         std::vector<std::pair<uint64_t, uint64_t>> src;  // (file offset, size) in `field` order; time first
@@ -376,7 +384,7 @@ tskv_status tskvtsm_load(const uint8_t *file, uint64_t len, const char *table, t
           const uint64_t off = r.u64(), size = r.u64();
           const uint32_t num_values = r.u32();
           const Column col = read_table_column(r);
-          skip_value_statistics(r, r.u32());
+          const tskv_value_stats vst = read_value_statistics(r, r.u32());
           if (!r.ok) break;
           if (size > len || off > len - size || size >= (1ull << 32)) { g_err = "page out of bounds"; return TSKV_ERR_PAGE_FORMAT; }
           const int pt = phys_type_of(col.type);
@@ -389,20 +397,23 @@ tskv_status tskvtsm_load(const uint8_t *file, uint64_t len, const char *table, t
           d.column_id = (uint16_t)col.id;
           d.phys_type = (uint8_t)pt;
           if (pt == TSKV_PT_TIME) { time_desc = d; have_time = true; time_src = off; }
-          else { field.push_back(d); }
+          else { field.push_back(d); field_stats.push_back(vst); }
         }
         if (!r.ok) break;
         if (!have_time) { g_err = "column group without a time page (column_group.rs:67-79)"; return TSKV_ERR_PAGE_FORMAT; }
-        std::stable_sort(field.begin(), field.end(), [](const tskv_page_desc &a, const tskv_page_desc &b) { return a.column_id < b.column_id; });
-        auto put = [&](tskv_page_desc d, uint64_t file_off) {
+        std::vector<size_t> forder(field.size());
+        for (size_t k = 0; k < forder.size(); k++) forder[k] = k;
+        std::stable_sort(forder.begin(), forder.end(), [&](size_t a, size_t b) { return field[a].column_id < field[b].column_id; });
+        auto put = [&](tskv_page_desc d, uint64_t file_off, const tskv_value_stats &vs) {
           const uint64_t pad = (16 - (arena.size() & 15)) & 15;
           arena.insert(arena.end(), pad, 0);
           d.offset = arena.size();
           arena.insert(arena.end(), file + file_off, file + file_off + d.size);
           descs.push_back(d);
+          vstats.push_back(vs);
         };
-        put(time_desc, time_src);
-        for (const tskv_page_desc &d : field) put(d, d.offset);
+        put(time_desc, time_src, tskv_value_stats{});
+        for (size_t k : forder) put(field[k], field[k].offset, field_stats[k]);
         bounds.push_back(tr);
       }
       if (!r.ok) { g_err = "chunk does not parse"; return TSKV_ERR_PAGE_FORMAT; }
@@ -413,7 +424,9 @@ tskv_status tskvtsm_load(const uint8_t *file, uint64_t len, const char *table, t
   out->arena = (uint8_t *)malloc(std::max<size_t>(arena.size(), 1));
   out->descs = (tskv_page_desc *)malloc(std::max<size_t>(descs.size(), 1) * sizeof(tskv_page_desc));
   out->cg_bounds = (tskv_time_range *)malloc(std::max<size_t>(bounds.size(), 1) * sizeof(tskv_time_range));
-  if (!out->arena || !out->descs || !out->cg_bounds) { tskvtsm_free(out); return TSKV_ERR_OOM; }
+  out->value_stats = (tskv_value_stats *)malloc(std::max<size_t>(vstats.size(), 1) * sizeof(tskv_value_stats));
+  if (!out->arena || !out->descs || !out->cg_bounds || !out->value_stats) { tskvtsm_free(out); return TSKV_ERR_OOM; }
+  if (!vstats.empty()) memcpy(out->value_stats, vstats.data(), vstats.size() * sizeof(tskv_value_stats));
   if (!arena.empty()) memcpy(out->arena, arena.data(), arena.size());
   if (!descs.empty()) memcpy(out->descs, descs.data(), descs.size() * sizeof(tskv_page_desc));
   if (!bounds.empty()) memcpy(out->cg_bounds, bounds.data(), bounds.size() * sizeof(tskv_time_range));
@@ -428,6 +441,12 @@ tskv_status tskvtsm_load(const uint8_t *file, uint64_t len, const char *table, t
 // column_names may be NULL (names "c<id>"). Returns the file size, or 0 (and sets the error) on bad input.
 uint64_t tskvtsm_write(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs, const tskv_time_range *cg_bounds,
                        uint64_t n_cg, const char *table_name, uint32_t meta_encoding, uint8_t *out, uint64_t cap) {
+  return tskvtsm_write_stats(arena, descs, n_descs, cg_bounds, n_cg, table_name, meta_encoding, nullptr, out, cap);
+}
+
+uint64_t tskvtsm_write_stats(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs, const tskv_time_range *cg_bounds,
+                             uint64_t n_cg, const char *table_name, uint32_t meta_encoding, const tskv_value_stats *value_stats,
+                             uint8_t *out, uint64_t cap) {
   g_err.clear();
   if (!table_name || (meta_encoding != 1 && meta_encoding != 7)) { g_err = "writer: table name / encoding"; return 0; }
   std::vector<uint8_t> file;
@@ -489,7 +508,18 @@ uint64_t tskvtsm_write(const uint8_t *arena, const tskv_page_desc *descs, uint64
         c.u32(d.num_values);
         column(c, d);
         c.u32(d.phys_type == TSKV_PT_F64 ? 1 : d.phys_type == TSKV_PT_U64 ? 3 : d.phys_type == TSKV_PT_BOOL ? 0 : 2);  // PageStatistics variant (time: I64)
-        c.u8(0); c.u8(0); c.u8(0); c.u64(0);  // min None, max None, distinct None, null_count
+        const tskv_value_stats *vs = value_stats ? &value_stats[cg.first + p] : nullptr;
+        if (vs && (vs->flags & TSKV_STATS_MINMAX) && d.phys_type != TSKV_PT_TIME) {  // Some(min), Some(max)
+          for (int k = 0; k < 2; k++) {
+            c.u8(1);
+            const uint64_t v = k == 0 ? vs->min : vs->max;
+            if (d.phys_type == TSKV_PT_BOOL) c.u8((uint8_t)(v != 0));
+            else c.u64(v);
+          }
+        } else {
+          c.u8(0); c.u8(0);                   // min None, max None
+        }
+        c.u8(0); c.u64(0);                    // distinct None, null_count
       }
       id++;
     }

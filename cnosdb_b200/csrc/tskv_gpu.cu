@@ -898,6 +898,34 @@ tskv_status tskvgpu_pages_set_time_bounds(tskv_ctx *ctx, tskv_pages *pg, const t
   return TSKV_OK;
 }
 
+// PageMeta.statistics of the caller -> the ordered min / max keys the work list prunes with.
+tskv_status tskvgpu_pages_set_value_stats(tskv_ctx *ctx, tskv_pages *pg, const tskv_value_stats *stats, uint64_t n_descs) {
+  if (!ctx || !pg || !stats || n_descs != pg->n_descs) return TSKV_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->set_error("");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> keys(2 * (size_t)n_descs);
+  for (uint64_t i = 0; i < n_descs; i++) {
+    const uint8_t pt = pg->h_descs[i].phys_type;
+    int64_t kmin = INT64_MIN, kmax = INT64_MAX;  // unknown: nothing can be ruled out
+    if ((stats[i].flags & TSKV_STATS_MINMAX) && pt != TSKV_PT_TIME) {
+      const bool nan = pt == TSKV_PT_F64 && ((stats[i].min & 0x7fffffffffffffffull) > 0x7ff0000000000000ull ||
+                                             (stats[i].max & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
+      if (!nan) {
+        kmin = stats_key(stats[i].min, pt);
+        kmax = stats_key(stats[i].max, pt);
+        if (kmin > kmax) { kmin = INT64_MAX; kmax = INT64_MIN; }  // no value
+      }
+    }
+    keys[2 * i] = kmin;
+    keys[2 * i + 1] = kmax;
+  }
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!pg->d_page_stats) CU_TRY(ctx, cudaMalloc(reinterpret_cast<void **>(&pg->d_page_stats), std::max<size_t>(keys.size(), 1) * 8));
+  CU_TRY(ctx, cudaMemcpy(pg->d_page_stats, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
+  return TSKV_OK;
+}
+
 // Overlapping chunks: file id of every column group -> merge groups (host_util.h, plan_overlap_groups) + the merge rows'
 // timestamps, decoded once.
 tskv_status tskvgpu_pages_set_chunk_files(tskv_ctx *ctx, tskv_pages *pg, const uint64_t *cg_file_id, uint64_t n_cg) {

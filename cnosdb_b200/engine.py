@@ -155,6 +155,12 @@ class PageSet:
         self.engine._check(self.engine.lib.tskvgpu_pages_set_chunk_files(
             self.engine.ctx, self.handle, ids.ctypes.data if len(ids) else None, len(ids)))
 
+    def set_value_stats(self, stats):
+        """PageMeta.statistics per descriptor (cabi.VALUE_STATS_DTYPE: min / max bit patterns + TSKV_STATS_MINMAX): scans
+        with field predicates skip the column groups the bounds rule out, also on host-resident page sets."""
+        st = np.ascontiguousarray(stats, dtype=cabi.VALUE_STATS_DTYPE)
+        self.engine._check(self.engine.lib.tskvgpu_pages_set_value_stats(self.engine.ctx, self.handle, st.ctypes.data, len(st)))
+
     def set_time_bounds(self, bounds):
         """Per-column-group (min_ts, max_ts), ColumnGroup::time_range() order = descriptor order: lets scans with time
         ranges skip whole column groups (statistics pruning). bounds: [(lo, hi), ...] or an int64 array of shape [n, 2]."""

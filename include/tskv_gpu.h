@@ -269,6 +269,22 @@ typedef struct tskv_tombstone {
 tskv_status tskvgpu_pages_set_tombstones(tskv_ctx *ctx, tskv_pages *pages, const tskv_tombstone *tombs,
                                          uint64_t n_tombs);
 
+/* Value statistics of the pages, handed in by the caller: PageMeta.statistics (tskv/src/tsm/page.rs:599-613,
+ * tskv/src/tsm/statistics/mod.rs:4-9; what `tskvtsm_load` reports). stats[i] belongs to descriptor i (time pages: ignored).
+ * With TSKV_STATS_MINMAX set, every non-null value of the page lies in [min, max] (bit patterns of the page's physical
+ * type; bounds may be loose; min > max = the page holds no value); without it nothing is known about the page.
+ * Scans with field predicates then skip the column groups the bounds rule out (filter_column_groups,
+ * tskv/src/reader/chunk.rs:12-50) - also for TSKV_UPLOAD_HOST_RESIDENT page sets, whose pages the library never reads
+ * ahead of a scan. Without this call, HBM-resident page sets compute exact statistics on the device on first use.
+ * f64 bounds that are NaN are treated as unknown. n_descs must equal the page set's descriptor count. */
+#define TSKV_STATS_MINMAX 1u
+typedef struct tskv_value_stats {
+  uint64_t min, max;
+  uint32_t flags;
+  uint32_t reserved;
+} tskv_value_stats;
+tskv_status tskvgpu_pages_set_value_stats(tskv_ctx *ctx, tskv_pages *pages, const tskv_value_stats *stats, uint64_t n_descs);
+
 /* Overlapping chunks. A page set may hold the column groups of SEVERAL files (TSM files, delta files) and of the
  * memcache (its row groups handed in as raw-encoded pages): cg_file_id[k] is the id of the file column group k (in
  * descriptor-table order) came from - ColumnFile::file_id() / the cache's file id. Replaces, for later scans,

@@ -6,6 +6,7 @@
  *   TsmReader::open                 tskv/src/tsm/reader.rs:120-168   footer -> metadata -> chunk groups -> chunks
  *   read_footer / read_chunk_*      tskv/src/tsm/reader.rs:399-474
  *   ColumnGroup::time_range()       tskv/src/tsm/column_group.rs:9-17 (reported per column group for statistics pruning)
+ *   PageMeta.statistics             tskv/src/tsm/page.rs:599-613 (reported per page for value-statistics pruning)
  * A host that already has a TsmReader (the Rust shim of INTEGRATION.md) does not need this: it hands the engine the
  * PageWriteSpec list it holds. The loader is for hosts that start from the file.
  */
@@ -25,6 +26,8 @@ typedef struct tskvtsm_result {
   uint64_t n_descs;
   tskv_time_range *cg_bounds; /* ColumnGroup::time_range() per column group, in descriptor order */
   uint64_t n_column_groups;
+  tskv_value_stats *value_stats; /* PageMeta.statistics per descriptor (min / max of I64 / U64 / F64 / Bool pages, when the
+                                    file holds them): what tskvgpu_pages_set_value_stats takes */
   uint64_t n_skipped_pages;   /* pages of column types outside this engine's path (tag / bool / string / geometry) */
   int64_t min_ts, max_ts;     /* Footer.time_range */
   uint32_t version;           /* TsmVersion: 1 | 2 */
@@ -49,6 +52,10 @@ const char *tskvtsm_last_error(void);
 uint64_t tskvtsm_write(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs,
                        const tskv_time_range *cg_bounds, uint64_t n_cg, const char *table_name, uint32_t meta_encoding,
                        uint8_t *out, uint64_t cap);
+/* The same with PageMeta.statistics: value_stats[i] (or NULL = min / max None everywhere) goes into page i's metadata. */
+uint64_t tskvtsm_write_stats(const uint8_t *arena, const tskv_page_desc *descs, uint64_t n_descs,
+                             const tskv_time_range *cg_bounds, uint64_t n_cg, const char *table_name, uint32_t meta_encoding,
+                             const tskv_value_stats *value_stats, uint8_t *out, uint64_t cap);
 
 #ifdef __cplusplus
 }

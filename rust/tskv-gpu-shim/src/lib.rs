@@ -182,6 +182,12 @@ impl PageSet<'_> {
         let st = unsafe { sys::tskvgpu_pages_set_tombstones(self.engine.ctx, self.pages, tombs.as_ptr(), tombs.len() as u64) };
         self.engine.check(st)
     }
+    /// `PageWriteSpec.meta.statistics` of every page, in descriptor order (`reader/column_group/statistics.rs:11-80`
+    /// reads the same numbers): scans with field predicates skip the column groups the bounds rule out.
+    pub fn set_value_stats(&mut self, stats: &[sys::tskv_value_stats]) -> GpuResult<()> {
+        let st = unsafe { sys::tskvgpu_pages_set_value_stats(self.engine.ctx, self.pages, stats.as_ptr(), stats.len() as u64) };
+        self.engine.check(st)
+    }
     /// `ColumnFile::file_id()` (or the memcache's file id) of every column group, in descriptor order: scans merge
     /// the chunks of a series whose time ranges overlap, the newest file's non-null value winning per column
     /// (`DataMerger`, `reader/merge.rs`; `build_series_reader`, `reader/iterator.rs:463-560`).

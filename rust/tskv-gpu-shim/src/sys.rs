@@ -107,6 +107,17 @@ pub struct tskv_tombstone {
     pub max_ts: i64,
 }
 
+pub const TSKV_STATS_MINMAX: u32 = 1;
+/// `PageMeta.statistics` of one page (tskv/src/tsm/page.rs:599-613): bit patterns of the page's physical type.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct tskv_value_stats {
+    pub min: u64,
+    pub max: u64,
+    pub flags: u32,
+    pub reserved: u32,
+}
+
 #[repr(C)]
 pub struct tskv_query {
     pub series_ids: *const u32,
@@ -178,6 +189,7 @@ const _: () = assert!(std::mem::size_of::<tskv_time_range>() == 16);
 const _: () = assert!(std::mem::size_of::<tskv_agg_column>() == 4);
 const _: () = assert!(std::mem::size_of::<tskv_field_predicate>() == 16);
 const _: () = assert!(std::mem::size_of::<tskv_tombstone>() == 24);
+const _: () = assert!(std::mem::size_of::<tskv_value_stats>() == 24);
 const _: () = assert!(std::mem::size_of::<tskv_query>() == 88);
 const _: () = assert!(std::mem::size_of::<tskv_output_layout>() == 48);
 const _: () = assert!(std::mem::size_of::<tskv_counters>() == 104);
@@ -214,6 +226,13 @@ extern "C" {
         pages: *mut tskv_pages,
         tombs: *const tskv_tombstone,
         n_tombs: u64,
+    ) -> tskv_status;
+    /// `PageMeta.statistics` per descriptor: scans with field predicates prune by them (reader/chunk.rs:12-50).
+    pub fn tskvgpu_pages_set_value_stats(
+        ctx: *mut tskv_ctx,
+        pages: *mut tskv_pages,
+        stats: *const tskv_value_stats,
+        n_descs: u64,
     ) -> tskv_status;
     /// File id of every column group: overlapping chunks of a series are merged (DataMerger, reader/merge.rs).
     pub fn tskvgpu_pages_set_chunk_files(

@@ -30,25 +30,25 @@ def test_tsm_loader_header_and_library_agree():
     txt = open(os.path.join(ROOT, "include", "tskv_tsm.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     names = sorted(set(re.findall(r"\b(tskvtsm_\w+)\s*\(", txt)))
-    assert names == ["tskvtsm_free", "tskvtsm_last_error", "tskvtsm_load", "tskvtsm_write"]
+    assert names == ["tskvtsm_free", "tskvtsm_last_error", "tskvtsm_load", "tskvtsm_write", "tskvtsm_write_stats"]
     lib = cabi.load_hostgen_library()
     for name in names:
         assert hasattr(lib, name), name
     from cnosdb_b200 import tsmfile
-    assert C.sizeof(tsmfile._Result) == 80
+    assert C.sizeof(tsmfile._Result) == 88
 
 
 def test_struct_sizes_match_header():
     assert C.sizeof(cabi.PageDesc) == 24 and cabi.PAGE_DESC_DTYPE.itemsize == 24
     assert C.sizeof(cabi.TimeRange) == 16 and C.sizeof(cabi.AggColumn) == 4
     assert C.sizeof(cabi.Query) == 88 and C.sizeof(cabi.FieldPredicate) == 16 and C.sizeof(cabi.OutputLayout) == 48
-    assert C.sizeof(cabi.Counters) == 104 and C.sizeof(cabi.PartialsView) == 96
+    assert C.sizeof(cabi.Counters) == 104 and C.sizeof(cabi.PartialsView) == 96 and cabi.VALUE_STATS_DTYPE.itemsize == 24
 
 
 def test_header_compiles_as_c(tmp_path):
     import subprocess
     src = tmp_path / "t.c"
-    src.write_text('#include "tskv_gpu.h"\n#include "tskv_tsm.h"\nint main(void){tskv_query q; (void)q; return sizeof(tskv_page_desc)==24 && sizeof(tskvtsm_result)==80?0:1;}\n')
+    src.write_text('#include "tskv_gpu.h"\n#include "tskv_tsm.h"\nint main(void){tskv_query q; (void)q; return sizeof(tskv_page_desc)==24 && sizeof(tskvtsm_result)==88?0:1;}\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t")])
     subprocess.check_call([str(tmp_path / "t")])
 
@@ -83,5 +83,5 @@ def test_rust_shim_declares_exactly_the_header_symbols():
                 "tskv_agg_column": C.sizeof(cabi.AggColumn), "tskv_field_predicate": C.sizeof(cabi.FieldPredicate),
                 "tskv_query": C.sizeof(cabi.Query), "tskv_output_layout": C.sizeof(cabi.OutputLayout),
                 "tskv_counters": C.sizeof(cabi.Counters), "tskv_partials_view": C.sizeof(cabi.PartialsView),
-                "tskv_tombstone": cabi.TOMBSTONE_DTYPE.itemsize}
+                "tskv_tombstone": cabi.TOMBSTONE_DTYPE.itemsize, "tskv_value_stats": cabi.VALUE_STATS_DTYPE.itemsize}
     assert {k: int(v) for k, v in sizes.items()} == expected

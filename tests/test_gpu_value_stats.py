@@ -76,3 +76,48 @@ def test_value_statistics_prune_column_groups(engine):
     engine.scan_aggregate(pages, q)
     assert engine.counters()["page_read_count"] == 0 and engine.counters()["points_decoded"] == 0
     pages.close()
+
+
+def test_statistics_handed_in_by_the_caller_prune_host_resident_page_sets(engine):
+    """tskvgpu_pages_set_value_stats: PageMeta.statistics from the TSM file. A host-resident page set (whose pages the
+    library never reads ahead of a scan) then prunes by values too: fewer bytes cross PCIe, same results; loose bounds
+    and pages without statistics are safe."""
+    from cnosdb_b200 import tsmfile
+    from tests.test_tsm_file import page_value_stats
+    rng = np.random.default_rng(5)
+    arena, descs = banded_arena(rng, n_series=80)
+    bounds = []
+    for i, d in enumerate(descs):
+        if d["phys_type"] == cabi.TSKV_PT_TIME:
+            t = orc.decode_pages(arena, descs, i, 1)[0][0].view(np.int64)
+            bounds.append((int(t.min()), int(t.max())))
+    stats = page_value_stats(arena, descs)
+    f = tsmfile.load(tsmfile.write(arena, descs, np.array(bounds, dtype=np.int64), value_stats=stats))   # through a real file image
+    assert (f.value_stats["flags"] == stats["flags"]).all()
+    fbs, nb = bucket_spec(1_000_000, 1_000_000 + 1_600_000, 50_000)
+    preds = [(1, cabi.TSKV_PT_I64, ">", 2500), (4, cabi.TSKV_PT_F64, ">=", 0.0)]
+    q = make_query(FIELDS[:2], aggs=("count", "sum", "min", "max", "mean"), width=50_000, first_bucket_start=fbs, n_buckets=nb, predicates=preds)
+    exp, pts = orc.scan_aggregate(f.arena, f.descs, q, return_points=True)
+    hp = engine.upload_pages(f.arena, f.descs, verify_crc=True, host_resident=True)
+    assert_results_equal(engine.scan_aggregate(hp, q), exp, what="host-resident, no statistics")
+    bytes_without = engine.counters()["page_read_bytes"]
+    assert engine.counters()["pruned_page_count"] == 0
+    hp.set_value_stats(f.value_stats)
+    assert_results_equal(engine.scan_aggregate(hp, q), exp, what="host-resident, caller statistics")
+    c = engine.counters()
+    assert c["pruned_page_count"] > 0 and c["page_read_bytes"] < bytes_without and c["points_decoded"] == pts
+    loose = f.value_stats.copy()   # bounds may be loose, and some pages may come without statistics
+    i64 = f.descs["phys_type"] == cabi.TSKV_PT_I64
+    loose["min"][i64] = (loose["min"][i64].view(np.int64) - 700).view(np.uint64)
+    loose["max"][i64] = (loose["max"][i64].view(np.int64) + 700).view(np.uint64)
+    loose["flags"][::3] = 0
+    hp.set_value_stats(loose)
+    assert_results_equal(engine.scan_aggregate(hp, q), exp, what="host-resident, loose statistics")
+    assert 0 < engine.counters()["pruned_page_count"] <= c["pruned_page_count"]
+    hp.close()
+    # an HBM-resident page set takes the caller's statistics instead of computing its own
+    pages = engine.upload_pages(f.arena, f.descs)
+    pages.set_value_stats(f.value_stats)
+    assert_results_equal(engine.scan_aggregate(pages, q), exp, what="HBM-resident, caller statistics")
+    assert engine.counters()["points_decoded"] == pts
+    pages.close()

@@ -97,3 +97,61 @@ def test_tsm_file_feeds_the_engine(engine):
     assert_results_equal(engine.scan_aggregate(pages, q), orc.scan_aggregate(arena, descs, q), what="scan of a loaded TSM file")
     assert engine.counters()["pruned_page_count"] > 0
     pages.close()
+
+
+def page_value_stats(arena, descs):
+    """min / max of every field page's non-null values (what the reference's writer keeps in PageMeta.statistics)."""
+    st = np.zeros(len(descs), dtype=cabi.VALUE_STATS_DTYPE)
+    pages = orc.decode_pages(arena, descs)
+    for i, (d, (vals, valid)) in enumerate(zip(descs, pages)):
+        pt = int(d["phys_type"])
+        if pt == cabi.TSKV_PT_TIME:
+            continue
+        if not valid.any():
+            st[i] = (1, 0, cabi.TSKV_STATS_MINMAX, 0)   # min > max: the page holds no value
+            continue
+        v = vals[valid]
+        if pt == cabi.TSKV_PT_I64:
+            lo, hi = v.view(np.int64).min(), v.view(np.int64).max()
+            st[i] = (np.array(lo, dtype=np.int64).view(np.uint64), np.array(hi, dtype=np.int64).view(np.uint64), cabi.TSKV_STATS_MINMAX, 0)
+        elif pt == cabi.TSKV_PT_F64:
+            f = v.view(np.float64)
+            f = f[~np.isnan(f)]
+            if f.size:
+                st[i] = (np.array(f.min()).view(np.uint64), np.array(f.max()).view(np.uint64), cabi.TSKV_STATS_MINMAX, 0)
+            else:
+                st[i] = (1, 0, cabi.TSKV_STATS_MINMAX, 0)
+        else:  # u64, bool
+            st[i] = (v.min(), v.max(), cabi.TSKV_STATS_MINMAX, 0)
+    return st
+
+
+@pytest.mark.parametrize("enc", ["null", "snappy"])
+def test_page_statistics_and_boolean_columns_round_trip(enc):
+    """PageMeta.statistics (page.rs:599-613): Some(min) / Some(max) of i64 / u64 / f64 / bool pages come back per descriptor,
+    None stays unknown; ValueType::Boolean columns are loaded as TSKV_PT_BOOL pages."""
+    rng = np.random.default_rng(3)
+    b = datagen.ArenaBuilder()
+    for sid in range(12):
+        n = int(rng.integers(1, 200))
+        ts = 1000 + np.arange(n, dtype=np.int64) * 10
+        b.add_column_group(sid, ts, [(1, cabi.TSKV_PT_I64, rng.integers(-500, 500, n), rng.random(n) > 0.2),
+                                     (2, cabi.TSKV_PT_F64, rng.normal(size=n) * 100, None),
+                                     (3, cabi.TSKV_PT_U64, np.uint64(2**63) + rng.integers(0, 1000, n).astype(np.uint64), None),
+                                     (4, cabi.TSKV_PT_BOOL, rng.random(n) < 0.5, rng.random(n) > 0.1)])
+    arena, descs = b.finish()
+    bounds = np.array([[1000, 1000 + (int(d["num_values"]) - 1) * 10] for d in descs if d["phys_type"] == cabi.TSKV_PT_TIME], dtype=np.int64)
+    stats = page_value_stats(arena, descs)
+    stats["flags"][5::5] = 0   # some pages without statistics (None / None)
+    f = tsmfile.load(tsmfile.write(arena, descs, bounds, meta_encoding=enc, value_stats=stats))
+    assert f.n_skipped_pages == 0 and [int(x) for x in f.descs["phys_type"][:5]] == [0, 1, 3, 2, 4]
+    assert len(f.value_stats) == len(descs)
+    for a, bst, d in zip(stats, f.value_stats, descs):
+        if d["phys_type"] == cabi.TSKV_PT_TIME or not a["flags"]:
+            assert bst["flags"] == 0
+        else:
+            assert (int(bst["min"]), int(bst["max"]), int(bst["flags"])) == (int(a["min"]), int(a["max"]), cabi.TSKV_STATS_MINMAX)
+    # without statistics everything is unknown
+    assert (tsmfile.load(tsmfile.write(arena, descs, bounds, meta_encoding=enc)).value_stats["flags"] == 0).all()
+    got, exp = orc.decode_pages(f.arena, f.descs), orc.decode_pages(arena, descs)
+    assert all((g[0] == e[0]).all() and (g[1] == e[1]).all() for g, e in zip(got, exp))
