@@ -295,7 +295,8 @@ tskv_status tskvgpu_pages_set_value_stats(tskv_ctx *ctx, tskv_pages *pages, cons
  *                        sort_merge.rs:153-400, batch_builder.rs:74-155)
  *   MemCacheReader       (tskv/src/reader/memcache_reader.rs:33-165): the cache is one more chunk.
  * Chunks of a series whose time ranges do not overlap are scanned as before. The column groups' time bounds are
- * taken from tskvgpu_pages_set_time_bounds when it was called, else computed from the time pages. n_cg = 0 clears;
+ * taken from tskvgpu_pages_set_time_bounds when it was called BEFORE this call, else computed from the time pages (bounds
+ * handed in later do not regroup the chunks: call this again). n_cg = 0 clears;
  * any change invalidates scans prepared earlier (TSKV_ERR_INVALID_ARG when run). Time pages of overlapping chunks
  * must not hold NULLs (TSKV_ERR_UNSUPPORTED; the reference's writer never produces them). The merged rows of one
  * overlap group count as ONE record batch for first / last (the reference cuts batches of QueryOption.batch_size). */
