@@ -315,3 +315,25 @@ def test_value_statistics_pruning_never_changes_the_result():
                 assert (a.validity[j] == b2.validity[j]).all() and (a.values[j] == b2.values[j]).all(), (preds, a.names[j])
     finally:
         orc.set_value_stats_pruning(True)
+
+
+def test_pruning_against_the_reference_chunk_tests():
+    """The column-group statistics table of tskv/src/reader/chunk.rs:69-176 (time [1,3] [4,5] [7,8] [9,14]; field1 [0,5]
+    [4,6] ...): `time > 5` keeps groups 3 and 4 (test_filter_time_column_groups_indices, :200-217), `field1 == 10` is
+    ruled out by the statistics [0,5] and [4,6] (the field branch of test_filter_multi_column_groups_indices, :240-276).
+    Pruned groups are not read: their values are not counted as decoded points."""
+    b = datagen.ArenaBuilder()
+    groups = [([1, 3], [0, 5]), ([4, 5], [4, 6]), ([7, 8], [2, 4]), ([9, 14], [3, 30])]
+    for ts, vals in groups:
+        b.add_column_group(1, np.array(ts, dtype=np.int64), [(2, cabi.TSKV_PT_I64, np.array(vals, dtype=np.int64), None)])
+    arena, descs = b.finish()
+    col = [PushedAggregate(2, cabi.TSKV_PT_I64, ["count", "sum"])]
+    # time > 5  ==  the closed range [6, +inf): groups 1 and 2 are never read
+    r, pts = orc.scan_aggregate(arena, descs, QueryOption(col, time_ranges=[(6, 2**62)]), return_points=True)
+    assert int(r.column(2, "count")[0][0, 0]) == 4 and pts == 4
+    # field1 == 10: [0,5], [4,6] and [2,4] are ruled out, [3,30] is not (it holds no 10: read, no row passes)
+    r, pts = orc.scan_aggregate(arena, descs, QueryOption(col, predicates=[(2, cabi.TSKV_PT_I64, "==", 10)]), return_points=True)
+    assert int(r.column(2, "count")[0][0, 0]) == 0 and pts == 2
+    # field1 >= 5: the groups whose max is below 5 go
+    r, pts = orc.scan_aggregate(arena, descs, QueryOption(col, predicates=[(2, cabi.TSKV_PT_I64, ">=", 5)]), return_points=True)
+    assert int(r.column(2, "count")[0][0, 0]) == 3 and int(r.column(2, "sum")[0][0, 0].view(np.int64)) == 5 + 6 + 30 and pts == 6
